@@ -1,0 +1,269 @@
+#!/usr/bin/env python3
+"""bench.py -- the hot path on BASELINE.json's headline workload.
+
+One "step" = one pass of the alignment kernel over one batch of synthetic (query, reference) pairs.
+Default workload = BASELINE.json configs[1]: "Nanopore X-drop" -- 100 000 DNA pairs of ~10 kbp, NW1,
+gaps -2/-1, x_drop 50, block 32..=256 (see block_aligner_b200/workloads.py). Under torchrun
+every rank aligns its own 100 k-pair shard (weak scaling, no data-path collective: pairs are independent).
+
+metric   GCUPS = computed DP cells / second / 1e9, cells = sum of h*w over every rectangle the adaptive
+         algorithm computes (path-determined: identical on GPU and CPU when results are bit-exact)
+value    kernel time only, inputs resident in HBM (CUDA events on the kernel's stream, max over ranks)
+e2e      through the C ABI with host buffers: H2D of raw bytes + convert/pad + align + D2H, every step
+roofline integer-ALU bound (max-plus DP on i16 values; not HBM, not tensor): achieved = cells/s x 13
+         algorithmic ops per cell vs. the add/max issue peak measured on this GPU
+cpu_baseline  the CPU oracle (C++ restatement of the reference's AVX2 path) on all host cores, bounded sample
+
+--impl reference times that CPU path alone (same metric/config) -- the reference is Rust and cannot be
+built in this image, so the "reference arm" is its AVX2-intrinsic restatement in oracle/ba_oracle.cpp.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+OPS_PER_CELL = {0: 10, 2: 13, 1: 16, 3: 19}   # flags -> algorithmic i16 ops per cell
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.idx, self.rows, self.stop_flag = gpu_index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.idx)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def load_workload(name):
+    from block_aligner_b200 import workloads
+    return workloads.WORKLOADS[name]
+
+
+def gen_shard(w, n, first, pinned):
+    """Synthetic shard -> (q_arena, q_off, r_arena, r_off); arenas live in pinned host memory when possible."""
+    from block_aligner_b200 import workloads
+    qa, qo, ra, ro = workloads.generate(w["gen"], n, first=first, seed=1234, stream=w["stream"])
+    if pinned:
+        import torch
+        keep = []
+        out = []
+        for a in (qa, qo, ra, ro):
+            t = torch.empty(a.shape, dtype={np.dtype("uint8"): torch.uint8, np.dtype("uint64"): torch.int64}[a.dtype]).pin_memory()
+            v = t.numpy().view(a.dtype)
+            v[...] = a
+            keep.append(t)
+            out.append(v)
+        return (*out, keep)
+    return qa, qo, ra, ro, None
+
+
+def cpu_sample(w, lib_for_matrix, n_pairs_hint, target_s, first=0):
+    """Time the oracle on a bounded sample with all host threads. -> dict for cpu_baseline."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ora
+    import parity
+    from block_aligner_b200 import workloads
+    threads = ora.lib().ora_hw_threads()
+    matrix = workloads.matrix_of(lib_for_matrix, w) if lib_for_matrix is not None else None
+    if matrix is None and isinstance(w["matrix"], str):
+        matrix = ora.nw1() if w["matrix"] == "NW1" else ora.builtin(w["matrix"])
+    elif matrix is None:
+        matrix = ora.nuc_matrix(*w["matrix"])
+
+    def run(n, first_pair):
+        qa, qo, ra, ro = workloads.generate(w["gen"], n, first=first_pair, seed=1234, stream=w["stream"])
+        res, cells, _ = parity.oracle_batch(w["scoring"], matrix, w["gaps"], w["size"], w["x_drop"], w["flags"] & ~1, False,
+                                            qa, qo, ra, ro, threads=threads)
+        dt = ora.lib().ora_last_batch_seconds()   # wall clock around the align calls only
+        return dt, int(cells.sum()), n
+    pilot = max(threads * 4, 32)
+    dt, cells, n = run(pilot, first)
+    rate = cells / max(dt, 1e-9)
+    per_pair = dt / n
+    n2 = int(min(n_pairs_hint, max(pilot, target_s / max(per_pair, 1e-9))))
+    dt, cells, n = run(n2, first)
+    return {"value": cells / dt / 1e9, "unit": "GCUPS", "cores": threads, "kind": "port",
+            "sample": f"first {n} pairs of the workload, oracle/libba_oracle.so (C++ restatement of the reference AVX2 path; "
+                      f"the Rust original cannot be built here), {threads} threads, {dt:.2f} s wall",
+            "alignments_per_s": n / dt, "seconds": dt, "pairs": n, "cells": cells}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2_nanopore_xdrop_10k")
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU (default: the workload's full size)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    w = load_workload(args.workload)
+    n = args.pairs or w["n"]
+    config = {"workload": f"{args.workload}: {n} pairs/GPU, {w['matrix']} gaps {w['gaps']}, block {w['size'][0]}..={w['size'][1]}, "
+                          f"x_drop {w['x_drop']}, flags {w['flags']} (1=TRACE, 2=X_DROP)",
+              "pairs_per_gpu": n, "l2": "inputs (~%.1f GB/GPU) are larger than L2; no flush needed" % (n * 21e3 / 1e9),
+              "parallelism": f"pairs sharded over {world} GPU(s), no collective on the data path"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        # the reference's CPU implementation of the path (restated), all host threads, bounded sample per step
+        vals = []
+        cb = None
+        for s in range(args.warmup + args.steps):
+            cb = cpu_sample(w, None, n, max(2.0, args.cpu_seconds / 2), first=0)
+            if s >= args.warmup:
+                vals.append(cb)
+        tot_cells = sum(v["cells"] for v in vals)
+        tot_s = sum(v["seconds"] for v in vals)
+        val = tot_cells / tot_s / 1e9
+        line = {"impl": "reference", "metric": "GCUPS (computed DP cells / s / 1e9)", "value": val, "unit": "GCUPS",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_s / max(len(vals), 1) * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": cb["cores"], "kind": "port", "sample": cb["sample"]},
+                "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "alignments_per_s": sum(v["pairs"] for v in vals) / tot_s}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from block_aligner_b200 import api
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = api.Library()
+    al = api.Aligner(lib, local_rank)
+    from block_aligner_b200 import workloads
+    matrix = workloads.matrix_of(lib, w)
+    qa, qo, ra, ro, keep = gen_shard(w, n, first=rank * n, pinned=True)
+    cfg = al.config(w["scoring"], matrix, w["gaps"], w["size"], w["x_drop"], w["flags"], bool(w.get("cigar_eq")))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: kernel only, inputs resident ----
+    batch = al.upload(cfg, qa, qo, ra, ro)
+    for _ in range(args.warmup):
+        batch.run()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    kernel_ms = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        st = batch.run()                       # CUDA events around the kernel on its own stream, synchronised
+        kernel_ms.append(st.kernel_ms)
+    barrier()
+    wall = time.perf_counter() - t0
+    sampler.stop_flag = True
+    batch.download()
+    tot = batch.total_stats()
+    cells_step = int(tot.cells)
+    n_failed = int(tot.n_failed)
+    batch.free()
+    dev_s = sum(kernel_ms) / 1e3
+
+    # ---- e2e: host buffers -> results, copies inside the timed region ----
+    out = np.zeros(n, dtype=np.dtype([("score", np.int32), ("q", np.uint64), ("r", np.uint64)], align=True))
+    import ctypes as C
+    st = api.BaStats()
+
+    def e2e_once():
+        lib.check(lib.L.ba_align_batch(al.h, C.byref(cfg), n, qa.ctypes.data, qo.ctypes.data, ra.ctypes.data, ro.ctypes.data,
+                                       out.ctypes.data, C.byref(st)))
+    e2e_once()
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_once()
+    barrier()
+    e2e_s = time.perf_counter() - t1
+    h2d = int(qa.nbytes + ra.nbytes + 2 * qo.nbytes + n * (8 + 8 + 4 + 4 + 4))
+    d2h = int(n * 56)
+
+    # ---- max over ranks ----
+    vals = torch.tensor([dev_s, e2e_s, wall], dtype=torch.float64, device="cuda")
+    cells_t = torch.tensor([cells_step], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cells_t, op=dist.ReduceOp.SUM)
+    dev_s, e2e_s, wall = [float(x) for x in vals.tolist()]
+    cells_all = float(cells_t.item())
+    gcups = cells_all * args.steps / dev_s / 1e9
+    e2e_gcups = cells_all * args.steps / e2e_s / 1e9
+
+    if rank == 0:
+        peak_gops = al.int_peak_gops()
+        ops = OPS_PER_CELL[w["flags"] & 3]
+        achieved = cells_step * args.steps / (sum(kernel_ms) / 1e3) * ops / 1e9     # this rank's kernel
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        alg_bytes = float(qa.nbytes + ra.nbytes + n * 56)
+        line = {
+            "metric": "GCUPS (computed DP cells / s / 1e9)", "value": gcups, "unit": "GCUPS", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "i16", "data": "synthetic", "config": config,
+            "alignments_per_s": n * world * args.steps / dev_s,
+            "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_s / args.steps * 1e3, "alignments_per_s": n * world * args.steps / e2e_s},
+            "gpu_launches": args.steps * 1 + args.steps * 2,
+            "roofline": {"bound": "int_alu", "achieved": achieved / 1e3, "peak": peak_gops / 1e3, "unit": "Tiop/s",
+                         "frac": achieved / peak_gops if peak_gops else None, "traffic": None,
+                         "ops_per_cell": ops, "peak_source": "ba_measure_int_peak (DPX add-max / max3 issue rate measured on this GPU)",
+                         "hbm": {"achieved": alg_bytes / (sum(kernel_ms) / args.steps / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "algorithmic_bytes_per_step": alg_bytes,
+                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"}},
+            "clocks": sampler.summary(), "n_failed_pairs": n_failed,
+            "wall_s_timed_region": wall,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cb = cpu_sample(w, lib, n, args.cpu_seconds)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "alignments_per_s")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,730 @@
+// ba_runtime.cu -- host side of the batch API (include/block_aligner_b200.h, Part 2) and the
+// __global__ entry points. One BaAligner per GPU; no CPU execution path exists in the product build.
+//
+// The same file is compiled by g++ with -DBA_EMU into tests/emu/libba_emu.so, where "device
+// memory" is host memory and kernels run under the fiber emulator. That artefact is test
+// infrastructure (it lets `pytest -m "not gpu"` check the device source and this host logic
+// against the oracle); it is never loaded by the product.
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/block_aligner_b200.h"
+#include "ba_host.h"
+#include "ba_kernel.cuh"
+
+using namespace ba;
+
+// -------------------------------------------------------------------------------------------------
+// device abstraction
+// -------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+
+#ifdef BA_EMU
+typedef int dev_stream_t;
+static int dmalloc(void** p, size_t n) { *p = malloc(n ? n : 1); if (!*p) return 1; memset(*p, 0xCD, n); return 0; }
+static void dfree(void* p) { free(p); }
+static int h2d(void* d, const void* s, size_t n, dev_stream_t) { if (n) memcpy(d, s, n); return 0; }
+static int d2h(void* d, const void* s, size_t n, dev_stream_t) { if (n) memcpy(d, s, n); return 0; }
+static int dzero(void* d, size_t n, dev_stream_t) { if (n) memset(d, 0, n); return 0; }
+static int dsync(dev_stream_t) { return 0; }
+#define CUDA_OK(x) (x)
+#else
+#include <cuda_runtime.h>
+typedef cudaStream_t dev_stream_t;
+static int cuda_fail(cudaError_t e, const char* what) {
+  g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return 1;
+}
+#define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return cuda_fail(_e, #x); } while (0)
+static int dmalloc(void** p, size_t n) { CK(cudaMalloc(p, n ? n : 1)); return 0; }
+static void dfree(void* p) { if (p) cudaFree(p); }
+static int h2d(void* d, const void* s, size_t n, dev_stream_t st) { if (n) CK(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, st)); return 0; }
+static int d2h(void* d, const void* s, size_t n, dev_stream_t st) { if (n) CK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, st)); return 0; }
+static int dzero(void* d, size_t n, dev_stream_t st) { if (n) CK(cudaMemsetAsync(d, 0, n, st)); return 0; }
+static int dsync(dev_stream_t st) { CK(cudaStreamSynchronize(st)); return 0; }
+#define CUDA_OK(x) (x)
+#endif
+
+// -------------------------------------------------------------------------------------------------
+// kernels
+// -------------------------------------------------------------------------------------------------
+// PaddedBytes::from_bytes (scan_block.rs:1829-1836): [NULL] + convert(bytes) + pad x [NULL]
+struct PackArgs {
+  const uint8_t* raw_q; const uint64_t* raw_q_off;
+  const uint8_t* raw_r; const uint64_t* raw_r_off;   // raw_r may be null (profiles)
+  uint8_t* seq; const uint64_t* pq_off; const uint64_t* pr_off;
+  uint32_t n; uint32_t pad; int32_t scoring; uint32_t* err;
+};
+
+#ifdef BA_EMU
+static void pack_all(const PackArgs& a) {
+  const int nseq = a.raw_r ? 2 : 1;
+  for (uint32_t k = 0; k < a.n; k++)
+    for (int which = 0; which < nseq; which++) {
+      const uint8_t* src = which ? a.raw_r + a.raw_r_off[k] : a.raw_q + a.raw_q_off[k];
+      const uint64_t len = which ? a.raw_r_off[k + 1] - a.raw_r_off[k] : a.raw_q_off[k + 1] - a.raw_q_off[k];
+      uint8_t* dst = a.seq + (which ? a.pr_off[k] : a.pq_off[k]);
+      const uint8_t nul = host::null_code(a.scoring);
+      dst[0] = nul;
+      for (uint64_t t = 0; t < len; t++) { bool ok; dst[1 + t] = host::convert_char(a.scoring, src[t], &ok); if (!ok) *a.err = 1; }
+      for (uint32_t t = 0; t < a.pad; t++) dst[1 + len + t] = nul;
+    }
+}
+template <int SCORING, int FLAGS>
+struct EmuLaunch { const Params* P; unsigned char* smem; uint32_t wg; };
+template <int SCORING, int FLAGS>
+static void emu_warp_entry(void* arg) {
+  auto* l = (EmuLaunch<SCORING, FLAGS>*)arg;
+  warp_main<SCORING, FLAGS>(*l->P, l->smem, 0, l->wg);
+}
+struct EmuTb { const Params* P; uint32_t pair, qi, rj; int eq; DevResult* out1; };
+static void emu_tb_entry(void* arg) { auto* t = (EmuTb*)arg; warp_traceback(*t->P, t->pair, t->qi, t->rj, t->eq != 0, t->out1); }
+static int launch_traceback(const Params& P, uint32_t pair, uint32_t qi, uint32_t rj, int eq, DevResult* out1, dev_stream_t) {
+  EmuTb t{&P, pair, qi, rj, eq, out1};
+  emu::run_warp(&emu_tb_entry, &t);
+  return 0;
+}
+template <int SCORING, int FLAGS>
+static int launch_align(const Params& P, int blocks, int wpb, size_t smem_bytes, dev_stream_t) {
+  (void)wpb;
+  for (int b = 0; b < blocks; b++) {
+    std::vector<unsigned char> smem(smem_bytes + 64, 0xAB);
+    const int nm = SCORING == kNuc ? 128 : (SCORING == kAA ? 864 : 0);
+    for (int i = 0; i < nm; i++) smem[i] = (unsigned char)P.matrix[i];
+    EmuLaunch<SCORING, FLAGS> l{&P, smem.data(), (uint32_t)b};
+    emu::run_warp(&emu_warp_entry<SCORING, FLAGS>, &l);
+  }
+  return 0;
+}
+#else
+__global__ void ba_pack_kernel(PackArgs a) {
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t nseq = a.raw_r ? 2 * a.n : a.n;
+  const uint8_t nul = a.scoring == kNuc ? (uint8_t)'Z' : (a.scoring == kByte ? (uint8_t)0 : (uint8_t)26);
+  bool bad = false;
+  for (uint32_t s = warp; s < nseq; s += nwarps) {
+    const uint32_t k = a.raw_r ? (s >> 1) : s;
+    const bool which = a.raw_r ? (s & 1) : false;
+    const uint8_t* src = which ? a.raw_r + a.raw_r_off[k] : a.raw_q + a.raw_q_off[k];
+    const uint64_t len = which ? a.raw_r_off[k + 1] - a.raw_r_off[k] : a.raw_q_off[k + 1] - a.raw_q_off[k];
+    uint8_t* dst = a.seq + (which ? a.pr_off[k] : a.pq_off[k]);
+    if (lane == 0) dst[0] = nul;
+    for (uint64_t t = lane; t < len; t += 32) {
+      uint8_t c = src[t];
+      if (a.scoring != kByte) {
+        if (c >= 'a' && c <= 'z') c -= 32;                      // to_ascii_uppercase
+        if (a.scoring == kNuc) { if (!(c >= 'A' && c <= 'Z')) bad = true; }          // scores.rs:212-216
+        else { if (!(c >= 'A' && c <= 'A' + 26)) bad = true; c = (uint8_t)(c - 'A'); } // scores.rs:130-134
+      }
+      dst[1 + t] = c;
+    }
+    for (uint32_t t = lane; t < a.pad; t += 32) dst[1 + len + t] = nul;
+  }
+  if (bad) atomicOr(a.err, 1u);
+}
+
+template <int SCORING, int FLAGS>
+__global__ void ba_align_kernel(const __grid_constant__ Params P) {
+  extern __shared__ __align__(16) unsigned char ba_smem[];
+  const int nm = SCORING == kNuc ? 128 : (SCORING == kAA ? 864 : 0);
+  for (int i = threadIdx.x; i < nm; i += blockDim.x) ba_smem[i] = (unsigned char)P.matrix[i];
+  __syncthreads();
+  const int wib = threadIdx.x >> 5;
+  warp_main<SCORING, FLAGS>(P, ba_smem, wib, blockIdx.x * (blockDim.x >> 5) + wib);
+}
+
+__global__ void ba_traceback_kernel(const __grid_constant__ Params P, uint32_t pair, uint32_t qi, uint32_t rj, int eq, DevResult* out1) {
+  warp_traceback(P, pair, qi, rj, eq != 0, out1);
+}
+static int launch_traceback(const Params& P, uint32_t pair, uint32_t qi, uint32_t rj, int eq, DevResult* out1, dev_stream_t st) {
+  ba_traceback_kernel<<<1, 32, 0, st>>>(P, pair, qi, rj, eq, out1);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+template <int SCORING, int FLAGS>
+static int launch_align(const Params& P, int blocks, int wpb, size_t smem_bytes, dev_stream_t st) {
+  CK(cudaFuncSetAttribute(ba_align_kernel<SCORING, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  ba_align_kernel<SCORING, FLAGS><<<blocks, wpb * 32, smem_bytes, st>>>(P);
+  CK(cudaGetLastError());
+  return 0;
+}
+template <int SCORING, int FLAGS>
+static int occupancy(int wpb, size_t smem_bytes, int* blocks_per_sm) {
+  CK(cudaFuncSetAttribute(ba_align_kernel<SCORING, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ba_align_kernel<SCORING, FLAGS>, wpb * 32, smem_bytes));
+  return 0;
+}
+#endif
+
+#define BA_FOR_KERNELS(X) \
+  X(kNuc, 0) X(kNuc, 1) X(kNuc, 2) X(kNuc, 3) X(kAA, 0) X(kAA, 1) X(kAA, 2) X(kAA, 3) \
+  X(kByte, 0) X(kByte, 1) X(kByte, 2) X(kByte, 3) X(kProfile, 0) X(kProfile, 1) X(kProfile, 2) X(kProfile, 3)
+
+static int launch_dispatch(int scoring, int flags, const Params& P, int blocks, int wpb, size_t smem, dev_stream_t st) {
+#define X(S, F) if (scoring == S && flags == F) return launch_align<S, F>(P, blocks, wpb, smem, st);
+  BA_FOR_KERNELS(X)
+#undef X
+  return fail(BA_ERR_ARG, "unsupported scoring/flags combination");
+}
+static int occupancy_dispatch(int scoring, int flags, int wpb, size_t smem, int* bps) {
+#ifdef BA_EMU
+  (void)scoring; (void)flags; (void)wpb; (void)smem; *bps = 1; return 0;
+#else
+#define X(S, F) if (scoring == S && flags == F) return occupancy<S, F>(wpb, smem, bps);
+  BA_FOR_KERNELS(X)
+#undef X
+  return fail(BA_ERR_ARG, "unsupported scoring/flags combination");
+#endif
+}
+
+// -------------------------------------------------------------------------------------------------
+// objects
+// -------------------------------------------------------------------------------------------------
+struct BaAligner {
+  int device = 0;
+  dev_stream_t stream = 0;
+  int sm_count = 1;
+  size_t smem_optin = 48 * 1024;
+  size_t mem_total = 0;
+#ifndef BA_EMU
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+#endif
+  int emu_warps = 3;   // emulation: number of (sequentially executed) warps, to exercise per-warp scratch
+};
+
+struct BaBatch {
+  BaAligner* al = nullptr;
+  BaConfig cfg;
+  size_t n = 0;
+  uint32_t min_size = 0, max_size = 0;
+  uint32_t max_pair_len = 0;
+  // device
+  uint8_t* d_seq = nullptr; uint64_t* d_qoff = nullptr; uint64_t* d_roff = nullptr;
+  uint32_t* d_qlen = nullptr; uint32_t* d_rlen = nullptr; uint32_t* d_order = nullptr;
+  int8_t* d_matrix = nullptr; ProfileDev* d_profiles = nullptr; uint8_t* d_prof_arena = nullptr;
+  DevResult* d_out = nullptr; uint32_t* d_ticket = nullptr;
+  int16_t* d_ckpt = nullptr; uint32_t* d_trace = nullptr; Rect* d_rects = nullptr; uint32_t* d_runs = nullptr;
+  uint32_t* d_cigar = nullptr; unsigned long long* d_cigar_used = nullptr; uint64_t cigar_cap = 0;
+  StepLog* d_steplog = nullptr; uint32_t* d_steplog_n = nullptr;
+  // launch geometry
+  int blocks = 0, wpb = 0; size_t smem_bytes = 0; bool ckpt_in_smem = false;
+  uint64_t trace_words_per_warp = 0; uint32_t rects_per_warp = 0, runs_per_warp = 0;
+  // host results
+  std::vector<DevResult> h_out;
+  std::vector<uint32_t> h_cigar;
+  std::vector<uint32_t> h_tb;      // runs of the last ba_batch_traceback
+  DevResult* d_tb_res = nullptr;
+  float pack_ms = 0;
+  bool downloaded = false;
+};
+
+static bool pow2(uint64_t x) { return x && !(x & (x - 1)); }
+
+extern "C" const char* ba_error_string(int code) {
+  switch (code) {
+    case BA_OK: return "ok";
+    case BA_ERR_CUDA: return "CUDA error (no usable device or a runtime failure)";
+    case BA_ERR_GAPS: return "Gap costs must be negative and gap open must cost more than gap extend!";
+    case BA_ERR_SIZE: return "Block sizes must be powers of two (and not exceed the supported maximum)!";
+    case BA_ERR_XDROP: return "X-drop threshold amount must be nonnegative!";
+    case BA_ERR_ARG: return "invalid argument";
+    case BA_ERR_CHAR: return "sequence byte outside the alphabet of the scoring matrix";
+    case BA_ERR_NOMEM: return "out of device memory";
+    case BA_ERR_OVERFLOW: return "a per-warp trace or CIGAR buffer overflowed";
+  }
+  return "unknown";
+}
+extern "C" const char* ba_last_error_message(void) { return g_last_error.c_str(); }
+
+extern "C" int ba_create(int device, BaAligner** out) {
+  if (!out) return fail(BA_ERR_ARG, "out is null");
+  BaAligner* a = new BaAligner();
+  a->device = device;
+#ifndef BA_EMU
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { delete a; return fail(BA_ERR_CUDA, "no CUDA device available; this library has no CPU fallback"); }
+  if (device < 0 || device >= ndev) { delete a; return fail(BA_ERR_CUDA, "device index out of range"); }
+  if (cudaSetDevice(device) != cudaSuccess) { delete a; return fail(BA_ERR_CUDA, "cudaSetDevice failed"); }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete a; return fail(BA_ERR_CUDA, "cudaGetDeviceProperties failed"); }
+  a->sm_count = prop.multiProcessorCount;
+  a->smem_optin = prop.sharedMemPerBlockOptin;
+  a->mem_total = prop.totalGlobalMem;
+  if (cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking) != cudaSuccess) { delete a; return fail(BA_ERR_CUDA, "cudaStreamCreate failed"); }
+  cudaEventCreate(&a->ev0); cudaEventCreate(&a->ev1); cudaEventCreate(&a->ev2);
+#else
+  a->smem_optin = 227 * 1024;
+  a->mem_total = (size_t)8 << 30;
+  if (const char* e = getenv("BA_EMU_WARPS")) a->emu_warps = std::max(1, atoi(e));
+#endif
+  *out = a;
+  return BA_OK;
+}
+
+extern "C" void ba_destroy(BaAligner* a) {
+  if (!a) return;
+#ifndef BA_EMU
+  cudaSetDevice(a->device);
+  if (a->ev0) cudaEventDestroy(a->ev0);
+  if (a->ev1) cudaEventDestroy(a->ev1);
+  if (a->ev2) cudaEventDestroy(a->ev2);
+  if (a->stream) cudaStreamDestroy(a->stream);
+#endif
+  delete a;
+}
+
+extern "C" void ba_batch_free(BaBatch* b) {
+  if (!b) return;
+#ifndef BA_EMU
+  cudaSetDevice(b->al->device);
+#endif
+  dfree(b->d_seq); dfree(b->d_qoff); dfree(b->d_roff); dfree(b->d_qlen); dfree(b->d_rlen); dfree(b->d_order);
+  dfree(b->d_matrix); dfree(b->d_profiles); dfree(b->d_prof_arena); dfree(b->d_out); dfree(b->d_ticket);
+  dfree(b->d_ckpt); dfree(b->d_trace); dfree(b->d_rects); dfree(b->d_runs); dfree(b->d_cigar); dfree(b->d_cigar_used);
+  dfree(b->d_steplog); dfree(b->d_steplog_n); dfree(b->d_tb_res);
+  delete b;
+}
+
+// argument rules of Block::align / align_profile (scan_block.rs:849-862, 944-954)
+static int check_config(const BaConfig* cfg, uint32_t* mn, uint32_t* mx) {
+  if (!cfg) return fail(BA_ERR_ARG, "cfg is null");
+  if (cfg->scoring < 0 || cfg->scoring > 3) return fail(BA_ERR_ARG, "bad scoring kind");
+  if (cfg->flags & ~(BA_TRACE | BA_XDROP)) return fail(BA_ERR_ARG, "unsupported flags");
+  if (cfg->scoring != BA_SCORING_PROFILE) {
+    if (!cfg->matrix) return fail(BA_ERR_ARG, "matrix is null");
+    if (!(cfg->gaps.open < 0 && cfg->gaps.extend < 0)) return fail(BA_ERR_GAPS, "Gap costs must be negative!");
+    if (!(cfg->gaps.open < cfg->gaps.extend)) return fail(BA_ERR_GAPS, "Gap open must cost more than gap extend!");
+  }
+  uint64_t a = cfg->size.min < (uint64_t)kL ? kL : cfg->size.min, b = cfg->size.max < (uint64_t)kL ? kL : cfg->size.max;
+  if (!(a < 65535 && b < 65535)) return fail(BA_ERR_SIZE, "Block sizes must be smaller than 2^16 - 1!");
+  if (!(pow2(a) && pow2(b))) return fail(BA_ERR_SIZE, "Block sizes must be powers of two!");
+  if (b > (uint64_t)kMaxBlock) return fail(BA_ERR_SIZE, "max block size above 8192 is not supported by this build");
+  if ((cfg->flags & BA_XDROP) && cfg->x_drop < 0) return fail(BA_ERR_XDROP, "X-drop threshold amount must be nonnegative!");
+  if (cfg->scoring == BA_SCORING_PROFILE && cfg->cigar_eq) return fail(BA_ERR_ARG, "cigar_eq needs a reference sequence");
+  *mn = (uint32_t)a; *mx = (uint32_t)b;
+  return BA_OK;
+}
+
+#define TRY(x) do { int _r = (x); if (_r) { ba_batch_free(b); return _r == 1 ? BA_ERR_CUDA : _r; } } while (0)
+
+static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uint8_t* q_bytes, const uint64_t* q_off,
+                         const uint8_t* r_bytes, const uint64_t* r_off, const AAProfile* const* profiles, BaBatch** out) {
+  if (!al || !out) return fail(BA_ERR_ARG, "null aligner/out");
+  uint32_t mn = 0, mx = 0;
+  int rc = check_config(cfg, &mn, &mx);
+  if (rc) return rc;
+  if (mn > mx && false) return fail(BA_ERR_SIZE, "min > max");
+  const bool prof = cfg->scoring == BA_SCORING_PROFILE;
+  if (prof != (profiles != nullptr)) return fail(BA_ERR_ARG, "profiles must be given exactly for BA_SCORING_PROFILE");
+  if (n >= ((size_t)1 << 31)) return fail(BA_ERR_ARG, "too many pairs");
+  if (n && (!q_off || (!prof && !r_off))) return fail(BA_ERR_ARG, "null offsets");
+#ifndef BA_EMU
+  if (cudaSetDevice(al->device) != cudaSuccess) return fail(BA_ERR_CUDA, "cudaSetDevice failed");
+#endif
+  BaBatch* b = new BaBatch();
+  b->al = al; b->cfg = *cfg; b->n = n; b->min_size = mn; b->max_size = mx;
+  dev_stream_t st = al->stream;
+  const uint32_t pad = mx + 32;
+
+  // host pass: lengths, padded offsets, processing order (longest first)
+  std::vector<uint64_t> pq(n), pr(n);
+  std::vector<uint32_t> ql(n), rl(n), order(n);
+  uint64_t pos = 0, max_len = 0;
+  for (size_t k = 0; k < n; k++) {
+    const uint64_t a = q_off[k + 1] - q_off[k];
+    uint64_t c;
+    if (prof) {
+      if (!profiles[k]) { ba_batch_free(b); return fail(BA_ERR_ARG, "null profile"); }
+      c = host::profile_len(profiles[k]);
+      if (host::profile_gap_extend(profiles[k]) >= 0) { ba_batch_free(b); return fail(BA_ERR_GAPS, "Gap extend cost must be negative!"); }
+      if (host::profile_curr_len(profiles[k]) < c + mx + 1) { ba_batch_free(b); return fail(BA_ERR_SIZE, "profile was created with a smaller block size than max block size"); }
+    } else {
+      c = r_off[k + 1] - r_off[k];
+    }
+    if (a >= ((uint64_t)1 << 31) || c >= ((uint64_t)1 << 31)) { ba_batch_free(b); return fail(BA_ERR_ARG, "sequence too long"); }
+    ql[k] = (uint32_t)a; rl[k] = (uint32_t)c;
+    pq[k] = pos; pos += (1 + a + pad + 15) & ~(uint64_t)15;
+    if (!prof) { pr[k] = pos; pos += (1 + c + pad + 15) & ~(uint64_t)15; }
+    max_len = std::max<uint64_t>(max_len, a + c);
+  }
+  b->max_pair_len = (uint32_t)std::min<uint64_t>(max_len, 0xffffffffu);
+  {  // counting sort by total length, descending (long alignments first -> short tail)
+    const int SH = 6;
+    const size_t nb = (size_t)(max_len >> SH) + 2;
+    std::vector<uint32_t> cnt(nb + 1, 0);
+    for (size_t k = 0; k < n; k++) cnt[nb - 1 - (((uint64_t)ql[k] + rl[k]) >> SH)]++;
+    uint32_t run = 0;
+    for (size_t i = 0; i < nb; i++) { uint32_t c = cnt[i]; cnt[i] = run; run += c; }
+    for (size_t k = 0; k < n; k++) order[cnt[nb - 1 - (((uint64_t)ql[k] + rl[k]) >> SH)]++] = (uint32_t)k;
+  }
+  const uint64_t seq_bytes = pos + 64;
+
+  const uint64_t qraw = n ? q_off[n] - q_off[0] : 0;
+  const uint64_t rraw = (!prof && n) ? r_off[n] - r_off[0] : 0;
+  uint8_t *d_rawq = nullptr, *d_rawr = nullptr; uint64_t *d_rawqoff = nullptr, *d_rawroff = nullptr; uint32_t* d_err = nullptr;
+  auto free_tmp = [&]() { dfree(d_rawq); dfree(d_rawr); dfree(d_rawqoff); dfree(d_rawroff); dfree(d_err); };
+#define TRY2(x) do { int _r = (x); if (_r) { free_tmp(); ba_batch_free(b); return _r == 1 ? BA_ERR_CUDA : _r; } } while (0)
+  TRY2(dmalloc((void**)&b->d_seq, seq_bytes));
+  TRY2(dmalloc((void**)&b->d_qoff, n * 8)); TRY2(dmalloc((void**)&b->d_qlen, n * 4));
+  TRY2(dmalloc((void**)&b->d_roff, n * 8)); TRY2(dmalloc((void**)&b->d_rlen, n * 4));
+  TRY2(dmalloc((void**)&b->d_order, n * 4));
+  TRY2(dmalloc((void**)&b->d_out, n * sizeof(DevResult)));
+  TRY2(dmalloc((void**)&b->d_ticket, 4));
+  TRY2(dmalloc((void**)&d_rawq, qraw)); TRY2(dmalloc((void**)&d_rawqoff, (n + 1) * 8));
+  if (!prof) { TRY2(dmalloc((void**)&d_rawr, rraw)); TRY2(dmalloc((void**)&d_rawroff, (n + 1) * 8)); }
+  TRY2(dmalloc((void**)&d_err, 4));
+  TRY2(dzero(d_err, 4, st));
+  // offsets are rebased so that the raw arenas start at 0
+  std::vector<uint64_t> qo(n + 1), ro(n + 1);
+  for (size_t k = 0; k <= n && n; k++) { qo[k] = q_off[k] - q_off[0]; if (!prof) ro[k] = r_off[k] - r_off[0]; }
+#ifndef BA_EMU
+  CUDA_OK(cudaEventRecord(al->ev0, st));
+#endif
+  if (n) {
+    TRY2(h2d(d_rawq, q_bytes + q_off[0], qraw, st)); TRY2(h2d(d_rawqoff, qo.data(), (n + 1) * 8, st));
+    if (!prof) { TRY2(h2d(d_rawr, r_bytes + r_off[0], rraw, st)); TRY2(h2d(d_rawroff, ro.data(), (n + 1) * 8, st)); }
+    TRY2(h2d(b->d_qoff, pq.data(), n * 8, st)); TRY2(h2d(b->d_qlen, ql.data(), n * 4, st));
+    if (!prof) TRY2(h2d(b->d_roff, pr.data(), n * 8, st));
+    TRY2(h2d(b->d_rlen, rl.data(), n * 4, st));
+    TRY2(h2d(b->d_order, order.data(), n * 4, st));
+  }
+  // scoring data
+  if (!prof) {
+    const size_t mb = cfg->scoring == BA_SCORING_NUC ? 128 : (cfg->scoring == BA_SCORING_AA ? 864 : 2);
+    TRY2(dmalloc((void**)&b->d_matrix, mb));
+    TRY2(h2d(b->d_matrix, cfg->matrix, mb, st));
+  } else {
+    // one arena: per profile pos_aa [curr_len*32] then three i16 arrays [curr_len]
+    std::vector<ProfileDev> pd(n);
+    std::vector<uint64_t> poff(n);
+    uint64_t ppos = 0;
+    for (size_t k = 0; k < n; k++) {
+      const uint64_t cl = host::profile_curr_len(profiles[k]);
+      poff[k] = ppos; ppos += ((cl * 32 + cl * 6) + 63) & ~(uint64_t)63;
+    }
+    TRY2(dmalloc((void**)&b->d_prof_arena, ppos + 64));
+    std::vector<uint8_t> stage(ppos + 64, 0);
+    for (size_t k = 0; k < n; k++) {
+      const uint64_t cl = host::profile_curr_len(profiles[k]);
+      uint8_t* base = stage.data() + poff[k];
+      host::profile_export(profiles[k], (int8_t*)base, (int16_t*)(base + cl * 32), (int16_t*)(base + cl * 34), (int16_t*)(base + cl * 36));
+      uint8_t* dbase = b->d_prof_arena + poff[k];
+      pd[k].pos_aa = (const int8_t*)dbase;
+      pd[k].gap_open_C = (const int16_t*)(dbase + cl * 32);
+      pd[k].gap_close_C = (const int16_t*)(dbase + cl * 34);
+      pd[k].gap_open_R = (const int16_t*)(dbase + cl * 36);
+      pd[k].len = (uint32_t)host::profile_len(profiles[k]);
+      pd[k].gap_extend = host::profile_gap_extend(profiles[k]);
+    }
+    TRY2(h2d(b->d_prof_arena, stage.data(), ppos, st));
+    TRY2(dmalloc((void**)&b->d_profiles, n * sizeof(ProfileDev)));
+    TRY2(h2d(b->d_profiles, pd.data(), n * sizeof(ProfileDev), st));
+    TRY2(dsync(st));
+  }
+  // convert + pad on the device
+  PackArgs pa;
+  pa.raw_q = d_rawq; pa.raw_q_off = d_rawqoff; pa.raw_r = d_rawr; pa.raw_r_off = d_rawroff;
+  pa.seq = b->d_seq; pa.pq_off = b->d_qoff; pa.pr_off = b->d_roff; pa.n = (uint32_t)n; pa.pad = pad;
+  pa.scoring = prof ? (int)kAA : cfg->scoring; pa.err = d_err;
+  if (n) {
+#ifdef BA_EMU
+    pack_all(pa);
+#else
+    const int threads = 256;
+    const uint64_t nseq = prof ? n : 2 * n;
+    const int blocks = (int)std::min<uint64_t>((nseq * 32 + threads - 1) / threads, (uint64_t)al->sm_count * 16);
+    CUDA_OK(cudaEventRecord(al->ev1, st));
+    ba_pack_kernel<<<blocks, threads, 0, st>>>(pa);
+    if (cudaGetLastError() != cudaSuccess) { free_tmp(); ba_batch_free(b); return fail(BA_ERR_CUDA, "pack kernel launch failed"); }
+    CUDA_OK(cudaEventRecord(al->ev2, st));
+#endif
+  }
+  uint32_t herr = 0;
+  TRY2(d2h(&herr, d_err, 4, st));
+  TRY2(dsync(st));
+#ifndef BA_EMU
+  if (n) cudaEventElapsedTime(&b->pack_ms, al->ev1, al->ev2);
+#endif
+  free_tmp();
+  if (herr) { ba_batch_free(b); return fail(BA_ERR_CHAR, "sequence byte outside the alphabet of the scoring matrix"); }
+
+  // launch geometry and per-warp scratch
+  b->ckpt_in_smem = mx <= 512;
+  const size_t wbytes = warp_smem_bytes(mx, b->ckpt_in_smem);
+  int wpb = 4;
+  while (wpb > 1 && 1024 + wpb * wbytes > al->smem_optin - 1024) wpb >>= 1;
+  if (1024 + wpb * wbytes > al->smem_optin) { ba_batch_free(b); return fail(BA_ERR_SIZE, "max block size does not fit in shared memory"); }
+  b->wpb = wpb; b->smem_bytes = 1024 + wpb * wbytes;
+  int bps = 1;
+  TRY(occupancy_dispatch(prof ? (int)kProfile : cfg->scoring, cfg->flags, wpb, b->smem_bytes, &bps));
+  if (bps < 1) bps = 1;
+  uint64_t max_blocks = (uint64_t)al->sm_count * bps;
+#ifdef BA_EMU
+  max_blocks = al->emu_warps; b->wpb = wpb = 1;
+#endif
+  const bool trace = (cfg->flags & BA_TRACE) != 0;
+  if (trace) {
+    // per-warp arena, sized like the reference's Trace::new (scan_block.rs:1364-1369)
+    const uint64_t len = (uint64_t)b->max_pair_len + 2;
+    uint64_t words = 2 * (uint64_t)(mx / 16) * (len + 2 * (uint64_t)mx);
+    if (mn == 16) words *= 2;   // 16-row rectangles still occupy a 32-lane word group
+    b->trace_words_per_warp = words + 64;
+    b->rects_per_warp = (uint32_t)std::min<uint64_t>(len * 2 + 8, 0x7fffffffu);
+    b->runs_per_warp = (uint32_t)std::min<uint64_t>(len + 8, 0x7fffffffu);
+    const uint64_t per_warp = b->trace_words_per_warp * 4 + (uint64_t)b->rects_per_warp * sizeof(Rect) + (uint64_t)b->runs_per_warp * 4;
+    const uint64_t budget = (uint64_t)(al->mem_total * 0.55);
+    const uint64_t fit_warps = std::max<uint64_t>(1, budget / std::max<uint64_t>(per_warp, 1));
+    max_blocks = std::max<uint64_t>(1, std::min<uint64_t>(max_blocks, fit_warps / wpb));
+  }
+  uint64_t want = (n + wpb - 1) / wpb;
+  if (want < 1) want = 1;
+  b->blocks = (int)std::min<uint64_t>(want, max_blocks);
+  const uint64_t nwarps = (uint64_t)b->blocks * wpb;
+  const size_t ms = mx < 32 ? 32 : mx;
+  if (!b->ckpt_in_smem) TRY(dmalloc((void**)&b->d_ckpt, nwarps * 4 * ms * sizeof(int16_t)));
+  if (trace) {
+    TRY(dmalloc((void**)&b->d_trace, nwarps * b->trace_words_per_warp * 4));
+    TRY(dmalloc((void**)&b->d_rects, nwarps * (uint64_t)b->rects_per_warp * sizeof(Rect)));
+    TRY(dmalloc((void**)&b->d_runs, nwarps * (uint64_t)b->runs_per_warp * 4));
+    uint64_t cap = 0;
+    for (size_t k = 0; k < n; k++) cap += (uint64_t)ql[k] + rl[k] + 5;
+    const uint64_t limit = (uint64_t)(al->mem_total * 0.15) / 4;
+    b->cigar_cap = std::min<uint64_t>(cap, std::max<uint64_t>(limit, 1024));
+    TRY(dmalloc((void**)&b->d_cigar, b->cigar_cap * 4));
+    TRY(dmalloc((void**)&b->d_cigar_used, 8));
+  }
+  if (getenv("BA_STEP_LOG") && n == 1) {
+    TRY(dmalloc((void**)&b->d_steplog, (size_t)(1 << 20) * sizeof(StepLog)));
+    TRY(dmalloc((void**)&b->d_steplog_n, 4));
+  }
+  *out = b;
+  return BA_OK;
+}
+
+extern "C" int ba_batch_upload(BaAligner* a, const BaConfig* cfg, size_t n, const uint8_t* q_bytes, const uint64_t* q_off,
+                               const uint8_t* r_bytes, const uint64_t* r_off, BaBatch** out) {
+  if (cfg && cfg->scoring == BA_SCORING_PROFILE) return fail(BA_ERR_ARG, "use ba_batch_upload_profiles");
+  return upload_common(a, cfg, n, q_bytes, q_off, r_bytes, r_off, nullptr, out);
+}
+extern "C" int ba_batch_upload_profiles(BaAligner* a, const BaConfig* cfg, size_t n, const uint8_t* q_bytes, const uint64_t* q_off,
+                                        const AAProfile* const* profiles, BaBatch** out) {
+  if (cfg && cfg->scoring != BA_SCORING_PROFILE) return fail(BA_ERR_ARG, "scoring must be BA_SCORING_PROFILE");
+  if (!profiles) return fail(BA_ERR_ARG, "profiles is null");
+  return upload_common(a, cfg, n, q_bytes, q_off, nullptr, nullptr, profiles, out);
+}
+
+static Params make_params(const BaBatch* b) {
+  Params P;
+  memset(&P, 0, sizeof(P));
+  const bool prof = b->cfg.scoring == BA_SCORING_PROFILE;
+  P.n_pairs = (uint32_t)b->n; P.order = b->d_order; P.seq = b->d_seq;
+  P.q_off = b->d_qoff; P.q_len = b->d_qlen; P.r_off = b->d_roff; P.r_len = b->d_rlen;
+  P.profiles = b->d_profiles; P.matrix = b->d_matrix;
+  P.gap_open = b->cfg.gaps.open; P.gap_extend = b->cfg.gaps.extend;
+  P.min_size = b->min_size; P.max_size = b->max_size; P.x_drop = b->cfg.x_drop;
+  P.flags = b->cfg.flags; P.scoring = prof ? (int)kProfile : b->cfg.scoring;
+  P.out = b->d_out; P.ticket = b->d_ticket;
+  P.ckpt = b->d_ckpt; P.ckpt_in_smem = b->ckpt_in_smem ? 1u : 0u;
+  P.trace_words = b->d_trace; P.trace_words_per_warp = b->trace_words_per_warp;
+  P.rects = b->d_rects; P.rects_per_warp = b->rects_per_warp;
+  P.run_scratch = b->d_runs; P.runs_per_warp = b->runs_per_warp;
+  P.cigar_stream = b->d_cigar; P.cigar_cap = b->cigar_cap; P.cigar_used = b->d_cigar_used;
+  P.cigar_eq = b->cfg.cigar_eq ? 1u : 0u;
+  P.step_log = b->d_steplog; P.step_log_cap = b->d_steplog ? (1u << 20) : 0u; P.step_log_n = b->d_steplog_n;
+  return P;
+}
+
+extern "C" int ba_batch_run(BaBatch* b, BaStats* stats) {
+  if (!b) return fail(BA_ERR_ARG, "batch is null");
+  BaAligner* al = b->al;
+  dev_stream_t st = al->stream;
+#ifndef BA_EMU
+  if (cudaSetDevice(al->device) != cudaSuccess) return fail(BA_ERR_CUDA, "cudaSetDevice failed");
+#endif
+  Params P = make_params(b);
+  int rc;
+  if ((rc = dzero(b->d_ticket, 4, st))) return BA_ERR_CUDA;
+  if (b->d_cigar_used && (rc = dzero(b->d_cigar_used, 8, st))) return BA_ERR_CUDA;
+  if (b->d_steplog_n && (rc = dzero(b->d_steplog_n, 4, st))) return BA_ERR_CUDA;
+  b->downloaded = false;
+  float ms = 0;
+  if (b->n) {
+#ifndef BA_EMU
+    cudaEventRecord(al->ev0, st);
+#endif
+    rc = launch_dispatch(P.scoring, P.flags, P, b->blocks, b->wpb, b->smem_bytes, st);
+    if (rc) return rc == 1 ? BA_ERR_CUDA : rc;
+#ifndef BA_EMU
+    cudaEventRecord(al->ev1, st);
+    cudaError_t e = cudaEventSynchronize(al->ev1);
+    if (e != cudaSuccess) { cuda_fail(e, "alignment kernel"); return BA_ERR_CUDA; }
+    cudaEventElapsedTime(&ms, al->ev0, al->ev1);
+#endif
+  }
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->kernel_ms = ms; stats->pack_ms = b->pack_ms; stats->kernel_launches = b->n ? 1 : 0;
+  }
+  return BA_OK;
+}
+
+extern "C" int ba_batch_download(BaBatch* b, AlignResult* out) {
+  if (!b) return fail(BA_ERR_ARG, "batch is null");
+  BaAligner* al = b->al;
+  dev_stream_t st = al->stream;
+#ifndef BA_EMU
+  if (cudaSetDevice(al->device) != cudaSuccess) return fail(BA_ERR_CUDA, "cudaSetDevice failed");
+#endif
+  b->h_out.resize(b->n);
+  if (d2h(b->h_out.data(), b->d_out, b->n * sizeof(DevResult), st)) return BA_ERR_CUDA;
+  unsigned long long used = 0;
+  if (b->d_cigar_used && d2h(&used, b->d_cigar_used, 8, st)) return BA_ERR_CUDA;
+  if (dsync(st)) return BA_ERR_CUDA;
+  if (b->d_cigar) {
+    used = std::min<unsigned long long>(used, b->cigar_cap);
+    b->h_cigar.resize(used);
+    if (d2h(b->h_cigar.data(), b->d_cigar, used * 4, st)) return BA_ERR_CUDA;
+    if (dsync(st)) return BA_ERR_CUDA;
+  }
+  int bad = 0;
+  for (size_t k = 0; k < b->n; k++) {
+    const DevResult& r = b->h_out[k];
+    if (out) { out[k].score = r.score; out[k].query_idx = r.query_idx; out[k].reference_idx = r.reference_idx; }
+    if (r.status != kOk) bad++;
+  }
+  b->downloaded = true;
+  if (bad) return fail(BA_ERR_OVERFLOW, "a per-warp trace or CIGAR buffer overflowed for " + std::to_string(bad) + " pair(s)");
+  return BA_OK;
+}
+
+extern "C" int ba_batch_cigar(const BaBatch* b, size_t k, const uint32_t** runs, size_t* n_runs) {
+  if (!b || !b->downloaded || k >= b->n || !(b->cfg.flags & BA_TRACE)) return fail(BA_ERR_ARG, "no CIGAR available");
+  const DevResult& r = b->h_out[k];
+  if (r.cigar_off + r.cigar_n > b->h_cigar.size()) return fail(BA_ERR_OVERFLOW, "cigar stream overflow");
+  *runs = b->h_cigar.data() + r.cigar_off; *n_runs = r.cigar_n;
+  return BA_OK;
+}
+
+extern "C" int ba_batch_pair_stats(const BaBatch* b, size_t k, uint64_t* cells, uint32_t* steps, uint32_t* status) {
+  if (!b || !b->downloaded || k >= b->n) return fail(BA_ERR_ARG, "no stats available");
+  if (cells) *cells = b->h_out[k].cells;
+  if (steps) *steps = b->h_out[k].steps;
+  if (status) *status = b->h_out[k].status;
+  return BA_OK;
+}
+
+// debug: fetch the per-step log of a single-pair batch run with BA_STEP_LOG=1
+extern "C" size_t ba_debug_step_log(BaBatch* b, StepLog* out, size_t cap) {
+  if (!b || !b->d_steplog) return 0;
+  uint32_t n = 0;
+  d2h(&n, b->d_steplog_n, 4, b->al->stream); dsync(b->al->stream);
+  const size_t m = std::min<size_t>(std::min<size_t>(n, cap), 1u << 20);
+  if (m) { d2h(out, b->d_steplog, m * sizeof(StepLog), b->al->stream); dsync(b->al->stream); }
+  return n;
+}
+
+extern "C" int ba_align_batch(BaAligner* a, const BaConfig* cfg, size_t n, const uint8_t* q_bytes, const uint64_t* q_off,
+                              const uint8_t* r_bytes, const uint64_t* r_off, AlignResult* out, BaStats* stats) {
+  BaBatch* b = nullptr;
+  int rc = ba_batch_upload(a, cfg, n, q_bytes, q_off, r_bytes, r_off, &b);
+  if (rc) return rc;
+  rc = ba_batch_run(b, stats);
+  if (!rc) rc = ba_batch_download(b, out);
+  if (stats && b->downloaded) {
+    for (size_t k = 0; k < n; k++) { stats->cells += b->h_out[k].cells; stats->steps += b->h_out[k].steps; if (b->h_out[k].status) stats->n_failed++; }
+  }
+  ba_batch_free(b);
+  return rc;
+}
+
+// Walk the stored trace of pair k back from an arbitrary end position (Trace::cigar / cigar_eq,
+// scan_block.rs:1469-1480). Only valid for the pair that ran last on its warp, i.e. batches of one
+// (the legacy block_cigar_* calls) or pair ids whose warp processed no later pair.
+extern "C" int ba_batch_traceback(BaBatch* b, size_t k, size_t query_idx, size_t reference_idx, int eq,
+                                  const uint32_t** runs, size_t* n_runs) {
+  if (!b || !(b->cfg.flags & BA_TRACE) || k >= b->n || !b->downloaded) return fail(BA_ERR_ARG, "no trace available");
+  if (eq && b->cfg.scoring == BA_SCORING_PROFILE) return fail(BA_ERR_ARG, "cigar_eq needs a reference sequence");
+  BaAligner* al = b->al;
+  dev_stream_t st = al->stream;
+#ifndef BA_EMU
+  if (cudaSetDevice(al->device) != cudaSuccess) return fail(BA_ERR_CUDA, "cudaSetDevice failed");
+#endif
+  Params P = make_params(b);
+  if (!b->d_tb_res && dmalloc((void**)&b->d_tb_res, sizeof(DevResult))) return BA_ERR_CUDA;
+  if (dzero(b->d_cigar_used, 8, st)) return BA_ERR_CUDA;
+  if (launch_traceback(P, (uint32_t)k, (uint32_t)query_idx, (uint32_t)reference_idx, eq, b->d_tb_res, st)) return BA_ERR_CUDA;
+  DevResult res;
+  if (d2h(&res, b->d_tb_res, sizeof(res), st) || dsync(st)) return BA_ERR_CUDA;
+  if (res.status != kOk) return fail(BA_ERR_OVERFLOW, "traceback failed (trace no longer resident or buffer overflow)");
+  b->h_tb.resize(res.cigar_n);
+  if (d2h(b->h_tb.data(), b->d_cigar + res.cigar_off, (size_t)res.cigar_n * 4, st) || dsync(st)) return BA_ERR_CUDA;
+  *runs = b->h_tb.data(); *n_runs = res.cigar_n;
+  return BA_OK;
+}
+
+extern "C" int ba_batch_total_stats(const BaBatch* b, BaStats* stats) {
+  if (!b || !b->downloaded || !stats) return fail(BA_ERR_ARG, "no stats available");
+  stats->cells = 0; stats->steps = 0; stats->n_failed = 0;
+  for (size_t k = 0; k < b->n; k++) { stats->cells += b->h_out[k].cells; stats->steps += b->h_out[k].steps; if (b->h_out[k].status) stats->n_failed++; }
+  return BA_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Integer-ALU peak micro-benchmark: the roofline denominator for this kernel family (integer max-plus
+// DP is bound by the issue rate of add/max on the INT pipes, not by HBM or tensor cores).
+// Each thread runs 8 independent chains of the two DPX forms the aligner uses (max(a+b,c), max3).
+// Reported: giga "i16-cell ops" per second, counting max(a+b,c) as 2 ops and max3 as 2 ops, which is
+// how the 13-ops-per-cell figure of the recurrence is counted.
+// -------------------------------------------------------------------------------------------------
+#ifndef BA_EMU
+__global__ void ba_int_peak_kernel(int* out, int iters, int seed) {
+  int a[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) a[k] = seed + k * 7 + threadIdx.x;
+  const int g = -(seed & 3) - 1;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      a[k] = __viaddmax_s32(a[k], g, a[(k + 1) & 7]);
+      a[k] = __vimax3_s32(a[k], a[(k + 3) & 7], g);
+    }
+  }
+  int r = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) r ^= a[k];
+  if (r == 0x7fffffff) out[0] = r;
+}
+#endif
+extern "C" int ba_measure_int_peak(BaAligner* al, double* giga_ops_per_s) {
+#ifdef BA_EMU
+  (void)al; *giga_ops_per_s = 0; return BA_OK;
+#else
+  if (!al || !giga_ops_per_s) return fail(BA_ERR_ARG, "null");
+  if (cudaSetDevice(al->device) != cudaSuccess) return fail(BA_ERR_CUDA, "cudaSetDevice failed");
+  int* d = nullptr;
+  if (dmalloc((void**)&d, 4)) return BA_ERR_CUDA;
+  const int blocks = al->sm_count * 8, threads = 256, iters = 4096;
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(al->ev0, al->stream);
+    ba_int_peak_kernel<<<blocks, threads, 0, al->stream>>>(d, iters, 12345 + rep);
+    cudaEventRecord(al->ev1, al->stream);
+    if (cudaEventSynchronize(al->ev1) != cudaSuccess) { dfree(d); return fail(BA_ERR_CUDA, "int peak kernel failed"); }
+    float ms = 0; cudaEventElapsedTime(&ms, al->ev0, al->ev1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  dfree(d);
+  const double ops = (double)blocks * threads * (double)iters * 8 * 4;   // 2 instr x 2 ops each per chain step
+  *giga_ops_per_s = ops / (best * 1e-3) / 1e9;
+  return BA_OK;
+#endif
+}

@@ -1,0 +1,87 @@
+// ba_types.h -- plain structs shared by the host runtime (ba_runtime.cu) and the device code
+// (ba_kernel.cuh). No CUDA or torch types here.
+#pragma once
+#include <stdint.h>
+
+namespace ba {
+
+// Constants of the reference's AVX2 build that leak into observable behaviour
+// (reference: src/avx2.rs:11-16, src/scan_block.rs:787-790).
+constexpr int kL = 16;             // AVX2 lanes: min block size clamp, argmax tie-break class, scan phantoms
+constexpr int kZero = 1 << 14;     // stored i16 v  <->  true score off + v - kZero
+constexpr int kStep = 8;
+constexpr int kXDropIter = 2;
+constexpr int kMaxBlock = 8192;    // our cap (reference allows < 65535; > 16384 "not recommended")
+
+// Block<TRACE, X_DROP, ...> const generics as bit flags (reference: src/scan_block.rs:89)
+enum Flags : int { kTrace = 1, kXDrop = 2, kLocalStart = 4, kFreeQueryStartGaps = 8, kFreeQueryEndGaps = 16 };
+// scoring kinds
+enum Scoring : int { kNuc = 0, kAA = 1, kByte = 2, kProfile = 3 };
+enum Dir : int { kRight = 0, kDown = 1, kGrow = 2 };
+
+// per-pair status written by the kernel
+enum Status : uint32_t { kOk = 0, kNotRun = 1, kTraceOverflow = 2, kRectOverflow = 3, kCigarOverflow = 4 };
+
+// Device-side view of one AAProfile (reference: src/scores.rs:454-468). `pos_aa` is the only score
+// layout kept on the device (row per position, 32 i8 each); the reference's transposed `aa_pos`
+// copy holds the same numbers.
+struct ProfileDev {
+  const int8_t* pos_aa;          // [curr_len][32]
+  const int16_t* gap_open_C;     // [curr_len]
+  const int16_t* gap_close_C;    // [curr_len]
+  const int16_t* gap_open_R;     // [curr_len]
+  uint32_t len;                  // str_len
+  int32_t gap_extend;
+};
+
+// one computed rectangle (reference: Trace::add_block, src/scan_block.rs:1428-1443)
+struct Rect {
+  uint32_t row, col;             // top-left cell in DP-matrix coordinates
+  uint16_t h, w;                 // h = extent along the vector direction, w = number of sequential columns
+  uint32_t right;                // 1: vectors run along rows (query); 0: along columns (reference)
+  uint32_t word_off;             // first trace word of this rectangle in the warp's arena
+};
+
+struct DevResult {
+  int32_t score;
+  uint32_t query_idx, reference_idx;
+  uint32_t status;
+  uint64_t cells;                // sum of h*w over every rectangle handed to place_rect
+  uint32_t steps;
+  uint32_t cigar_n;              // number of runs written for this pair
+  uint64_t cigar_off;            // offset (in runs) into the cigar stream
+  uint32_t rect_n;               // rectangles on the trace stack at the end (TRACE)
+  uint32_t warp;                 // global warp id that ran this pair (its trace arena holds the trace)
+};
+
+// one record per step, debug builds only (mirrors ora_step in oracle/ba_oracle.h)
+struct StepLog { int32_t dir; uint32_t i, j, block_size; int32_t off; int16_t max, right_max, down_max; };
+
+struct Params {
+  uint32_t n_pairs;
+  const uint32_t* order;         // optional processing order (pair ids), longest first
+  const uint8_t* seq;            // arena of padded, converted sequences (pad byte at index 0 of each)
+  const uint64_t* q_off; const uint32_t* q_len;
+  const uint64_t* r_off; const uint32_t* r_len;
+  const ProfileDev* profiles;    // kProfile: one per pair (r_off/r_len unused)
+  const int8_t* matrix;          // kNuc: 128 B, kAA: 864 B, kByte: {match, mismatch}
+  int32_t gap_open, gap_extend;
+  uint32_t min_size, max_size;   // already clamped to >= kL, powers of two
+  int32_t x_drop;
+  int32_t flags, scoring;
+  DevResult* out;
+  uint32_t* ticket;              // work counter
+  // per-warp scratch in global memory
+  int16_t* ckpt;                 // 4 * max_size int16 per warp (used when the checkpoint does not fit in smem)
+  uint32_t ckpt_in_smem;
+  uint32_t* trace_words; uint64_t trace_words_per_warp;
+  Rect* rects; uint32_t rects_per_warp;
+  uint32_t* run_scratch; uint32_t runs_per_warp;  // reversed CIGAR runs while walking back
+  // cigar output stream: runs packed as (len << 4) | op, allocated with atomicAdd on *cigar_used
+  uint32_t* cigar_stream; uint64_t cigar_cap; unsigned long long* cigar_used;
+  uint32_t cigar_eq;
+  // debug
+  StepLog* step_log; uint32_t step_log_cap; uint32_t* step_log_n;   // only honoured for n_pairs == 1
+};
+
+}  // namespace ba

@@ -25,6 +25,7 @@
 #include <string.h>
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -1103,6 +1104,7 @@ void ora_prefix_scan_consts(int16_t gap, int16_t* gap_all16, int16_t* consts16) 
   memcpy(gap_all16, a, 32); memcpy(consts16, b, 32);
 }
 
+static double g_last_batch_seconds = 0;
 // ---- batch driver: the CPU baseline: one reusable Block per thread ----
 // Sequences arrive already padded (see ora_pad) inside one arena; pair k uses q at q_off[k]
 // (pad byte included) with length q_len[k], same for r. For profile batches `profiles[k]`
@@ -1145,12 +1147,33 @@ int ora_batch_align(const ora_batch* b, int n_threads, ora_result* out, uint64_t
     }
     ora_block_free(B);
   };
+  // wall clock around the align (+cigar) calls only; Block allocation is inside too but is amortised
+  // over the thread's share exactly like the reference's documented reuse pattern (scan_block.rs:795-797)
+  const auto t0 = std::chrono::steady_clock::now();
   std::vector<std::thread> th;
   for (int t = 1; t < n_threads; t++) th.emplace_back(worker, t);
   worker(0);
   for (auto& t : th) t.join();
+  g_last_batch_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return err.load();
 }
+
+// Pads a whole arena of raw sequences (PaddedBytes::from_bytes per sequence). `out_off` (n entries) receives the
+// start of each padded sequence inside `out`, which must hold sum(1 + len + block_size) bytes.
+int ora_pad_batch(int matrix_kind, const uint8_t* raw, const uint64_t* off, size_t n, size_t block_size, uint8_t* out,
+                  uint64_t* out_off, uint32_t* out_len) {
+  uint64_t pos = 0;
+  for (size_t k = 0; k < n; k++) {
+    const size_t len = (size_t)(off[k + 1] - off[k]);
+    int e = ora_pad(matrix_kind, raw + off[k], len, block_size, 0, out + pos);
+    if (e) return e;
+    out_off[k] = pos; out_len[k] = (uint32_t)len;
+    pos += 1 + len + block_size;
+  }
+  return 0;
+}
+
+double ora_last_batch_seconds(void) { return g_last_batch_seconds; }
 
 int ora_hw_threads(void) { unsigned n = std::thread::hardware_concurrency(); return n ? (int)n : 1; }
 

@@ -90,6 +90,9 @@ typedef struct ora_batch {
 } ora_batch;
 int ora_batch_align(const ora_batch*, int n_threads, ora_result* out, uint64_t* out_cells,
                     ora_oplen* cigar_arena, const uint64_t* cigar_off, uint32_t* cigar_len);
+int ora_pad_batch(int matrix_kind, const uint8_t* raw, const uint64_t* off, size_t n, size_t block_size, uint8_t* out,
+                  uint64_t* out_off, uint32_t* out_len);
+double ora_last_batch_seconds(void);
 int ora_hw_threads(void);
 
 #ifdef __cplusplus

@@ -103,6 +103,8 @@ def lib():
     L.ora_prefix_scan.argtypes = [C.c_void_p, C.c_int16, C.c_void_p]
     L.ora_prefix_scan_consts.argtypes = [C.c_int16, C.c_void_p, C.c_void_p]
     L.ora_batch_align.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ora_pad_batch.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ora_last_batch_seconds.restype = C.c_double
     L.ora_hw_threads.restype = C.c_int
     _LIB = L
     return L

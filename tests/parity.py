@@ -1,0 +1,166 @@
+"""Parity harness: run a batch through the C-ABI library (CUDA product or the emulated test build)
+and through the CPU oracle on identical inputs, compare score, end indices, CIGAR, and the
+path-determined work counters (cells, steps). Test infrastructure.
+"""
+import ctypes as C
+
+import numpy as np
+
+import ora
+from block_aligner_b200 import api, workloads
+
+
+def pad_arena(scoring, arena, off, pad):
+    """PaddedBytes::from_bytes for every sequence of an arena (done by the oracle library in C).
+    Returns (padded arena, padded offsets uint64[n], lengths uint32[n])."""
+    n = len(off) - 1
+    kind = {api.SCORING_NUC: ora.NUC, api.SCORING_AA: ora.AA, api.SCORING_PROFILE: ora.AA, api.SCORING_BYTE: ora.BYTE}[scoring]
+    off = np.ascontiguousarray(off, dtype=np.uint64)
+    arena = np.ascontiguousarray(arena, dtype=np.uint8)
+    total = int(off[-1] - off[0]) + n * (1 + pad)
+    out = np.zeros(total + 64, dtype=np.uint8)
+    poff = np.zeros(max(n, 1), dtype=np.uint64)
+    lens = np.zeros(max(n, 1), dtype=np.uint32)
+    e = ora.lib().ora_pad_batch(kind, arena.ctypes.data, off.ctypes.data, n, pad, out.ctypes.data, poff.ctypes.data, lens.ctypes.data)
+    if e:
+        raise ValueError(f"ora_pad_batch error {e}")
+    return out, poff[:n], lens[:n]
+
+
+def oracle_batch(scoring, matrix, gaps, size, x_drop, flags, cigar_eq, qa, qo, ra, ro, profiles=None, threads=None):
+    """-> results (n x 3 int64), cells (uint64[n]), cigars (list of run arrays or None)"""
+    L = ora.lib()
+    n = len(qo) - 1
+    pad = max(size[1], 16) + 32
+    pq, pqo, ql = pad_arena(scoring, qa, qo, pad)
+    if profiles is None:
+        pr, pro, rl = pad_arena(scoring, ra, ro, pad)
+        arena = np.concatenate([pq, pr])
+        pro = pro + np.uint64(pq.size)
+    else:
+        arena, pro, rl = pq, np.zeros(n, dtype=np.uint64), np.array([len(p) for p in profiles], dtype=np.uint32)
+    b = ora.Batch()
+    b.n = n
+    b.arena = arena.ctypes.data
+    b.q_off, b.q_len = pqo.ctypes.data, ql.ctypes.data
+    b.r_off, b.r_len = pro.ctypes.data, rl.ctypes.data
+    parr = None
+    if profiles is not None:
+        parr = (C.c_void_p * n)(*[p.h for p in profiles])
+        b.profiles = C.cast(parr, C.c_void_p)
+    else:
+        b.profiles = None
+    mat = None
+    if matrix is not None:
+        mat = np.ascontiguousarray(matrix, dtype=np.int8)
+        b.matrix = mat.ctypes.data
+    b.matrix_kind = {api.SCORING_NUC: ora.NUC, api.SCORING_AA: ora.AA, api.SCORING_BYTE: ora.BYTE,
+                     api.SCORING_PROFILE: ora.AA}[scoring]
+    if gaps:
+        b.gap_open, b.gap_extend = gaps
+    b.min_size, b.max_size = size
+    b.x_drop, b.flags, b.cigar_eq = x_drop, flags, int(bool(cigar_eq))
+    out = (ora.Result * max(n, 1))()
+    cells = np.zeros(max(n, 1), dtype=np.uint64)
+    trace = bool(flags & api.TRACE)
+    coff = clen = carena = None
+    if trace:
+        caps = ql.astype(np.uint64) + rl.astype(np.uint64) + 5
+        coff = np.zeros(n + 1, dtype=np.uint64)
+        np.cumsum(caps, out=coff[1:])
+        carena = (ora.OpLen * int(coff[-1] + 1))()
+        clen = np.zeros(max(n, 1), dtype=np.uint32)
+    threads = threads or ora.lib().ora_hw_threads()
+    e = L.ora_batch_align(C.byref(b), threads, out, cells.ctypes.data, carena, coff.ctypes.data if trace else None,
+                          clen.ctypes.data if trace else None)
+    if e:
+        raise ValueError(f"oracle batch error {e}")
+    res = np.array([[out[k].score, out[k].query_idx, out[k].reference_idx] for k in range(n)], dtype=np.int64).reshape(n, 3)
+    cigs = None
+    if trace:
+        cigs = []
+        for k in range(n):
+            base = int(coff[k])
+            cigs.append(np.array([(carena[base + t].len << 4) | carena[base + t].op for t in range(int(clen[k]))], dtype=np.uint64))
+    return res, cells[:n], cigs
+
+
+def make_profiles(lib, b62, ra, ro, block_size, gap_open, gap_extend, seed):
+    """C4 profiles: the reference side of each pair is the consensus; PSSM = BLOSUM62 row + noise;
+    gaps set for positions 1..=len like examples/pssm_bench.rs:67-83 (position 0 keeps the -128 defaults).
+    Built twice from the same numbers: for the library (block_*_aaprofile) and for the oracle."""
+    n = len(ro) - 1
+    rng = np.random.default_rng(seed)
+    lib_profs, ora_profs = [], []
+    for k in range(n):
+        cons = ra[int(ro[k]):int(ro[k + 1])].tobytes()
+        sc = workloads.pssm_scores(b62, cons, rng)
+        p = api.AAProfile(lib, len(cons), block_size, gap_extend)
+        o = ora.Profile.new(len(cons), block_size, gap_extend)
+        if len(cons):
+            p.set_all(workloads.MAP20, sc)
+            assert ora.lib().ora_profile_set_all(o.h, workloads.MAP20, 20, sc.ctypes.data, sc.size, 0, 0, 0) == 0
+        for i in range(1, len(cons) + 1):
+            p.set_gap_open_C(i, gap_open); p.set_gap_close_C(i, 0); p.set_gap_open_R(i, gap_open)
+            o.set_gap_open_C(i, gap_open); o.set_gap_close_C(i, 0); o.set_gap_open_R(i, gap_open)
+        lib_profs.append(p)
+        ora_profs.append(o)
+    return lib_profs, ora_profs
+
+
+def run_lib(lib, al, scoring, matrix, gaps, size, x_drop, flags, cigar_eq, qa, qo, ra, ro, profiles=None):
+    cfg = al.config(scoring, matrix, gaps, size, x_drop, flags, cigar_eq)
+    b = al.upload(cfg, qa, qo, ra, ro, profiles)
+    try:
+        st = b.run()
+        r = b.download()
+        n = len(qo) - 1
+        res = np.stack([r["score"].astype(np.int64), r["query_idx"].astype(np.int64), r["reference_idx"].astype(np.int64)], axis=1).reshape(n, 3)
+        cells = np.array([b.pair_stats(k)[0] for k in range(n)], dtype=np.uint64)
+        cigs = [b.cigar_runs(k).astype(np.uint64) for k in range(n)] if flags & api.TRACE else None
+        return res, cells, cigs, st
+    finally:
+        b.free()
+
+
+def compare(tag, got, exp, verbose=True, limit=5):
+    """got/exp = (res, cells, cigs). Returns the number of mismatching pairs."""
+    res_g, cells_g, cig_g = got[:3]
+    res_e, cells_e, cig_e = exp
+    n = len(res_e)
+    bad = []
+    for k in range(n):
+        ok = (res_g[k] == res_e[k]).all() and int(cells_g[k]) == int(cells_e[k])
+        if ok and cig_e is not None:
+            ok = len(cig_g[k]) == len(cig_e[k]) and (cig_g[k] == cig_e[k]).all()
+        if not ok:
+            bad.append(k)
+    if bad and verbose:
+        for k in bad[:limit]:
+            msg = f"[{tag}] pair {k}: got {res_g[k].tolist()} cells {int(cells_g[k])}  expected {res_e[k].tolist()} cells {int(cells_e[k])}"
+            if cig_e is not None:
+                msg += f"\n   cigar got {api.runs_to_string(cig_g[k])[:120]}\n   cigar exp {api.runs_to_string(cig_e[k])[:120]}"
+            print(msg)
+        print(f"[{tag}] {len(bad)} / {n} pairs differ")
+    return len(bad)
+
+
+def check_workload(lib, al, w, n, first=0, seed=1234, with_trace=None, size=None, flags=None, verbose=True):
+    """Generate n pairs of workload dict `w`, run library and oracle, return the mismatch count."""
+    scoring = w["scoring"]
+    flags = w["flags"] if flags is None else flags
+    if with_trace is True:
+        flags |= api.TRACE
+    elif with_trace is False:
+        flags &= ~api.TRACE
+    size = size or w["size"]
+    cigar_eq = bool(flags & api.TRACE) and scoring != api.SCORING_PROFILE
+    qa, qo, ra, ro = workloads.generate(w["gen"], n, first=first, seed=seed, stream=w.get("stream", 0))
+    matrix = workloads.matrix_of(lib, w)
+    lp = op = None
+    if scoring == api.SCORING_PROFILE:
+        b62 = lib.builtin_matrix("BLOSUM62")[1]
+        lp, op = make_profiles(lib, b62, ra, ro, size[1], -10, -1, seed + first)
+    got = run_lib(lib, al, scoring, matrix, w["gaps"], size, w["x_drop"], flags, cigar_eq, qa, qo, ra, ro, lp)
+    exp = oracle_batch(scoring, matrix, w["gaps"], size, w["x_drop"], flags, cigar_eq, qa, qo, ra, ro, op)
+    return compare(f"{scoring}/{flags}/{size}", got, exp, verbose)

@@ -1,0 +1,69 @@
+"""Device source (emulated on the CPU) vs the oracle on seeded random inputs: every scoring kind, every
+TRACE/X_DROP combination, fixed and adaptive block ranges from 16 up to the multi-chunk (>256) path.
+Bit-exact bar: score, query_idx, reference_idx, CIGAR runs and the path-determined cell count."""
+import pytest
+
+import backend
+import parity
+from block_aligner_b200 import api, workloads
+
+P = workloads.params
+NOISY = dict(sub_rate=0.05, ins_rate=0.04, del_rate=0.04, long_indel_mean=1.5, long_indel_len=50.0)
+
+
+@pytest.fixture(scope="module")
+def env():
+    lib = backend.emu_lib()
+    return lib, api.Aligner(lib)
+
+
+@pytest.mark.parametrize("flags", [0, api.XDROP, api.TRACE, api.TRACE | api.XDROP])
+@pytest.mark.parametrize("size", [(16, 16), (16, 64), (32, 32), (32, 256), (128, 512), (256, 2048)])
+def test_dna(env, flags, size):
+    w = dict(scoring=api.SCORING_NUC, matrix="NW1", gaps=(-2, -1), size=size, x_drop=50, flags=flags, stream=11,
+             gen=P(alphabet=0, len_dist=0, len_min=300, len_max=1500, suffix_len=150, **NOISY))
+    assert parity.check_workload(*env, w, 12, seed=7 + flags) == 0
+
+
+@pytest.mark.parametrize("flags", [0, api.TRACE, api.TRACE | api.XDROP])
+def test_dna_big_indels_force_growth(env, flags):
+    w = dict(scoring=api.SCORING_NUC, matrix=(2, -4), gaps=(-6, -2), size=(32, 512), x_drop=200, flags=flags, stream=12,
+             gen=P(alphabet=0, len_dist=0, len_min=1500, len_max=3000, suffix_len=100, big_indel_prob=0.8,
+                   big_indel_min=100, big_indel_max=400, **NOISY))
+    assert parity.check_workload(*env, w, 12) == 0
+
+
+@pytest.mark.parametrize("flags", [0, api.XDROP, api.TRACE, api.TRACE | api.XDROP])
+@pytest.mark.parametrize("size", [(16, 128), (32, 256)])
+def test_protein(env, flags, size):
+    w = dict(workloads.WORKLOADS["C3_uniclust_protein_global"])
+    w["flags"], w["x_drop"], w["size"] = flags, 30, size
+    assert parity.check_workload(*env, w, 40, seed=3) == 0
+
+
+@pytest.mark.parametrize("flags", [0, api.XDROP, api.TRACE, api.TRACE | api.XDROP])
+@pytest.mark.parametrize("size", [(16, 16), (32, 256), (64, 512)])
+def test_profile(env, flags, size):
+    w = dict(workloads.WORKLOADS["C4_seq_to_profile_xdrop"])
+    w["flags"] = flags
+    assert parity.check_workload(*env, w, 16, size=size, seed=5) == 0
+
+
+@pytest.mark.parametrize("flags", [api.TRACE, api.TRACE | api.XDROP])
+def test_tiny_and_empty(env, flags):
+    w = dict(scoring=api.SCORING_NUC, matrix="NW1", gaps=(-2, -1), size=(32, 128), x_drop=20, flags=flags, stream=13,
+             gen=P(alphabet=0, len_dist=0, len_min=0, len_max=40, sub_rate=0.1, ins_rate=0.1, del_rate=0.1))
+    assert parity.check_workload(*env, w, 100) == 0
+
+
+def test_byte_matrix(env):
+    w = dict(scoring=api.SCORING_BYTE, matrix="BYTES1", gaps=(-2, -1), size=(32, 64), x_drop=0, flags=api.TRACE, stream=14,
+             gen=P(alphabet=1, len_dist=0, len_min=50, len_max=300, sub_rate=0.1, ins_rate=0.03, del_rate=0.03))
+    assert parity.check_workload(*env, w, 20) == 0
+
+
+@pytest.mark.parametrize("name", ["C1_rand_scan_dna1k", "C2_nanopore_xdrop_10k", "C3_uniclust_protein_global"])
+def test_baseline_configs_small_sample(env, name):
+    """The BASELINE.json workloads themselves, first few pairs (full sizes run on the GPU)."""
+    w = workloads.WORKLOADS[name]
+    assert parity.check_workload(*env, w, 4 if "C2" in name else 16) == 0

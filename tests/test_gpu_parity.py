@@ -1,0 +1,110 @@
+"""Parity tests proper: the CUDA product (through its C ABI) against the CPU oracle on identical seeded
+inputs, plus the reference's golden vectors. Bit-exact bar for score, query_idx, reference_idx, CIGAR
+runs and the path-determined cell count. Needs a GPU: `pytest -m gpu`."""
+import numpy as np
+import pytest
+
+import backend
+import golden_cases as G
+import parity
+from block_aligner_b200 import api, workloads
+
+pytestmark = pytest.mark.gpu
+P = workloads.params
+NOISY = dict(sub_rate=0.05, ins_rate=0.04, del_rate=0.04, long_indel_mean=1.5, long_indel_len=50.0)
+
+
+@pytest.fixture(scope="module")
+def env():
+    lib = backend.cuda_lib()
+    return lib, api.Aligner(lib, 0)
+
+
+def test_golden_batch_api(env):
+    G.run_batch_golden(*env)
+
+
+def test_golden_legacy_api(env):
+    G.run_legacy_golden(env[0])
+
+
+@pytest.mark.parametrize("flags", [0, api.XDROP, api.TRACE, api.TRACE | api.XDROP])
+@pytest.mark.parametrize("size", [(16, 16), (16, 64), (32, 32), (32, 256), (64, 64), (128, 512), (256, 2048), (32, 1024)])
+def test_dna(env, flags, size):
+    w = dict(scoring=api.SCORING_NUC, matrix="NW1", gaps=(-2, -1), size=size, x_drop=50, flags=flags, stream=11,
+             gen=P(alphabet=0, len_dist=0, len_min=300, len_max=3000, suffix_len=150, **NOISY))
+    assert parity.check_workload(*env, w, 600, seed=7 + flags) == 0
+
+
+@pytest.mark.parametrize("flags", [0, api.XDROP, api.TRACE, api.TRACE | api.XDROP])
+def test_dna_big_indels_force_growth(env, flags):
+    w = dict(scoring=api.SCORING_NUC, matrix=(2, -4), gaps=(-6, -2), size=(32, 512), x_drop=200, flags=flags, stream=12,
+             gen=P(alphabet=0, len_dist=0, len_min=1500, len_max=4000, suffix_len=100, big_indel_prob=0.8,
+                   big_indel_min=100, big_indel_max=400, **NOISY))
+    assert parity.check_workload(*env, w, 400) == 0
+
+
+@pytest.mark.parametrize("flags", [0, api.XDROP, api.TRACE, api.TRACE | api.XDROP])
+@pytest.mark.parametrize("size", [(16, 128), (32, 256), (32, 32)])
+def test_protein(env, flags, size):
+    w = dict(workloads.WORKLOADS["C3_uniclust_protein_global"])
+    w["flags"], w["x_drop"], w["size"] = flags, 30, size
+    assert parity.check_workload(*env, w, 3000, seed=3) == 0
+
+
+@pytest.mark.parametrize("flags", [0, api.XDROP, api.TRACE, api.TRACE | api.XDROP])
+@pytest.mark.parametrize("size", [(16, 16), (32, 256), (64, 512)])
+def test_profile(env, flags, size):
+    w = dict(workloads.WORKLOADS["C4_seq_to_profile_xdrop"])
+    w["flags"] = flags
+    assert parity.check_workload(*env, w, 300, size=size, seed=5) == 0
+
+
+@pytest.mark.parametrize("flags", [0, api.TRACE, api.TRACE | api.XDROP])
+def test_tiny_and_empty(env, flags):
+    w = dict(scoring=api.SCORING_NUC, matrix="NW1", gaps=(-2, -1), size=(32, 128), x_drop=20, flags=flags, stream=13,
+             gen=P(alphabet=0, len_dist=0, len_min=0, len_max=40, sub_rate=0.1, ins_rate=0.1, del_rate=0.1))
+    assert parity.check_workload(*env, w, 2000) == 0
+
+
+def test_byte_matrix(env):
+    w = dict(scoring=api.SCORING_BYTE, matrix="BYTES1", gaps=(-2, -1), size=(32, 64), x_drop=0, flags=api.TRACE, stream=14,
+             gen=P(alphabet=1, len_dist=0, len_min=50, len_max=300, sub_rate=0.1, ins_rate=0.03, del_rate=0.03))
+    assert parity.check_workload(*env, w, 500) == 0
+
+
+# ---- the BASELINE.json workloads ---------------------------------------------------------------------
+def test_C1_full(env):
+    w = workloads.WORKLOADS["C1_rand_scan_dna1k"]
+    assert parity.check_workload(*env, w, w["n"]) == 0
+
+
+def test_C2_sample_full_length(env):
+    assert parity.check_workload(*env, workloads.WORKLOADS["C2_nanopore_xdrop_10k"], 1500) == 0
+
+
+def test_C2_with_trace(env):
+    assert parity.check_workload(*env, workloads.WORKLOADS["C2_nanopore_xdrop_10k"], 300, first=5000, with_trace=True) == 0
+
+
+def test_C3_sample(env):
+    assert parity.check_workload(*env, workloads.WORKLOADS["C3_uniclust_protein_global"], 30000) == 0
+
+
+def test_C4_sample(env):
+    assert parity.check_workload(*env, workloads.WORKLOADS["C4_seq_to_profile_xdrop"], 1500) == 0
+
+
+def test_C5_sample_long_reads_with_trace(env):
+    assert parity.check_workload(*env, workloads.WORKLOADS["C5_longread_trace_50k"], 24) == 0
+
+
+def test_results_independent_of_batch_order_and_reuse(env):
+    """Block reuse invariance (scan_block.rs:795-797): same pairs, shuffled and re-run on the same aligner."""
+    lib, al = env
+    w = workloads.WORKLOADS["C2_nanopore_xdrop_10k"]
+    qa, qo, ra, ro = workloads.generate(w["gen"], 400, stream=w["stream"])
+    m = workloads.matrix_of(lib, w)
+    r1 = parity.run_lib(lib, al, w["scoring"], m, w["gaps"], w["size"], w["x_drop"], w["flags"], False, qa, qo, ra, ro)
+    r2 = parity.run_lib(lib, al, w["scoring"], m, w["gaps"], w["size"], w["x_drop"], w["flags"], False, qa, qo, ra, ro)
+    assert (r1[0] == r2[0]).all() and (r1[1] == r2[1]).all()

@@ -1,0 +1,81 @@
+"""Host-side logic of the C ABI, exercised through the emulated build (no GPU): argument rules of
+Block::align (scan_block.rs:849-862), alphabet checks (scores.rs:130-134, 212-216), helper functions."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import backend
+from block_aligner_b200 import api
+
+
+@pytest.fixture(scope="module")
+def env():
+    lib = backend.emu_lib()
+    return lib, api.Aligner(lib)
+
+
+def _run(al, q, r, gaps=(-2, -1), size=(32, 32), x_drop=0, flags=0, scoring=api.SCORING_NUC, matrix=None):
+    matrix = api.nuc_matrix(1, -1) if matrix is None else matrix
+    return al.align_batch([q], [r], scoring, matrix, gaps, size, x_drop, flags)[0][0]
+
+
+def test_argument_rules(env):
+    lib, al = env
+    with pytest.raises(api.BlockAlignerError, match="negative"):
+        _run(al, b"ACGT", b"ACGT", gaps=(1, -1))
+    with pytest.raises(api.BlockAlignerError, match="more than gap extend"):
+        _run(al, b"ACGT", b"ACGT", gaps=(-1, -1))
+    with pytest.raises(api.BlockAlignerError, match="powers of two"):
+        _run(al, b"ACGT", b"ACGT", size=(24, 32))
+    with pytest.raises(api.BlockAlignerError, match="nonnegative"):
+        _run(al, b"ACGT", b"ACGT", x_drop=-1, flags=api.XDROP)
+    with pytest.raises(api.BlockAlignerError, match="8192"):
+        _run(al, b"ACGT", b"ACGT", size=(32, 16384))
+    assert _run(al, b"ACGT", b"ACGT", size=(4, 8)) == (4, 4, 4)     # sizes below L are clamped up to 16
+
+
+def test_alphabet_checks(env):
+    lib, al = env
+    assert _run(al, b"acgt", b"ACGT") == (4, 4, 4)                   # lowercase is uppercased
+    with pytest.raises(api.BlockAlignerError, match="alphabet"):
+        _run(al, b"AC-T", b"ACGT")
+    b62 = lib.builtin_matrix("BLOSUM62")[1]
+    with pytest.raises(api.BlockAlignerError, match="alphabet"):
+        _run(al, b"AC*T", b"ACGT", scoring=api.SCORING_AA, matrix=b62, gaps=(-11, -1))
+
+
+def test_empty_batch(env):
+    lib, al = env
+    res, cig, st = al.align_batch([], [], api.SCORING_NUC, api.nuc_matrix(1, -1), (-2, -1), (32, 32))
+    assert res == [] and st.cells == 0
+
+
+def test_percent_len(env):
+    lib, _ = env
+    # lib.rs:109-111: round(p * len) -> max 32 -> next power of two -> min 16384
+    assert lib.percent_len(10_000, 0.01) == 128
+    assert lib.percent_len(50_000, 0.1) == 8192
+    assert lib.percent_len(100, 0.01) == 32
+    assert lib.percent_len(10_000_000, 0.5) == 16384
+
+
+def test_cigar_format(env):
+    lib, _ = env
+    runs = np.array([(9 << 4) | 2, (2 << 4) | 4, (4 << 4) | 2, (1 << 4) | 4], dtype=np.uint32)
+    buf = C.create_string_buffer(64)
+    n = lib.L.ba_cigar_format(runs.ctypes.data, len(runs), buf, 64)
+    assert buf.value == b"9=2I4=1I" and n == 8
+
+
+def test_builtin_matrices_match_reference_layout(env):
+    lib, _ = env
+    # NW1 = NucMatrix::new_simple(1, -1) (scores.rs:277): index (a & 7) * 16 + (b & 15)
+    assert (lib.builtin_matrix("NW1")[1] == api.nuc_matrix(1, -1)).all()
+    b62 = lib.builtin_matrix("BLOSUM62")[1].reshape(27, 32)
+    assert b62[0, 0] == 4 and b62[ord("W") - 65, ord("W") - 65] == 11 and b62[ord("A") - 65, ord("R") - 65] == -1
+    assert (b62[26] == -128).all() and (b62[:, 26:] == -128).all()
+    assert (b62[:26, :26] == b62[:26, :26].T).all()
+    for name in ("BLOSUM45", "BLOSUM50", "BLOSUM80", "BLOSUM90", "PAM100", "PAM120", "PAM160", "PAM200", "PAM250"):
+        m = lib.builtin_matrix(name)[1].reshape(27, 32)
+        assert (m[:26, :26] == m[:26, :26].T).all() and (m[26] == -128).all()
