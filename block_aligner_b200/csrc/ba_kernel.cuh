@@ -41,7 +41,7 @@ BA_DEV int sat_add_lo(int a, int b) { return wp::viaddmax(a, b, kI16Min); }
 struct WarpMem {
   int16_t *Dc, *Cc, *Dr, *Rr;       // D_col, C_col, D_row, R_row        [max_size]
   int16_t *t1, *t2;                 // temp_buf1/2                       [16]
-  int16_t *kDc, *kCc, *kDr, *kRr;   // checkpoint copies (smem or global) [max_size]
+  int16_t *kDc, *kCc, *kDr, *kRr;   // checkpoint copies of the current slot (global) [max_size]
   int32_t *misc;                    // [0..1]: A_old at the row above a chunk (double buffered)
   uint8_t *ecarry;                  // trace bit carried across chunks    [max_size] (only blocks > 256)
   const int8_t *mat;                // staged matrix (smem)
@@ -96,7 +96,11 @@ struct ProfArgs {
   const uint8_t* q;              // padded query
 };
 
-template <int SCORING, bool RIGHT, int R, bool TRACE, bool XDROP, bool MULTI>
+// Column loop is rolled (code size: the whole kernel must stay I-cache friendly); rows per lane R is
+// 1 for rectangles up to 128 rows (swept in 32-row chunks) and 8 from 256 rows up (256-row chunks).
+BA_HD int rect_rows_per_lane(int H) { return H >= 256 ? 8 : 1; }
+
+template <int SCORING, bool RIGHT, int R, bool TRACE, bool XDROP>
 BA_DEV void place_rect_r(const SeqScorer<(SCORING == kProfile ? kAA : SCORING)>& sc, const ProfArgs& pa,
                          const RectArgs& a, const WarpMem& w, int& bv, unsigned& bkey) {
   constexpr bool PROF = SCORING == kProfile;
@@ -114,12 +118,10 @@ BA_DEV void place_rect_r(const SeqScorer<(SCORING == kProfile ? kAA : SCORING)>&
     // zeros shifted in by _mm256_slli_si256 act as extra candidates (avx2.rs:321-337)
     ph[k] = (m == 15) ? kI16Min : (m == 7 ? 12 * ge : ((m & 7) + 1) * ge);
   }
-  int dec[5];
-#pragma unroll
-  for (int s = 0; s < 5; s++) dec[s] = (R << s) * ge;
   const int lane_rg = lane * R * ge;
 
   const int nchunks = (a.H + CH - 1) / CH;
+  const bool multi = nchunks > 1;
   const int ngroups = a.W >> 3;
   const bool origin = (a.vec_base == 0 && a.col_base == 0);  // scan_block.rs:1130
 
@@ -130,8 +132,7 @@ BA_DEV void place_rect_r(const SeqScorer<(SCORING == kProfile ? kAA : SCORING)>&
     const int last_lane = rows_here / R - 1;
 
     int D10[R], C10[R], rtok[R];
-    // profile-down per-row data
-    int p_openC[R], p_openR[R], p_closeR[R];
+    int p_openC[R], p_openR[R], p_closeR[R];   // profile-down per-row data
     const int8_t* p_row[R];
 #pragma unroll
     for (int k = 0; k < R; k++) {
@@ -151,7 +152,7 @@ BA_DEV void place_rect_r(const SeqScorer<(SCORING == kProfile ? kAA : SCORING)>&
       }
     }
     int diag_carry = a.corner;
-    if (MULTI) {
+    if (multi) {
       // value of the old border at the row just above this chunk = diagonal input of column 0
       if (ch > 0) diag_carry = w.misc[ch & 1];
       if (lane == 31) w.misc[(ch + 1) & 1] = D10[R - 1];
@@ -159,135 +160,120 @@ BA_DEV void place_rect_r(const SeqScorer<(SCORING == kProfile ? kAA : SCORING)>&
     }
 
     int mx[R];
-    unsigned mcol[R];
+    unsigned mcol[R], twd[R];
 #pragma unroll
-    for (int k = 0; k < R; k++) { mx[k] = 0; mcol[k] = 0; }
-    unsigned twd[R];
-#pragma unroll
-    for (int k = 0; k < R; k++) twd[k] = 0;
+    for (int k = 0; k < R; k++) { mx[k] = 0; mcol[k] = 0; twd[k] = 0; }
 
-    for (int cg = 0; cg < a.ncols; cg += 8) {
-      int Ttop[8], Dtop[8], etop[8];
-#pragma unroll
-      for (int c = 0; c < 8; c++) { Ttop[c] = 0; Dtop[c] = 0; etop[c] = 0; }
-      if (MULTI) {
-        if (ch > 0) {
-#pragma unroll
-          for (int c = 0; c < 8; c++) {
-            if (cg + c < a.ncols) {
-              Ttop[c] = (int)a.OR_[cg + c];
-              Dtop[c] = (int)a.OD[cg + c];
-              if (TRACE) etop[c] = (int)w.ecarry[cg + c];
-            }
-          }
+#pragma unroll 1
+    for (int cidx = 0; cidx < a.ncols; cidx++) {
+      const int c4 = (cidx & 7) * 4;
+      int Ttop = 0, Dtop = 0, etop = 0;
+      if (multi) {
+        if (ch > 0) {   // bottom row of the chunk above, written there for exactly this purpose
+          Ttop = (int)a.OR_[cidx];
+          Dtop = (int)a.OD[cidx];
+          if (TRACE) etop = (int)w.ecarry[cidx];
         }
         wp::syncwarp();
       }
-#pragma unroll
-      for (int c = 0; c < 8; c++) {
-        if (cg + c < a.ncols) {
-          const int cidx = cg + c;
-          // ---- per-column uniform data ----
-          int ctok = 0, openC_col = 0, closeC_col = 0, openR_col = 0;
-          const int8_t* prow_col = nullptr;
-          if (!PROF) {
-            ctok = sc.col_token(a.col_base + cidx);
-          } else if (RIGHT) {
-            const uint32_t idx = a.col_base + cidx;                   // scan_block.rs:658-661
-            openC_col = (int)wp::ldg(pa.p->gap_open_C + idx) + ge;
-            closeC_col = (int)wp::ldg(pa.p->gap_close_C + idx);
-            openR_col = (int)wp::ldg(pa.p->gap_open_R + idx);
-            prow_col = pa.p->pos_aa + (size_t)idx * 32;
-          } else {
-            ctok = pa.q[a.col_base + cidx];                            // query byte of this "column"
-          }
-          // ---- diagonal input of the lane's first row ----
-          int up = wp::shfl_up(D10[R - 1], 1);
-          if (lane == 0) up = diag_carry;
-          diag_carry = Dtop[c];
+      // ---- per-column uniform data ----
+      int ctok = 0, openC_col = 0, closeC_col = 0, openR_col = 0;
+      const int8_t* prow_col = nullptr;
+      if (!PROF) {
+        ctok = sc.col_token(a.col_base + cidx);
+      } else if (RIGHT) {
+        const uint32_t idx = a.col_base + cidx;                   // scan_block.rs:658-661
+        openC_col = (int)wp::ldg(pa.p->gap_open_C + idx) + ge;
+        closeC_col = (int)wp::ldg(pa.p->gap_close_C + idx);
+        openR_col = (int)wp::ldg(pa.p->gap_open_R + idx);
+        prow_col = pa.p->pos_aa + (size_t)idx * 32;
+      } else {
+        ctok = pa.q[a.col_base + cidx];                            // query byte of this "column"
+      }
+      // ---- diagonal input of the lane's first row ----
+      int up = wp::shfl_up(D10[R - 1], 1);
+      if (lane == 0) up = diag_carry;
+      diag_carry = Dtop;
 
-          int dd[R], xx[R], c11[R], c11o[R], c11e[R], tt[R];
+      int dd[R], xx[R], c11[R], c11o[R], c11e[R], tt[R];
 #pragma unroll
-          for (int k = 0; k < R; k++) {
-            int s;
-            if (!PROF) s = sc.score(ctok, rtok[k]);
-            else if (RIGHT) s = (int)wp::ldg(prow_col + rtok[k]);
-            else s = (int)wp::ldg(p_row[k] + ctok);
-            int d00 = (k == 0) ? up : D10[k - 1];
-            if (origin && cidx == 0 && ch == 0 && k == 0 && lane == 0) { d00 = a.rz; s = 0; }
-            const int oc = PROF ? (RIGHT ? openC_col : p_openC[k]) : go;
-            c11o[k] = sat_add_lo(D10[k], oc);
-            c11[k] = wp::viaddmax(C10[k], ge, c11o[k]);
-            c11e[k] = c11[k];
-            if (PROF && RIGHT) c11e[k] = sat_add(c11[k], closeC_col);   // C11_end (scan_block.rs:694)
-            dd[k] = wp::imin(wp::viaddmax(d00, s, c11e[k]), kI16Max);
-            const int orr = PROF ? (RIGHT ? openR_col : p_openR[k]) : open_r;
-            xx[k] = sat_add_lo(dd[k], orr);
-            tt[k] = (k == 0) ? xx[0] : wp::viaddmax(tt[k - 1], ge, xx[k]);
-          }
-          // ---- cross-lane max-plus scan of the lane aggregates ----
-          int inc = tt[R - 1];
+      for (int k = 0; k < R; k++) {
+        int s;
+        if (!PROF) s = sc.score(ctok, rtok[k]);
+        else if (RIGHT) s = (int)wp::ldg(prow_col + rtok[k]);
+        else s = (int)wp::ldg(p_row[k] + ctok);
+        int d00 = (k == 0) ? up : D10[k - 1];
+        if (origin && cidx == 0 && ch == 0 && k == 0 && lane == 0) { d00 = a.rz; s = 0; }
+        const int oc = PROF ? (RIGHT ? openC_col : p_openC[k]) : go;
+        c11o[k] = sat_add_lo(D10[k], oc);
+        c11[k] = wp::viaddmax(C10[k], ge, c11o[k]);
+        c11e[k] = c11[k];
+        if (PROF && RIGHT) c11e[k] = sat_add(c11[k], closeC_col);   // C11_end (scan_block.rs:694)
+        dd[k] = wp::imin(wp::viaddmax(d00, s, c11e[k]), kI16Max);
+        const int orr = PROF ? (RIGHT ? openR_col : p_openR[k]) : open_r;
+        xx[k] = sat_add_lo(dd[k], orr);
+        tt[k] = (k == 0) ? xx[0] : wp::viaddmax(tt[k - 1], ge, xx[k]);
+      }
+      // ---- cross-lane max-plus scan of the lane aggregates ----
+      int inc = tt[R - 1];
 #pragma unroll
-          for (int s = 0; s < 5; s++) {
-            const int u = wp::shfl_up(inc, 1 << s);
-            inc = wp::viaddmax(u, dec[s], inc);
-          }
-          int ex = wp::shfl_up(inc, 1);
-          if (lane == 0) ex = kNegBig;
-          const int cin = wp::viaddmax(Ttop[c], lane_rg, ex);
+      for (int s = 0; s < 5; s++) {
+        const int u = wp::shfl_up(inc, 1 << s);
+        inc = wp::viaddmax(u, (R << s) * ge, inc);
+      }
+      int ex = wp::shfl_up(inc, 1);
+      if (lane == 0) ex = kNegBig;
+      const int cin = wp::viaddmax(Ttop, lane_rg, ex);
 
-          int Dn[R], Tn[R];
-          unsigned ebits = 0;
+      int Dn[R], Tn[R];
+      unsigned ebits = 0;
 #pragma unroll
-          for (int k = 0; k < R; k++) {
-            Tn[k] = wp::viaddmax(cin, kg[k], tt[k]);
-            const int Rv = wp::imax(Tn[k], ph[k]);
-            int Rend = Rv;
-            if (PROF && !RIGHT) Rend = sat_add(Rv, p_closeR[k]);
-            Dn[k] = wp::imax(dd[k], Rend);
-            if (TRACE) {
-              unsigned nib = (Dn[k] == c11e[k] ? 1u : 0u) | (Dn[k] == Rend ? 2u : 0u);
-              nib |= (c11[k] == c11o[k] ? 4u : 0u);
-              ebits |= (Rv == xx[k] ? 1u : 0u) << k;
-              twd[k] |= nib << (4 * c);
-            }
-            if (XDROP) {
-              const int nm = wp::imax(mx[k], Dn[k]);
-              if (Dn[k] == nm) mcol[k] = (unsigned)cidx + 1u;
-              mx[k] = nm;
-            } else {
-              mx[0] = wp::imax(mx[0], act ? Dn[k] : 0);
-            }
-          }
-          if (TRACE) {
-            // "R gap at this row was opened at the row above" = e of the row above (scan_block.rs:1179-1181)
-            const unsigned eb = wp::ballot(((ebits >> (R - 1)) & 1u) != 0);
-            unsigned above = lane == 0 ? (unsigned)etop[c] : ((eb >> (lane - 1)) & 1u);
-#pragma unroll
-            for (int k = 0; k < R; k++) {
-              const unsigned b3 = (k == 0) ? above : ((ebits >> (k - 1)) & 1u);
-              twd[k] |= (b3 << 3) << (4 * c);
-            }
-            if (MULTI && lane == last_lane) w.ecarry[cidx] = (uint8_t)((ebits >> (R - 1)) & 1u);
-          }
-          // ---- bottom row of the rectangle (or of this chunk) ----
-          if (lane == last_lane) {
-            a.OD[cidx] = (int16_t)Dn[R - 1];
-            a.OR_[cidx] = (int16_t)Tn[R - 1];
-          }
-#pragma unroll
-          for (int k = 0; k < R; k++) { D10[k] = Dn[k]; C10[k] = c11[k]; }
+      for (int k = 0; k < R; k++) {
+        Tn[k] = wp::viaddmax(cin, kg[k], tt[k]);
+        const int Rv = wp::imax(Tn[k], ph[k]);
+        int Rend = Rv;
+        if (PROF && !RIGHT) Rend = sat_add(Rv, p_closeR[k]);
+        Dn[k] = wp::imax(dd[k], Rend);
+        if (TRACE) {
+          unsigned nib = (Dn[k] == c11e[k] ? 1u : 0u) | (Dn[k] == Rend ? 2u : 0u);
+          nib |= (c11[k] == c11o[k] ? 4u : 0u);
+          ebits |= (Rv == xx[k] ? 1u : 0u) << k;
+          twd[k] |= nib << c4;
+        }
+        if (XDROP) {
+          const int nm = wp::imax(mx[k], Dn[k]);
+          if (Dn[k] == nm) mcol[k] = (unsigned)cidx + 1u;
+          mx[k] = nm;
+        } else {
+          mx[0] = wp::imax(mx[0], act ? Dn[k] : 0);
         }
       }
       if (TRACE) {
-        const int cgi = cg >> 3;
+        // "R gap at this row was opened at the row above" = e of the row above (scan_block.rs:1179-1181)
+        const unsigned eb = wp::ballot(((ebits >> (R - 1)) & 1u) != 0);
+        const unsigned above = lane == 0 ? (unsigned)etop : ((eb >> (lane - 1)) & 1u);
 #pragma unroll
         for (int k = 0; k < R; k++) {
-          a.tw[(((size_t)ch * ngroups + cgi) * R + k) * 32 + lane] = twd[k];
-          twd[k] = 0;
+          const unsigned b3 = (k == 0) ? above : ((ebits >> (k - 1)) & 1u);
+          twd[k] |= (b3 << 3) << c4;
+        }
+        if (multi && lane == last_lane) w.ecarry[cidx] = (uint8_t)((ebits >> (R - 1)) & 1u);
+        if ((cidx & 7) == 7 || cidx == a.ncols - 1) {
+          const int cgi = cidx >> 3;
+#pragma unroll
+          for (int k = 0; k < R; k++) {
+            a.tw[(((size_t)ch * ngroups + cgi) * R + k) * 32 + lane] = twd[k];
+            twd[k] = 0;
+          }
         }
       }
-      if (MULTI) wp::syncwarp();
+      // ---- bottom row of the rectangle (or of this chunk) ----
+      if (lane == last_lane) {
+        a.OD[cidx] = (int16_t)Dn[R - 1];
+        a.OR_[cidx] = (int16_t)Tn[R - 1];
+      }
+#pragma unroll
+      for (int k = 0; k < R; k++) { D10[k] = Dn[k]; C10[k] = c11[k]; }
     }
 
     if (act) {
@@ -313,21 +299,22 @@ BA_DEV void place_rect_r(const SeqScorer<(SCORING == kProfile ? kAA : SCORING)>&
     } else {
       bv = wp::imax(bv, mx[0]);
     }
+    if (multi) wp::syncwarp();
   }
   wp::syncwarp();
 }
 
+// RIGHT only changes behaviour for profiles (sequence-sequence right/down differ only in which
+// sequence plays which role), so sequence scorers always instantiate RIGHT = true.
 template <int SCORING, bool RIGHT, bool TRACE, bool XDROP>
 BA_DEV void place_rect(const SeqScorer<(SCORING == kProfile ? kAA : SCORING)>& sc, const ProfArgs& pa,
                        const RectArgs& a, const WarpMem& w, int& bv, unsigned& bkey) {
+  constexpr bool RT = (SCORING == kProfile) ? RIGHT : true;
   bv = 0;                // D_max starts at MIN = 0 (scan_block.rs:1101)
   bkey = 15u << 27;      // "no cell": AVX lane 0 with argmax (0, 0)
   if (a.W == 0 || a.H == 0) return;   // scan_block.rs:1105-1107
-  if (a.H <= 32) place_rect_r<SCORING, RIGHT, 1, TRACE, XDROP, false>(sc, pa, a, w, bv, bkey);
-  else if (a.H == 64) place_rect_r<SCORING, RIGHT, 2, TRACE, XDROP, false>(sc, pa, a, w, bv, bkey);
-  else if (a.H == 128) place_rect_r<SCORING, RIGHT, 4, TRACE, XDROP, false>(sc, pa, a, w, bv, bkey);
-  else if (a.H == 256) place_rect_r<SCORING, RIGHT, 8, TRACE, XDROP, false>(sc, pa, a, w, bv, bkey);
-  else place_rect_r<SCORING, RIGHT, 8, TRACE, XDROP, true>(sc, pa, a, w, bv, bkey);
+  if (a.H >= 256) place_rect_r<SCORING, RT, 8, TRACE, XDROP>(sc, pa, a, w, bv, bkey);
+  else place_rect_r<SCORING, RT, 1, TRACE, XDROP>(sc, pa, a, w, bv, bkey);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -392,31 +379,55 @@ BA_DEV int shrink_max(const int16_t* Dc, const int16_t* Dr, int B) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Trace bookkeeping (stack of rectangles + packed words; scan_block.rs:1344-1463)
+// Per-alignment state. Everything the reference keeps in locals of align_core (scan_block.rs:
+// 102-128) plus the trace stack indices, so that an alignment can be parked and resumed: the
+// block-32 shift steps run four alignments per warp out of registers (fast phase, below), everything
+// else runs one alignment per warp out of shared memory (generic phase).
 // ---------------------------------------------------------------------------------------------
-struct TraceState {
+struct AlnState {
+  uint32_t pair, qlen, rlen;
+  uint32_t si, sj;
+  int B, prev_size, dir, prev_dir;
+  int off, off_max, best_max;
+  uint32_t best_i, best_j, i_ckpt, j_ckpt;
+  int off_ckpt, y_drop_iter, x_drop_iter, D_corner;
+  uint32_t cells_lo, cells_hi, steps;
+  uint32_t widx, ridx, ck_widx, ck_ridx, overflow;   // trace stack (scan_block.rs:1351-1354)
+};
+
+// per-slot scratch in global memory (slot = one alignment in flight)
+struct SlotMem {
+  int16_t *kDc, *kCc, *kDr, *kRr;     // checkpoint borders (scan_block.rs:1262-1265)
   uint32_t* words; uint64_t words_cap;
   Rect* rects; uint32_t rects_cap;
-  uint64_t widx; uint32_t ridx;
-  uint64_t ck_widx; uint32_t ck_ridx;
-  bool overflow;
 };
-BA_DEV uint64_t rect_words(int H, int W) {
-  const int R = H <= 32 ? 1 : (H >= 256 ? 8 : H / 32);
+
+BA_DEV void add_cells(AlnState& st, uint32_t n) {
+  const uint32_t lo = st.cells_lo + n;
+  st.cells_hi += (lo < st.cells_lo) ? 1u : 0u;
+  st.cells_lo = lo;
+}
+
+BA_HD uint64_t rect_words(int H, int W) {
+  const int R = rect_rows_per_lane(H);
   const int CH = 32 * R;
   const int nch = (H + CH - 1) / CH;
   return (uint64_t)nch * (uint64_t)(W >> 3) * R * 32;
 }
-BA_DEV uint32_t* trace_push(TraceState& ts, uint32_t row, uint32_t col, int W, int H, bool right) {
+// Trace::add_block (scan_block.rs:1428-1443); returns where this rectangle's words go
+BA_DEV uint32_t* trace_push(AlnState& st, const SlotMem& sm, uint32_t row, uint32_t col, int W, int H, bool right, bool writer) {
   const uint64_t need = rect_words(H, W);
-  if (ts.ridx >= ts.rects_cap || ts.widx + need > ts.words_cap || (ts.widx + need) >> 32) { ts.overflow = true; return ts.words; }
-  if (wp::lane_id() == 0) {
-    Rect r; r.row = row; r.col = col; r.h = (uint16_t)H; r.w = (uint16_t)W; r.right = right ? 1u : 0u; r.word_off = (uint32_t)ts.widx;
-    ts.rects[ts.ridx] = r;
+  if (st.ridx >= sm.rects_cap || (uint64_t)st.widx + need > sm.words_cap || ((uint64_t)st.widx + need) >> 32) {
+    st.overflow = 1u;
+    return sm.words;
   }
-  uint32_t* p = ts.words + ts.widx;
-  ts.widx += need;
-  ts.ridx += 1;
+  if (writer) {
+    Rect r; r.row = row; r.col = col; r.h = (uint16_t)H; r.w = (uint16_t)W; r.right = right ? 1u : 0u; r.word_off = st.widx;
+    sm.rects[st.ridx] = r;
+  }
+  uint32_t* p = sm.words + st.widx;
+  st.widx += (uint32_t)need;
+  st.ridx += 1;
   return p;
 }
 
@@ -441,7 +452,7 @@ BA_DEV void traceback_walk(const uint32_t* words, const Rect* rects, uint32_t ri
     }
     if (bad) break;
     const int H = rc.h, W = rc.w;
-    const int R = H <= 32 ? 1 : (H >= 256 ? 8 : H / 32);
+    const int R = rect_rows_per_lane(H);
     const int CH = 32 * R;
     const int ngroups = W >> 3;
     const uint32_t* tw = words + rc.word_off;
@@ -498,135 +509,163 @@ BA_DEV void emit_cigar(const Params& P, const uint32_t* words, const Rect* rects
 }
 
 // ---------------------------------------------------------------------------------------------
-// The per-alignment state machine (scan_block.rs:94-595)
+// Generic phase: one alignment per warp, borders in shared memory (scan_block.rs:94-595)
 // ---------------------------------------------------------------------------------------------
+enum { kRunDone = 0, kRunFast = 1 };
+
 template <int SCORING, int FLAGS>
-BA_DEV void align_pair(const Params& P, uint32_t pair, const WarpMem& w, TraceState& ts, uint32_t warp_global) {
+BA_DEV void init_alignment(const Params& P, AlnState& st, uint32_t pair, const WarpMem& w) {
+  const int lane = wp::lane_id();
+  st.pair = pair;
+  st.qlen = P.q_len[pair];
+  st.rlen = (SCORING == kProfile) ? P.profiles[pair].len : P.r_len[pair];
+  // Allocated::clear (scan_block.rs:1322-1339): every border starts at MIN = 0
+  for (int idx = lane; idx < (int)P.max_size; idx += 32) {
+    w.Dc[idx] = 0; w.Cc[idx] = 0; w.Dr[idx] = 0; w.Rr[idx] = 0;
+    w.kDc[idx] = 0; w.kCc[idx] = 0; w.kDr[idx] = 0; w.kRr[idx] = 0;
+  }
+  if (lane < 16) { w.t1[lane] = 0; w.t2[lane] = 0; }
+  wp::syncwarp();
+  st.si = 0; st.sj = 0;
+  st.B = (int)P.min_size; st.prev_size = 0; st.dir = kGrow; st.prev_dir = kGrow;
+  st.off = 0; st.off_max = 0; st.best_max = 0; st.best_i = 0; st.best_j = 0;
+  st.i_ckpt = 0; st.j_ckpt = 0; st.off_ckpt = 0;
+  st.y_drop_iter = 0; st.x_drop_iter = 0; st.D_corner = 0;
+  st.cells_lo = 0; st.cells_hi = 0; st.steps = 0;
+  st.widx = 0; st.ridx = 0; st.ck_widx = 0; st.ck_ridx = 0; st.overflow = 0;
+}
+
+// grow transition (scan_block.rs:477-500): back to the checkpoint with a doubled block
+BA_DEV void apply_grow(AlnState& st, const WarpMem& w, bool trace) {
+  st.prev_size = st.B; st.B = st.B * 2; st.dir = kGrow;
+  st.si = st.i_ckpt; st.sj = st.j_ckpt; st.off = st.off_ckpt;
+  copy4(st.prev_size, w.Dc, w.Cc, w.Dr, w.Rr, w.kDc, w.kCc, w.kDr, w.kRr, 0);
+  if (trace) { st.widx = st.ck_widx; st.ridx = st.ck_ridx; }
+  st.y_drop_iter = 0;
+}
+
+// Is the pending step (st.dir already chosen, st.si/sj already moved) a plain block-32 shift that the
+// fast phase can execute? (no early break: scan_block.rs:1216-1224)
+template <int SCORING, bool XDROP>
+BA_DEV bool fast_eligible(const Params& P, const AlnState& st) {
+  if (SCORING == kProfile || !P.use_fast) return false;
+  if (st.B != 32 || st.dir == kGrow) return false;
+  if (!XDROP) {
+    const uint32_t vec_base = st.dir == kRight ? st.si : st.sj, vec_len = st.dir == kRight ? st.qlen : st.rlen;
+    const uint32_t col_base = (st.dir == kRight ? st.sj : st.si) + 24, col_len = st.dir == kRight ? st.rlen : st.qlen;
+    if (vec_base + 32 > vec_len && col_base + 7 > col_len) return false;
+  }
+  return true;
+}
+
+template <int SCORING, int FLAGS>
+BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const SlotMem& sm) {
   constexpr bool TRACE = (FLAGS & kTrace) != 0, XDROP = (FLAGS & kXDrop) != 0;
   constexpr bool PROF = SCORING == kProfile;
   const int lane = wp::lane_id();
-
-  const uint8_t* q = P.seq + P.q_off[pair];
-  const uint32_t qlen = P.q_len[pair];
+  const uint8_t* q = P.seq + P.q_off[st.pair];
   const uint8_t* r = nullptr;
-  uint32_t rlen;
   ProfArgs pa; pa.p = nullptr; pa.q = q;
-  if (PROF) { pa.p = P.profiles + pair; rlen = pa.p->len; }
-  else { r = P.seq + P.r_off[pair]; rlen = P.r_len[pair]; }
+  if (PROF) pa.p = P.profiles + st.pair;
+  else r = P.seq + P.r_off[st.pair];
+  const uint32_t qlen = st.qlen, rlen = st.rlen;
 
   SeqScorer<(SCORING == kProfile ? kAA : SCORING)> sc;
   sc.mat = w.mat; sc.vec = q; sc.col = r; sc.go = P.gap_open; sc.ge = P.gap_extend;
   sc.b_match = sc.b_mismatch = 0;
   if (SCORING == kByte) { sc.b_match = (int)P.matrix[0]; sc.b_mismatch = (int)P.matrix[1]; }
-
   const int min_size = (int)P.min_size, max_size = (int)P.max_size;
 
-  // Allocated::clear (scan_block.rs:1322-1339): every border starts at MIN = 0
-  for (int idx = lane; idx < max_size; idx += 32) {
-    w.Dc[idx] = 0; w.Cc[idx] = 0; w.Dr[idx] = 0; w.Rr[idx] = 0;
-    w.kDc[idx] = 0; w.kCc[idx] = 0; w.kDr[idx] = 0; w.kRr[idx] = 0;
-  }
-  if (lane < 16) { w.t1[lane] = 0; w.t2[lane] = 0; }
-  ts.widx = 0; ts.ridx = 0; ts.ck_widx = 0; ts.ck_ridx = 0; ts.overflow = false;
-  wp::syncwarp();
-
-  uint32_t si = 0, sj = 0;
-  int best_max = 0; uint32_t best_i = 0, best_j = 0;
-  int prev_dir = kGrow, dir = kGrow;
-  int prev_size = 0, B = min_size;
-  int off = 0, prev_off, off_max = 0;
-  int y_drop_iter = 0, x_drop_iter = 0;
-  uint32_t i_ckpt = 0, j_ckpt = 0; int off_ckpt = 0;
-  int D_corner = 0;
-  uint64_t cells = 0; uint32_t steps = 0;
-
   for (;;) {
-    prev_off = off;
+    if (fast_eligible<SCORING, XDROP>(P, st)) return kRunFast;
+    const int prev_off = st.off;
     int bv = 0, gbv = 0; unsigned bkey = 15u << 27, gbkey = 15u << 27;
     int right_max, down_max;
-    steps++;
-    RectArgs a;
-    if (dir == kRight) {
-      off = off_max;
-      const int off_add = clamp16(prev_off - off);
-      a.vec_base = si; a.col_base = sj + B - kStep; a.W = kStep; a.H = B;
-      a.AD = w.Dc; a.AC = w.Cc; a.OD = w.t1; a.OR_ = w.t2;
-      a.corner = (prev_dir == kDown) ? sat_add(D_corner, off_add) : 0;
-      a.off_add = off_add; a.rz = clamp16(kZero - off);
+    const int B = st.B;
+    const uint32_t si = st.si, sj = st.sj;
+    st.steps++;
+    // One shift step computes one rectangle, a grow step two (down part, then right part). A single
+    // place_rect call site serves all of them: the kernel has to stay small enough for the I-cache.
+    int off_add = 0;
+    if (st.dir == kGrow) st.D_corner = 0;
+    else { st.off = st.off_max; off_add = clamp16(prev_off - st.off); }
+    const int nparts = st.dir == kGrow ? 2 : 1;
+    const int prev_size = st.prev_size;
+    for (int part = 0; part < nparts; part++) {
+      RectArgs a;
+      bool rect_right;
+      a.off_add = off_add; a.rz = clamp16(kZero - st.off); a.corner = 0;
+      if (st.dir == kRight) {            // scan_block.rs:147-196
+        rect_right = true;
+        a.vec_base = si; a.col_base = sj + B - kStep; a.W = kStep; a.H = B;
+        a.AD = w.Dc; a.AC = w.Cc; a.OD = w.t1; a.OR_ = w.t2;
+        if (st.prev_dir == kDown) a.corner = sat_add(st.D_corner, off_add);
+      } else if (st.dir == kDown) {      // scan_block.rs:197-246
+        rect_right = false;
+        a.vec_base = sj; a.col_base = si + B - kStep; a.W = kStep; a.H = B;
+        a.AD = w.Dr; a.AC = w.Rr; a.OD = w.t1; a.OR_ = w.t2;
+        if (st.prev_dir == kRight) a.corner = sat_add(st.D_corner, off_add);
+      } else if (part == 0) {            // grow, down part: rows si+prev.. x cols sj..sj+prev (scan_block.rs:262-278)
+        rect_right = false;
+        a.vec_base = sj; a.col_base = si + prev_size; a.W = B - prev_size; a.H = prev_size;
+        a.AD = w.Dr; a.AC = w.Rr; a.OD = w.Dc + prev_size; a.OR_ = w.Cc + prev_size;
+      } else {                           // grow, right part: rows si..si+B x cols sj+prev..sj+B (scan_block.rs:289-305)
+        rect_right = true;
+        a.vec_base = si; a.col_base = sj + prev_size; a.W = B - prev_size; a.H = B;
+        a.AD = w.Dc; a.AC = w.Cc; a.OD = w.Dr + prev_size; a.OR_ = w.Rr + prev_size;
+      }
+      const uint32_t vec_len = rect_right ? qlen : rlen, col_len = rect_right ? rlen : qlen;
       a.ncols = a.W;
-      if (!XDROP && a.vec_base + a.H > qlen) { int lim = (int)rlen - (int)a.col_base; if (lim < 0) lim = 0; if (lim + 1 < a.ncols) a.ncols = lim + 1; }
+      if (!XDROP && a.vec_base + a.H > vec_len) {   // early break (scan_block.rs:1216-1224)
+        int lim = (int)col_len - (int)a.col_base;
+        if (lim < 0) lim = 0;
+        if (lim + 1 < a.ncols) a.ncols = lim + 1;
+      }
       a.tw = nullptr;
-      if (TRACE) a.tw = trace_push(ts, si, sj + B - kStep, kStep, B, true);
-      cells += (uint64_t)kStep * B;
-      sc.vec = q; sc.col = r;
-      if (!ts.overflow) place_rect<SCORING, true, TRACE, XDROP>(sc, pa, a, w, bv, bkey);
-      D_corner = shift_and_offset(B, w.Dr, w.Rr, w.t1, w.t2, off_add);
-      border_maxes(w.Dc, w.Dr, right_max, down_max);
-    } else if (dir == kDown) {
-      off = off_max;
-      const int off_add = clamp16(prev_off - off);
-      a.vec_base = sj; a.col_base = si + B - kStep; a.W = kStep; a.H = B;
-      a.AD = w.Dr; a.AC = w.Rr; a.OD = w.t1; a.OR_ = w.t2;
-      a.corner = (prev_dir == kRight) ? sat_add(D_corner, off_add) : 0;
-      a.off_add = off_add; a.rz = clamp16(kZero - off);
-      a.ncols = a.W;
-      if (!XDROP && a.vec_base + a.H > rlen) { int lim = (int)qlen - (int)a.col_base; if (lim < 0) lim = 0; if (lim + 1 < a.ncols) a.ncols = lim + 1; }
-      a.tw = nullptr;
-      if (TRACE) a.tw = trace_push(ts, si + B - kStep, sj, kStep, B, false);
-      cells += (uint64_t)kStep * B;
-      sc.vec = r; sc.col = q;
-      if (!ts.overflow) place_rect<SCORING, false, TRACE, XDROP>(sc, pa, a, w, bv, bkey);
-      D_corner = shift_and_offset(B, w.Dc, w.Cc, w.t1, w.t2, off_add);
-      border_maxes(w.Dc, w.Dr, right_max, down_max);
-    } else {
-      D_corner = 0;
-      const int grow_step = B - prev_size;
-      // down part: rows si+prev.. x cols sj..sj+prev (scan_block.rs:262-278)
-      a.vec_base = sj; a.col_base = si + prev_size; a.W = grow_step; a.H = prev_size;
-      a.AD = w.Dr; a.AC = w.Rr; a.OD = w.Dc + prev_size; a.OR_ = w.Cc + prev_size;
-      a.corner = 0; a.off_add = 0; a.rz = clamp16(kZero - off);
-      a.ncols = a.W;
-      if (!XDROP && a.vec_base + a.H > rlen) { int lim = (int)qlen - (int)a.col_base; if (lim < 0) lim = 0; if (lim + 1 < a.ncols) a.ncols = lim + 1; }
-      a.tw = nullptr;
-      if (TRACE) a.tw = trace_push(ts, si + prev_size, sj, grow_step, prev_size, false);
-      cells += (uint64_t)grow_step * prev_size;
-      sc.vec = r; sc.col = q;
-      if (!ts.overflow) place_rect<SCORING, false, TRACE, XDROP>(sc, pa, a, w, gbv, gbkey);
-      // right part: rows si..si+B x cols sj+prev..sj+B (scan_block.rs:289-305)
-      a.vec_base = si; a.col_base = sj + prev_size; a.W = grow_step; a.H = B;
-      a.AD = w.Dc; a.AC = w.Cc; a.OD = w.Dr + prev_size; a.OR_ = w.Rr + prev_size;
-      a.ncols = a.W;
-      if (!XDROP && a.vec_base + a.H > qlen) { int lim = (int)rlen - (int)a.col_base; if (lim < 0) lim = 0; if (lim + 1 < a.ncols) a.ncols = lim + 1; }
-      if (TRACE) a.tw = trace_push(ts, si, sj + prev_size, grow_step, B, true);
-      cells += (uint64_t)grow_step * B;
-      sc.vec = q; sc.col = r;
-      if (!ts.overflow) place_rect<SCORING, true, TRACE, XDROP>(sc, pa, a, w, bv, bkey);
-      border_maxes(w.Dc, w.Dr, right_max, down_max);
-      copy4(B, w.kDc, w.kCc, w.kDr, w.kRr, w.Dc, w.Cc, w.Dr, w.Rr, 0);   // scan_block.rs:315-322
-      if (TRACE) { ts.ck_widx = ts.widx; ts.ck_ridx = ts.ridx; }
+      if (TRACE && a.W > 0 && a.H >= 0) {
+        a.tw = trace_push(st, sm, rect_right ? a.vec_base : a.col_base, rect_right ? a.col_base : a.vec_base, a.W, a.H, rect_right, lane == 0);
+      }
+      add_cells(st, (uint32_t)(a.W * a.H));
+      sc.vec = rect_right ? q : r; sc.col = rect_right ? r : q;
+      int pbv = 0; unsigned pkey = 15u << 27;
+      if (!st.overflow) {
+        if (PROF && !rect_right) place_rect<SCORING, false, TRACE, XDROP>(sc, pa, a, w, pbv, pkey);
+        else place_rect<SCORING, true, TRACE, XDROP>(sc, pa, a, w, pbv, pkey);
+      }
+      if (st.dir == kGrow && part == 0) { gbv = pbv; gbkey = pkey; }
+      else { bv = pbv; bkey = pkey; }
     }
-    if (ts.overflow) break;
+    if (st.dir != kGrow) {
+      int16_t *o1 = st.dir == kRight ? w.Dr : w.Dc, *o2 = st.dir == kRight ? w.Rr : w.Cc;
+      st.D_corner = shift_and_offset(B, o1, o2, w.t1, w.t2, off_add);
+    }
+    border_maxes(w.Dc, w.Dr, right_max, down_max);
+    if (st.dir == kGrow) {
+      copy4(B, w.kDc, w.kCc, w.kDr, w.kRr, w.Dc, w.Cc, w.Dr, w.Rr, 0);   // scan_block.rs:315-322
+      if (TRACE) { st.ck_widx = st.widx; st.ck_ridx = st.ridx; }
+    }
+    if (st.overflow) return kRunDone;
 
-    const int this_dir = dir;
-    prev_dir = dir;
+    const int this_dir = st.dir;
+    st.prev_dir = st.dir;
     const int D_max_max = wp::red_max(bv);
     const int grow_max = wp::red_max(gbv);
     const int mx = wp::imax(D_max_max, grow_max);
-    off_max = off + mx - kZero;
-    y_drop_iter++;
-    bool grow_no_max = (dir == kGrow);
+    st.off_max = st.off + mx - kZero;
+    st.y_drop_iter++;
+    bool grow_no_max = (this_dir == kGrow);
 
     if (P.step_log && lane == 0) {
       const uint32_t n = *P.step_log_n;
       if (n < P.step_log_cap) {
-        StepLog s; s.dir = dir; s.i = si; s.j = sj; s.block_size = (uint32_t)B; s.off = off;
+        StepLog s; s.dir = this_dir; s.i = si; s.j = sj; s.block_size = (uint32_t)B; s.off = st.off;
         s.max = (int16_t)mx; s.right_max = (int16_t)right_max; s.down_max = (int16_t)down_max;
         P.step_log[n] = s;
       }
       *P.step_log_n = n + 1;
     }
 
-    if (off_max > best_max) {
+    if (st.off_max > st.best_max) {
       if (XDROP) {
         // decode the argmax (scan_block.rs:370-404)
         const bool use_right = (this_dir != kGrow) || (D_max_max >= grow_max);
@@ -637,147 +676,523 @@ BA_DEV void align_pair(const Params& P, uint32_t pair, const WarpMem& w, TraceSt
         const unsigned cp1 = (key >> 13) & 0x3fffu;
         uint32_t v = key & 0x1fffu, c = 0;
         if (cp1 == 0) v = 0; else c = cp1 - 1;
-        if (this_dir == kRight) { best_i = si + v; best_j = sj + (uint32_t)(B - kStep) + c; }
-        else if (this_dir == kDown) { best_i = si + (uint32_t)(B - kStep) + c; best_j = sj + v; }
-        else if (use_right) { best_i = si + v; best_j = sj + (uint32_t)prev_size + c; }
-        else { best_i = si + (uint32_t)prev_size + c; best_j = sj + v; }
+        if (this_dir == kRight) { st.best_i = si + v; st.best_j = sj + (uint32_t)(B - kStep) + c; }
+        else if (this_dir == kDown) { st.best_i = si + (uint32_t)(B - kStep) + c; st.best_j = sj + v; }
+        else if (use_right) { st.best_i = si + v; st.best_j = sj + (uint32_t)st.prev_size + c; }
+        else { st.best_i = si + (uint32_t)st.prev_size + c; st.best_j = sj + v; }
       }
       if (B < max_size) {
-        i_ckpt = si; j_ckpt = sj; off_ckpt = off;
+        st.i_ckpt = si; st.j_ckpt = sj; st.off_ckpt = st.off;
         copy4(B, w.kDc, w.kCc, w.kDr, w.kRr, w.Dc, w.Cc, w.Dr, w.Rr, 0);
-        if (TRACE) { ts.ck_widx = ts.widx; ts.ck_ridx = ts.ridx; }
+        if (TRACE) { st.ck_widx = st.widx; st.ck_ridx = st.ridx; }
         grow_no_max = false;
       }
-      best_max = off_max;
-      y_drop_iter = 0;
+      st.best_max = st.off_max;
+      st.y_drop_iter = 0;
     }
 
     if (XDROP) {
-      if (off_max < best_max - P.x_drop) {
-        if (x_drop_iter < kXDropIter - 1) x_drop_iter++;
-        else break;
+      if (st.off_max < st.best_max - P.x_drop) {
+        if (st.x_drop_iter < kXDropIter - 1) st.x_drop_iter++;
+        else return kRunDone;
       } else {
-        x_drop_iter = 0;
+        st.x_drop_iter = 0;
       }
     }
 
-    if (si + B > qlen && sj + B > rlen) break;
-    if (sj + B > rlen) { si += kStep; dir = kDown; continue; }
-    if (si + B > qlen) { sj += kStep; dir = kRight; continue; }
+    if (si + B > qlen && sj + B > rlen) return kRunDone;
+    if (sj + B > rlen) { st.si += kStep; st.dir = kDown; continue; }
+    if (si + B > qlen) { st.sj += kStep; st.dir = kRight; continue; }
 
-    const int next_size = B * 2;
-    if (next_size <= max_size) {
-      if (y_drop_iter > (B / kStep) - 1 || grow_no_max) {
-        prev_size = B; B = next_size; dir = kGrow;
-        si = i_ckpt; sj = j_ckpt; off = off_ckpt;
-        copy4(prev_size, w.Dc, w.Cc, w.Dr, w.Rr, w.kDc, w.kCc, w.kDr, w.kRr, 0);
-        if (TRACE) { ts.widx = ts.ck_widx; ts.ridx = ts.ck_ridx; }
-        y_drop_iter = 0;
+    if (B * 2 <= max_size) {
+      if (st.y_drop_iter > (B / kStep) - 1 || grow_no_max) {
+        apply_grow(st, w, TRACE);
         continue;
       }
     }
 
-    if (B > min_size && y_drop_iter == 0) {
-      const int sm = shrink_max(w.Dc, w.Dr, B);
-      if (sm >= mx) {
-        prev_dir = kGrow;
-        B /= 2;
-        copy4(B, w.Dc, w.Cc, w.Dr, w.Rr, w.Dc, w.Cc, w.Dr, w.Rr, B);
-        si += (uint32_t)B; sj += (uint32_t)B;
-        i_ckpt = si; j_ckpt = sj; off_ckpt = off;
-        copy4(B, w.kDc, w.kCc, w.kDr, w.kRr, w.Dc, w.Cc, w.Dr, w.Rr, 0);
+    if (B > min_size && st.y_drop_iter == 0) {
+      const int smx = shrink_max(w.Dc, w.Dr, B);
+      if (smx >= mx) {
+        st.prev_dir = kGrow;
+        const int nb = B / 2;
+        st.B = nb;
+        copy4(nb, w.Dc, w.Cc, w.Dr, w.Rr, w.Dc, w.Cc, w.Dr, w.Rr, nb);
+        st.si += (uint32_t)nb; st.sj += (uint32_t)nb;
+        st.i_ckpt = st.si; st.j_ckpt = st.sj; st.off_ckpt = st.off;
+        copy4(nb, w.kDc, w.kCc, w.kDr, w.kRr, w.Dc, w.Cc, w.Dr, w.Rr, 0);
         border_maxes(w.Dc, w.Dr, right_max, down_max);
-        if (TRACE) { ts.ck_widx = ts.widx; ts.ck_ridx = ts.ridx; }
-        y_drop_iter = 0;
+        if (TRACE) { st.ck_widx = st.widx; st.ck_ridx = st.ridx; }
+        st.y_drop_iter = 0;
       }
     }
 
-    if (down_max > right_max) { si += kStep; dir = kDown; }
-    else { sj += kStep; dir = kRight; }
+    if (down_max > right_max) { st.si += kStep; st.dir = kDown; }
+    else { st.sj += kStep; st.dir = kRight; }
   }
+}
 
-  // result (scan_block.rs:567-592)
+// result (scan_block.rs:567-592) + traceback. Borders must be in shared memory.
+template <int SCORING, int FLAGS>
+BA_DEV void finish_alignment(const Params& P, const AlnState& st, const WarpMem& w, const SlotMem& sm, uint32_t slot, uint32_t warp_global) {
+  constexpr bool TRACE = (FLAGS & kTrace) != 0, XDROP = (FLAGS & kXDrop) != 0;
+  const int lane = wp::lane_id();
   wp::syncwarp();
   DevResult res;
-  res.status = ts.overflow ? (uint32_t)kTraceOverflow : (uint32_t)kOk;
-  res.cells = cells; res.steps = steps; res.cigar_n = 0; res.cigar_off = 0;
+  res.status = st.overflow ? (uint32_t)kTraceOverflow : (uint32_t)kOk;
+  res.cells = ((uint64_t)st.cells_hi << 32) | st.cells_lo; res.steps = st.steps; res.cigar_n = 0; res.cigar_off = 0;
   if (XDROP) {
-    res.score = best_max; res.query_idx = best_i; res.reference_idx = best_j;
+    res.score = st.best_max; res.query_idx = st.best_i; res.reference_idx = st.best_j;
   } else {
     int sv;
-    if (dir == kRight || dir == kGrow) sv = (int)w.Dc[qlen - si];
-    else sv = (int)w.Dr[rlen - sj];
-    res.score = off + sv - kZero; res.query_idx = qlen; res.reference_idx = rlen;
+    if (st.dir == kRight || st.dir == kGrow) sv = (int)w.Dc[st.qlen - st.si];
+    else sv = (int)w.Dr[st.rlen - st.sj];
+    res.score = st.off + sv - kZero; res.query_idx = st.qlen; res.reference_idx = st.rlen;
   }
-
-  res.rect_n = ts.ridx; res.warp = warp_global;
-  // traceback -> CIGAR runs (scan_block.rs:1482-1672; cigar.rs:71-79)
-  if (TRACE && !ts.overflow && P.cigar_stream) {
+  res.rect_n = st.ridx; res.warp = slot;
+  if (TRACE && !st.overflow && P.cigar_stream) {
+    const uint8_t* q = P.seq + P.q_off[st.pair];
+    const uint8_t* r = (SCORING == kProfile) ? nullptr : P.seq + P.r_off[st.pair];
     uint32_t* runs = P.run_scratch + (size_t)warp_global * P.runs_per_warp;
-    emit_cigar(P, ts.words, ts.rects, ts.ridx, res.query_idx, res.reference_idx, q, r, P.cigar_eq != 0, runs, res);
+    emit_cigar(P, sm.words, sm.rects, st.ridx, res.query_idx, res.reference_idx, q, r, P.cigar_eq != 0, runs, res);
   }
-  if (lane == 0) P.out[pair] = res;
+  if (lane == 0) P.out[st.pair] = res;
   wp::syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------
-// Warp main: carve shared memory, then pull pairs off the ticket counter until none are left.
+// Fast phase: four alignments per warp, 8 lanes x 4 rows each, block size 32, borders in registers.
+// Lane g*8+l of group g owns border entries 4l..4l+3. One iteration = one Right/Down shift step
+// (scan_block.rs:147-246) of every group, followed by the post-step decisions (scan_block.rs:332-558)
+// as straight-line predicated code. Anything else (grow, early break, end of the alignment) parks
+// the group: its status changes and the generic phase services it with the whole warp.
 // ---------------------------------------------------------------------------------------------
-BA_HD size_t warp_smem_bytes(uint32_t max_size, bool ckpt_in_smem) {
+enum { kStFast = 0, kStNeedGeneric = 1, kStNeedGrow = 2, kStDone = 3, kStEmpty = 4 };
+
+struct FastRegs {
+  int aD[4], aC[4];   // border that moves with the step (D_col/C_col for Right, D_row/R_row for Down)
+  int oD[4], oR[4];   // the orthogonal border
+};
+
+BA_DEV int pack16(int lo, int hi) { return (lo & 0xffff) | (hi << 16); }
+BA_DEV int lo16(int p) { return (int)(int16_t)(p & 0xffff); }
+BA_DEV int hi16(int p) { return p >> 16; }
+
+BA_DEV int group_max(int v) {
+  v = wp::imax(v, wp::shfl_xor8(v, 1));
+  v = wp::imax(v, wp::shfl_xor8(v, 2));
+  v = wp::imax(v, wp::shfl_xor8(v, 4));
+  return v;
+}
+BA_DEV unsigned group_max_u(unsigned v) {
+  unsigned u = (unsigned)wp::shfl_xor8((int)v, 1); v = u > v ? u : v;
+  u = (unsigned)wp::shfl_xor8((int)v, 2); v = u > v ? u : v;
+  u = (unsigned)wp::shfl_xor8((int)v, 4); v = u > v ? u : v;
+  return v;
+}
+
+// registers <-> shared-memory borders for the lanes of group g (oriented by st.dir)
+BA_DEV void fast_load(FastRegs& f, const WarpMem& w, int dir, bool mine) {
+  const int i0 = (wp::lane_id() & 7) * 4;
+  const int16_t *ad = dir == kRight ? w.Dc : w.Dr, *ac = dir == kRight ? w.Cc : w.Rr;
+  const int16_t *od = dir == kRight ? w.Dr : w.Dc, *orr = dir == kRight ? w.Rr : w.Cc;
+  if (mine) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) { f.aD[k] = ad[i0 + k]; f.aC[k] = ac[i0 + k]; f.oD[k] = od[i0 + k]; f.oR[k] = orr[i0 + k]; }
+  }
+}
+BA_DEV void fast_spill(const FastRegs& f, const WarpMem& w, int dir, bool mine) {
+  const int lg = wp::lane_id() & 7, i0 = lg * 4;
+  int16_t *ad = dir == kRight ? w.Dc : w.Dr, *ac = dir == kRight ? w.Cc : w.Rr;
+  int16_t *od = dir == kRight ? w.Dr : w.Dc, *orr = dir == kRight ? w.Rr : w.Cc;
+  wp::syncwarp();
+  if (mine) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      ad[i0 + k] = (int16_t)f.aD[k]; ac[i0 + k] = (int16_t)f.aC[k]; od[i0 + k] = (int16_t)f.oD[k]; orr[i0 + k] = (int16_t)f.oR[k];
+    }
+    // temp_buf1/2 hold the 8 fresh values of the last shift = entries 24..31 of the orthogonal border
+    if (lg >= 6) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) { w.t1[(lg - 6) * 4 + k] = (int16_t)f.oD[k]; w.t2[(lg - 6) * 4 + k] = (int16_t)f.oR[k]; }
+    }
+  }
+  wp::syncwarp();
+}
+
+template <int SCORING, int FLAGS>
+BA_DEV void fast_step(const Params& P, const int8_t* mat, AlnState& st, FastRegs& f, int& status,
+                      const uint8_t* qp, const uint8_t* rp, const SlotMem& sm) {
+  constexpr bool TRACE = (FLAGS & kTrace) != 0, XDROP = (FLAGS & kXDrop) != 0;
+  constexpr int KIND = (SCORING == kProfile) ? kAA : SCORING;
+  const int lane = wp::lane_id(), lg = lane & 7;
+  const bool active = status == kStFast;
+  const int ge = P.gap_extend, go = P.gap_open, open_r = go - ge;
+  SeqScorer<KIND> sc;
+  sc.mat = mat; sc.go = go; sc.ge = ge; sc.b_match = sc.b_mismatch = 0;
+  if (KIND == kByte) { sc.b_match = (int)P.matrix[0]; sc.b_mismatch = (int)P.matrix[1]; }
+
+  const bool right = st.dir == kRight;
+  const uint32_t si = st.si, sj = st.sj;
+  const uint8_t* vec = right ? qp : rp;
+  const uint8_t* col = right ? rp : qp;
+  const uint32_t vec_base = right ? si : sj;
+  const uint32_t col_base = (right ? sj : si) + 24;
+
+  // ---- step prologue (scan_block.rs:148-158) ----
+  const int prev_off = st.off;
+  const int off = st.off_max;
+  const int off_add = clamp16(prev_off - off);
+  const int other = right ? kDown : kRight;
+  const int corner = (st.prev_dir == other) ? sat_add(st.D_corner, off_add) : 0;
+
+  // tokens: 4 bytes of the vector-direction sequence per lane, 8 bytes of the column sequence per group
+  uint32_t vword = 0, cw0 = 0, cw1 = 0;
+  if (active) {
+    vword = *(const uint32_t*)(vec + vec_base + lg * 4);
+    const uint2 cw = *(const uint2*)(col + col_base);
+    cw0 = cw.x; cw1 = cw.y;
+  }
+  int rtok[4], kg[4], ph[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int b = (int)((vword >> (8 * k)) & 0xffu);
+    rtok[k] = KIND == kNuc ? (b & 15) : (KIND == kAA ? (b & 31) : b);
+    kg[k] = (k + 1) * ge;
+    const int m = (lg * 4 + k) & 15;
+    ph[k] = (m == 15) ? kI16Min : (m == 7 ? 12 * ge : ((m & 7) + 1) * ge);
+  }
+  const int lane_rg = lg * 4 * ge;
+
+  uint32_t* tw = nullptr;
+  AlnState nst = st;
+  nst.off = off;
+  nst.steps = st.steps + 1;
+  add_cells(nst, 256u);
+  if (TRACE) {
+    tw = trace_push(nst, sm, right ? si : si + 24, right ? sj + 24 : sj, kStep, 32, right, active && lg == 0);
+  }
+
+  int D10[4], C10[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) { D10[k] = sat_add(f.aD[k], off_add); C10[k] = sat_add(f.aC[k], off_add); }
+
+  int mx[4];
+  unsigned mcol[4], twd[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) { mx[k] = 0; mcol[k] = 0; twd[k] = 0; }
+  int nb[4] = {0, 0, 0, 0};   // fresh bottom-row values (packed D | T << 16), held by lanes 6 and 7 of the group
+
+#pragma unroll 1
+  for (int h = 0; h < 2; h++) {
+    const uint32_t cwh = h ? cw1 : cw0;
+#pragma unroll
+    for (int cc = 0; cc < 4; cc++) {
+      const int cidx = h * 4 + cc;
+      const int cb = (int)((cwh >> (8 * cc)) & 0xffu);
+      const int ctok = KIND == kNuc ? ((cb & 7) * 16) : (KIND == kAA ? cb * 32 : cb);
+      int up = wp::shfl_up8(D10[3], 1);
+      if (lg == 0) up = (cidx == 0) ? corner : 0;
+      int dd[4], xx[4], c11[4], c11o[4], tt[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int s = sc.score(ctok, rtok[k]);
+        const int d00 = (k == 0) ? up : D10[k - 1];
+        c11o[k] = sat_add_lo(D10[k], go);
+        c11[k] = wp::viaddmax(C10[k], ge, c11o[k]);
+        dd[k] = wp::imin(wp::viaddmax(d00, s, c11[k]), kI16Max);
+        xx[k] = sat_add_lo(dd[k], open_r);
+        tt[k] = (k == 0) ? xx[0] : wp::viaddmax(tt[k - 1], ge, xx[k]);
+      }
+      int inc = tt[3];
+#pragma unroll
+      for (int s = 0; s < 3; s++) {
+        const int u = wp::shfl_up8(inc, 1 << s);
+        inc = wp::viaddmax(u, (4 << s) * ge, inc);
+      }
+      int ex = wp::shfl_up8(inc, 1);
+      if (lg == 0) ex = kNegBig;
+      const int cin = wp::viaddmax(0, lane_rg, ex);
+      int Dn[4], Tn[4];
+      unsigned ebits = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        Tn[k] = wp::viaddmax(cin, kg[k], tt[k]);
+        const int Rv = wp::imax(Tn[k], ph[k]);
+        Dn[k] = wp::imax(dd[k], Rv);
+        if (TRACE) {
+          unsigned nib = (Dn[k] == c11[k] ? 1u : 0u) | (Dn[k] == Rv ? 2u : 0u) | (c11[k] == c11o[k] ? 4u : 0u);
+          ebits |= (Rv == xx[k] ? 1u : 0u) << k;
+          twd[k] |= nib << (4 * cidx);
+        }
+        if (XDROP) {
+          const int nm = wp::imax(mx[k], Dn[k]);
+          if (Dn[k] == nm) mcol[k] = (unsigned)cidx + 1u;
+          mx[k] = nm;
+        } else {
+          mx[0] = wp::imax(mx[0], Dn[k]);
+        }
+      }
+      if (TRACE) {
+        const unsigned eb = wp::ballot(((ebits >> 3) & 1u) != 0);
+        const unsigned above = lg == 0 ? 0u : ((eb >> (lane - 1)) & 1u);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const unsigned b3 = (k == 0) ? above : ((ebits >> (k - 1)) & 1u);
+          twd[k] |= (b3 << 3) << (4 * cidx);
+        }
+      }
+      const int bot = wp::shfl_idx8(pack16(Dn[3], Tn[3]), 7);
+      if (lg == 6 + h) nb[cc] = bot;
+#pragma unroll
+      for (int k = 0; k < 4; k++) { D10[k] = Dn[k]; C10[k] = c11[k]; }
+    }
+  }
+  if (TRACE && active) {
+    // same layout as a generic 32 x 8 rectangle (R = 1): word index = row
+    uint4 wv; wv.x = twd[0]; wv.y = twd[1]; wv.z = twd[2]; wv.w = twd[3];
+    *(uint4*)(tw + lg * 4) = wv;
+  }
+
+  // ---- borders after the step ----
+  // D_corner = old orthogonal[STEP-1] + off_add (scan_block.rs:1041-1042): entry 7 = lane 1, k = 3
+  const int d_corner = sat_add(wp::shfl_idx8(f.oD[3], 1), off_add);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    f.aD[k] = D10[k]; f.aC[k] = C10[k];
+    const int p = wp::shfl_down8(pack16(f.oD[k], f.oR[k]), 2);   // slide by 8 entries = 2 lanes
+    if (lg < 6) { f.oD[k] = sat_add(lo16(p), off_add); f.oR[k] = sat_add(hi16(p), off_add); }
+    else { f.oD[k] = lo16(nb[k]); f.oR[k] = hi16(nb[k]); }
+  }
+
+  // ---- reductions (scan_block.rs:332-345) ----
+  int bv = 0; unsigned bkey = 15u << 27;
+  if (XDROP) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (mcol[k] != 0) {
+        const unsigned cls = (unsigned)((lg * 4 + k) & 15);
+        const unsigned key = ((15u - cls) << 27) | (mcol[k] << 13) | (unsigned)(lg * 4 + k);
+        if (mx[k] > bv || (mx[k] == bv && key > bkey)) { bv = mx[k]; bkey = key; }
+      }
+    }
+  } else {
+    bv = wp::imax(0, mx[0]);
+  }
+  const int mxv = group_max(bv);
+  const int a_loc = wp::imax(wp::imax(f.aD[0], f.aD[1]), wp::imax(f.aD[2], f.aD[3]));
+  const int o_loc = wp::imax(wp::imax(f.oD[0], f.oD[1]), wp::imax(f.oD[2], f.oD[3]));
+  const int pm0 = wp::shfl_idx8(pack16(a_loc, o_loc), 0), pm1 = wp::shfl_idx8(pack16(a_loc, o_loc), 1);
+  const int a_max = wp::imax(lo16(pm0), lo16(pm1)), o_max = wp::imax(hi16(pm0), hi16(pm1));   // prefix_max over 8 entries
+  const int right_max = right ? a_max : o_max, down_max = right ? o_max : a_max;
+  unsigned key = 0;
+  if (XDROP) key = group_max_u(bv == mxv ? bkey : 0u);
+
+  // ---- post-step decisions (scan_block.rs:332-558 restricted to B == min_size == 32, shift steps) ----
+  nst.prev_dir = st.dir;
+  nst.D_corner = d_corner;
+  nst.off_max = off + mxv - kZero;
+  nst.y_drop_iter = st.y_drop_iter + 1;
+  int nstatus = kStFast;
+  bool save_ckpt = false;
+  if (nst.off_max > st.best_max) {
+    if (XDROP) {
+      const unsigned cp1 = (key >> 13) & 0x3fffu;
+      uint32_t v = key & 0x1fffu, c = 0;
+      if (cp1 == 0) v = 0; else c = cp1 - 1;
+      if (right) { nst.best_i = si + v; nst.best_j = sj + 24 + c; }
+      else { nst.best_i = si + 24 + c; nst.best_j = sj + v; }
+    }
+    if (32 < (int)P.max_size) {
+      nst.i_ckpt = si; nst.j_ckpt = sj; nst.off_ckpt = off;
+      if (TRACE) { nst.ck_widx = nst.widx; nst.ck_ridx = nst.ridx; }
+      save_ckpt = true;
+    }
+    nst.best_max = nst.off_max;
+    nst.y_drop_iter = 0;
+  }
+  bool done = false;
+  if (XDROP) {
+    if (nst.off_max < nst.best_max - P.x_drop) {
+      if (st.x_drop_iter < kXDropIter - 1) nst.x_drop_iter = st.x_drop_iter + 1;
+      else done = true;
+    } else {
+      nst.x_drop_iter = 0;
+    }
+  }
+  if (!done) {
+    if (si + 32 > st.qlen && sj + 32 > st.rlen) done = true;
+    else if (sj + 32 > st.rlen) { nst.si = si + kStep; nst.dir = kDown; }
+    else if (si + 32 > st.qlen) { nst.sj = sj + kStep; nst.dir = kRight; }
+    else if (64 <= (int)P.max_size && nst.y_drop_iter > (32 / kStep) - 1) nstatus = kStNeedGrow;   // state left untouched
+    else if (down_max > right_max) { nst.si = si + kStep; nst.dir = kDown; }
+    else { nst.sj = sj + kStep; nst.dir = kRight; }
+  }
+  if (TRACE && nst.overflow) { done = true; }
+  if (done) nstatus = kStDone;
+  else if (nstatus == kStFast && !fast_eligible<SCORING, XDROP>(P, nst)) nstatus = kStNeedGeneric;
+
+  if (P.step_log && active && lg == 0) {
+    const uint32_t n = *P.step_log_n;
+    if (n < P.step_log_cap) {
+      StepLog s; s.dir = st.dir; s.i = si; s.j = sj; s.block_size = 32u; s.off = off;
+      s.max = (int16_t)mxv; s.right_max = (int16_t)right_max; s.down_max = (int16_t)down_max;
+      P.step_log[n] = s;
+    }
+    *P.step_log_n = n + 1;
+  }
+
+  if (active) {
+    if (save_ckpt) {
+      // checkpoint copy of all four borders (scan_block.rs:413-420), 4 entries per lane and array
+      int16_t *ka = right ? sm.kDc : sm.kDr, *kc = right ? sm.kCc : sm.kRr;
+      int16_t *ko = right ? sm.kDr : sm.kDc, *kr = right ? sm.kRr : sm.kCc;
+      uint2 v;
+      v.x = (uint32_t)pack16(f.aD[0], f.aD[1]); v.y = (uint32_t)pack16(f.aD[2], f.aD[3]); *(uint2*)(ka + lg * 4) = v;
+      v.x = (uint32_t)pack16(f.aC[0], f.aC[1]); v.y = (uint32_t)pack16(f.aC[2], f.aC[3]); *(uint2*)(kc + lg * 4) = v;
+      v.x = (uint32_t)pack16(f.oD[0], f.oD[1]); v.y = (uint32_t)pack16(f.oD[2], f.oD[3]); *(uint2*)(ko + lg * 4) = v;
+      v.x = (uint32_t)pack16(f.oR[0], f.oR[1]); v.y = (uint32_t)pack16(f.oR[2], f.oR[3]); *(uint2*)(kr + lg * 4) = v;
+    }
+    st = nst;
+    status = nstatus;
+    // the registers are laid out for st.dir; a change of direction swaps the roles of the borders
+    if (nstatus == kStFast && nst.dir != (right ? kRight : kDown)) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        int t = f.aD[k]; f.aD[k] = f.oD[k]; f.oD[k] = t;
+        t = f.aC[k]; f.aC[k] = f.oR[k]; f.oR[k] = t;
+      }
+    }
+  }
+}
+
+BA_DEV void bcast_state(AlnState& d, const AlnState& s, int src) {
+#define BA_BC(F) d.F = (decltype(d.F))wp::shfl_idx((int)s.F, src)
+  BA_BC(pair); BA_BC(qlen); BA_BC(rlen); BA_BC(si); BA_BC(sj); BA_BC(B); BA_BC(prev_size); BA_BC(dir); BA_BC(prev_dir);
+  BA_BC(off); BA_BC(off_max); BA_BC(best_max); BA_BC(best_i); BA_BC(best_j); BA_BC(i_ckpt); BA_BC(j_ckpt);
+  BA_BC(off_ckpt); BA_BC(y_drop_iter); BA_BC(x_drop_iter); BA_BC(D_corner); BA_BC(cells_lo); BA_BC(cells_hi); BA_BC(steps);
+  BA_BC(widx); BA_BC(ridx); BA_BC(ck_widx); BA_BC(ck_ridx); BA_BC(overflow);
+#undef BA_BC
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp main: carve shared memory, then keep up to four alignments in flight until the ticket
+// counter runs dry.
+// ---------------------------------------------------------------------------------------------
+BA_HD size_t warp_smem_bytes(uint32_t max_size) {
   const size_t ms = max_size < 32 ? 32 : max_size;
   size_t b = 4 * ms * sizeof(int16_t) + 2 * 16 * sizeof(int16_t) + 4 * sizeof(int32_t);
-  if (ckpt_in_smem) b += 4 * ms * sizeof(int16_t);
-  if (max_size > 256) b += ms;  // ecarry
+  if (max_size > 32) b += ms;   // ecarry (rectangles swept in several chunks, TRACE)
   return (b + 15) & ~(size_t)15;
+}
+
+BA_DEV void bind_slot(const Params& P, uint32_t slot, WarpMem& w, SlotMem& sm, bool trace) {
+  const size_t ms = P.max_size < 32 ? 32 : P.max_size;
+  int16_t* g = P.ckpt + (size_t)slot * 4 * ms;
+  sm.kDc = g; sm.kCc = g + ms; sm.kDr = g + 2 * ms; sm.kRr = g + 3 * ms;
+  w.kDc = sm.kDc; w.kCc = sm.kCc; w.kDr = sm.kDr; w.kRr = sm.kRr;
+  sm.words = nullptr; sm.words_cap = 0; sm.rects = nullptr; sm.rects_cap = 0;
+  if (trace) {
+    sm.words = P.trace_words + (size_t)slot * P.trace_words_per_warp;
+    sm.words_cap = P.trace_words_per_warp;
+    sm.rects = P.rects + (size_t)slot * P.rects_per_warp;
+    sm.rects_cap = P.rects_per_warp;
+  }
 }
 
 template <int SCORING, int FLAGS>
 BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, uint32_t warp_global) {
+  constexpr bool TRACE = (FLAGS & kTrace) != 0;
   const int lane = wp::lane_id();
   const size_t ms = P.max_size < 32 ? 32 : P.max_size;
   WarpMem w;
   w.mat = (const int8_t*)smem;                     // first 1 KB: matrix
-  unsigned char* base = smem + 1024 + (size_t)warp_in_block * warp_smem_bytes(P.max_size, P.ckpt_in_smem != 0);
+  unsigned char* base = smem + 1024 + (size_t)warp_in_block * warp_smem_bytes(P.max_size);
   int16_t* p16 = (int16_t*)base;
   w.Dc = p16; p16 += ms; w.Cc = p16; p16 += ms; w.Dr = p16; p16 += ms; w.Rr = p16; p16 += ms;
   w.t1 = p16; p16 += 16; w.t2 = p16; p16 += 16;
   w.misc = (int32_t*)p16; p16 += 8;
-  if (P.ckpt_in_smem) {
-    w.kDc = p16; p16 += ms; w.kCc = p16; p16 += ms; w.kDr = p16; p16 += ms; w.kRr = p16; p16 += ms;
-  } else {
-    int16_t* g = P.ckpt + (size_t)warp_global * 4 * ms;
-    w.kDc = g; w.kCc = g + ms; w.kDr = g + 2 * ms; w.kRr = g + 3 * ms;
-  }
   w.ecarry = (uint8_t*)p16;
+  w.kDc = w.kCc = w.kDr = w.kRr = nullptr;
+  const uint32_t spw = P.slots_per_warp;
 
-  TraceState ts;
-  ts.words = nullptr; ts.words_cap = 0; ts.rects = nullptr; ts.rects_cap = 0;
-  ts.widx = 0; ts.ridx = 0; ts.ck_widx = 0; ts.ck_ridx = 0; ts.overflow = false;
-  if (FLAGS & kTrace) {
-    ts.words = P.trace_words + (size_t)warp_global * P.trace_words_per_warp;
-    ts.words_cap = P.trace_words_per_warp;
-    ts.rects = P.rects + (size_t)warp_global * P.rects_per_warp;
-    ts.rects_cap = P.rects_per_warp;
-  }
+  // Four groups of eight lanes; every lane carries the state of its group's alignment. Without the fast
+  // phase (profiles, min block size != 32) only group 0 is used and every alignment runs start to end in
+  // the generic phase.
+  const int my_g = lane >> 3;
+  AlnState st;
+  st.pair = 0; st.qlen = 0; st.rlen = 0; st.si = 0; st.sj = 0; st.B = 32; st.prev_size = 0; st.dir = kRight; st.prev_dir = kGrow;
+  st.off = 0; st.off_max = 0; st.best_max = 0; st.best_i = 0; st.best_j = 0; st.i_ckpt = 0; st.j_ckpt = 0; st.off_ckpt = 0;
+  st.y_drop_iter = 0; st.x_drop_iter = 0; st.D_corner = 0; st.cells_lo = 0; st.cells_hi = 0; st.steps = 0;
+  st.widx = 0; st.ridx = 0; st.ck_widx = 0; st.ck_ridx = 0; st.overflow = 0;
+  FastRegs f;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { f.aD[k] = 0; f.aC[k] = 0; f.oD[k] = 0; f.oR[k] = 0; }
+  int status = kStEmpty;
+  const uint8_t* qp = P.seq;
+  const uint8_t* rp = P.seq;
+  SlotMem my_sm;
+  { WarpMem tmpw = w; bind_slot(P, warp_global * spw + my_g, tmpw, my_sm, TRACE); }
+  bool tickets_left = true;
 
   for (;;) {
-    uint32_t t = 0;
-    if (lane == 0) t = wp::atomic_add(P.ticket, 1u);
-    t = (uint32_t)wp::shfl_idx((int)t, 0);
-    if (t >= P.n_pairs) break;
-    const uint32_t pair = P.order ? P.order[t] : t;
-    align_pair<SCORING, FLAGS>(P, pair, w, ts, warp_global);
+    // ---- service: refill empty groups, run the generic phase for parked ones ----
+    for (int g = 0; g < (int)spw; g++) {
+      const int sg = wp::shfl_idx(status, g * 8);
+      if (sg == kStFast) continue;
+      if (sg == kStEmpty && !tickets_left) continue;
+      SlotMem sm;
+      const uint32_t slot = warp_global * spw + (uint32_t)g;
+      bind_slot(P, slot, w, sm, TRACE);
+      AlnState gs;
+      const bool mine = my_g == g;
+      if (sg == kStEmpty) {
+        uint32_t t = 0;
+        if (lane == 0) t = wp::atomic_add(P.ticket, 1u);
+        t = (uint32_t)wp::shfl_idx((int)t, 0);
+        if (t >= P.n_pairs) { tickets_left = false; continue; }
+        init_alignment<SCORING, FLAGS>(P, gs, P.order ? P.order[t] : t, w);
+      } else {
+        bcast_state(gs, st, g * 8);
+        // a parked group's registers are still laid out for the step it executed last (= prev_dir)
+        fast_spill(f, w, gs.prev_dir, mine);
+        if (sg == kStNeedGrow) apply_grow(gs, w, TRACE);
+      }
+      int r = kRunDone;
+      if (sg != kStDone) r = run_generic<SCORING, FLAGS>(P, gs, w, sm);
+      if (r == kRunDone) {
+        finish_alignment<SCORING, FLAGS>(P, gs, w, sm, slot, warp_global);
+        if (mine) status = kStEmpty;
+        g--;            // try to refill this slot right away
+        continue;
+      }
+      wp::syncwarp();
+      fast_load(f, w, gs.dir, mine);
+      if (mine) {
+        st = gs; status = kStFast;
+        qp = P.seq + P.q_off[gs.pair];
+        rp = P.seq + P.r_off[gs.pair];
+      }
+      wp::syncwarp();
+    }
+    if (wp::ballot(status == kStFast) == 0u) break;
+    // ---- fast phase: run until some group needs the generic phase ----
+    for (;;) {
+      fast_step<SCORING, FLAGS>(P, w.mat, st, f, status, qp, rp, my_sm);
+      if (wp::ballot(status != kStFast && status != kStEmpty) != 0u) break;
+      if (wp::ballot(status == kStFast) == 0u) break;
+    }
   }
 }
 
 // Traceback from an arbitrary end position of a pair that already ran (legacy block_cigar_* calls):
-// the trace of pair `pair` is still in the arena of the warp that aligned it.
+// the trace of pair `pair` is still in the arena of the slot that aligned it.
 BA_DEV void warp_traceback(const Params& P, uint32_t pair, uint32_t qi, uint32_t rj, bool eq, DevResult* out1) {
   DevResult res = P.out[pair];
-  const uint32_t wg = res.warp;
-  const uint32_t* words = P.trace_words + (size_t)wg * P.trace_words_per_warp;
-  const Rect* rects = P.rects + (size_t)wg * P.rects_per_warp;
-  uint32_t* runs = P.run_scratch + (size_t)wg * P.runs_per_warp;
+  const uint32_t slot = res.warp;
+  const uint32_t* words = P.trace_words + (size_t)slot * P.trace_words_per_warp;
+  const Rect* rects = P.rects + (size_t)slot * P.rects_per_warp;
+  uint32_t* runs = P.run_scratch;   // single-warp launch: warp 0's scratch
   const uint8_t* q = P.seq + P.q_off[pair];
   const uint8_t* r = P.profiles ? nullptr : P.seq + P.r_off[pair];
   res.status = (uint32_t)kOk;

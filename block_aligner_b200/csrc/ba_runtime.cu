@@ -99,6 +99,9 @@ static int launch_align(const Params& P, int blocks, int wpb, size_t smem_bytes,
     for (int i = 0; i < nm; i++) smem[i] = (unsigned char)P.matrix[i];
     EmuLaunch<SCORING, FLAGS> l{&P, smem.data(), (uint32_t)b};
     emu::run_warp(&emu_warp_entry<SCORING, FLAGS>, &l);
+    // guard: the device code must stay inside the shared memory it was given
+    for (size_t i = smem_bytes; i < smem_bytes + 64; i++)
+      if (smem[i] != 0xAB) { fprintf(stderr, "emu: shared memory overrun at byte %zu (limit %zu)\n", i, smem_bytes); abort(); }
   }
   return 0;
 }
@@ -216,7 +219,7 @@ struct BaBatch {
   uint32_t* d_cigar = nullptr; unsigned long long* d_cigar_used = nullptr; uint64_t cigar_cap = 0;
   StepLog* d_steplog = nullptr; uint32_t* d_steplog_n = nullptr;
   // launch geometry
-  int blocks = 0, wpb = 0; size_t smem_bytes = 0; bool ckpt_in_smem = false;
+  int blocks = 0, wpb = 0; size_t smem_bytes = 0; uint32_t slots_per_warp = 1; bool use_fast = false;
   uint64_t trace_words_per_warp = 0; uint32_t rects_per_warp = 0, runs_per_warp = 0;
   // host results
   std::vector<DevResult> h_out;
@@ -457,9 +460,10 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
   free_tmp();
   if (herr) { ba_batch_free(b); return fail(BA_ERR_CHAR, "sequence byte outside the alphabet of the scoring matrix"); }
 
-  // launch geometry and per-warp scratch
-  b->ckpt_in_smem = mx <= 512;
-  const size_t wbytes = warp_smem_bytes(mx, b->ckpt_in_smem);
+  // launch geometry and per-slot scratch
+  b->use_fast = !prof && mn == 32 && !getenv("BA_NO_FAST");
+  b->slots_per_warp = b->use_fast ? 4 : 1;
+  const size_t wbytes = warp_smem_bytes(mx);
   int wpb = 4;
   while (wpb > 1 && 1024 + wpb * wbytes > al->smem_optin - 1024) wpb >>= 1;
   if (1024 + wpb * wbytes > al->smem_optin) { ba_batch_free(b); return fail(BA_ERR_SIZE, "max block size does not fit in shared memory"); }
@@ -472,28 +476,31 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
   max_blocks = al->emu_warps; b->wpb = wpb = 1;
 #endif
   const bool trace = (cfg->flags & BA_TRACE) != 0;
+  const size_t ms = mx < 32 ? 32 : mx;
+  const uint64_t spw = b->slots_per_warp;
   if (trace) {
-    // per-warp arena, sized like the reference's Trace::new (scan_block.rs:1364-1369)
+    // per-slot arena, sized like the reference's Trace::new (scan_block.rs:1364-1369)
     const uint64_t len = (uint64_t)b->max_pair_len + 2;
     uint64_t words = 2 * (uint64_t)(mx / 16) * (len + 2 * (uint64_t)mx);
     if (mn == 16) words *= 2;   // 16-row rectangles still occupy a 32-lane word group
+    if (words + 64 >= ((uint64_t)1 << 32)) { ba_batch_free(b); return fail(BA_ERR_SIZE, "trace arena of one alignment exceeds 2^32 words"); }
     b->trace_words_per_warp = words + 64;
     b->rects_per_warp = (uint32_t)std::min<uint64_t>(len * 2 + 8, 0x7fffffffu);
     b->runs_per_warp = (uint32_t)std::min<uint64_t>(len + 8, 0x7fffffffu);
-    const uint64_t per_warp = b->trace_words_per_warp * 4 + (uint64_t)b->rects_per_warp * sizeof(Rect) + (uint64_t)b->runs_per_warp * 4;
+    const uint64_t per_warp = spw * (b->trace_words_per_warp * 4 + (uint64_t)b->rects_per_warp * sizeof(Rect)) + (uint64_t)b->runs_per_warp * 4;
     const uint64_t budget = (uint64_t)(al->mem_total * 0.55);
     const uint64_t fit_warps = std::max<uint64_t>(1, budget / std::max<uint64_t>(per_warp, 1));
     max_blocks = std::max<uint64_t>(1, std::min<uint64_t>(max_blocks, fit_warps / wpb));
   }
-  uint64_t want = (n + wpb - 1) / wpb;
+  uint64_t want = (n + wpb * spw - 1) / (wpb * spw);
   if (want < 1) want = 1;
   b->blocks = (int)std::min<uint64_t>(want, max_blocks);
   const uint64_t nwarps = (uint64_t)b->blocks * wpb;
-  const size_t ms = mx < 32 ? 32 : mx;
-  if (!b->ckpt_in_smem) TRY(dmalloc((void**)&b->d_ckpt, nwarps * 4 * ms * sizeof(int16_t)));
+  const uint64_t nslots = nwarps * spw;
+  TRY(dmalloc((void**)&b->d_ckpt, nslots * 4 * ms * sizeof(int16_t)));
   if (trace) {
-    TRY(dmalloc((void**)&b->d_trace, nwarps * b->trace_words_per_warp * 4));
-    TRY(dmalloc((void**)&b->d_rects, nwarps * (uint64_t)b->rects_per_warp * sizeof(Rect)));
+    TRY(dmalloc((void**)&b->d_trace, nslots * b->trace_words_per_warp * 4));
+    TRY(dmalloc((void**)&b->d_rects, nslots * (uint64_t)b->rects_per_warp * sizeof(Rect)));
     TRY(dmalloc((void**)&b->d_runs, nwarps * (uint64_t)b->runs_per_warp * 4));
     uint64_t cap = 0;
     for (size_t k = 0; k < n; k++) cap += (uint64_t)ql[k] + rl[k] + 5;
@@ -533,7 +540,7 @@ static Params make_params(const BaBatch* b) {
   P.min_size = b->min_size; P.max_size = b->max_size; P.x_drop = b->cfg.x_drop;
   P.flags = b->cfg.flags; P.scoring = prof ? (int)kProfile : b->cfg.scoring;
   P.out = b->d_out; P.ticket = b->d_ticket;
-  P.ckpt = b->d_ckpt; P.ckpt_in_smem = b->ckpt_in_smem ? 1u : 0u;
+  P.ckpt = b->d_ckpt; P.slots_per_warp = b->slots_per_warp; P.use_fast = b->use_fast ? 1u : 0u;
   P.trace_words = b->d_trace; P.trace_words_per_warp = b->trace_words_per_warp;
   P.rects = b->d_rects; P.rects_per_warp = b->rects_per_warp;
   P.run_scratch = b->d_runs; P.runs_per_warp = b->runs_per_warp;

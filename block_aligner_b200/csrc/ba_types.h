@@ -51,7 +51,7 @@ struct DevResult {
   uint32_t cigar_n;              // number of runs written for this pair
   uint64_t cigar_off;            // offset (in runs) into the cigar stream
   uint32_t rect_n;               // rectangles on the trace stack at the end (TRACE)
-  uint32_t warp;                 // global warp id that ran this pair (its trace arena holds the trace)
+  uint32_t warp;                 // slot that ran this pair (its trace arena holds the trace)
 };
 
 // one record per step, debug builds only (mirrors ora_step in oracle/ba_oracle.h)
@@ -72,10 +72,11 @@ struct Params {
   DevResult* out;
   uint32_t* ticket;              // work counter
   // per-warp scratch in global memory
-  int16_t* ckpt;                 // 4 * max_size int16 per warp (used when the checkpoint does not fit in smem)
-  uint32_t ckpt_in_smem;
-  uint32_t* trace_words; uint64_t trace_words_per_warp;
-  Rect* rects; uint32_t rects_per_warp;
+  // a "slot" is one alignment in flight: 1 per warp, or 4 per warp when the block-32 fast phase is on
+  uint32_t slots_per_warp, use_fast;
+  int16_t* ckpt;                 // 4 * max(max_size, 32) int16 per slot: checkpoint borders
+  uint32_t* trace_words; uint64_t trace_words_per_warp;   // per slot (name kept: per-"warp" arena of v0)
+  Rect* rects; uint32_t rects_per_warp;                   // per slot
   uint32_t* run_scratch; uint32_t runs_per_warp;  // reversed CIGAR runs while walking back
   // cigar output stream: runs packed as (len << 4) | op, allocated with atomicAdd on *cigar_used
   uint32_t* cigar_stream; uint64_t cigar_cap; unsigned long long* cigar_used;
