@@ -159,10 +159,11 @@ BA_DEV void place_rect_r(const SeqScorer<(SCORING == kProfile ? kAA : SCORING)>&
       wp::syncwarp();
     }
 
-    int mx[R];
-    unsigned mcol[R], twd[R];
+    // per-row tracker: max of value * 16384 + (column + 1); 0 = "no cell >= 0" (D_max starts at MIN = 0)
+    int trk[R];
+    unsigned twd[R];
 #pragma unroll
-    for (int k = 0; k < R; k++) { mx[k] = 0; mcol[k] = 0; twd[k] = 0; }
+    for (int k = 0; k < R; k++) { trk[k] = 0; twd[k] = 0; }
 
 #pragma unroll 1
     for (int cidx = 0; cidx < a.ncols; cidx++) {
@@ -230,23 +231,22 @@ BA_DEV void place_rect_r(const SeqScorer<(SCORING == kProfile ? kAA : SCORING)>&
 #pragma unroll
       for (int k = 0; k < R; k++) {
         Tn[k] = wp::viaddmax(cin, kg[k], tt[k]);
-        const int Rv = wp::imax(Tn[k], ph[k]);
-        int Rend = Rv;
-        if (PROF && !RIGHT) Rend = sat_add(Rv, p_closeR[k]);
-        Dn[k] = wp::imax(dd[k], Rend);
-        if (TRACE) {
-          unsigned nib = (Dn[k] == c11e[k] ? 1u : 0u) | (Dn[k] == Rend ? 2u : 0u);
-          nib |= (c11[k] == c11o[k] ? 4u : 0u);
-          ebits |= (Rv == xx[k] ? 1u : 0u) << k;
-          twd[k] |= nib << c4;
-        }
-        if (XDROP) {
-          const int nm = wp::imax(mx[k], Dn[k]);
-          if (Dn[k] == nm) mcol[k] = (unsigned)cidx + 1u;
-          mx[k] = nm;
+        if (TRACE || (PROF && !RIGHT)) {
+          const int Rv = wp::imax(Tn[k], ph[k]);
+          int Rend = Rv;
+          if (PROF && !RIGHT) Rend = sat_add(Rv, p_closeR[k]);
+          Dn[k] = wp::imax(dd[k], Rend);
+          if (TRACE) {
+            unsigned nib = (Dn[k] == c11e[k] ? 1u : 0u) | (Dn[k] == Rend ? 2u : 0u);
+            nib |= (c11[k] == c11o[k] ? 4u : 0u);
+            ebits |= (Rv == xx[k] ? 1u : 0u) << k;
+            twd[k] |= nib << c4;
+          }
         } else {
-          mx[0] = wp::imax(mx[0], act ? Dn[k] : 0);
+          Dn[k] = wp::vimax3(dd[k], Tn[k], ph[k]);
         }
+        if (XDROP) trk[k] = wp::imax(trk[k], Dn[k] * 16384 + (cidx + 1));
+        else trk[0] = wp::imax(trk[0], act ? Dn[k] : 0);
       }
       if (TRACE) {
         // "R gap at this row was opened at the row above" = e of the row above (scan_block.rs:1179-1181)
@@ -289,15 +289,15 @@ BA_DEV void place_rect_r(const SeqScorer<(SCORING == kProfile ? kAA : SCORING)>&
       if (act) {
 #pragma unroll
         for (int k = 0; k < R; k++) {
-          if (mcol[k] != 0) {
-            const unsigned cls = (unsigned)((lane * R + k) & 15);
-            const unsigned key = ((15u - cls) << 27) | (mcol[k] << 13) | (unsigned)(v0 + k);
-            if (mx[k] > bv || (mx[k] == bv && key > bkey)) { bv = mx[k]; bkey = key; }
-          }
+          const int v = trk[k] >> 14;
+          const unsigned c1 = (unsigned)(trk[k] & 16383);
+          const unsigned cls = (unsigned)((lane * R + k) & 15);
+          const unsigned key = ((15u - cls) << 27) | (c1 << 13) | (unsigned)(v0 + k);
+          if (c1 != 0 && (v > bv || (v == bv && key > bkey))) { bv = v; bkey = key; }
         }
       }
     } else {
-      bv = wp::imax(bv, mx[0]);
+      bv = wp::imax(bv, trk[0]);
     }
     if (multi) wp::syncwarp();
   }
@@ -820,8 +820,23 @@ BA_DEV void fast_spill(const FastRegs& f, const WarpMem& w, int dir, bool mine) 
   wp::syncwarp();
 }
 
+// per-lane constants of the fast phase (hoisted out of the step)
+struct FastConst {
+  int ph[4];       // scan phantoms of the lane's four rows (avx2.rs:321-337)
+  int lane_rg;     // (lane in group) * 4 * gap_extend
+};
+BA_DEV void fast_consts(FastConst& fc, int ge) {
+  const int lg = wp::lane_id() & 7;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int m = (lg * 4 + k) & 15;
+    fc.ph[k] = (m == 15) ? kI16Min : (m == 7 ? 12 * ge : ((m & 7) + 1) * ge);
+  }
+  fc.lane_rg = lg * 4 * ge;
+}
+
 template <int SCORING, int FLAGS>
-BA_DEV void fast_step(const Params& P, const int8_t* mat, AlnState& st, FastRegs& f, int& status,
+BA_DEV void fast_step(const Params& P, const int8_t* mat, const FastConst& fc, AlnState& st, FastRegs& f, int& status,
                       const uint8_t* qp, const uint8_t* rp, const SlotMem& sm) {
   constexpr bool TRACE = (FLAGS & kTrace) != 0, XDROP = (FLAGS & kXDrop) != 0;
   constexpr int KIND = (SCORING == kProfile) ? kAA : SCORING;
@@ -840,11 +855,9 @@ BA_DEV void fast_step(const Params& P, const int8_t* mat, AlnState& st, FastRegs
   const uint32_t col_base = (right ? sj : si) + 24;
 
   // ---- step prologue (scan_block.rs:148-158) ----
-  const int prev_off = st.off;
   const int off = st.off_max;
-  const int off_add = clamp16(prev_off - off);
-  const int other = right ? kDown : kRight;
-  const int corner = (st.prev_dir == other) ? sat_add(st.D_corner, off_add) : 0;
+  const int off_add = clamp16(st.off - off);
+  const int corner = (st.prev_dir == (right ? kDown : kRight)) ? sat_add(st.D_corner, off_add) : 0;
 
   // tokens: 4 bytes of the vector-direction sequence per lane, 8 bytes of the column sequence per group
   uint32_t vword = 0, cw0 = 0, cw1 = 0;
@@ -853,34 +866,23 @@ BA_DEV void fast_step(const Params& P, const int8_t* mat, AlnState& st, FastRegs
     const uint2 cw = *(const uint2*)(col + col_base);
     cw0 = cw.x; cw1 = cw.y;
   }
-  int rtok[4], kg[4], ph[4];
+  int rtok[4];
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     const int b = (int)((vword >> (8 * k)) & 0xffu);
     rtok[k] = KIND == kNuc ? (b & 15) : (KIND == kAA ? (b & 31) : b);
-    kg[k] = (k + 1) * ge;
-    const int m = (lg * 4 + k) & 15;
-    ph[k] = (m == 15) ? kI16Min : (m == 7 ? 12 * ge : ((m & 7) + 1) * ge);
   }
-  const int lane_rg = lg * 4 * ge;
 
   uint32_t* tw = nullptr;
-  AlnState nst = st;
-  nst.off = off;
-  nst.steps = st.steps + 1;
-  add_cells(nst, 256u);
-  if (TRACE) {
-    tw = trace_push(nst, sm, right ? si : si + 24, right ? sj + 24 : sj, kStep, 32, right, active && lg == 0);
-  }
+  if (TRACE && active) tw = trace_push(st, sm, right ? si : si + 24, right ? sj + 24 : sj, kStep, 32, right, lg == 0);
 
   int D10[4], C10[4];
 #pragma unroll
   for (int k = 0; k < 4; k++) { D10[k] = sat_add(f.aD[k], off_add); C10[k] = sat_add(f.aC[k], off_add); }
 
-  int mx[4];
-  unsigned mcol[4], twd[4];
-#pragma unroll
-  for (int k = 0; k < 4; k++) { mx[k] = 0; mcol[k] = 0; twd[k] = 0; }
+  // per-row tracker: max over the step of value * 16 + (column + 1); 0 = "no cell >= 0" (D_max starts at 0)
+  int trk[4] = {0, 0, 0, 0};
+  unsigned twd[4] = {0, 0, 0, 0};
   int nb[4] = {0, 0, 0, 0};   // fresh bottom-row values (packed D | T << 16), held by lanes 6 and 7 of the group
 
 #pragma unroll 1
@@ -912,26 +914,23 @@ BA_DEV void fast_step(const Params& P, const int8_t* mat, AlnState& st, FastRegs
       }
       int ex = wp::shfl_up8(inc, 1);
       if (lg == 0) ex = kNegBig;
-      const int cin = wp::viaddmax(0, lane_rg, ex);
+      const int cin = wp::imax(fc.lane_rg, ex);
       int Dn[4], Tn[4];
       unsigned ebits = 0;
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        Tn[k] = wp::viaddmax(cin, kg[k], tt[k]);
-        const int Rv = wp::imax(Tn[k], ph[k]);
-        Dn[k] = wp::imax(dd[k], Rv);
+        Tn[k] = wp::viaddmax(cin, (k + 1) * ge, tt[k]);
         if (TRACE) {
+          const int Rv = wp::imax(Tn[k], fc.ph[k]);
+          Dn[k] = wp::imax(dd[k], Rv);
           unsigned nib = (Dn[k] == c11[k] ? 1u : 0u) | (Dn[k] == Rv ? 2u : 0u) | (c11[k] == c11o[k] ? 4u : 0u);
           ebits |= (Rv == xx[k] ? 1u : 0u) << k;
           twd[k] |= nib << (4 * cidx);
-        }
-        if (XDROP) {
-          const int nm = wp::imax(mx[k], Dn[k]);
-          if (Dn[k] == nm) mcol[k] = (unsigned)cidx + 1u;
-          mx[k] = nm;
         } else {
-          mx[0] = wp::imax(mx[0], Dn[k]);
+          Dn[k] = wp::vimax3(dd[k], Tn[k], fc.ph[k]);
         }
+        if (XDROP) trk[k] = wp::imax(trk[k], Dn[k] * 16 + (cidx + 1));
+        else trk[0] = wp::imax(trk[0], Dn[k]);
       }
       if (TRACE) {
         const unsigned eb = wp::ballot(((ebits >> 3) & 1u) != 0);
@@ -966,97 +965,96 @@ BA_DEV void fast_step(const Params& P, const int8_t* mat, AlnState& st, FastRegs
   }
 
   // ---- reductions (scan_block.rs:332-345) ----
+  // tie-break order of the reference: value desc, AVX lane (row mod 16) asc, column desc, row desc
   int bv = 0; unsigned bkey = 15u << 27;
   if (XDROP) {
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      if (mcol[k] != 0) {
-        const unsigned cls = (unsigned)((lg * 4 + k) & 15);
-        const unsigned key = ((15u - cls) << 27) | (mcol[k] << 13) | (unsigned)(lg * 4 + k);
-        if (mx[k] > bv || (mx[k] == bv && key > bkey)) { bv = mx[k]; bkey = key; }
-      }
+      const int v = trk[k] >> 4;
+      const unsigned c1 = (unsigned)(trk[k] & 15);
+      const unsigned cls = (unsigned)((lg * 4 + k) & 15);
+      const unsigned key = ((15u - cls) << 27) | (c1 << 13) | (unsigned)(lg * 4 + k);
+      if (c1 != 0 && (v > bv || (v == bv && key > bkey))) { bv = v; bkey = key; }
     }
   } else {
-    bv = wp::imax(0, mx[0]);
+    bv = trk[0];
   }
   const int mxv = group_max(bv);
   const int a_loc = wp::imax(wp::imax(f.aD[0], f.aD[1]), wp::imax(f.aD[2], f.aD[3]));
   const int o_loc = wp::imax(wp::imax(f.oD[0], f.oD[1]), wp::imax(f.oD[2], f.oD[3]));
-  const int pm0 = wp::shfl_idx8(pack16(a_loc, o_loc), 0), pm1 = wp::shfl_idx8(pack16(a_loc, o_loc), 1);
+  const int pm = pack16(a_loc, o_loc);
+  const int pm0 = wp::shfl_idx8(pm, 0), pm1 = wp::shfl_idx8(pm, 1);
   const int a_max = wp::imax(lo16(pm0), lo16(pm1)), o_max = wp::imax(hi16(pm0), hi16(pm1));   // prefix_max over 8 entries
   const int right_max = right ? a_max : o_max, down_max = right ? o_max : a_max;
   unsigned key = 0;
   if (XDROP) key = group_max_u(bv == mxv ? bkey : 0u);
 
-  // ---- post-step decisions (scan_block.rs:332-558 restricted to B == min_size == 32, shift steps) ----
-  nst.prev_dir = st.dir;
-  nst.D_corner = d_corner;
-  nst.off_max = off + mxv - kZero;
-  nst.y_drop_iter = st.y_drop_iter + 1;
-  int nstatus = kStFast;
-  bool save_ckpt = false;
-  if (nst.off_max > st.best_max) {
-    if (XDROP) {
-      const unsigned cp1 = (key >> 13) & 0x3fffu;
-      uint32_t v = key & 0x1fffu, c = 0;
-      if (cp1 == 0) v = 0; else c = cp1 - 1;
-      if (right) { nst.best_i = si + v; nst.best_j = sj + 24 + c; }
-      else { nst.best_i = si + 24 + c; nst.best_j = sj + v; }
-    }
-    if (32 < (int)P.max_size) {
-      nst.i_ckpt = si; nst.j_ckpt = sj; nst.off_ckpt = off;
-      if (TRACE) { nst.ck_widx = nst.widx; nst.ck_ridx = nst.ridx; }
-      save_ckpt = true;
-    }
-    nst.best_max = nst.off_max;
-    nst.y_drop_iter = 0;
-  }
-  bool done = false;
-  if (XDROP) {
-    if (nst.off_max < nst.best_max - P.x_drop) {
-      if (st.x_drop_iter < kXDropIter - 1) nst.x_drop_iter = st.x_drop_iter + 1;
-      else done = true;
-    } else {
-      nst.x_drop_iter = 0;
-    }
-  }
-  if (!done) {
-    if (si + 32 > st.qlen && sj + 32 > st.rlen) done = true;
-    else if (sj + 32 > st.rlen) { nst.si = si + kStep; nst.dir = kDown; }
-    else if (si + 32 > st.qlen) { nst.sj = sj + kStep; nst.dir = kRight; }
-    else if (64 <= (int)P.max_size && nst.y_drop_iter > (32 / kStep) - 1) nstatus = kStNeedGrow;   // state left untouched
-    else if (down_max > right_max) { nst.si = si + kStep; nst.dir = kDown; }
-    else { nst.sj = sj + kStep; nst.dir = kRight; }
-  }
-  if (TRACE && nst.overflow) { done = true; }
-  if (done) nstatus = kStDone;
-  else if (nstatus == kStFast && !fast_eligible<SCORING, XDROP>(P, nst)) nstatus = kStNeedGeneric;
-
   if (P.step_log && active && lg == 0) {
     const uint32_t n = *P.step_log_n;
     if (n < P.step_log_cap) {
-      StepLog s; s.dir = st.dir; s.i = si; s.j = sj; s.block_size = 32u; s.off = off;
-      s.max = (int16_t)mxv; s.right_max = (int16_t)right_max; s.down_max = (int16_t)down_max;
-      P.step_log[n] = s;
+      StepLog sl; sl.dir = st.dir; sl.i = si; sl.j = sj; sl.block_size = 32u; sl.off = off;
+      sl.max = (int16_t)mxv; sl.right_max = (int16_t)right_max; sl.down_max = (int16_t)down_max;
+      P.step_log[n] = sl;
     }
     *P.step_log_n = n + 1;
   }
 
+  // ---- post-step decisions (scan_block.rs:332-558 restricted to B == min_size == 32, shift steps) ----
+  // No warp collectives below: groups diverge freely.
   if (active) {
-    if (save_ckpt) {
-      // checkpoint copy of all four borders (scan_block.rs:413-420), 4 entries per lane and array
-      int16_t *ka = right ? sm.kDc : sm.kDr, *kc = right ? sm.kCc : sm.kRr;
-      int16_t *ko = right ? sm.kDr : sm.kDc, *kr = right ? sm.kRr : sm.kCc;
-      uint2 v;
-      v.x = (uint32_t)pack16(f.aD[0], f.aD[1]); v.y = (uint32_t)pack16(f.aD[2], f.aD[3]); *(uint2*)(ka + lg * 4) = v;
-      v.x = (uint32_t)pack16(f.aC[0], f.aC[1]); v.y = (uint32_t)pack16(f.aC[2], f.aC[3]); *(uint2*)(kc + lg * 4) = v;
-      v.x = (uint32_t)pack16(f.oD[0], f.oD[1]); v.y = (uint32_t)pack16(f.oD[2], f.oD[3]); *(uint2*)(ko + lg * 4) = v;
-      v.x = (uint32_t)pack16(f.oR[0], f.oR[1]); v.y = (uint32_t)pack16(f.oR[2], f.oR[3]); *(uint2*)(kr + lg * 4) = v;
+    st.off = off;
+    st.steps++;
+    add_cells(st, 256u);
+    st.prev_dir = st.dir;
+    st.D_corner = d_corner;
+    st.off_max = off + mxv - kZero;
+    st.y_drop_iter++;
+    if (st.off_max > st.best_max) {
+      if (XDROP) {
+        const unsigned cp1 = (key >> 13) & 0x3fffu;
+        uint32_t v = key & 0x1fffu, c = 0;
+        if (cp1 == 0) v = 0; else c = cp1 - 1;
+        if (right) { st.best_i = si + v; st.best_j = sj + 24 + c; }
+        else { st.best_i = si + 24 + c; st.best_j = sj + v; }
+      }
+      if (32 < (int)P.max_size) {
+        st.i_ckpt = si; st.j_ckpt = sj; st.off_ckpt = off;
+        if (TRACE) { st.ck_widx = st.widx; st.ck_ridx = st.ridx; }
+        // checkpoint copy of all four borders (scan_block.rs:413-420), 4 entries per lane and array
+        int16_t *ka = right ? sm.kDc : sm.kDr, *kc = right ? sm.kCc : sm.kRr;
+        int16_t *ko = right ? sm.kDr : sm.kDc, *kr = right ? sm.kRr : sm.kCc;
+        uint2 v;
+        v.x = (uint32_t)pack16(f.aD[0], f.aD[1]); v.y = (uint32_t)pack16(f.aD[2], f.aD[3]); *(uint2*)(ka + lg * 4) = v;
+        v.x = (uint32_t)pack16(f.aC[0], f.aC[1]); v.y = (uint32_t)pack16(f.aC[2], f.aC[3]); *(uint2*)(kc + lg * 4) = v;
+        v.x = (uint32_t)pack16(f.oD[0], f.oD[1]); v.y = (uint32_t)pack16(f.oD[2], f.oD[3]); *(uint2*)(ko + lg * 4) = v;
+        v.x = (uint32_t)pack16(f.oR[0], f.oR[1]); v.y = (uint32_t)pack16(f.oR[2], f.oR[3]); *(uint2*)(kr + lg * 4) = v;
+      }
+      st.best_max = st.off_max;
+      st.y_drop_iter = 0;
     }
-    st = nst;
+    int nstatus = kStFast;
+    if (XDROP) {
+      if (st.off_max < st.best_max - P.x_drop) {
+        if (st.x_drop_iter < kXDropIter - 1) st.x_drop_iter++;
+        else nstatus = kStDone;
+      } else {
+        st.x_drop_iter = 0;
+      }
+    }
+    if (TRACE && st.overflow) nstatus = kStDone;
+    if (nstatus == kStFast) {
+      if (si + 32 > st.qlen && sj + 32 > st.rlen) nstatus = kStDone;
+      else if (sj + 32 > st.rlen) { st.si = si + kStep; st.dir = kDown; }
+      else if (si + 32 > st.qlen) { st.sj = sj + kStep; st.dir = kRight; }
+      else if (64 <= (int)P.max_size && st.y_drop_iter > (32 / kStep) - 1) nstatus = kStNeedGrow;   // state left untouched
+      else if (down_max > right_max) { st.si = si + kStep; st.dir = kDown; }
+      else { st.sj = sj + kStep; st.dir = kRight; }
+      if (nstatus == kStFast && !fast_eligible<SCORING, XDROP>(P, st)) nstatus = kStNeedGeneric;
+    }
     status = nstatus;
-    // the registers are laid out for st.dir; a change of direction swaps the roles of the borders
-    if (nstatus == kStFast && nst.dir != (right ? kRight : kDown)) {
+    // the registers are laid out for the executed direction; if the next fast step goes the other way the
+    // borders swap roles
+    if (nstatus == kStFast && st.dir != st.prev_dir) {
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         int t = f.aD[k]; f.aD[k] = f.oD[k]; f.oD[k] = t;
@@ -1134,6 +1132,8 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
   SlotMem my_sm;
   { WarpMem tmpw = w; bind_slot(P, warp_global * spw + my_g, tmpw, my_sm, TRACE); }
   bool tickets_left = true;
+  FastConst fc;
+  fast_consts(fc, P.gap_extend);
 
   for (;;) {
     // ---- service: refill empty groups, run the generic phase for parked ones ----
@@ -1178,7 +1178,7 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
     if (wp::ballot(status == kStFast) == 0u) break;
     // ---- fast phase: run until some group needs the generic phase ----
     for (;;) {
-      fast_step<SCORING, FLAGS>(P, w.mat, st, f, status, qp, rp, my_sm);
+      fast_step<SCORING, FLAGS>(P, w.mat, fc, st, f, status, qp, rp, my_sm);
       if (wp::ballot(status != kStFast && status != kStEmpty) != 0u) break;
       if (wp::ballot(status == kStFast) == 0u) break;
     }
