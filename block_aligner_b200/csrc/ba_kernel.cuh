@@ -165,7 +165,7 @@ BA_DEV void place_rect_r(const SeqScorer<(SCORING == kProfile ? kAA : SCORING)>&
 #pragma unroll
     for (int k = 0; k < R; k++) { trk[k] = 0; twd[k] = 0; }
 
-#pragma unroll 1
+#pragma unroll (R >= 8 ? 2 : 1)
     for (int cidx = 0; cidx < a.ncols; cidx++) {
       const int c4 = (cidx & 7) * 4;
       int Ttop = 0, Dtop = 0, etop = 0;
@@ -968,13 +968,18 @@ BA_DEV void fast_step(const Params& P, const int8_t* mat, const FastConst& fc, A
   // tie-break order of the reference: value desc, AVX lane (row mod 16) asc, column desc, row desc
   int bv = 0; unsigned bkey = 15u << 27;
   if (XDROP) {
+    // Within a lane the four rows have ascending AVX lanes, so among equal values the lowest k wins;
+    // rows that saw no cell >= 0 (trk == 0) compare as -1 and never win.
+    int bw = (trk[0] - 1) >> 4, bt = trk[0], bk = 0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int v = trk[k] >> 4;
-      const unsigned c1 = (unsigned)(trk[k] & 15);
-      const unsigned cls = (unsigned)((lg * 4 + k) & 15);
-      const unsigned key = ((15u - cls) << 27) | (c1 << 13) | (unsigned)(lg * 4 + k);
-      if (c1 != 0 && (v > bv || (v == bv && key > bkey))) { bv = v; bkey = key; }
+    for (int k = 1; k < 4; k++) {
+      const int wv = (trk[k] - 1) >> 4;
+      if (wv > bw) { bw = wv; bt = trk[k]; bk = k; }
+    }
+    if (bw >= 0) {
+      const unsigned row = (unsigned)(lg * 4 + bk);
+      bv = bw;
+      bkey = ((15u - (row & 15u)) << 27) | ((unsigned)(bt & 15) << 13) | row;
     }
   } else {
     bv = trk[0];
