@@ -27,6 +27,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NCCL writes its "NCCL version ..." banner to stdout; rank 0 must print exactly one JSON line there
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import numpy as np  # noqa: E402
 
@@ -240,6 +242,13 @@ def main():
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         alg_bytes = float(qa.nbytes + ra.nbytes + n * 56)
+        traffic = None   # DRAM bytes per launch from the committed `ncu --set full` capture (per pair x pairs)
+        try:
+            caps = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_align_kernel_summary.json")))["captures"]
+            if args.workload.startswith("C2"):
+                traffic = caps[-1]["dram_bytes_per_pair"] * n
+        except Exception:
+            pass
         line = {
             "metric": "GCUPS (computed DP cells / s / 1e9)", "value": gcups, "unit": "GCUPS", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True,
@@ -249,7 +258,8 @@ def main():
                     "ms_per_step": e2e_s / args.steps * 1e3, "alignments_per_s": n * world * args.steps / e2e_s},
             "gpu_launches": args.steps * 1 + args.steps * 2,
             "roofline": {"bound": "int_alu", "achieved": achieved / 1e3, "peak": peak_gops / 1e3, "unit": "Tiop/s",
-                         "frac": achieved / peak_gops if peak_gops else None, "traffic": None,
+                         "frac": achieved / peak_gops if peak_gops else None, "traffic": traffic,
+                         "traffic_source": "profiles/r01_ncu_align_kernel_summary.json (dram bytes per pair of the 16000-pair capture x pairs)",
                          "ops_per_cell": ops, "peak_source": "ba_measure_int_peak (DPX add-max / max3 issue rate measured on this GPU)",
                          "hbm": {"achieved": alg_bytes / (sum(kernel_ms) / args.steps / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "algorithmic_bytes_per_step": alg_bytes,
