@@ -548,12 +548,13 @@ BA_DEV void apply_grow(AlnState& st, const WarpMem& w, bool trace) {
 // fast phase can execute? (no early break: scan_block.rs:1216-1224)
 template <int SCORING, bool XDROP>
 BA_DEV bool fast_eligible(const Params& P, const AlnState& st) {
-  if (SCORING == kProfile || !P.use_fast) return false;
-  if (st.B != 32 || st.dir == kGrow) return false;
+  const int FB = (int)P.fast_block;     // 0 (fast phase off), 32 or 64 == min block size
+  if (SCORING == kProfile || FB == 0) return false;
+  if (st.B != FB || st.dir == kGrow) return false;
   if (!XDROP) {
     const uint32_t vec_base = st.dir == kRight ? st.si : st.sj, vec_len = st.dir == kRight ? st.qlen : st.rlen;
-    const uint32_t col_base = (st.dir == kRight ? st.sj : st.si) + 24, col_len = st.dir == kRight ? st.rlen : st.qlen;
-    if (vec_base + 32 > vec_len && col_base + 7 > col_len) return false;
+    const uint32_t col_base = (st.dir == kRight ? st.sj : st.si) + (uint32_t)(FB - kStep), col_len = st.dir == kRight ? st.rlen : st.qlen;
+    if (vec_base + (uint32_t)FB > vec_len && col_base + 7 > col_len) return false;
   }
   return true;
 }
@@ -743,6 +744,9 @@ BA_DEV void finish_alignment(const Params& P, const AlnState& st, const WarpMem&
   res.cells = ((uint64_t)st.cells_hi << 32) | st.cells_lo; res.steps = st.steps; res.cigar_n = 0; res.cigar_off = 0;
   if (XDROP) {
     res.score = st.best_max; res.query_idx = st.best_i; res.reference_idx = st.best_j;
+  } else if (st.overflow) {
+    // aborted mid-way (trace arena full): the block is not at the end of the sequences, there is no result yet
+    res.score = 0; res.query_idx = 0; res.reference_idx = 0;
   } else {
     int sv;
     if (st.dir == kRight || st.dir == kGrow) sv = (int)w.Dc[st.qlen - st.si];
@@ -756,7 +760,10 @@ BA_DEV void finish_alignment(const Params& P, const AlnState& st, const WarpMem&
     uint32_t* runs = P.run_scratch + (size_t)warp_global * P.runs_per_warp;
     emit_cigar(P, sm.words, sm.rects, st.ridx, res.query_idx, res.reference_idx, q, r, P.cigar_eq != 0, runs, res);
   }
-  if (lane == 0) P.out[st.pair] = res;
+  if (lane == 0) {
+    P.out[st.pair] = res;
+    if (TRACE && st.overflow && P.overflow_list) P.overflow_list[wp::atomic_add(P.overflow_n, 1u)] = st.pair;
+  }
   wp::syncwarp();
 }
 
@@ -769,9 +776,9 @@ BA_DEV void finish_alignment(const Params& P, const AlnState& st, const WarpMem&
 // ---------------------------------------------------------------------------------------------
 enum { kStFast = 0, kStNeedGeneric = 1, kStNeedGrow = 2, kStDone = 3, kStEmpty = 4 };
 
-struct FastRegs {
-  int aD[4], aC[4];   // border that moves with the step (D_col/C_col for Right, D_row/R_row for Down)
-  int oD[4], oR[4];   // the orthogonal border
+template <int FR> struct FastRegs {
+  int aD[FR], aC[FR];   // border that moves with the step (D_col/C_col for Right, D_row/R_row for Down)
+  int oD[FR], oR[FR];   // the orthogonal border
 };
 
 BA_DEV int pack16(int lo, int hi) { return (lo & 0xffff) | (hi << 16); }
@@ -791,55 +798,60 @@ BA_DEV unsigned group_max_u(unsigned v) {
   return v;
 }
 
-// registers <-> shared-memory borders for the lanes of group g (oriented by st.dir)
-BA_DEV void fast_load(FastRegs& f, const WarpMem& w, int dir, bool mine) {
-  const int i0 = (wp::lane_id() & 7) * 4;
+// registers <-> shared-memory borders for the lanes of group g (laid out for direction `dir`)
+template <int FR>
+BA_DEV void fast_load(FastRegs<FR>& f, const WarpMem& w, int dir, bool mine) {
+  const int i0 = (wp::lane_id() & 7) * FR;
   const int16_t *ad = dir == kRight ? w.Dc : w.Dr, *ac = dir == kRight ? w.Cc : w.Rr;
   const int16_t *od = dir == kRight ? w.Dr : w.Dc, *orr = dir == kRight ? w.Rr : w.Cc;
   if (mine) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) { f.aD[k] = ad[i0 + k]; f.aC[k] = ac[i0 + k]; f.oD[k] = od[i0 + k]; f.oR[k] = orr[i0 + k]; }
+    for (int k = 0; k < FR; k++) { f.aD[k] = ad[i0 + k]; f.aC[k] = ac[i0 + k]; f.oD[k] = od[i0 + k]; f.oR[k] = orr[i0 + k]; }
   }
 }
-BA_DEV void fast_spill(const FastRegs& f, const WarpMem& w, int dir, bool mine) {
-  const int lg = wp::lane_id() & 7, i0 = lg * 4;
+template <int FR>
+BA_DEV void fast_spill(const FastRegs<FR>& f, const WarpMem& w, int dir, bool mine) {
+  constexpr int B = 8 * FR;
+  const int lg = wp::lane_id() & 7, i0 = lg * FR;
   int16_t *ad = dir == kRight ? w.Dc : w.Dr, *ac = dir == kRight ? w.Cc : w.Rr;
   int16_t *od = dir == kRight ? w.Dr : w.Dc, *orr = dir == kRight ? w.Rr : w.Cc;
   wp::syncwarp();
   if (mine) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < FR; k++) {
       ad[i0 + k] = (int16_t)f.aD[k]; ac[i0 + k] = (int16_t)f.aC[k]; od[i0 + k] = (int16_t)f.oD[k]; orr[i0 + k] = (int16_t)f.oR[k];
-    }
-    // temp_buf1/2 hold the 8 fresh values of the last shift = entries 24..31 of the orthogonal border
-    if (lg >= 6) {
-#pragma unroll
-      for (int k = 0; k < 4; k++) { w.t1[(lg - 6) * 4 + k] = (int16_t)f.oD[k]; w.t2[(lg - 6) * 4 + k] = (int16_t)f.oR[k]; }
+      // temp_buf1/2 hold the 8 fresh values of the last shift = the last 8 entries of the orthogonal border
+      if (i0 + k >= B - kStep) { w.t1[i0 + k - (B - kStep)] = (int16_t)f.oD[k]; w.t2[i0 + k - (B - kStep)] = (int16_t)f.oR[k]; }
     }
   }
   wp::syncwarp();
 }
 
 // per-lane constants of the fast phase (hoisted out of the step)
-struct FastConst {
-  int ph[4];       // scan phantoms of the lane's four rows (avx2.rs:321-337)
-  int lane_rg;     // (lane in group) * 4 * gap_extend
+template <int FR> struct FastConst {
+  int ph[FR];      // scan phantoms of the lane's rows (avx2.rs:321-337)
+  int lane_rg;     // (lane in group) * FR * gap_extend
 };
-BA_DEV void fast_consts(FastConst& fc, int ge) {
+template <int FR>
+BA_DEV void fast_consts(FastConst<FR>& fc, int ge) {
   const int lg = wp::lane_id() & 7;
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int m = (lg * 4 + k) & 15;
+  for (int k = 0; k < FR; k++) {
+    const int m = (lg * FR + k) & 15;
     fc.ph[k] = (m == 15) ? kI16Min : (m == 7 ? 12 * ge : ((m & 7) + 1) * ge);
   }
-  fc.lane_rg = lg * 4 * ge;
+  fc.lane_rg = lg * FR * ge;
 }
 
-template <int SCORING, int FLAGS>
-BA_DEV void fast_step(const Params& P, const int8_t* mat, const FastConst& fc, AlnState& st, FastRegs& f, int& status,
+// One shift step of up to four alignments (one per 8-lane group) with block size B = 8 * FR.
+template <int SCORING, int FLAGS, int FR>
+BA_DEV void fast_step(const Params& P, const int8_t* mat, const FastConst<FR>& fc, AlnState& st, FastRegs<FR>& f, int& status,
                       const uint8_t* qp, const uint8_t* rp, const SlotMem& sm) {
   constexpr bool TRACE = (FLAGS & kTrace) != 0, XDROP = (FLAGS & kXDrop) != 0;
   constexpr int KIND = (SCORING == kProfile) ? kAA : SCORING;
+  constexpr int B = 8 * FR;               // block size
+  constexpr int NEWL = kStep / FR;        // lanes that hold the 8 fresh entries of the orthogonal border (2 or 1)
+  constexpr int TM = 16;                  // tracker multiplier: value * TM + (column + 1), column + 1 <= 8
   const int lane = wp::lane_id(), lg = lane & 7;
   const bool active = status == kStFast;
   const int ge = P.gap_extend, go = P.gap_open, open_r = go - ge;
@@ -852,38 +864,48 @@ BA_DEV void fast_step(const Params& P, const int8_t* mat, const FastConst& fc, A
   const uint8_t* vec = right ? qp : rp;
   const uint8_t* col = right ? rp : qp;
   const uint32_t vec_base = right ? si : sj;
-  const uint32_t col_base = (right ? sj : si) + 24;
+  const uint32_t col_base = (right ? sj : si) + (B - kStep);
 
   // ---- step prologue (scan_block.rs:148-158) ----
   const int off = st.off_max;
   const int off_add = clamp16(st.off - off);
   const int corner = (st.prev_dir == (right ? kDown : kRight)) ? sat_add(st.D_corner, off_add) : 0;
 
-  // tokens: 4 bytes of the vector-direction sequence per lane, 8 bytes of the column sequence per group
-  uint32_t vword = 0, cw0 = 0, cw1 = 0;
+  // tokens: FR bytes of the vector-direction sequence per lane, 8 bytes of the column sequence per group
+  uint32_t vw[FR / 4], cw0 = 0, cw1 = 0;
+#pragma unroll
+  for (int t = 0; t < FR / 4; t++) vw[t] = 0;
   if (active) {
-    vword = *(const uint32_t*)(vec + vec_base + lg * 4);
+#pragma unroll
+    for (int t = 0; t < FR / 4; t++) vw[t] = *(const uint32_t*)(vec + vec_base + lg * FR + 4 * t);
     const uint2 cw = *(const uint2*)(col + col_base);
     cw0 = cw.x; cw1 = cw.y;
   }
-  int rtok[4];
+  int rtok[FR];
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int b = (int)((vword >> (8 * k)) & 0xffu);
+  for (int k = 0; k < FR; k++) {
+    const int b = (int)((vw[k / 4] >> (8 * (k & 3))) & 0xffu);
     rtok[k] = KIND == kNuc ? (b & 15) : (KIND == kAA ? (b & 31) : b);
   }
 
   uint32_t* tw = nullptr;
-  if (TRACE && active) tw = trace_push(st, sm, right ? si : si + 24, right ? sj + 24 : sj, kStep, 32, right, lg == 0);
+  if (TRACE && active) tw = trace_push(st, sm, right ? si : si + (B - kStep), right ? sj + (B - kStep) : sj, kStep, B, right, lg == 0);
 
-  int D10[4], C10[4];
+  int D10[FR], C10[FR];
 #pragma unroll
-  for (int k = 0; k < 4; k++) { D10[k] = sat_add(f.aD[k], off_add); C10[k] = sat_add(f.aC[k], off_add); }
+  for (int k = 0; k < FR; k++) { D10[k] = sat_add(f.aD[k], off_add); C10[k] = sat_add(f.aC[k], off_add); }
 
-  // per-row tracker: max over the step of value * 16 + (column + 1); 0 = "no cell >= 0" (D_max starts at 0)
-  int trk[4] = {0, 0, 0, 0};
-  unsigned twd[4] = {0, 0, 0, 0};
-  int nb[4] = {0, 0, 0, 0};   // fresh bottom-row values (packed D | T << 16), held by lanes 6 and 7 of the group
+  // per-row tracker: max over the step of value * TM + (column + 1); 0 = "no cell >= 0" (D_max starts at 0)
+  int trk[FR];
+  unsigned twd[FR];
+#pragma unroll
+  for (int k = 0; k < FR; k++) { trk[k] = 0; twd[k] = 0; }
+  // fresh bottom-row values (packed D | T << 16). FR == 4: lanes 6 and 7 of the group keep 4 each (columns 0..3 /
+  // 4..7 = border entries 24..27 / 28..31); FR == 8: every lane keeps all 8, lane 7 uses them.
+  constexpr int NB = FR == 4 ? 4 : 8;
+  int nb[NB];
+#pragma unroll
+  for (int t = 0; t < NB; t++) nb[t] = 0;
 
 #pragma unroll 1
   for (int h = 0; h < 2; h++) {
@@ -893,11 +915,11 @@ BA_DEV void fast_step(const Params& P, const int8_t* mat, const FastConst& fc, A
       const int cidx = h * 4 + cc;
       const int cb = (int)((cwh >> (8 * cc)) & 0xffu);
       const int ctok = KIND == kNuc ? ((cb & 7) * 16) : (KIND == kAA ? cb * 32 : cb);
-      int up = wp::shfl_up8(D10[3], 1);
+      int up = wp::shfl_up8(D10[FR - 1], 1);
       if (lg == 0) up = (cidx == 0) ? corner : 0;
-      int dd[4], xx[4], c11[4], c11o[4], tt[4];
+      int dd[FR], xx[FR], c11[FR], c11o[FR], tt[FR];
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
+      for (int k = 0; k < FR; k++) {
         const int s = sc.score(ctok, rtok[k]);
         const int d00 = (k == 0) ? up : D10[k - 1];
         c11o[k] = sat_add_lo(D10[k], go);
@@ -906,19 +928,19 @@ BA_DEV void fast_step(const Params& P, const int8_t* mat, const FastConst& fc, A
         xx[k] = sat_add_lo(dd[k], open_r);
         tt[k] = (k == 0) ? xx[0] : wp::viaddmax(tt[k - 1], ge, xx[k]);
       }
-      int inc = tt[3];
+      int inc = tt[FR - 1];
 #pragma unroll
       for (int s = 0; s < 3; s++) {
         const int u = wp::shfl_up8(inc, 1 << s);
-        inc = wp::viaddmax(u, (4 << s) * ge, inc);
+        inc = wp::viaddmax(u, (FR << s) * ge, inc);
       }
       int ex = wp::shfl_up8(inc, 1);
       if (lg == 0) ex = kNegBig;
       const int cin = wp::imax(fc.lane_rg, ex);
-      int Dn[4], Tn[4];
+      int Dn[FR], Tn[FR];
       unsigned ebits = 0;
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
+      for (int k = 0; k < FR; k++) {
         Tn[k] = wp::viaddmax(cin, (k + 1) * ge, tt[k]);
         if (TRACE) {
           const int Rv = wp::imax(Tn[k], fc.ph[k]);
@@ -929,67 +951,83 @@ BA_DEV void fast_step(const Params& P, const int8_t* mat, const FastConst& fc, A
         } else {
           Dn[k] = wp::vimax3(dd[k], Tn[k], fc.ph[k]);
         }
-        if (XDROP) trk[k] = wp::imax(trk[k], Dn[k] * 16 + (cidx + 1));
+        if (XDROP) trk[k] = wp::imax(trk[k], Dn[k] * TM + (cidx + 1));
         else trk[0] = wp::imax(trk[0], Dn[k]);
       }
       if (TRACE) {
-        const unsigned eb = wp::ballot(((ebits >> 3) & 1u) != 0);
+        const unsigned eb = wp::ballot(((ebits >> (FR - 1)) & 1u) != 0);
         const unsigned above = lg == 0 ? 0u : ((eb >> (lane - 1)) & 1u);
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < FR; k++) {
           const unsigned b3 = (k == 0) ? above : ((ebits >> (k - 1)) & 1u);
           twd[k] |= (b3 << 3) << (4 * cidx);
         }
       }
-      const int bot = wp::shfl_idx8(pack16(Dn[3], Tn[3]), 7);
-      if (lg == 6 + h) nb[cc] = bot;
+      const int bot = wp::shfl_idx8(pack16(Dn[FR - 1], Tn[FR - 1]), 7);
+      if (FR == 4) { if (lg == 6 + h) nb[cc] = bot; }
+      else { if (h == 0) nb[cc] = bot; else nb[(NB - 4) + cc] = bot; }
 #pragma unroll
-      for (int k = 0; k < 4; k++) { D10[k] = Dn[k]; C10[k] = c11[k]; }
+      for (int k = 0; k < FR; k++) { D10[k] = Dn[k]; C10[k] = c11[k]; }
     }
   }
   if (TRACE && active) {
-    // same layout as a generic 32 x 8 rectangle (R = 1): word index = row
-    uint4 wv; wv.x = twd[0]; wv.y = twd[1]; wv.z = twd[2]; wv.w = twd[3];
-    *(uint4*)(tw + lg * 4) = wv;
+    // same layout as a generic B x 8 rectangle with one row per lane: word index = row
+#pragma unroll
+    for (int t = 0; t < FR / 4; t++) {
+      uint4 wv; wv.x = twd[4 * t]; wv.y = twd[4 * t + 1]; wv.z = twd[4 * t + 2]; wv.w = twd[4 * t + 3];
+      *(uint4*)(tw + lg * FR + 4 * t) = wv;
+    }
   }
 
   // ---- borders after the step ----
-  // D_corner = old orthogonal[STEP-1] + off_add (scan_block.rs:1041-1042): entry 7 = lane 1, k = 3
-  const int d_corner = sat_add(wp::shfl_idx8(f.oD[3], 1), off_add);
+  // D_corner = old orthogonal[STEP-1] + off_add (scan_block.rs:1041-1042): entry 7
+  const int d_corner = sat_add(wp::shfl_idx8(f.oD[(kStep - 1) % FR], (kStep - 1) / FR), off_add);
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
+  for (int k = 0; k < FR; k++) {
     f.aD[k] = D10[k]; f.aC[k] = C10[k];
-    const int p = wp::shfl_down8(pack16(f.oD[k], f.oR[k]), 2);   // slide by 8 entries = 2 lanes
-    if (lg < 6) { f.oD[k] = sat_add(lo16(p), off_add); f.oR[k] = sat_add(hi16(p), off_add); }
-    else { f.oD[k] = lo16(nb[k]); f.oR[k] = hi16(nb[k]); }
+    const int p = wp::shfl_down8(pack16(f.oD[k], f.oR[k]), NEWL);   // slide by 8 entries
+    if (lg < 8 - NEWL) { f.oD[k] = sat_add(lo16(p), off_add); f.oR[k] = sat_add(hi16(p), off_add); }
+    else {
+      // entry (lg * FR + k) - (B - 8) of the fresh values
+      const int v = nb[k & (NB - 1)];
+      f.oD[k] = lo16(v); f.oR[k] = hi16(v);
+    }
   }
 
   // ---- reductions (scan_block.rs:332-345) ----
   // tie-break order of the reference: value desc, AVX lane (row mod 16) asc, column desc, row desc
   int bv = 0; unsigned bkey = 15u << 27;
   if (XDROP) {
-    // Within a lane the four rows have ascending AVX lanes, so among equal values the lowest k wins;
-    // rows that saw no cell >= 0 (trk == 0) compare as -1 and never win.
-    int bw = (trk[0] - 1) >> 4, bt = trk[0], bk = 0;
+    // rows that saw no cell >= 0 (trk == 0) compare as -1 and never win
+    // (within a lane the rows have distinct, ascending AVX lanes, so among equal values the lowest k wins)
+    int bw = -1, bt = 0, bk = 0;
 #pragma unroll
-    for (int k = 1; k < 4; k++) {
+    for (int k = 0; k < FR; k++) {
       const int wv = (trk[k] - 1) >> 4;
       if (wv > bw) { bw = wv; bt = trk[k]; bk = k; }
     }
     if (bw >= 0) {
-      const unsigned row = (unsigned)(lg * 4 + bk);
+      const unsigned row = (unsigned)(lg * FR + bk);
       bv = bw;
-      bkey = ((15u - (row & 15u)) << 27) | ((unsigned)(bt & 15) << 13) | row;
+      bkey = ((15u - (row & 15u)) << 27) | ((unsigned)(bt & (TM - 1)) << 13) | row;
     }
   } else {
     bv = trk[0];
   }
   const int mxv = group_max(bv);
-  const int a_loc = wp::imax(wp::imax(f.aD[0], f.aD[1]), wp::imax(f.aD[2], f.aD[3]));
-  const int o_loc = wp::imax(wp::imax(f.oD[0], f.oD[1]), wp::imax(f.oD[2], f.oD[3]));
+  // prefix_max over entries 0..7 of both borders (scan_block.rs:1020-1022)
+  int a_loc = f.aD[0], o_loc = f.oD[0];
+#pragma unroll
+  for (int k = 1; k < FR; k++) { a_loc = wp::imax(a_loc, f.aD[k]); o_loc = wp::imax(o_loc, f.oD[k]); }
   const int pm = pack16(a_loc, o_loc);
-  const int pm0 = wp::shfl_idx8(pm, 0), pm1 = wp::shfl_idx8(pm, 1);
-  const int a_max = wp::imax(lo16(pm0), lo16(pm1)), o_max = wp::imax(hi16(pm0), hi16(pm1));   // prefix_max over 8 entries
+  int a_max, o_max;
+  if (FR == 4) {
+    const int pm0 = wp::shfl_idx8(pm, 0), pm1 = wp::shfl_idx8(pm, 1);
+    a_max = wp::imax(lo16(pm0), lo16(pm1)); o_max = wp::imax(hi16(pm0), hi16(pm1));
+  } else {
+    const int pm0 = wp::shfl_idx8(pm, 0);
+    a_max = lo16(pm0); o_max = hi16(pm0);
+  }
   const int right_max = right ? a_max : o_max, down_max = right ? o_max : a_max;
   unsigned key = 0;
   if (XDROP) key = group_max_u(bv == mxv ? bkey : 0u);
@@ -997,19 +1035,19 @@ BA_DEV void fast_step(const Params& P, const int8_t* mat, const FastConst& fc, A
   if (P.step_log && active && lg == 0) {
     const uint32_t n = *P.step_log_n;
     if (n < P.step_log_cap) {
-      StepLog sl; sl.dir = st.dir; sl.i = si; sl.j = sj; sl.block_size = 32u; sl.off = off;
+      StepLog sl; sl.dir = st.dir; sl.i = si; sl.j = sj; sl.block_size = (uint32_t)B; sl.off = off;
       sl.max = (int16_t)mxv; sl.right_max = (int16_t)right_max; sl.down_max = (int16_t)down_max;
       P.step_log[n] = sl;
     }
     *P.step_log_n = n + 1;
   }
 
-  // ---- post-step decisions (scan_block.rs:332-558 restricted to B == min_size == 32, shift steps) ----
+  // ---- post-step decisions (scan_block.rs:332-558 restricted to B == min_size, shift steps) ----
   // No warp collectives below: groups diverge freely.
   if (active) {
     st.off = off;
     st.steps++;
-    add_cells(st, 256u);
+    add_cells(st, (uint32_t)(kStep * B));
     st.prev_dir = st.dir;
     st.D_corner = d_corner;
     st.off_max = off + mxv - kZero;
@@ -1019,20 +1057,23 @@ BA_DEV void fast_step(const Params& P, const int8_t* mat, const FastConst& fc, A
         const unsigned cp1 = (key >> 13) & 0x3fffu;
         uint32_t v = key & 0x1fffu, c = 0;
         if (cp1 == 0) v = 0; else c = cp1 - 1;
-        if (right) { st.best_i = si + v; st.best_j = sj + 24 + c; }
-        else { st.best_i = si + 24 + c; st.best_j = sj + v; }
+        if (right) { st.best_i = si + v; st.best_j = sj + (B - kStep) + c; }
+        else { st.best_i = si + (B - kStep) + c; st.best_j = sj + v; }
       }
-      if (32 < (int)P.max_size) {
+      if (B < (int)P.max_size) {
         st.i_ckpt = si; st.j_ckpt = sj; st.off_ckpt = off;
         if (TRACE) { st.ck_widx = st.widx; st.ck_ridx = st.ridx; }
-        // checkpoint copy of all four borders (scan_block.rs:413-420), 4 entries per lane and array
+        // checkpoint copy of all four borders (scan_block.rs:413-420), FR entries per lane and array
         int16_t *ka = right ? sm.kDc : sm.kDr, *kc = right ? sm.kCc : sm.kRr;
         int16_t *ko = right ? sm.kDr : sm.kDc, *kr = right ? sm.kRr : sm.kCc;
-        uint2 v;
-        v.x = (uint32_t)pack16(f.aD[0], f.aD[1]); v.y = (uint32_t)pack16(f.aD[2], f.aD[3]); *(uint2*)(ka + lg * 4) = v;
-        v.x = (uint32_t)pack16(f.aC[0], f.aC[1]); v.y = (uint32_t)pack16(f.aC[2], f.aC[3]); *(uint2*)(kc + lg * 4) = v;
-        v.x = (uint32_t)pack16(f.oD[0], f.oD[1]); v.y = (uint32_t)pack16(f.oD[2], f.oD[3]); *(uint2*)(ko + lg * 4) = v;
-        v.x = (uint32_t)pack16(f.oR[0], f.oR[1]); v.y = (uint32_t)pack16(f.oR[2], f.oR[3]); *(uint2*)(kr + lg * 4) = v;
+#pragma unroll
+        for (int t = 0; t < FR / 4; t++) {
+          uint2 v;
+          v.x = (uint32_t)pack16(f.aD[4 * t], f.aD[4 * t + 1]); v.y = (uint32_t)pack16(f.aD[4 * t + 2], f.aD[4 * t + 3]); *(uint2*)(ka + lg * FR + 4 * t) = v;
+          v.x = (uint32_t)pack16(f.aC[4 * t], f.aC[4 * t + 1]); v.y = (uint32_t)pack16(f.aC[4 * t + 2], f.aC[4 * t + 3]); *(uint2*)(kc + lg * FR + 4 * t) = v;
+          v.x = (uint32_t)pack16(f.oD[4 * t], f.oD[4 * t + 1]); v.y = (uint32_t)pack16(f.oD[4 * t + 2], f.oD[4 * t + 3]); *(uint2*)(ko + lg * FR + 4 * t) = v;
+          v.x = (uint32_t)pack16(f.oR[4 * t], f.oR[4 * t + 1]); v.y = (uint32_t)pack16(f.oR[4 * t + 2], f.oR[4 * t + 3]); *(uint2*)(kr + lg * FR + 4 * t) = v;
+        }
       }
       st.best_max = st.off_max;
       st.y_drop_iter = 0;
@@ -1048,10 +1089,10 @@ BA_DEV void fast_step(const Params& P, const int8_t* mat, const FastConst& fc, A
     }
     if (TRACE && st.overflow) nstatus = kStDone;
     if (nstatus == kStFast) {
-      if (si + 32 > st.qlen && sj + 32 > st.rlen) nstatus = kStDone;
-      else if (sj + 32 > st.rlen) { st.si = si + kStep; st.dir = kDown; }
-      else if (si + 32 > st.qlen) { st.sj = sj + kStep; st.dir = kRight; }
-      else if (64 <= (int)P.max_size && st.y_drop_iter > (32 / kStep) - 1) nstatus = kStNeedGrow;   // state left untouched
+      if (si + B > st.qlen && sj + B > st.rlen) nstatus = kStDone;
+      else if (sj + B > st.rlen) { st.si = si + kStep; st.dir = kDown; }
+      else if (si + B > st.qlen) { st.sj = sj + kStep; st.dir = kRight; }
+      else if (2 * B <= (int)P.max_size && st.y_drop_iter > (B / kStep) - 1) nstatus = kStNeedGrow;   // state left untouched
       else if (down_max > right_max) { st.si = si + kStep; st.dir = kDown; }
       else { st.sj = sj + kStep; st.dir = kRight; }
       if (nstatus == kStFast && !fast_eligible<SCORING, XDROP>(P, st)) nstatus = kStNeedGeneric;
@@ -1061,7 +1102,7 @@ BA_DEV void fast_step(const Params& P, const int8_t* mat, const FastConst& fc, A
     // borders swap roles
     if (nstatus == kStFast && st.dir != st.prev_dir) {
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
+      for (int k = 0; k < FR; k++) {
         int t = f.aD[k]; f.aD[k] = f.oD[k]; f.oD[k] = t;
         t = f.aC[k]; f.aC[k] = f.oR[k]; f.oR[k] = t;
       }
@@ -1103,7 +1144,7 @@ BA_DEV void bind_slot(const Params& P, uint32_t slot, WarpMem& w, SlotMem& sm, b
   }
 }
 
-template <int SCORING, int FLAGS>
+template <int SCORING, int FLAGS, int FR>
 BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, uint32_t warp_global) {
   constexpr bool TRACE = (FLAGS & kTrace) != 0;
   const int lane = wp::lane_id();
@@ -1128,16 +1169,17 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
   st.off = 0; st.off_max = 0; st.best_max = 0; st.best_i = 0; st.best_j = 0; st.i_ckpt = 0; st.j_ckpt = 0; st.off_ckpt = 0;
   st.y_drop_iter = 0; st.x_drop_iter = 0; st.D_corner = 0; st.cells_lo = 0; st.cells_hi = 0; st.steps = 0;
   st.widx = 0; st.ridx = 0; st.ck_widx = 0; st.ck_ridx = 0; st.overflow = 0;
-  FastRegs f;
+  constexpr int FRR = FR ? FR : 4;   // FR == 0: no fast phase (the fast code below is never reached)
+  FastRegs<FRR> f;
 #pragma unroll
-  for (int k = 0; k < 4; k++) { f.aD[k] = 0; f.aC[k] = 0; f.oD[k] = 0; f.oR[k] = 0; }
+  for (int k = 0; k < FRR; k++) { f.aD[k] = 0; f.aC[k] = 0; f.oD[k] = 0; f.oR[k] = 0; }
   int status = kStEmpty;
   const uint8_t* qp = P.seq;
   const uint8_t* rp = P.seq;
   SlotMem my_sm;
   { WarpMem tmpw = w; bind_slot(P, warp_global * spw + my_g, tmpw, my_sm, TRACE); }
   bool tickets_left = true;
-  FastConst fc;
+  FastConst<FRR> fc;
   fast_consts(fc, P.gap_extend);
 
   for (;;) {
@@ -1183,7 +1225,8 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
     if (wp::ballot(status == kStFast) == 0u) break;
     // ---- fast phase: run until some group needs the generic phase ----
     for (;;) {
-      fast_step<SCORING, FLAGS>(P, w.mat, fc, st, f, status, qp, rp, my_sm);
+      if (FR) fast_step<SCORING, FLAGS, FRR>(P, w.mat, fc, st, f, status, qp, rp, my_sm);
+      else break;
       if (wp::ballot(status != kStFast && status != kStEmpty) != 0u) break;
       if (wp::ballot(status == kStFast) == 0u) break;
     }

@@ -76,12 +76,11 @@ static void pack_all(const PackArgs& a) {
       for (uint32_t t = 0; t < a.pad; t++) dst[1 + len + t] = nul;
     }
 }
-template <int SCORING, int FLAGS>
 struct EmuLaunch { const Params* P; unsigned char* smem; uint32_t wg; };
-template <int SCORING, int FLAGS>
+template <int SCORING, int FLAGS, int FR>
 static void emu_warp_entry(void* arg) {
-  auto* l = (EmuLaunch<SCORING, FLAGS>*)arg;
-  warp_main<SCORING, FLAGS>(*l->P, l->smem, 0, l->wg);
+  auto* l = (EmuLaunch*)arg;
+  warp_main<SCORING, FLAGS, FR>(*l->P, l->smem, 0, l->wg);
 }
 struct EmuTb { const Params* P; uint32_t pair, qi, rj; int eq; DevResult* out1; };
 static void emu_tb_entry(void* arg) { auto* t = (EmuTb*)arg; warp_traceback(*t->P, t->pair, t->qi, t->rj, t->eq != 0, t->out1); }
@@ -90,15 +89,15 @@ static int launch_traceback(const Params& P, uint32_t pair, uint32_t qi, uint32_
   emu::run_warp(&emu_tb_entry, &t);
   return 0;
 }
-template <int SCORING, int FLAGS>
+template <int SCORING, int FLAGS, int FR>
 static int launch_align(const Params& P, int blocks, int wpb, size_t smem_bytes, dev_stream_t) {
   (void)wpb;
   for (int b = 0; b < blocks; b++) {
     std::vector<unsigned char> smem(smem_bytes + 64, 0xAB);
     const int nm = SCORING == kNuc ? 128 : (SCORING == kAA ? 864 : 0);
     for (int i = 0; i < nm; i++) smem[i] = (unsigned char)P.matrix[i];
-    EmuLaunch<SCORING, FLAGS> l{&P, smem.data(), (uint32_t)b};
-    emu::run_warp(&emu_warp_entry<SCORING, FLAGS>, &l);
+    EmuLaunch l{&P, smem.data(), (uint32_t)b};
+    emu::run_warp(&emu_warp_entry<SCORING, FLAGS, FR>, &l);
     // guard: the device code must stay inside the shared memory it was given
     for (size_t i = smem_bytes; i < smem_bytes + 64; i++)
       if (smem[i] != 0xAB) { fprintf(stderr, "emu: shared memory overrun at byte %zu (limit %zu)\n", i, smem_bytes); abort(); }
@@ -136,14 +135,14 @@ __global__ void ba_pack_kernel(PackArgs a) {
 
 // 128 threads per block, at least 4 blocks per SM: caps the kernel at 128 registers/thread. Measured on
 // B200 (C2 workload): uncapped (207 regs, 8 warps/SM) 476 GCUPS, 160 regs 580, 128 regs 634, 96 regs 596.
-template <int SCORING, int FLAGS>
+template <int SCORING, int FLAGS, int FR>
 __global__ void __launch_bounds__(128, 4) ba_align_kernel(const __grid_constant__ Params P) {
   extern __shared__ __align__(16) unsigned char ba_smem[];
   const int nm = SCORING == kNuc ? 128 : (SCORING == kAA ? 864 : 0);
   for (int i = threadIdx.x; i < nm; i += blockDim.x) ba_smem[i] = (unsigned char)P.matrix[i];
   __syncthreads();
   const int wib = threadIdx.x >> 5;
-  warp_main<SCORING, FLAGS>(P, ba_smem, wib, blockIdx.x * (blockDim.x >> 5) + wib);
+  warp_main<SCORING, FLAGS, FR>(P, ba_smem, wib, blockIdx.x * (blockDim.x >> 5) + wib);
 }
 
 __global__ void ba_traceback_kernel(const __grid_constant__ Params P, uint32_t pair, uint32_t qi, uint32_t rj, int eq, DevResult* out1) {
@@ -155,36 +154,38 @@ static int launch_traceback(const Params& P, uint32_t pair, uint32_t qi, uint32_
   return 0;
 }
 
-template <int SCORING, int FLAGS>
+template <int SCORING, int FLAGS, int FR>
 static int launch_align(const Params& P, int blocks, int wpb, size_t smem_bytes, dev_stream_t st) {
-  CK(cudaFuncSetAttribute(ba_align_kernel<SCORING, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  ba_align_kernel<SCORING, FLAGS><<<blocks, wpb * 32, smem_bytes, st>>>(P);
+  CK(cudaFuncSetAttribute(ba_align_kernel<SCORING, FLAGS, FR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  ba_align_kernel<SCORING, FLAGS, FR><<<blocks, wpb * 32, smem_bytes, st>>>(P);
   CK(cudaGetLastError());
   return 0;
 }
-template <int SCORING, int FLAGS>
+template <int SCORING, int FLAGS, int FR>
 static int occupancy(int wpb, size_t smem_bytes, int* blocks_per_sm) {
-  CK(cudaFuncSetAttribute(ba_align_kernel<SCORING, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ba_align_kernel<SCORING, FLAGS>, wpb * 32, smem_bytes));
+  CK(cudaFuncSetAttribute(ba_align_kernel<SCORING, FLAGS, FR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ba_align_kernel<SCORING, FLAGS, FR>, wpb * 32, smem_bytes));
   return 0;
 }
 #endif
 
-#define BA_FOR_KERNELS(X) \
-  X(kNuc, 0) X(kNuc, 1) X(kNuc, 2) X(kNuc, 3) X(kAA, 0) X(kAA, 1) X(kAA, 2) X(kAA, 3) \
-  X(kByte, 0) X(kByte, 1) X(kByte, 2) X(kByte, 3) X(kProfile, 0) X(kProfile, 1) X(kProfile, 2) X(kProfile, 3)
+// kernel instantiations: scoring x flags x rows-per-lane of the fast phase (0 = generic phase only)
+#define BA_FOR_SEQ(X, S) X(S, 0, 0) X(S, 1, 0) X(S, 2, 0) X(S, 3, 0) X(S, 0, 4) X(S, 1, 4) X(S, 2, 4) X(S, 3, 4) \
+                         X(S, 0, 8) X(S, 1, 8) X(S, 2, 8) X(S, 3, 8)
+#define BA_FOR_KERNELS(X) BA_FOR_SEQ(X, kNuc) BA_FOR_SEQ(X, kAA) BA_FOR_SEQ(X, kByte) \
+  X(kProfile, 0, 0) X(kProfile, 1, 0) X(kProfile, 2, 0) X(kProfile, 3, 0)
 
-static int launch_dispatch(int scoring, int flags, const Params& P, int blocks, int wpb, size_t smem, dev_stream_t st) {
-#define X(S, F) if (scoring == S && flags == F) return launch_align<S, F>(P, blocks, wpb, smem, st);
+static int launch_dispatch(int scoring, int flags, int fr, const Params& P, int blocks, int wpb, size_t smem, dev_stream_t st) {
+#define X(S, F, R) if (scoring == S && flags == F && fr == R) return launch_align<S, F, R>(P, blocks, wpb, smem, st);
   BA_FOR_KERNELS(X)
 #undef X
   return fail(BA_ERR_ARG, "unsupported scoring/flags combination");
 }
-static int occupancy_dispatch(int scoring, int flags, int wpb, size_t smem, int* bps) {
+static int occupancy_dispatch(int scoring, int flags, int fr, int wpb, size_t smem, int* bps) {
 #ifdef BA_EMU
-  (void)scoring; (void)flags; (void)wpb; (void)smem; *bps = 1; return 0;
+  (void)scoring; (void)flags; (void)fr; (void)wpb; (void)smem; *bps = 1; return 0;
 #else
-#define X(S, F) if (scoring == S && flags == F) return occupancy<S, F>(wpb, smem, bps);
+#define X(S, F, R) if (scoring == S && flags == F && fr == R) return occupancy<S, F, R>(wpb, smem, bps);
   BA_FOR_KERNELS(X)
 #undef X
   return fail(BA_ERR_ARG, "unsupported scoring/flags combination");
@@ -220,8 +221,11 @@ struct BaBatch {
   int16_t* d_ckpt = nullptr; uint32_t* d_trace = nullptr; Rect* d_rects = nullptr; uint32_t* d_runs = nullptr;
   uint32_t* d_cigar = nullptr; unsigned long long* d_cigar_used = nullptr; uint64_t cigar_cap = 0;
   StepLog* d_steplog = nullptr; uint32_t* d_steplog_n = nullptr;
+  uint32_t* d_overflow_list = nullptr; uint32_t* d_overflow_n = nullptr;
+  uint64_t trace_words_bound = 0;   // worst case per alignment (the reference's Trace::new size)
+  uint64_t mem_budget = 0; uint64_t max_blocks_hw = 1;
   // launch geometry
-  int blocks = 0, wpb = 0; size_t smem_bytes = 0; uint32_t slots_per_warp = 1; bool use_fast = false;
+  int blocks = 0, wpb = 0; size_t smem_bytes = 0; uint32_t slots_per_warp = 1; int fast_rows = 0;
   uint64_t trace_words_per_warp = 0; uint32_t rects_per_warp = 0, runs_per_warp = 0;
   // host results
   std::vector<DevResult> h_out;
@@ -295,7 +299,7 @@ extern "C" void ba_batch_free(BaBatch* b) {
   dfree(b->d_seq); dfree(b->d_qoff); dfree(b->d_roff); dfree(b->d_qlen); dfree(b->d_rlen); dfree(b->d_order);
   dfree(b->d_matrix); dfree(b->d_profiles); dfree(b->d_prof_arena); dfree(b->d_out); dfree(b->d_ticket);
   dfree(b->d_ckpt); dfree(b->d_trace); dfree(b->d_rects); dfree(b->d_runs); dfree(b->d_cigar); dfree(b->d_cigar_used);
-  dfree(b->d_steplog); dfree(b->d_steplog_n); dfree(b->d_tb_res);
+  dfree(b->d_steplog); dfree(b->d_steplog_n); dfree(b->d_tb_res); dfree(b->d_overflow_list); dfree(b->d_overflow_n);
   delete b;
 }
 
@@ -463,15 +467,16 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
   if (herr) { ba_batch_free(b); return fail(BA_ERR_CHAR, "sequence byte outside the alphabet of the scoring matrix"); }
 
   // launch geometry and per-slot scratch
-  b->use_fast = !prof && mn == 32 && !getenv("BA_NO_FAST");
-  b->slots_per_warp = b->use_fast ? 4 : 1;
+  // fast phase: four alignments per warp while the block sits at its minimum size (32 or 64)
+  b->fast_rows = (!prof && !getenv("BA_NO_FAST")) ? (mn == 32 ? 4 : (mn == 64 ? 8 : 0)) : 0;
+  b->slots_per_warp = b->fast_rows ? 4 : 1;
   const size_t wbytes = warp_smem_bytes(mx);
   int wpb = 4;
   while (wpb > 1 && 1024 + wpb * wbytes > al->smem_optin - 1024) wpb >>= 1;
   if (1024 + wpb * wbytes > al->smem_optin) { ba_batch_free(b); return fail(BA_ERR_SIZE, "max block size does not fit in shared memory"); }
   b->wpb = wpb; b->smem_bytes = 1024 + wpb * wbytes;
   int bps = 1;
-  TRY(occupancy_dispatch(prof ? (int)kProfile : cfg->scoring, cfg->flags, wpb, b->smem_bytes, &bps));
+  TRY(occupancy_dispatch(prof ? (int)kProfile : cfg->scoring, cfg->flags, b->fast_rows, wpb, b->smem_bytes, &bps));
   if (bps < 1) bps = 1;
   uint64_t max_blocks = (uint64_t)al->sm_count * bps;
 #ifdef BA_EMU
@@ -480,18 +485,25 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
   const bool trace = (cfg->flags & BA_TRACE) != 0;
   const size_t ms = mx < 32 ? 32 : mx;
   const uint64_t spw = b->slots_per_warp;
+  b->max_blocks_hw = max_blocks;
   if (trace) {
-    // per-slot arena, sized like the reference's Trace::new (scan_block.rs:1364-1369)
+    // Worst case per alignment = the reference's Trace::new (scan_block.rs:1364-1369): the block sits at its
+    // maximum size all the time. Real alignments spend most steps at the minimum size, so the first pass runs
+    // with arenas sized for 4x the all-minimum-size path plus one maximum-size grow; alignments that overflow
+    // are re-run with worst-case arenas (ba_batch_run).
     const uint64_t len = (uint64_t)b->max_pair_len + 2;
     uint64_t words = 2 * (uint64_t)(mx / 16) * (len + 2 * (uint64_t)mx);
     if (mn == 16) words *= 2;   // 16-row rectangles still occupy a 32-lane word group
     if (words + 64 >= ((uint64_t)1 << 32)) { ba_batch_free(b); return fail(BA_ERR_SIZE, "trace arena of one alignment exceeds 2^32 words"); }
-    b->trace_words_per_warp = words + 64;
+    b->trace_words_bound = words + 64;
+    uint64_t first = 4 * len * (uint64_t)std::max<uint32_t>(mn, 32) / 8 + (uint64_t)mx * mx / 4 + 4096;
+    if (getenv("BA_TRACE_WORST_CASE")) first = b->trace_words_bound;
+    b->trace_words_per_warp = std::min<uint64_t>(b->trace_words_bound, first);
     b->rects_per_warp = (uint32_t)std::min<uint64_t>(len * 2 + 8, 0x7fffffffu);
     b->runs_per_warp = (uint32_t)std::min<uint64_t>(len + 8, 0x7fffffffu);
     const uint64_t per_warp = spw * (b->trace_words_per_warp * 4 + (uint64_t)b->rects_per_warp * sizeof(Rect)) + (uint64_t)b->runs_per_warp * 4;
-    const uint64_t budget = (uint64_t)(al->mem_total * 0.55);
-    const uint64_t fit_warps = std::max<uint64_t>(1, budget / std::max<uint64_t>(per_warp, 1));
+    b->mem_budget = (uint64_t)(al->mem_total * 0.55);
+    const uint64_t fit_warps = std::max<uint64_t>(1, b->mem_budget / std::max<uint64_t>(per_warp, 1));
     max_blocks = std::max<uint64_t>(1, std::min<uint64_t>(max_blocks, fit_warps / wpb));
   }
   uint64_t want = (n + wpb * spw - 1) / (wpb * spw);
@@ -510,6 +522,8 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
     b->cigar_cap = std::min<uint64_t>(cap, std::max<uint64_t>(limit, 1024));
     TRY(dmalloc((void**)&b->d_cigar, b->cigar_cap * 4));
     TRY(dmalloc((void**)&b->d_cigar_used, 8));
+    TRY(dmalloc((void**)&b->d_overflow_list, std::max<size_t>(n, 1) * 4));
+    TRY(dmalloc((void**)&b->d_overflow_n, 4));
   }
   if (getenv("BA_STEP_LOG") && n == 1) {
     TRY(dmalloc((void**)&b->d_steplog, (size_t)(1 << 20) * sizeof(StepLog)));
@@ -542,12 +556,13 @@ static Params make_params(const BaBatch* b) {
   P.min_size = b->min_size; P.max_size = b->max_size; P.x_drop = b->cfg.x_drop;
   P.flags = b->cfg.flags; P.scoring = prof ? (int)kProfile : b->cfg.scoring;
   P.out = b->d_out; P.ticket = b->d_ticket;
-  P.ckpt = b->d_ckpt; P.slots_per_warp = b->slots_per_warp; P.use_fast = b->use_fast ? 1u : 0u;
+  P.ckpt = b->d_ckpt; P.slots_per_warp = b->slots_per_warp; P.fast_block = (uint32_t)(8 * b->fast_rows);
   P.trace_words = b->d_trace; P.trace_words_per_warp = b->trace_words_per_warp;
   P.rects = b->d_rects; P.rects_per_warp = b->rects_per_warp;
   P.run_scratch = b->d_runs; P.runs_per_warp = b->runs_per_warp;
   P.cigar_stream = b->d_cigar; P.cigar_cap = b->cigar_cap; P.cigar_used = b->d_cigar_used;
   P.cigar_eq = b->cfg.cigar_eq ? 1u : 0u;
+  P.overflow_list = b->d_overflow_list; P.overflow_n = b->d_overflow_n;
   P.step_log = b->d_steplog; P.step_log_cap = b->d_steplog ? (1u << 20) : 0u; P.step_log_n = b->d_steplog_n;
   return P;
 }
@@ -563,15 +578,51 @@ extern "C" int ba_batch_run(BaBatch* b, BaStats* stats) {
   int rc;
   if ((rc = dzero(b->d_ticket, 4, st))) return BA_ERR_CUDA;
   if (b->d_cigar_used && (rc = dzero(b->d_cigar_used, 8, st))) return BA_ERR_CUDA;
+  if (b->d_overflow_n && (rc = dzero(b->d_overflow_n, 4, st))) return BA_ERR_CUDA;
   if (b->d_steplog_n && (rc = dzero(b->d_steplog_n, 4, st))) return BA_ERR_CUDA;
   b->downloaded = false;
   float ms = 0;
+  uint32_t launches = 0;
   if (b->n) {
 #ifndef BA_EMU
     cudaEventRecord(al->ev0, st);
 #endif
-    rc = launch_dispatch(P.scoring, P.flags, P, b->blocks, b->wpb, b->smem_bytes, st);
+    rc = launch_dispatch(P.scoring, P.flags, b->fast_rows, P, b->blocks, b->wpb, b->smem_bytes, st);
     if (rc) return rc == 1 ? BA_ERR_CUDA : rc;
+    launches++;
+    // second pass for alignments whose (deliberately small) trace arena overflowed: worst-case arenas
+    if (b->d_overflow_n && b->trace_words_per_warp < b->trace_words_bound) {
+      uint32_t n_over = 0;
+      if (d2h(&n_over, b->d_overflow_n, 4, st) || dsync(st)) return BA_ERR_CUDA;
+      if (n_over) {
+        const uint64_t spw = b->slots_per_warp;
+        const uint64_t per_warp = spw * (b->trace_words_bound * 4 + (uint64_t)b->rects_per_warp * sizeof(Rect)) + (uint64_t)b->runs_per_warp * 4;
+        const uint64_t fit_warps = std::max<uint64_t>(1, b->mem_budget / std::max<uint64_t>(per_warp, 1));
+        uint64_t blocks2 = std::max<uint64_t>(1, std::min<uint64_t>(b->max_blocks_hw, fit_warps / b->wpb));
+        blocks2 = std::min<uint64_t>(blocks2, (n_over + b->wpb * spw - 1) / (b->wpb * spw));
+        const uint64_t nslots2 = blocks2 * b->wpb * spw;
+        dfree(b->d_trace); b->d_trace = nullptr;
+        dfree(b->d_rects); b->d_rects = nullptr;
+        if (dmalloc((void**)&b->d_trace, nslots2 * b->trace_words_bound * 4)) return BA_ERR_NOMEM;
+        if (dmalloc((void**)&b->d_rects, nslots2 * (uint64_t)b->rects_per_warp * sizeof(Rect))) return BA_ERR_NOMEM;
+        if ((uint64_t)b->blocks < blocks2) {   // per-slot / per-warp scratch of the first pass is too small: regrow
+          const size_t msz = b->max_size < 32 ? 32 : b->max_size;
+          dfree(b->d_ckpt); dfree(b->d_runs); b->d_ckpt = nullptr; b->d_runs = nullptr;
+          if (dmalloc((void**)&b->d_ckpt, nslots2 * 4 * msz * sizeof(int16_t))) return BA_ERR_NOMEM;
+          if (dmalloc((void**)&b->d_runs, blocks2 * b->wpb * (uint64_t)b->runs_per_warp * 4)) return BA_ERR_NOMEM;
+        }
+        b->trace_words_per_warp = b->trace_words_bound;
+        b->blocks = (int)std::max<uint64_t>((uint64_t)b->blocks, blocks2);
+        Params P2 = make_params(b);
+        P2.order = b->d_overflow_list;     // the kernel appends to this list only on overflow, which cannot
+        P2.n_pairs = n_over;               // happen with worst-case arenas, so reading it as the work list is safe
+        P2.overflow_list = nullptr; P2.overflow_n = nullptr;
+        if (dzero(b->d_ticket, 4, st)) return BA_ERR_CUDA;
+        rc = launch_dispatch(P2.scoring, P2.flags, b->fast_rows, P2, (int)blocks2, b->wpb, b->smem_bytes, st);
+        if (rc) return rc == 1 ? BA_ERR_CUDA : rc;
+        launches++;
+      }
+    }
 #ifndef BA_EMU
     cudaEventRecord(al->ev1, st);
     cudaError_t e = cudaEventSynchronize(al->ev1);
@@ -581,7 +632,7 @@ extern "C" int ba_batch_run(BaBatch* b, BaStats* stats) {
   }
   if (stats) {
     memset(stats, 0, sizeof(*stats));
-    stats->kernel_ms = ms; stats->pack_ms = b->pack_ms; stats->kernel_launches = b->n ? 1 : 0;
+    stats->kernel_ms = ms; stats->pack_ms = b->pack_ms; stats->kernel_launches = launches;
   }
   return BA_OK;
 }

@@ -73,7 +73,8 @@ struct Params {
   uint32_t* ticket;              // work counter
   // per-warp scratch in global memory
   // a "slot" is one alignment in flight: 1 per warp, or 4 per warp when the block-32 fast phase is on
-  uint32_t slots_per_warp, use_fast;
+  uint32_t slots_per_warp;
+  uint32_t fast_block;           // 0: fast phase off; 32 / 64: block size served by the fast phase (== min_size)
   int16_t* ckpt;                 // 4 * max(max_size, 32) int16 per slot: checkpoint borders
   uint32_t* trace_words; uint64_t trace_words_per_warp;   // per slot (name kept: per-"warp" arena of v0)
   Rect* rects; uint32_t rects_per_warp;                   // per slot
@@ -81,6 +82,8 @@ struct Params {
   // cigar output stream: runs packed as (len << 4) | op, allocated with atomicAdd on *cigar_used
   uint32_t* cigar_stream; uint64_t cigar_cap; unsigned long long* cigar_used;
   uint32_t cigar_eq;
+  // pairs whose trace arena overflowed (they are re-run with worst-case arenas)
+  uint32_t* overflow_list; uint32_t* overflow_n;
   // debug
   StepLog* step_log; uint32_t step_log_cap; uint32_t* step_log_n;   // only honoured for n_pairs == 1
 };

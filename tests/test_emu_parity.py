@@ -8,6 +8,7 @@ import parity
 from block_aligner_b200 import api, workloads
 
 P = workloads.params
+N_MIN64 = 12
 NOISY = dict(sub_rate=0.05, ins_rate=0.04, del_rate=0.04, long_indel_mean=1.5, long_indel_len=50.0)
 
 
@@ -23,6 +24,16 @@ def test_dna(env, flags, size):
     w = dict(scoring=api.SCORING_NUC, matrix="NW1", gaps=(-2, -1), size=size, x_drop=50, flags=flags, stream=11,
              gen=P(alphabet=0, len_dist=0, len_min=300, len_max=1500, suffix_len=150, **NOISY))
     assert parity.check_workload(*env, w, 12, seed=7 + flags) == 0
+
+
+@pytest.mark.parametrize("flags", [0, api.XDROP, api.TRACE, api.TRACE | api.XDROP])
+@pytest.mark.parametrize("size", [(64, 64), (64, 256), (64, 2048)])
+def test_dna_min64(env, flags, size):
+    """min block 64: the fast phase with 8 rows per lane (C5 shape)"""
+    w = dict(scoring=api.SCORING_NUC, matrix=(2, -4), gaps=(-6, -2), size=size, x_drop=100, flags=flags, stream=21,
+             gen=P(alphabet=0, len_dist=0, len_min=300, len_max=2500, suffix_len=150, big_indel_prob=0.5, big_indel_min=80,
+                   big_indel_max=300, **NOISY))
+    assert parity.check_workload(*env, w, N_MIN64, seed=11 + flags) == 0
 
 
 @pytest.mark.parametrize("flags", [0, api.TRACE, api.TRACE | api.XDROP])
@@ -67,3 +78,17 @@ def test_baseline_configs_small_sample(env, name):
     """The BASELINE.json workloads themselves, first few pairs (full sizes run on the GPU)."""
     w = workloads.WORKLOADS[name]
     assert parity.check_workload(*env, w, 4 if "C2" in name else 16) == 0
+
+
+def test_trace_arena_overflow_is_retried(env):
+    """Unrelated sequences keep the block at its maximum size, which overflows the (deliberately small) first-pass
+    trace arenas; those pairs are re-run with worst-case arenas and must still be bit-exact."""
+    lib, al = env
+    w = dict(scoring=api.SCORING_NUC, matrix="NW1", gaps=(-2, -1), size=(32, 512), x_drop=0, flags=api.TRACE, stream=31,
+             gen=P(alphabet=0, len_dist=0, len_min=1500, len_max=2500, sub_rate=0.75, ins_rate=0.0, del_rate=0.0))
+    qa, qo, ra, ro = workloads.generate(w["gen"], 6, stream=31)
+    m = workloads.matrix_of(lib, w)
+    got = parity.run_lib(lib, al, w["scoring"], m, w["gaps"], w["size"], 0, api.TRACE, True, qa, qo, ra, ro)
+    assert got[3].kernel_launches == 2, "expected the overflow retry pass to run"
+    exp = parity.oracle_batch(w["scoring"], m, w["gaps"], w["size"], 0, api.TRACE, True, qa, qo, ra, ro)
+    assert parity.compare("overflow-retry", got, exp) == 0

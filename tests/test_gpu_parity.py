@@ -11,6 +11,7 @@ from block_aligner_b200 import api, workloads
 
 pytestmark = pytest.mark.gpu
 P = workloads.params
+N_MIN64 = 400
 NOISY = dict(sub_rate=0.05, ins_rate=0.04, del_rate=0.04, long_indel_mean=1.5, long_indel_len=50.0)
 
 
@@ -34,6 +35,16 @@ def test_dna(env, flags, size):
     w = dict(scoring=api.SCORING_NUC, matrix="NW1", gaps=(-2, -1), size=size, x_drop=50, flags=flags, stream=11,
              gen=P(alphabet=0, len_dist=0, len_min=300, len_max=3000, suffix_len=150, **NOISY))
     assert parity.check_workload(*env, w, 600, seed=7 + flags) == 0
+
+
+@pytest.mark.parametrize("flags", [0, api.XDROP, api.TRACE, api.TRACE | api.XDROP])
+@pytest.mark.parametrize("size", [(64, 64), (64, 256), (64, 2048)])
+def test_dna_min64(env, flags, size):
+    """min block 64: the fast phase with 8 rows per lane (C5 shape)"""
+    w = dict(scoring=api.SCORING_NUC, matrix=(2, -4), gaps=(-6, -2), size=size, x_drop=100, flags=flags, stream=21,
+             gen=P(alphabet=0, len_dist=0, len_min=300, len_max=2500, suffix_len=150, big_indel_prob=0.5, big_indel_min=80,
+                   big_indel_max=300, **NOISY))
+    assert parity.check_workload(*env, w, N_MIN64, seed=11 + flags) == 0
 
 
 @pytest.mark.parametrize("flags", [0, api.XDROP, api.TRACE, api.TRACE | api.XDROP])
@@ -108,3 +119,17 @@ def test_results_independent_of_batch_order_and_reuse(env):
     r1 = parity.run_lib(lib, al, w["scoring"], m, w["gaps"], w["size"], w["x_drop"], w["flags"], False, qa, qo, ra, ro)
     r2 = parity.run_lib(lib, al, w["scoring"], m, w["gaps"], w["size"], w["x_drop"], w["flags"], False, qa, qo, ra, ro)
     assert (r1[0] == r2[0]).all() and (r1[1] == r2[1]).all()
+
+
+def test_trace_arena_overflow_is_retried(env):
+    """Unrelated sequences keep the block at its maximum size, which overflows the (deliberately small) first-pass
+    trace arenas; those pairs are re-run with worst-case arenas and must still be bit-exact."""
+    lib, al = env
+    w = dict(scoring=api.SCORING_NUC, matrix="NW1", gaps=(-2, -1), size=(32, 512), x_drop=0, flags=api.TRACE, stream=31,
+             gen=P(alphabet=0, len_dist=0, len_min=1500, len_max=2500, sub_rate=0.75, ins_rate=0.0, del_rate=0.0))
+    qa, qo, ra, ro = workloads.generate(w["gen"], 200, stream=31)
+    m = workloads.matrix_of(lib, w)
+    got = parity.run_lib(lib, al, w["scoring"], m, w["gaps"], w["size"], 0, api.TRACE, True, qa, qo, ra, ro)
+    assert got[3].kernel_launches == 2, "expected the overflow retry pass to run"
+    exp = parity.oracle_batch(w["scoring"], m, w["gaps"], w["size"], 0, api.TRACE, True, qa, qo, ra, ro)
+    assert parity.compare("overflow-retry", got, exp) == 0
