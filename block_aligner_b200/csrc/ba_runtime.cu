@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -205,7 +206,55 @@ struct BaAligner {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
 #endif
   int emu_warps = 3;   // emulation: number of (sequentially executed) warps, to exercise per-warp scratch
+  // Device-buffer pool: cudaMalloc / cudaFree cost tens to hundreds of milliseconds for GB-sized buffers
+  // (measured: 26-257 ms and 8-613 ms per call on B200), far more than the 40 ms H2D copy of a 2 GB batch,
+  // so buffers of freed batches are kept and handed to the next batch.
+  std::vector<std::pair<void*, size_t>> pool_free;
+  std::vector<std::pair<void*, size_t>> pool_live;
+  size_t pool_cached = 0;
 };
+
+static int pool_alloc(BaAligner* al, void** p, size_t n) {
+  if (n == 0) n = 1;
+  int best = -1;
+  for (size_t i = 0; i < al->pool_free.size(); i++) {
+    const size_t sz = al->pool_free[i].second;
+    if (sz >= n && sz <= 2 * n + (1 << 20) && (best < 0 || sz < al->pool_free[best].second)) best = (int)i;
+  }
+  if (best >= 0) {
+    *p = al->pool_free[best].first;
+    al->pool_live.push_back(al->pool_free[best]);
+    al->pool_cached -= al->pool_free[best].second;
+    al->pool_free.erase(al->pool_free.begin() + best);
+    return 0;
+  }
+  int rc = dmalloc(p, n);
+  if (rc) {   // out of memory: drop the cache and retry once
+    for (auto& e : al->pool_free) dfree(e.first);
+    al->pool_free.clear(); al->pool_cached = 0;
+#ifndef BA_EMU
+    cudaGetLastError();
+#endif
+    rc = dmalloc(p, n);
+    if (rc) return rc;
+  }
+  al->pool_live.push_back({*p, n});
+  return 0;
+}
+static void pool_release(BaAligner* al, void* p) {
+  if (!p) return;
+  for (size_t i = 0; i < al->pool_live.size(); i++) {
+    if (al->pool_live[i].first == p) {
+      const size_t sz = al->pool_live[i].second;
+      al->pool_live.erase(al->pool_live.begin() + i);
+      // keep at most half of the device memory cached
+      if (al->pool_cached + sz <= al->mem_total / 2) { al->pool_free.push_back({p, sz}); al->pool_cached += sz; }
+      else dfree(p);
+      return;
+    }
+  }
+  dfree(p);   // not from the pool
+}
 
 struct BaBatch {
   BaAligner* al = nullptr;
@@ -283,6 +332,11 @@ extern "C" void ba_destroy(BaAligner* a) {
   if (!a) return;
 #ifndef BA_EMU
   cudaSetDevice(a->device);
+#endif
+  for (auto& e : a->pool_free) dfree(e.first);
+  for (auto& e : a->pool_live) dfree(e.first);   // batches must be freed before the aligner; be forgiving
+  a->pool_free.clear(); a->pool_live.clear();
+#ifndef BA_EMU
   if (a->ev0) cudaEventDestroy(a->ev0);
   if (a->ev1) cudaEventDestroy(a->ev1);
   if (a->ev2) cudaEventDestroy(a->ev2);
@@ -296,10 +350,11 @@ extern "C" void ba_batch_free(BaBatch* b) {
 #ifndef BA_EMU
   cudaSetDevice(b->al->device);
 #endif
-  dfree(b->d_seq); dfree(b->d_qoff); dfree(b->d_roff); dfree(b->d_qlen); dfree(b->d_rlen); dfree(b->d_order);
-  dfree(b->d_matrix); dfree(b->d_profiles); dfree(b->d_prof_arena); dfree(b->d_out); dfree(b->d_ticket);
-  dfree(b->d_ckpt); dfree(b->d_trace); dfree(b->d_rects); dfree(b->d_runs); dfree(b->d_cigar); dfree(b->d_cigar_used);
-  dfree(b->d_steplog); dfree(b->d_steplog_n); dfree(b->d_tb_res); dfree(b->d_overflow_list); dfree(b->d_overflow_n);
+  BaAligner* al = b->al;
+  void* bufs[] = {b->d_seq, b->d_qoff, b->d_roff, b->d_qlen, b->d_rlen, b->d_order, b->d_matrix, b->d_profiles, b->d_prof_arena,
+                  b->d_out, b->d_ticket, b->d_ckpt, b->d_trace, b->d_rects, b->d_runs, b->d_cigar, b->d_cigar_used,
+                  b->d_steplog, b->d_steplog_n, b->d_tb_res, b->d_overflow_list, b->d_overflow_n};
+  for (void* q : bufs) pool_release(al, q);
   delete b;
 }
 
@@ -339,6 +394,8 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
 #ifndef BA_EMU
   if (cudaSetDevice(al->device) != cudaSuccess) return fail(BA_ERR_CUDA, "cudaSetDevice failed");
 #endif
+  const bool timing = getenv("BA_TIMING") != nullptr;
+  const auto tu0 = std::chrono::steady_clock::now();
   BaBatch* b = new BaBatch();
   b->al = al; b->cfg = *cfg; b->n = n; b->min_size = mn; b->max_size = mx;
   dev_stream_t st = al->stream;
@@ -376,22 +433,24 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
     for (size_t k = 0; k < n; k++) order[cnt[nb - 1 - (((uint64_t)ql[k] + rl[k]) >> SH)]++] = (uint32_t)k;
   }
   const uint64_t seq_bytes = pos + 64;
+  const auto tu1 = std::chrono::steady_clock::now();
 
   const uint64_t qraw = n ? q_off[n] - q_off[0] : 0;
   const uint64_t rraw = (!prof && n) ? r_off[n] - r_off[0] : 0;
   uint8_t *d_rawq = nullptr, *d_rawr = nullptr; uint64_t *d_rawqoff = nullptr, *d_rawroff = nullptr; uint32_t* d_err = nullptr;
-  auto free_tmp = [&]() { dfree(d_rawq); dfree(d_rawr); dfree(d_rawqoff); dfree(d_rawroff); dfree(d_err); };
+  auto free_tmp = [&]() { pool_release(al, d_rawq); pool_release(al, d_rawr); pool_release(al, d_rawqoff); pool_release(al, d_rawroff); pool_release(al, d_err); };
 #define TRY2(x) do { int _r = (x); if (_r) { free_tmp(); ba_batch_free(b); return _r == 1 ? BA_ERR_CUDA : _r; } } while (0)
-  TRY2(dmalloc((void**)&b->d_seq, seq_bytes));
-  TRY2(dmalloc((void**)&b->d_qoff, n * 8)); TRY2(dmalloc((void**)&b->d_qlen, n * 4));
-  TRY2(dmalloc((void**)&b->d_roff, n * 8)); TRY2(dmalloc((void**)&b->d_rlen, n * 4));
-  TRY2(dmalloc((void**)&b->d_order, n * 4));
-  TRY2(dmalloc((void**)&b->d_out, n * sizeof(DevResult)));
-  TRY2(dmalloc((void**)&b->d_ticket, 4));
-  TRY2(dmalloc((void**)&d_rawq, qraw)); TRY2(dmalloc((void**)&d_rawqoff, (n + 1) * 8));
-  if (!prof) { TRY2(dmalloc((void**)&d_rawr, rraw)); TRY2(dmalloc((void**)&d_rawroff, (n + 1) * 8)); }
-  TRY2(dmalloc((void**)&d_err, 4));
+  TRY2(pool_alloc(al, (void**)&b->d_seq, seq_bytes));
+  TRY2(pool_alloc(al, (void**)&b->d_qoff, n * 8)); TRY2(pool_alloc(al, (void**)&b->d_qlen, n * 4));
+  TRY2(pool_alloc(al, (void**)&b->d_roff, n * 8)); TRY2(pool_alloc(al, (void**)&b->d_rlen, n * 4));
+  TRY2(pool_alloc(al, (void**)&b->d_order, n * 4));
+  TRY2(pool_alloc(al, (void**)&b->d_out, n * sizeof(DevResult)));
+  TRY2(pool_alloc(al, (void**)&b->d_ticket, 4));
+  TRY2(pool_alloc(al, (void**)&d_rawq, qraw)); TRY2(pool_alloc(al, (void**)&d_rawqoff, (n + 1) * 8));
+  if (!prof) { TRY2(pool_alloc(al, (void**)&d_rawr, rraw)); TRY2(pool_alloc(al, (void**)&d_rawroff, (n + 1) * 8)); }
+  TRY2(pool_alloc(al, (void**)&d_err, 4));
   TRY2(dzero(d_err, 4, st));
+  const auto tu2 = std::chrono::steady_clock::now();
   // offsets are rebased so that the raw arenas start at 0
   std::vector<uint64_t> qo(n + 1), ro(n + 1);
   for (size_t k = 0; k <= n && n; k++) { qo[k] = q_off[k] - q_off[0]; if (!prof) ro[k] = r_off[k] - r_off[0]; }
@@ -409,7 +468,7 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
   // scoring data
   if (!prof) {
     const size_t mb = cfg->scoring == BA_SCORING_NUC ? 128 : (cfg->scoring == BA_SCORING_AA ? 864 : 2);
-    TRY2(dmalloc((void**)&b->d_matrix, mb));
+    TRY2(pool_alloc(al, (void**)&b->d_matrix, mb));
     TRY2(h2d(b->d_matrix, cfg->matrix, mb, st));
   } else {
     // one arena: per profile pos_aa [curr_len*32] then three i16 arrays [curr_len]
@@ -420,7 +479,7 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
       const uint64_t cl = host::profile_curr_len(profiles[k]);
       poff[k] = ppos; ppos += ((cl * 32 + cl * 6) + 63) & ~(uint64_t)63;
     }
-    TRY2(dmalloc((void**)&b->d_prof_arena, ppos + 64));
+    TRY2(pool_alloc(al, (void**)&b->d_prof_arena, ppos + 64));
     std::vector<uint8_t> stage(ppos + 64, 0);
     for (size_t k = 0; k < n; k++) {
       const uint64_t cl = host::profile_curr_len(profiles[k]);
@@ -435,7 +494,7 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
       pd[k].gap_extend = host::profile_gap_extend(profiles[k]);
     }
     TRY2(h2d(b->d_prof_arena, stage.data(), ppos, st));
-    TRY2(dmalloc((void**)&b->d_profiles, n * sizeof(ProfileDev)));
+    TRY2(pool_alloc(al, (void**)&b->d_profiles, n * sizeof(ProfileDev)));
     TRY2(h2d(b->d_profiles, pd.data(), n * sizeof(ProfileDev), st));
     TRY2(dsync(st));
   }
@@ -463,7 +522,13 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
 #ifndef BA_EMU
   if (n) cudaEventElapsedTime(&b->pack_ms, al->ev1, al->ev2);
 #endif
+  const auto tu3 = std::chrono::steady_clock::now();
   free_tmp();
+  const auto tu4 = std::chrono::steady_clock::now();
+  if (timing) {
+    auto d = [](std::chrono::steady_clock::time_point x, std::chrono::steady_clock::time_point y) { return std::chrono::duration<double, std::milli>(y - x).count(); };
+    fprintf(stderr, "upload: host pass %.1f ms, cudaMalloc %.1f ms, h2d+pack %.1f ms, free tmp %.1f ms\n", d(tu0, tu1), d(tu1, tu2), d(tu2, tu3), d(tu3, tu4));
+  }
   if (herr) { ba_batch_free(b); return fail(BA_ERR_CHAR, "sequence byte outside the alphabet of the scoring matrix"); }
 
   // launch geometry and per-slot scratch
@@ -511,23 +576,23 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
   b->blocks = (int)std::min<uint64_t>(want, max_blocks);
   const uint64_t nwarps = (uint64_t)b->blocks * wpb;
   const uint64_t nslots = nwarps * spw;
-  TRY(dmalloc((void**)&b->d_ckpt, nslots * 4 * ms * sizeof(int16_t)));
+  TRY(pool_alloc(al, (void**)&b->d_ckpt, nslots * 4 * ms * sizeof(int16_t)));
   if (trace) {
-    TRY(dmalloc((void**)&b->d_trace, nslots * b->trace_words_per_warp * 4));
-    TRY(dmalloc((void**)&b->d_rects, nslots * (uint64_t)b->rects_per_warp * sizeof(Rect)));
-    TRY(dmalloc((void**)&b->d_runs, nwarps * (uint64_t)b->runs_per_warp * 4));
+    TRY(pool_alloc(al, (void**)&b->d_trace, nslots * b->trace_words_per_warp * 4));
+    TRY(pool_alloc(al, (void**)&b->d_rects, nslots * (uint64_t)b->rects_per_warp * sizeof(Rect)));
+    TRY(pool_alloc(al, (void**)&b->d_runs, nwarps * (uint64_t)b->runs_per_warp * 4));
     uint64_t cap = 0;
     for (size_t k = 0; k < n; k++) cap += (uint64_t)ql[k] + rl[k] + 5;
     const uint64_t limit = (uint64_t)(al->mem_total * 0.15) / 4;
     b->cigar_cap = std::min<uint64_t>(cap, std::max<uint64_t>(limit, 1024));
-    TRY(dmalloc((void**)&b->d_cigar, b->cigar_cap * 4));
-    TRY(dmalloc((void**)&b->d_cigar_used, 8));
-    TRY(dmalloc((void**)&b->d_overflow_list, std::max<size_t>(n, 1) * 4));
-    TRY(dmalloc((void**)&b->d_overflow_n, 4));
+    TRY(pool_alloc(al, (void**)&b->d_cigar, b->cigar_cap * 4));
+    TRY(pool_alloc(al, (void**)&b->d_cigar_used, 8));
+    TRY(pool_alloc(al, (void**)&b->d_overflow_list, std::max<size_t>(n, 1) * 4));
+    TRY(pool_alloc(al, (void**)&b->d_overflow_n, 4));
   }
   if (getenv("BA_STEP_LOG") && n == 1) {
-    TRY(dmalloc((void**)&b->d_steplog, (size_t)(1 << 20) * sizeof(StepLog)));
-    TRY(dmalloc((void**)&b->d_steplog_n, 4));
+    TRY(pool_alloc(al, (void**)&b->d_steplog, (size_t)(1 << 20) * sizeof(StepLog)));
+    TRY(pool_alloc(al, (void**)&b->d_steplog_n, 4));
   }
   *out = b;
   return BA_OK;
@@ -601,15 +666,15 @@ extern "C" int ba_batch_run(BaBatch* b, BaStats* stats) {
         uint64_t blocks2 = std::max<uint64_t>(1, std::min<uint64_t>(b->max_blocks_hw, fit_warps / b->wpb));
         blocks2 = std::min<uint64_t>(blocks2, (n_over + b->wpb * spw - 1) / (b->wpb * spw));
         const uint64_t nslots2 = blocks2 * b->wpb * spw;
-        dfree(b->d_trace); b->d_trace = nullptr;
-        dfree(b->d_rects); b->d_rects = nullptr;
-        if (dmalloc((void**)&b->d_trace, nslots2 * b->trace_words_bound * 4)) return BA_ERR_NOMEM;
-        if (dmalloc((void**)&b->d_rects, nslots2 * (uint64_t)b->rects_per_warp * sizeof(Rect))) return BA_ERR_NOMEM;
+        pool_release(al, b->d_trace); b->d_trace = nullptr;
+        pool_release(al, b->d_rects); b->d_rects = nullptr;
+        if (pool_alloc(al, (void**)&b->d_trace, nslots2 * b->trace_words_bound * 4)) return BA_ERR_NOMEM;
+        if (pool_alloc(al, (void**)&b->d_rects, nslots2 * (uint64_t)b->rects_per_warp * sizeof(Rect))) return BA_ERR_NOMEM;
         if ((uint64_t)b->blocks < blocks2) {   // per-slot / per-warp scratch of the first pass is too small: regrow
           const size_t msz = b->max_size < 32 ? 32 : b->max_size;
-          dfree(b->d_ckpt); dfree(b->d_runs); b->d_ckpt = nullptr; b->d_runs = nullptr;
-          if (dmalloc((void**)&b->d_ckpt, nslots2 * 4 * msz * sizeof(int16_t))) return BA_ERR_NOMEM;
-          if (dmalloc((void**)&b->d_runs, blocks2 * b->wpb * (uint64_t)b->runs_per_warp * 4)) return BA_ERR_NOMEM;
+          pool_release(al, b->d_ckpt); pool_release(al, b->d_runs); b->d_ckpt = nullptr; b->d_runs = nullptr;
+          if (pool_alloc(al, (void**)&b->d_ckpt, nslots2 * 4 * msz * sizeof(int16_t))) return BA_ERR_NOMEM;
+          if (pool_alloc(al, (void**)&b->d_runs, blocks2 * b->wpb * (uint64_t)b->runs_per_warp * 4)) return BA_ERR_NOMEM;
         }
         b->trace_words_per_warp = b->trace_words_bound;
         b->blocks = (int)std::max<uint64_t>((uint64_t)b->blocks, blocks2);
@@ -694,15 +759,25 @@ extern "C" size_t ba_debug_step_log(BaBatch* b, StepLog* out, size_t cap) {
 
 extern "C" int ba_align_batch(BaAligner* a, const BaConfig* cfg, size_t n, const uint8_t* q_bytes, const uint64_t* q_off,
                               const uint8_t* r_bytes, const uint64_t* r_off, AlignResult* out, BaStats* stats) {
+  const bool timing = getenv("BA_TIMING") != nullptr;
+  auto now = []() { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a0, std::chrono::steady_clock::time_point a1) {
+    return std::chrono::duration<double, std::milli>(a1 - a0).count(); };
+  const auto t0 = now();
   BaBatch* b = nullptr;
   int rc = ba_batch_upload(a, cfg, n, q_bytes, q_off, r_bytes, r_off, &b);
   if (rc) return rc;
+  const auto t1 = now();
   rc = ba_batch_run(b, stats);
+  const auto t2 = now();
   if (!rc) rc = ba_batch_download(b, out);
+  const auto t3 = now();
   if (stats && b->downloaded) {
     for (size_t k = 0; k < n; k++) { stats->cells += b->h_out[k].cells; stats->steps += b->h_out[k].steps; if (b->h_out[k].status) stats->n_failed++; }
   }
   ba_batch_free(b);
+  const auto t4 = now();
+  if (timing) fprintf(stderr, "ba_align_batch: upload %.1f ms, run %.1f ms, download %.1f ms, free %.1f ms\n", ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4));
   return rc;
 }
 
@@ -719,7 +794,7 @@ extern "C" int ba_batch_traceback(BaBatch* b, size_t k, size_t query_idx, size_t
   if (cudaSetDevice(al->device) != cudaSuccess) return fail(BA_ERR_CUDA, "cudaSetDevice failed");
 #endif
   Params P = make_params(b);
-  if (!b->d_tb_res && dmalloc((void**)&b->d_tb_res, sizeof(DevResult))) return BA_ERR_CUDA;
+  if (!b->d_tb_res && pool_alloc(al, (void**)&b->d_tb_res, sizeof(DevResult))) return BA_ERR_CUDA;
   if (dzero(b->d_cigar_used, 8, st)) return BA_ERR_CUDA;
   if (launch_traceback(P, (uint32_t)k, (uint32_t)query_idx, (uint32_t)reference_idx, eq, b->d_tb_res, st)) return BA_ERR_CUDA;
   DevResult res;
