@@ -196,6 +196,14 @@ static int occupancy_dispatch(int scoring, int flags, int fr, int wpb, size_t sm
 // -------------------------------------------------------------------------------------------------
 // objects
 // -------------------------------------------------------------------------------------------------
+// one stream + events per batch in flight, so that the H2D copies of one batch overlap the kernel of another
+struct StreamSet {
+  dev_stream_t stream = 0;
+#ifndef BA_EMU
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr;
+#endif
+};
+
 struct BaAligner {
   int device = 0;
   dev_stream_t stream = 0;
@@ -209,10 +217,21 @@ struct BaAligner {
   // Device-buffer pool: cudaMalloc / cudaFree cost tens to hundreds of milliseconds for GB-sized buffers
   // (measured: 26-257 ms and 8-613 ms per call on B200), far more than the 40 ms H2D copy of a 2 GB batch,
   // so buffers of freed batches are kept and handed to the next batch.
+  std::vector<struct StreamSet> streams_free;
   std::vector<std::pair<void*, size_t>> pool_free;
   std::vector<std::pair<void*, size_t>> pool_live;
   size_t pool_cached = 0;
 };
+
+static int streams_acquire(BaAligner* al, StreamSet* ss) {
+  if (!al->streams_free.empty()) { *ss = al->streams_free.back(); al->streams_free.pop_back(); return 0; }
+#ifndef BA_EMU
+  CK(cudaStreamCreateWithFlags(&ss->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&ss->ev0)); CK(cudaEventCreate(&ss->ev1)); CK(cudaEventCreate(&ss->evp0)); CK(cudaEventCreate(&ss->evp1));
+#endif
+  return 0;
+}
+static void streams_release(BaAligner* al, const StreamSet& ss) { al->streams_free.push_back(ss); }
 
 static int pool_alloc(BaAligner* al, void** p, size_t n) {
   if (n == 0) n = 1;
@@ -283,6 +302,8 @@ struct BaBatch {
   DevResult* d_tb_res = nullptr;
   float pack_ms = 0;
   bool downloaded = false;
+  StreamSet ss; bool has_ss = false;
+  bool launched = false; uint32_t launches = 0;
 };
 
 static bool pow2(uint64_t x) { return x && !(x & (x - 1)); }
@@ -333,6 +354,12 @@ extern "C" void ba_destroy(BaAligner* a) {
 #ifndef BA_EMU
   cudaSetDevice(a->device);
 #endif
+#ifndef BA_EMU
+  for (auto& ss : a->streams_free) {
+    cudaStreamDestroy(ss.stream); cudaEventDestroy(ss.ev0); cudaEventDestroy(ss.ev1); cudaEventDestroy(ss.evp0); cudaEventDestroy(ss.evp1);
+  }
+#endif
+  a->streams_free.clear();
   for (auto& e : a->pool_free) dfree(e.first);
   for (auto& e : a->pool_live) dfree(e.first);   // batches must be freed before the aligner; be forgiving
   a->pool_free.clear(); a->pool_live.clear();
@@ -355,6 +382,7 @@ extern "C" void ba_batch_free(BaBatch* b) {
                   b->d_out, b->d_ticket, b->d_ckpt, b->d_trace, b->d_rects, b->d_runs, b->d_cigar, b->d_cigar_used,
                   b->d_steplog, b->d_steplog_n, b->d_tb_res, b->d_overflow_list, b->d_overflow_n};
   for (void* q : bufs) pool_release(al, q);
+  if (b->has_ss) { dsync(b->ss.stream); streams_release(al, b->ss); }
   delete b;
 }
 
@@ -398,7 +426,9 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
   const auto tu0 = std::chrono::steady_clock::now();
   BaBatch* b = new BaBatch();
   b->al = al; b->cfg = *cfg; b->n = n; b->min_size = mn; b->max_size = mx;
-  dev_stream_t st = al->stream;
+  if (streams_acquire(al, &b->ss)) { delete b; return BA_ERR_CUDA; }
+  b->has_ss = true;
+  dev_stream_t st = b->ss.stream;
   const uint32_t pad = mx + 32;
 
   // host pass: lengths, padded offsets, processing order (longest first)
@@ -454,9 +484,6 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
   // offsets are rebased so that the raw arenas start at 0
   std::vector<uint64_t> qo(n + 1), ro(n + 1);
   for (size_t k = 0; k <= n && n; k++) { qo[k] = q_off[k] - q_off[0]; if (!prof) ro[k] = r_off[k] - r_off[0]; }
-#ifndef BA_EMU
-  CUDA_OK(cudaEventRecord(al->ev0, st));
-#endif
   if (n) {
     TRY2(h2d(d_rawq, q_bytes + q_off[0], qraw, st)); TRY2(h2d(d_rawqoff, qo.data(), (n + 1) * 8, st));
     if (!prof) { TRY2(h2d(d_rawr, r_bytes + r_off[0], rraw, st)); TRY2(h2d(d_rawroff, ro.data(), (n + 1) * 8, st)); }
@@ -510,17 +537,17 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
     const int threads = 256;
     const uint64_t nseq = prof ? n : 2 * n;
     const int blocks = (int)std::min<uint64_t>((nseq * 32 + threads - 1) / threads, (uint64_t)al->sm_count * 16);
-    CUDA_OK(cudaEventRecord(al->ev1, st));
+    CUDA_OK(cudaEventRecord(b->ss.evp0, st));
     ba_pack_kernel<<<blocks, threads, 0, st>>>(pa);
     if (cudaGetLastError() != cudaSuccess) { free_tmp(); ba_batch_free(b); return fail(BA_ERR_CUDA, "pack kernel launch failed"); }
-    CUDA_OK(cudaEventRecord(al->ev2, st));
+    CUDA_OK(cudaEventRecord(b->ss.evp1, st));
 #endif
   }
   uint32_t herr = 0;
   TRY2(d2h(&herr, d_err, 4, st));
   TRY2(dsync(st));
 #ifndef BA_EMU
-  if (n) cudaEventElapsedTime(&b->pack_ms, al->ev1, al->ev2);
+  if (n) cudaEventElapsedTime(&b->pack_ms, b->ss.evp0, b->ss.evp1);
 #endif
   const auto tu3 = std::chrono::steady_clock::now();
   free_tmp();
@@ -632,30 +659,42 @@ static Params make_params(const BaBatch* b) {
   return P;
 }
 
-extern "C" int ba_batch_run(BaBatch* b, BaStats* stats) {
+// Launch the alignment kernel of a resident batch on the batch's own stream (no host synchronisation).
+static int batch_launch(BaBatch* b) {
   if (!b) return fail(BA_ERR_ARG, "batch is null");
   BaAligner* al = b->al;
-  dev_stream_t st = al->stream;
+  dev_stream_t st = b->ss.stream;
 #ifndef BA_EMU
   if (cudaSetDevice(al->device) != cudaSuccess) return fail(BA_ERR_CUDA, "cudaSetDevice failed");
 #endif
   Params P = make_params(b);
-  int rc;
-  if ((rc = dzero(b->d_ticket, 4, st))) return BA_ERR_CUDA;
-  if (b->d_cigar_used && (rc = dzero(b->d_cigar_used, 8, st))) return BA_ERR_CUDA;
-  if (b->d_overflow_n && (rc = dzero(b->d_overflow_n, 4, st))) return BA_ERR_CUDA;
-  if (b->d_steplog_n && (rc = dzero(b->d_steplog_n, 4, st))) return BA_ERR_CUDA;
+  if (dzero(b->d_ticket, 4, st)) return BA_ERR_CUDA;
+  if (b->d_cigar_used && dzero(b->d_cigar_used, 8, st)) return BA_ERR_CUDA;
+  if (b->d_overflow_n && dzero(b->d_overflow_n, 4, st)) return BA_ERR_CUDA;
+  if (b->d_steplog_n && dzero(b->d_steplog_n, 4, st)) return BA_ERR_CUDA;
   b->downloaded = false;
-  float ms = 0;
-  uint32_t launches = 0;
+  b->launches = 0;
   if (b->n) {
 #ifndef BA_EMU
-    cudaEventRecord(al->ev0, st);
+    cudaEventRecord(b->ss.ev0, st);
 #endif
-    rc = launch_dispatch(P.scoring, P.flags, b->fast_rows, P, b->blocks, b->wpb, b->smem_bytes, st);
+    int rc = launch_dispatch(P.scoring, P.flags, b->fast_rows, P, b->blocks, b->wpb, b->smem_bytes, st);
     if (rc) return rc == 1 ? BA_ERR_CUDA : rc;
-    launches++;
-    // second pass for alignments whose (deliberately small) trace arena overflowed: worst-case arenas
+    b->launches++;
+  }
+  b->launched = true;
+  return BA_OK;
+}
+
+// Wait for a launched batch; re-run alignments whose (deliberately small) trace arena overflowed with
+// worst-case arenas; report the device time between the first launch and the last completion.
+static int batch_wait(BaBatch* b, BaStats* stats) {
+  if (!b || !b->launched) return fail(BA_ERR_ARG, "batch was not launched");
+  BaAligner* al = b->al;
+  dev_stream_t st = b->ss.stream;
+  float ms = 0;
+  int rc;
+  if (b->n) {
     if (b->d_overflow_n && b->trace_words_per_warp < b->trace_words_bound) {
       uint32_t n_over = 0;
       if (d2h(&n_over, b->d_overflow_n, 4, st) || dsync(st)) return BA_ERR_CUDA;
@@ -685,27 +724,34 @@ extern "C" int ba_batch_run(BaBatch* b, BaStats* stats) {
         if (dzero(b->d_ticket, 4, st)) return BA_ERR_CUDA;
         rc = launch_dispatch(P2.scoring, P2.flags, b->fast_rows, P2, (int)blocks2, b->wpb, b->smem_bytes, st);
         if (rc) return rc == 1 ? BA_ERR_CUDA : rc;
-        launches++;
+        b->launches++;
       }
     }
 #ifndef BA_EMU
-    cudaEventRecord(al->ev1, st);
-    cudaError_t e = cudaEventSynchronize(al->ev1);
+    cudaEventRecord(b->ss.ev1, st);
+    cudaError_t e = cudaEventSynchronize(b->ss.ev1);
     if (e != cudaSuccess) { cuda_fail(e, "alignment kernel"); return BA_ERR_CUDA; }
-    cudaEventElapsedTime(&ms, al->ev0, al->ev1);
+    cudaEventElapsedTime(&ms, b->ss.ev0, b->ss.ev1);
 #endif
   }
+  b->launched = false;
   if (stats) {
     memset(stats, 0, sizeof(*stats));
-    stats->kernel_ms = ms; stats->pack_ms = b->pack_ms; stats->kernel_launches = launches;
+    stats->kernel_ms = ms; stats->pack_ms = b->pack_ms; stats->kernel_launches = b->launches;
   }
   return BA_OK;
+}
+
+extern "C" int ba_batch_run(BaBatch* b, BaStats* stats) {
+  int rc = batch_launch(b);
+  if (rc) return rc;
+  return batch_wait(b, stats);
 }
 
 extern "C" int ba_batch_download(BaBatch* b, AlignResult* out) {
   if (!b) return fail(BA_ERR_ARG, "batch is null");
   BaAligner* al = b->al;
-  dev_stream_t st = al->stream;
+  dev_stream_t st = b->ss.stream;
 #ifndef BA_EMU
   if (cudaSetDevice(al->device) != cudaSuccess) return fail(BA_ERR_CUDA, "cudaSetDevice failed");
 #endif
@@ -751,33 +797,60 @@ extern "C" int ba_batch_pair_stats(const BaBatch* b, size_t k, uint64_t* cells, 
 extern "C" size_t ba_debug_step_log(BaBatch* b, StepLog* out, size_t cap) {
   if (!b || !b->d_steplog) return 0;
   uint32_t n = 0;
-  d2h(&n, b->d_steplog_n, 4, b->al->stream); dsync(b->al->stream);
+  d2h(&n, b->d_steplog_n, 4, b->ss.stream); dsync(b->ss.stream);
   const size_t m = std::min<size_t>(std::min<size_t>(n, cap), 1u << 20);
-  if (m) { d2h(out, b->d_steplog, m * sizeof(StepLog), b->al->stream); dsync(b->al->stream); }
+  if (m) { d2h(out, b->d_steplog, m * sizeof(StepLog), b->ss.stream); dsync(b->ss.stream); }
   return n;
 }
 
+// upload + run + download. Large batches are cut into chunks that are pipelined: every chunk has its own
+// stream, so the H2D copy (and convert/pad) of chunk k+1 overlaps the alignment kernel of chunk k, and the
+// tail of kernel k overlaps the head of kernel k+1.
 extern "C" int ba_align_batch(BaAligner* a, const BaConfig* cfg, size_t n, const uint8_t* q_bytes, const uint64_t* q_off,
                               const uint8_t* r_bytes, const uint64_t* r_off, AlignResult* out, BaStats* stats) {
+  if (!a) return fail(BA_ERR_ARG, "aligner is null");
+  if (n && (!q_off || !r_off)) return fail(BA_ERR_ARG, "null offsets");
   const bool timing = getenv("BA_TIMING") != nullptr;
-  auto now = []() { return std::chrono::steady_clock::now(); };
-  auto ms = [](std::chrono::steady_clock::time_point a0, std::chrono::steady_clock::time_point a1) {
-    return std::chrono::duration<double, std::milli>(a1 - a0).count(); };
-  const auto t0 = now();
-  BaBatch* b = nullptr;
-  int rc = ba_batch_upload(a, cfg, n, q_bytes, q_off, r_bytes, r_off, &b);
-  if (rc) return rc;
-  const auto t1 = now();
-  rc = ba_batch_run(b, stats);
-  const auto t2 = now();
-  if (!rc) rc = ba_batch_download(b, out);
-  const auto t3 = now();
-  if (stats && b->downloaded) {
-    for (size_t k = 0; k < n; k++) { stats->cells += b->h_out[k].cells; stats->steps += b->h_out[k].steps; if (b->h_out[k].status) stats->n_failed++; }
+  const auto t0 = std::chrono::steady_clock::now();
+  size_t K = 1;
+  const uint64_t bytes = n ? (q_off[n] - q_off[0]) + (r_off[n] - r_off[0]) : 0;
+  if (n >= 8192 && bytes >= ((uint64_t)32 << 20)) K = 4;
+  if (const char* e = getenv("BA_PIPELINE_CHUNKS")) K = std::max<size_t>(1, std::min<size_t>((size_t)atoi(e), 64));
+  if (K > n) K = n ? n : 1;
+  // chunk boundaries with roughly equal input bytes
+  std::vector<size_t> cut(K + 1, 0);
+  cut[K] = n;
+  for (size_t c = 1, k = 0; c < K; c++) {
+    const uint64_t target = bytes * c / K;
+    while (k < n && (q_off[k] - q_off[0]) + (r_off[k] - r_off[0]) < target) k++;
+    cut[c] = k;
   }
-  ba_batch_free(b);
-  const auto t4 = now();
-  if (timing) fprintf(stderr, "ba_align_batch: upload %.1f ms, run %.1f ms, download %.1f ms, free %.1f ms\n", ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4));
+  std::vector<BaBatch*> bs(K, nullptr);
+  int rc = BA_OK;
+  BaStats tot;
+  memset(&tot, 0, sizeof(tot));
+  for (size_t c = 0; c < K && !rc; c++) {
+    const size_t lo = cut[c], hi = cut[c + 1];
+    rc = ba_batch_upload(a, cfg, hi - lo, q_bytes, q_off + lo, r_bytes, r_off + lo, &bs[c]);
+    if (!rc) rc = batch_launch(bs[c]);
+  }
+  for (size_t c = 0; c < K; c++) {
+    if (!bs[c]) continue;
+    BaStats st1;
+    if (!rc) rc = batch_wait(bs[c], &st1);
+    if (!rc) rc = ba_batch_download(bs[c], out ? out + cut[c] : nullptr);
+    if (!rc) {
+      tot.kernel_ms += st1.kernel_ms; tot.pack_ms += st1.pack_ms; tot.kernel_launches += st1.kernel_launches + (bs[c]->n ? 1 : 0);
+      for (size_t k = 0; k < bs[c]->n; k++) {
+        tot.cells += bs[c]->h_out[k].cells; tot.steps += bs[c]->h_out[k].steps;
+        if (bs[c]->h_out[k].status) tot.n_failed++;
+      }
+    }
+    ba_batch_free(bs[c]);
+  }
+  if (stats) *stats = tot;
+  if (timing) fprintf(stderr, "ba_align_batch: %zu chunk(s), %.1f ms wall\n", K,
+                      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
   return rc;
 }
 
@@ -789,7 +862,7 @@ extern "C" int ba_batch_traceback(BaBatch* b, size_t k, size_t query_idx, size_t
   if (!b || !(b->cfg.flags & BA_TRACE) || k >= b->n || !b->downloaded) return fail(BA_ERR_ARG, "no trace available");
   if (eq && b->cfg.scoring == BA_SCORING_PROFILE) return fail(BA_ERR_ARG, "cigar_eq needs a reference sequence");
   BaAligner* al = b->al;
-  dev_stream_t st = al->stream;
+  dev_stream_t st = b->ss.stream;
 #ifndef BA_EMU
   if (cudaSetDevice(al->device) != cudaSuccess) return fail(BA_ERR_CUDA, "cudaSetDevice failed");
 #endif

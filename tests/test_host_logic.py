@@ -79,3 +79,24 @@ def test_builtin_matrices_match_reference_layout(env):
     for name in ("BLOSUM45", "BLOSUM50", "BLOSUM80", "BLOSUM90", "PAM100", "PAM120", "PAM160", "PAM200", "PAM250"):
         m = lib.builtin_matrix(name)[1].reshape(27, 32)
         assert (m[:26, :26] == m[:26, :26].T).all() and (m[26] == -128).all()
+
+
+def test_align_batch_pipelined_chunks(env, monkeypatch):
+    """ba_align_batch cuts big batches into pipelined chunks; results must not depend on the cut."""
+    import parity
+    from block_aligner_b200 import workloads
+    lib, al = env
+    w = workloads.WORKLOADS["C2_nanopore_xdrop_10k"]
+    gen = workloads.params(alphabet=0, len_dist=0, len_min=100, len_max=900, sub_rate=0.04, ins_rate=0.04, del_rate=0.04, suffix_len=60)
+    qa, qo, ra, ro = workloads.generate(gen, 37, stream=2)
+    m = workloads.matrix_of(lib, w)
+    ref = parity.run_lib(lib, al, w["scoring"], m, w["gaps"], w["size"], w["x_drop"], w["flags"], False, qa, qo, ra, ro)
+    cfg = al.config(w["scoring"], m, w["gaps"], w["size"], w["x_drop"], w["flags"], False)
+    for chunks in ("1", "3", "64"):
+        monkeypatch.setenv("BA_PIPELINE_CHUNKS", chunks)
+        out = np.zeros(37, dtype=np.dtype([("score", np.int32), ("q", np.uint64), ("r", np.uint64)], align=True))
+        st = api.BaStats()
+        lib.check(lib.L.ba_align_batch(al.h, C.byref(cfg), 37, qa.ctypes.data, qo.ctypes.data, ra.ctypes.data, ro.ctypes.data,
+                                       out.ctypes.data, C.byref(st)))
+        assert (out["score"] == ref[0][:, 0]).all() and (out["q"] == ref[0][:, 1]).all() and (out["r"] == ref[0][:, 2]).all()
+        assert st.cells == int(ref[1].sum()) and st.n_failed == 0
