@@ -174,6 +174,9 @@ def main():
     matrix = workloads.matrix_of(lib, w)
     qa, qo, ra, ro, keep = gen_shard(w, n, first=rank * n, pinned=True)
     cfg = al.config(w["scoring"], matrix, w["gaps"], w["size"], w["x_drop"], w["flags"], bool(w.get("cigar_eq")))
+    profiles = None
+    if w["scoring"] == api.SCORING_PROFILE:
+        profiles = workloads.make_lib_profiles(lib, ra, ro, w["size"][1], seed=1234 + rank)
 
     def barrier():
         if world > 1:
@@ -181,7 +184,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---- value: kernel only, inputs resident ----
-    batch = al.upload(cfg, qa, qo, ra, ro)
+    batch = al.upload(cfg, qa, qo, ra, ro, profiles)
     for _ in range(args.warmup):
         batch.run()
     sampler = ClockSampler(local_rank)
@@ -207,9 +210,15 @@ def main():
     import ctypes as C
     st = api.BaStats()
 
+    parr = (C.c_void_p * n)(*[p.h for p in profiles]) if profiles is not None else None
+
     def e2e_once():
-        lib.check(lib.L.ba_align_batch(al.h, C.byref(cfg), n, qa.ctypes.data, qo.ctypes.data, ra.ctypes.data, ro.ctypes.data,
-                                       out.ctypes.data, C.byref(st)))
+        if profiles is not None:
+            lib.check(lib.L.ba_align_batch_profiles(al.h, C.byref(cfg), n, qa.ctypes.data, qo.ctypes.data, parr,
+                                                    out.ctypes.data, C.byref(st)))
+        else:
+            lib.check(lib.L.ba_align_batch(al.h, C.byref(cfg), n, qa.ctypes.data, qo.ctypes.data, ra.ctypes.data, ro.ctypes.data,
+                                           out.ctypes.data, C.byref(st)))
     e2e_once()
     barrier()
     t1 = time.perf_counter()
@@ -267,7 +276,7 @@ def main():
             "clocks": sampler.summary(), "n_failed_pairs": n_failed,
             "wall_s_timed_region": wall,
         }
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and profiles is None:
             cb = cpu_sample(w, lib, n, args.cpu_seconds)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "alignments_per_s")}
         print(json.dumps(line))

@@ -83,7 +83,7 @@ PART1_DATA = ["NW1", "BLOSUM45", "BLOSUM50", "BLOSUM62", "BLOSUM80", "BLOSUM90",
 PART2_FUNCTIONS = ["ba_error_string", "ba_last_error_message", "ba_create", "ba_destroy", "ba_batch_upload",
                    "ba_batch_upload_profiles", "ba_batch_run", "ba_batch_download", "ba_batch_cigar",
                    "ba_batch_traceback", "ba_batch_total_stats", "ba_batch_pair_stats", "ba_batch_free",
-                   "ba_align_batch", "ba_new_simple_nucmatrix", "ba_set_nucmatrix", "ba_free_nucmatrix",
+                   "ba_align_batch", "ba_align_batch_profiles", "ba_new_simple_nucmatrix", "ba_set_nucmatrix", "ba_free_nucmatrix",
                    "ba_percent_len", "ba_cigar_format", "ba_measure_int_peak"]
 
 
@@ -114,6 +114,7 @@ class Library:
         L.ba_batch_pair_stats.argtypes = [vp, sz, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.ba_batch_free.argtypes = [vp]
         L.ba_align_batch.argtypes = [vp, C.POINTER(BaConfig), sz, vp, vp, vp, vp, vp, C.POINTER(BaStats)]
+        L.ba_align_batch_profiles.argtypes = [vp, C.POINTER(BaConfig), sz, vp, vp, vp, vp, C.POINTER(BaStats)]
         L.ba_new_simple_nucmatrix.restype = vp
         L.ba_new_simple_nucmatrix.argtypes = [i8, i8]
         L.ba_set_nucmatrix.argtypes = [vp, u8, u8, i8]

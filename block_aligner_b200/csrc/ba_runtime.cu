@@ -854,6 +854,21 @@ extern "C" int ba_align_batch(BaAligner* a, const BaConfig* cfg, size_t n, const
   return rc;
 }
 
+// sequence-to-profile counterpart of ba_align_batch (no chunking: profiles are uploaded as one arena)
+extern "C" int ba_align_batch_profiles(BaAligner* a, const BaConfig* cfg, size_t n, const uint8_t* q_bytes, const uint64_t* q_off,
+                                       const AAProfile* const* profiles, AlignResult* out, BaStats* stats) {
+  BaBatch* b = nullptr;
+  int rc = ba_batch_upload_profiles(a, cfg, n, q_bytes, q_off, profiles, &b);
+  if (rc) return rc;
+  rc = ba_batch_run(b, stats);
+  if (!rc) rc = ba_batch_download(b, out);
+  if (!rc && stats) {
+    for (size_t k = 0; k < n; k++) { stats->cells += b->h_out[k].cells; stats->steps += b->h_out[k].steps; if (b->h_out[k].status) stats->n_failed++; }
+  }
+  ba_batch_free(b);
+  return rc;
+}
+
 // Walk the stored trace of pair k back from an arbitrary end position (Trace::cigar / cigar_eq,
 // scan_block.rs:1469-1480). Only valid for the pair that ran last on its warp, i.e. batches of one
 // (the legacy block_cigar_* calls) or pair ids whose warp processed no later pair.

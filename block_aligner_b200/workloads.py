@@ -120,3 +120,25 @@ def pssm_scores(blosum62, consensus, rng):
     base = blosum62.reshape(27, 32)[cons][:, cols].astype(np.int16)
     noise = rng.integers(-1, 2, size=base.shape, dtype=np.int16)
     return np.clip(base + noise, -128, 127).astype(np.int8)
+
+
+def make_lib_profiles(lib, ra, ro, block_size, gap_open=-10, gap_extend=-1, seed=1234):
+    """C4 profiles for the library side: consensus = the reference side of each pair, PSSM = BLOSUM62 row + noise,
+    gap open/close set for positions 1..=len like examples/pssm_bench.rs:67-83 (position 0 keeps -128)."""
+    b62 = lib.builtin_matrix("BLOSUM62")[1]
+    rng = np.random.default_rng(seed)
+    out = []
+    n = len(ro) - 1
+    for k in range(n):
+        cons = ra[int(ro[k]):int(ro[k + 1])].tobytes()
+        p = api.AAProfile(lib, len(cons), block_size, gap_extend)
+        if len(cons):
+            p.set_all(MAP20, pssm_scores(b62, cons, rng))
+        p.set_all_gap_open_C(gap_open)
+        p.set_all_gap_close_C(0)
+        p.set_all_gap_open_R(gap_open)
+        p.set_gap_open_C(0, -128)
+        p.set_gap_close_C(0, -128)
+        p.set_gap_open_R(0, -128)
+        out.append(p)
+    return out

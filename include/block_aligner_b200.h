@@ -184,6 +184,10 @@ int ba_align_batch(BaAligner* a, const BaConfig* cfg, size_t n,
                    const uint8_t* r_bytes, const uint64_t* r_off,
                    AlignResult* out, BaStats* stats);
 
+int ba_align_batch_profiles(BaAligner* a, const BaConfig* cfg, size_t n,
+                            const uint8_t* q_bytes, const uint64_t* q_off,
+                            const struct AAProfile* const* profiles, AlignResult* out, BaStats* stats);
+
 /* Measured integer-ALU roofline denominator (giga i16-cell ops / s) for this device; see DESIGN.md. */
 int ba_measure_int_peak(BaAligner* a, double* giga_ops_per_s);
 
