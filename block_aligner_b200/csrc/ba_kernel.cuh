@@ -88,6 +88,10 @@ struct RectArgs {
   int off_add;                   // just_offset folded into the load of AD/AC
   int rz;                        // relative_zero
   uint32_t* tw;                  // trace words of this rectangle (TRACE only)
+  // extended modes (Block<_, _, LOCAL_START, FREE_QUERY_START_GAPS>; only read by EXT instantiations)
+  bool local;                    // LOCAL_START: every cell is floored at relative_zero (scan_block.rs:1134-1136)
+  bool fqs0;                     // FREE_QUERY_START_GAPS and this rectangle's vectors start at row 0 (:1130)
+  uint32_t* tz;                  // zero-mask words (TRACE && LOCAL_START, scan_block.rs:1184-1187), same indexing as tw
 };
 
 // profile context handed to the rectangle (scan_block.rs:612-783)
@@ -100,7 +104,7 @@ struct ProfArgs {
 // 1 for rectangles up to 128 rows (swept in 32-row chunks) and 8 from 256 rows up (256-row chunks).
 BA_HD int rect_rows_per_lane(int H) { return H >= 256 ? 8 : 1; }
 
-template <int SCORING, bool RIGHT, int R, bool TRACE, bool XDROP>
+template <int SCORING, bool RIGHT, int R, bool TRACE, bool XDROP, bool EXT>
 BA_DEV void place_rect_r(const SeqScorer<(SCORING == kProfile ? kAA : SCORING)>& sc, const ProfArgs& pa,
                          const RectArgs& a, const WarpMem& w, int& bv, unsigned& bkey) {
   constexpr bool PROF = SCORING == kProfile;
@@ -161,9 +165,9 @@ BA_DEV void place_rect_r(const SeqScorer<(SCORING == kProfile ? kAA : SCORING)>&
 
     // per-row tracker: max of value * 16384 + (column + 1); 0 = "no cell >= 0" (D_max starts at MIN = 0)
     int trk[R];
-    unsigned twd[R];
+    unsigned twd[R], zwd[R];
 #pragma unroll
-    for (int k = 0; k < R; k++) { trk[k] = 0; twd[k] = 0; }
+    for (int k = 0; k < R; k++) { trk[k] = 0; twd[k] = 0; zwd[k] = 0; }
 
 #pragma unroll (R >= 8 ? 2 : 1)
     for (int cidx = 0; cidx < a.ncols; cidx++) {
@@ -204,13 +208,15 @@ BA_DEV void place_rect_r(const SeqScorer<(SCORING == kProfile ? kAA : SCORING)>&
         else if (RIGHT) s = (int)wp::ldg(prow_col + rtok[k]);
         else s = (int)wp::ldg(p_row[k] + ctok);
         int d00 = (k == 0) ? up : D10[k - 1];
-        if (origin && cidx == 0 && ch == 0 && k == 0 && lane == 0) { d00 = a.rz; s = 0; }
+        if (ch == 0 && k == 0 && lane == 0 &&
+            ((cidx == 0 && origin && !(EXT && a.local)) || (EXT && a.fqs0))) { d00 = a.rz; s = 0; }   // scan_block.rs:1130-1132
         const int oc = PROF ? (RIGHT ? openC_col : p_openC[k]) : go;
         c11o[k] = sat_add_lo(D10[k], oc);
         c11[k] = wp::viaddmax(C10[k], ge, c11o[k]);
         c11e[k] = c11[k];
         if (PROF && RIGHT) c11e[k] = sat_add(c11[k], closeC_col);   // C11_end (scan_block.rs:694)
         dd[k] = wp::imin(wp::viaddmax(d00, s, c11e[k]), kI16Max);
+        if (EXT && a.local) dd[k] = wp::imax(dd[k], a.rz);
         const int orr = PROF ? (RIGHT ? openR_col : p_openR[k]) : open_r;
         xx[k] = sat_add_lo(dd[k], orr);
         tt[k] = (k == 0) ? xx[0] : wp::viaddmax(tt[k - 1], ge, xx[k]);
@@ -241,6 +247,7 @@ BA_DEV void place_rect_r(const SeqScorer<(SCORING == kProfile ? kAA : SCORING)>&
             nib |= (c11[k] == c11o[k] ? 4u : 0u);
             ebits |= (Rv == xx[k] ? 1u : 0u) << k;
             twd[k] |= nib << c4;
+            if (EXT && a.local) zwd[k] |= (Dn[k] == a.rz ? 1u : 0u) << (cidx & 7);
           }
         } else {
           Dn[k] = wp::vimax3(dd[k], Tn[k], ph[k]);
@@ -264,6 +271,7 @@ BA_DEV void place_rect_r(const SeqScorer<(SCORING == kProfile ? kAA : SCORING)>&
           for (int k = 0; k < R; k++) {
             a.tw[(((size_t)ch * ngroups + cgi) * R + k) * 32 + lane] = twd[k];
             twd[k] = 0;
+            if (EXT && a.local) { a.tz[(((size_t)ch * ngroups + cgi) * R + k) * 32 + lane] = zwd[k]; zwd[k] = 0; }
           }
         }
       }
@@ -306,15 +314,15 @@ BA_DEV void place_rect_r(const SeqScorer<(SCORING == kProfile ? kAA : SCORING)>&
 
 // RIGHT only changes behaviour for profiles (sequence-sequence right/down differ only in which
 // sequence plays which role), so sequence scorers always instantiate RIGHT = true.
-template <int SCORING, bool RIGHT, bool TRACE, bool XDROP>
+template <int SCORING, bool RIGHT, bool TRACE, bool XDROP, bool EXT>
 BA_DEV void place_rect(const SeqScorer<(SCORING == kProfile ? kAA : SCORING)>& sc, const ProfArgs& pa,
                        const RectArgs& a, const WarpMem& w, int& bv, unsigned& bkey) {
   constexpr bool RT = (SCORING == kProfile) ? RIGHT : true;
   bv = 0;                // D_max starts at MIN = 0 (scan_block.rs:1101)
   bkey = 15u << 27;      // "no cell": AVX lane 0 with argmax (0, 0)
   if (a.W == 0 || a.H == 0) return;   // scan_block.rs:1105-1107
-  if (a.H >= 256) place_rect_r<SCORING, RT, 8, TRACE, XDROP>(sc, pa, a, w, bv, bkey);
-  else place_rect_r<SCORING, RT, 1, TRACE, XDROP>(sc, pa, a, w, bv, bkey);
+  if (a.H >= 256) place_rect_r<SCORING, RT, 8, TRACE, XDROP, EXT>(sc, pa, a, w, bv, bkey);
+  else place_rect_r<SCORING, RT, 1, TRACE, XDROP, EXT>(sc, pa, a, w, bv, bkey);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -399,6 +407,7 @@ struct AlnState {
 struct SlotMem {
   int16_t *kDc, *kCc, *kDr, *kRr;     // checkpoint borders (scan_block.rs:1262-1265)
   uint32_t* words; uint64_t words_cap;
+  uint32_t* zwords;                   // zero masks (TRACE && LOCAL_START only)
   Rect* rects; uint32_t rects_cap;
 };
 
@@ -436,13 +445,14 @@ BA_DEV uint32_t* trace_push(AlnState& st, const SlotMem& sm, uint32_t row, uint3
 // origin through the stack of rectangles; runs are produced reversed and run-length merged
 // exactly like Cigar::add (cigar.rs:71-79), then written forward into the output stream.
 // ---------------------------------------------------------------------------------------------
-BA_DEV void traceback_walk(const uint32_t* words, const Rect* rects, uint32_t ridx, uint32_t i, uint32_t j,
-                           const uint8_t* q, const uint8_t* r, bool eq, uint32_t* runs, uint32_t cap,
-                           uint32_t& nruns, uint32_t& bad) {
+BA_DEV void traceback_walk(const uint32_t* words, const uint32_t* zwords, bool fqs, const Rect* rects, uint32_t ridx,
+                           uint32_t i, uint32_t j, const uint8_t* q, const uint8_t* r, bool eq, uint32_t* runs,
+                           uint32_t cap, uint32_t& nruns, uint32_t& bad) {
   int table = 0;  // 0 = D, 1 = C, 2 = R
   uint32_t cur_op = 0, cur_len = 0;
   nruns = 0; bad = 0;
-  while ((i > 0 || j > 0) && !bad) {
+  bool stop = false;
+  while ((i > 0 || j > 0) && !bad && !stop) {
     Rect rc;
     for (;;) {   // find the newest rectangle containing (i, j) (scan_block.rs:1578-1590)
       if (ridx == 0) { bad = 1; break; }
@@ -462,10 +472,15 @@ BA_DEV void traceback_walk(const uint32_t* words, const Rect* rects, uint32_t ri
     const int tabA = rc.right ? 1 : 2, tabB = rc.right ? 2 : 1;
     const uint32_t opA = rc.right ? 5u : 4u, opB = rc.right ? 4u : 5u;   // D : I
     while (i >= rc.row && j >= rc.col && (i > 0 || j > 0)) {
+      // FREE_QUERY_START_GAPS: stop on row 0, which always lies in right rectangles (scan_block.rs:1597-1600)
+      if (fqs && rc.right && i == 0) { stop = true; break; }
       const uint32_t v = rc.right ? i - rc.row : j - rc.col;
       const uint32_t c = rc.right ? j - rc.col : i - rc.row;
       const uint32_t ch = v / CH, ln = (v % CH) / R, k = v % R;
-      const uint32_t word = tw[(((size_t)ch * ngroups + (c >> 3)) * R + k) * 32 + ln];
+      const size_t widx = (((size_t)ch * ngroups + (c >> 3)) * R + k) * 32 + ln;
+      // LOCAL_START: the alignment starts at a cell equal to relative_zero (scan_block.rs:1606-1612)
+      if (zwords && table == 0 && ((zwords[rc.word_off + widx] >> (c & 7)) & 1u)) { stop = true; break; }
+      const uint32_t word = tw[widx];
       const uint32_t nib = (word >> (4 * (c & 7))) & 15u;
       const uint32_t t = nib & 3u, t2 = nib >> 2;
       uint32_t op; int ntab;
@@ -488,11 +503,12 @@ BA_DEV void traceback_walk(const uint32_t* words, const Rect* rects, uint32_t ri
   if (cur_len) { if (nruns < cap) runs[nruns] = (cur_len << 4) | cur_op; nruns++; }
 }
 
-BA_DEV void emit_cigar(const Params& P, const uint32_t* words, const Rect* rects, uint32_t ridx, uint32_t qi, uint32_t rj,
-                       const uint8_t* q, const uint8_t* r, bool eq, uint32_t* runs, DevResult& res) {
+BA_DEV void emit_cigar(const Params& P, const uint32_t* words, const uint32_t* zwords, bool fqs, const Rect* rects,
+                       uint32_t ridx, uint32_t qi, uint32_t rj, const uint8_t* q, const uint8_t* r, bool eq, uint32_t* runs,
+                       DevResult& res) {
   const int lane = wp::lane_id();
   uint32_t nruns = 0, bad = 0;
-  if (lane == 0) traceback_walk(words, rects, ridx, qi, rj, q, r, eq, runs, P.runs_per_warp, nruns, bad);
+  if (lane == 0) traceback_walk(words, zwords, fqs, rects, ridx, qi, rj, q, r, eq, runs, P.runs_per_warp, nruns, bad);
   nruns = (uint32_t)wp::shfl_idx((int)nruns, 0);
   bad = (uint32_t)wp::shfl_idx((int)bad, 0);
   res.cigar_n = 0; res.cigar_off = 0;
@@ -561,8 +577,9 @@ BA_DEV bool fast_eligible(const Params& P, const AlnState& st) {
 
 template <int SCORING, int FLAGS>
 BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const SlotMem& sm) {
-  constexpr bool TRACE = (FLAGS & kTrace) != 0, XDROP = (FLAGS & kXDrop) != 0;
+  constexpr bool TRACE = (FLAGS & kTrace) != 0, XDROP = (FLAGS & kXDrop) != 0, EXT = (FLAGS & kExt) != 0;
   constexpr bool PROF = SCORING == kProfile;
+  const bool m_local = EXT && (P.ext_flags & kLocalStart), m_fqs = EXT && (P.ext_flags & kFreeQueryStartGaps);
   const int lane = wp::lane_id();
   const uint8_t* q = P.seq + P.q_off[st.pair];
   const uint8_t* r = nullptr;
@@ -622,16 +639,19 @@ BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const Sl
         if (lim < 0) lim = 0;
         if (lim + 1 < a.ncols) a.ncols = lim + 1;
       }
-      a.tw = nullptr;
+      a.tw = nullptr; a.tz = nullptr;
+      a.local = m_local; a.fqs0 = m_fqs && rect_right && a.vec_base == 0;
       if (TRACE && a.W > 0 && a.H >= 0) {
+        const uint32_t woff = st.widx;
+        if (m_local && sm.zwords) a.tz = sm.zwords + woff;
         a.tw = trace_push(st, sm, rect_right ? a.vec_base : a.col_base, rect_right ? a.col_base : a.vec_base, a.W, a.H, rect_right, lane == 0);
       }
       add_cells(st, (uint32_t)(a.W * a.H));
       sc.vec = rect_right ? q : r; sc.col = rect_right ? r : q;
       int pbv = 0; unsigned pkey = 15u << 27;
       if (!st.overflow) {
-        if (PROF && !rect_right) place_rect<SCORING, false, TRACE, XDROP>(sc, pa, a, w, pbv, pkey);
-        else place_rect<SCORING, true, TRACE, XDROP>(sc, pa, a, w, pbv, pkey);
+        if (PROF && !rect_right) place_rect<SCORING, false, TRACE, XDROP, EXT>(sc, pa, a, w, pbv, pkey);
+        else place_rect<SCORING, true, TRACE, XDROP, EXT>(sc, pa, a, w, pbv, pkey);
       }
       if (st.dir == kGrow && part == 0) { gbv = pbv; gbkey = pkey; }
       else { bv = pbv; bkey = pkey; }
@@ -758,7 +778,8 @@ BA_DEV void finish_alignment(const Params& P, const AlnState& st, const WarpMem&
     const uint8_t* q = P.seq + P.q_off[st.pair];
     const uint8_t* r = (SCORING == kProfile) ? nullptr : P.seq + P.r_off[st.pair];
     uint32_t* runs = P.run_scratch + (size_t)warp_global * P.runs_per_warp;
-    emit_cigar(P, sm.words, sm.rects, st.ridx, res.query_idx, res.reference_idx, q, r, P.cigar_eq != 0, runs, res);
+    emit_cigar(P, sm.words, (P.ext_flags & kLocalStart) ? sm.zwords : nullptr, (P.ext_flags & kFreeQueryStartGaps) != 0,
+               sm.rects, st.ridx, res.query_idx, res.reference_idx, q, r, P.cigar_eq != 0, runs, res);
   }
   if (lane == 0) {
     P.out[st.pair] = res;
@@ -1135,10 +1156,11 @@ BA_DEV void bind_slot(const Params& P, uint32_t slot, WarpMem& w, SlotMem& sm, b
   int16_t* g = P.ckpt + (size_t)slot * 4 * ms;
   sm.kDc = g; sm.kCc = g + ms; sm.kDr = g + 2 * ms; sm.kRr = g + 3 * ms;
   w.kDc = sm.kDc; w.kCc = sm.kCc; w.kDr = sm.kDr; w.kRr = sm.kRr;
-  sm.words = nullptr; sm.words_cap = 0; sm.rects = nullptr; sm.rects_cap = 0;
+  sm.words = nullptr; sm.words_cap = 0; sm.zwords = nullptr; sm.rects = nullptr; sm.rects_cap = 0;
   if (trace) {
     sm.words = P.trace_words + (size_t)slot * P.trace_words_per_warp;
     sm.words_cap = P.trace_words_per_warp;
+    if (P.trace_zwords) sm.zwords = P.trace_zwords + (size_t)slot * P.trace_words_per_warp;
     sm.rects = P.rects + (size_t)slot * P.rects_per_warp;
     sm.rects_cap = P.rects_per_warp;
   }
@@ -1244,7 +1266,8 @@ BA_DEV void warp_traceback(const Params& P, uint32_t pair, uint32_t qi, uint32_t
   const uint8_t* q = P.seq + P.q_off[pair];
   const uint8_t* r = P.profiles ? nullptr : P.seq + P.r_off[pair];
   res.status = (uint32_t)kOk;
-  emit_cigar(P, words, rects, res.rect_n, qi, rj, q, r, eq, runs, res);
+  const uint32_t* zwords = ((P.ext_flags & kLocalStart) && P.trace_zwords) ? P.trace_zwords + (size_t)slot * P.trace_words_per_warp : nullptr;
+  emit_cigar(P, words, zwords, (P.ext_flags & kFreeQueryStartGaps) != 0, rects, res.rect_n, qi, rj, q, r, eq, runs, res);
   if (wp::lane_id() == 0) *out1 = res;
 }
 

@@ -171,10 +171,12 @@ static int occupancy(int wpb, size_t smem_bytes, int* blocks_per_sm) {
 #endif
 
 // kernel instantiations: scoring x flags x rows-per-lane of the fast phase (0 = generic phase only)
+// flags 4..7 = kExt | {TRACE, X_DROP}: LOCAL_START / FREE_QUERY_START_GAPS selected at run time, generic phase only
 #define BA_FOR_SEQ(X, S) X(S, 0, 0) X(S, 1, 0) X(S, 2, 0) X(S, 3, 0) X(S, 0, 4) X(S, 1, 4) X(S, 2, 4) X(S, 3, 4) \
-                         X(S, 0, 8) X(S, 1, 8) X(S, 2, 8) X(S, 3, 8)
+                         X(S, 0, 8) X(S, 1, 8) X(S, 2, 8) X(S, 3, 8) X(S, 4, 0) X(S, 5, 0) X(S, 6, 0) X(S, 7, 0)
 #define BA_FOR_KERNELS(X) BA_FOR_SEQ(X, kNuc) BA_FOR_SEQ(X, kAA) BA_FOR_SEQ(X, kByte) \
-  X(kProfile, 0, 0) X(kProfile, 1, 0) X(kProfile, 2, 0) X(kProfile, 3, 0)
+  X(kProfile, 0, 0) X(kProfile, 1, 0) X(kProfile, 2, 0) X(kProfile, 3, 0) \
+  X(kProfile, 4, 0) X(kProfile, 5, 0) X(kProfile, 6, 0) X(kProfile, 7, 0)
 
 static int launch_dispatch(int scoring, int flags, int fr, const Params& P, int blocks, int wpb, size_t smem, dev_stream_t st) {
 #define X(S, F, R) if (scoring == S && flags == F && fr == R) return launch_align<S, F, R>(P, blocks, wpb, smem, st);
@@ -290,6 +292,8 @@ struct BaBatch {
   uint32_t* d_cigar = nullptr; unsigned long long* d_cigar_used = nullptr; uint64_t cigar_cap = 0;
   StepLog* d_steplog = nullptr; uint32_t* d_steplog_n = nullptr;
   uint32_t* d_overflow_list = nullptr; uint32_t* d_overflow_n = nullptr;
+  uint32_t* d_zwords = nullptr;     // zero masks (TRACE && LOCAL_START)
+  int kflags = 0;                   // template FLAGS of the kernel: (flags & 3) | kExt
   uint64_t trace_words_bound = 0;   // worst case per alignment (the reference's Trace::new size)
   uint64_t mem_budget = 0; uint64_t max_blocks_hw = 1;
   // launch geometry
@@ -380,7 +384,7 @@ extern "C" void ba_batch_free(BaBatch* b) {
   BaAligner* al = b->al;
   void* bufs[] = {b->d_seq, b->d_qoff, b->d_roff, b->d_qlen, b->d_rlen, b->d_order, b->d_matrix, b->d_profiles, b->d_prof_arena,
                   b->d_out, b->d_ticket, b->d_ckpt, b->d_trace, b->d_rects, b->d_runs, b->d_cigar, b->d_cigar_used,
-                  b->d_steplog, b->d_steplog_n, b->d_tb_res, b->d_overflow_list, b->d_overflow_n};
+                  b->d_steplog, b->d_steplog_n, b->d_tb_res, b->d_overflow_list, b->d_overflow_n, b->d_zwords};
   for (void* q : bufs) pool_release(al, q);
   if (b->has_ss) { dsync(b->ss.stream); streams_release(al, b->ss); }
   delete b;
@@ -390,7 +394,10 @@ extern "C" void ba_batch_free(BaBatch* b) {
 static int check_config(const BaConfig* cfg, uint32_t* mn, uint32_t* mx) {
   if (!cfg) return fail(BA_ERR_ARG, "cfg is null");
   if (cfg->scoring < 0 || cfg->scoring > 3) return fail(BA_ERR_ARG, "bad scoring kind");
-  if (cfg->flags & ~(BA_TRACE | BA_XDROP)) return fail(BA_ERR_ARG, "unsupported flags");
+  if (cfg->flags & BA_FREE_QUERY_END_GAPS) return fail(BA_ERR_ARG, "FREE_QUERY_END_GAPS is not implemented yet");
+  if (cfg->flags & ~(BA_TRACE | BA_XDROP | BA_LOCAL_START | BA_FREE_QUERY_START_GAPS)) return fail(BA_ERR_ARG, "unsupported flags");
+  if ((cfg->flags & BA_LOCAL_START) && (cfg->flags & BA_FREE_QUERY_START_GAPS))
+    return fail(BA_ERR_ARG, "Cannot set both LOCAL_START and FREE_QUERY_START_GAPS!");   // scan_block.rs:860
   if (cfg->scoring != BA_SCORING_PROFILE) {
     if (!cfg->matrix) return fail(BA_ERR_ARG, "matrix is null");
     if (!(cfg->gaps.open < 0 && cfg->gaps.extend < 0)) return fail(BA_ERR_GAPS, "Gap costs must be negative!");
@@ -560,7 +567,9 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
 
   // launch geometry and per-slot scratch
   // fast phase: four alignments per warp while the block sits at its minimum size (32 or 64)
-  b->fast_rows = (!prof && !getenv("BA_NO_FAST")) ? (mn == 32 ? 4 : (mn == 64 ? 8 : 0)) : 0;
+  const bool ext = (cfg->flags & (BA_LOCAL_START | BA_FREE_QUERY_START_GAPS)) != 0;
+  b->kflags = (cfg->flags & 3) | (ext ? kExt : 0);
+  b->fast_rows = (!prof && !ext && !getenv("BA_NO_FAST")) ? (mn == 32 ? 4 : (mn == 64 ? 8 : 0)) : 0;
   b->slots_per_warp = b->fast_rows ? 4 : 1;
   const size_t wbytes = warp_smem_bytes(mx);
   int wpb = 4;
@@ -568,7 +577,7 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
   if (1024 + wpb * wbytes > al->smem_optin) { ba_batch_free(b); return fail(BA_ERR_SIZE, "max block size does not fit in shared memory"); }
   b->wpb = wpb; b->smem_bytes = 1024 + wpb * wbytes;
   int bps = 1;
-  TRY(occupancy_dispatch(prof ? (int)kProfile : cfg->scoring, cfg->flags, b->fast_rows, wpb, b->smem_bytes, &bps));
+  TRY(occupancy_dispatch(prof ? (int)kProfile : cfg->scoring, b->kflags, b->fast_rows, wpb, b->smem_bytes, &bps));
   if (bps < 1) bps = 1;
   uint64_t max_blocks = (uint64_t)al->sm_count * bps;
 #ifdef BA_EMU
@@ -593,7 +602,8 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
     b->trace_words_per_warp = std::min<uint64_t>(b->trace_words_bound, first);
     b->rects_per_warp = (uint32_t)std::min<uint64_t>(len * 2 + 8, 0x7fffffffu);
     b->runs_per_warp = (uint32_t)std::min<uint64_t>(len + 8, 0x7fffffffu);
-    const uint64_t per_warp = spw * (b->trace_words_per_warp * 4 + (uint64_t)b->rects_per_warp * sizeof(Rect)) + (uint64_t)b->runs_per_warp * 4;
+    const uint64_t zmul = (cfg->flags & BA_LOCAL_START) ? 2 : 1;
+    const uint64_t per_warp = spw * (zmul * b->trace_words_per_warp * 4 + (uint64_t)b->rects_per_warp * sizeof(Rect)) + (uint64_t)b->runs_per_warp * 4;
     b->mem_budget = (uint64_t)(al->mem_total * 0.55);
     const uint64_t fit_warps = std::max<uint64_t>(1, b->mem_budget / std::max<uint64_t>(per_warp, 1));
     max_blocks = std::max<uint64_t>(1, std::min<uint64_t>(max_blocks, fit_warps / wpb));
@@ -606,6 +616,7 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
   TRY(pool_alloc(al, (void**)&b->d_ckpt, nslots * 4 * ms * sizeof(int16_t)));
   if (trace) {
     TRY(pool_alloc(al, (void**)&b->d_trace, nslots * b->trace_words_per_warp * 4));
+    if (cfg->flags & BA_LOCAL_START) TRY(pool_alloc(al, (void**)&b->d_zwords, nslots * b->trace_words_per_warp * 4));
     TRY(pool_alloc(al, (void**)&b->d_rects, nslots * (uint64_t)b->rects_per_warp * sizeof(Rect)));
     TRY(pool_alloc(al, (void**)&b->d_runs, nwarps * (uint64_t)b->runs_per_warp * 4));
     uint64_t cap = 0;
@@ -646,7 +657,8 @@ static Params make_params(const BaBatch* b) {
   P.profiles = b->d_profiles; P.matrix = b->d_matrix;
   P.gap_open = b->cfg.gaps.open; P.gap_extend = b->cfg.gaps.extend;
   P.min_size = b->min_size; P.max_size = b->max_size; P.x_drop = b->cfg.x_drop;
-  P.flags = b->cfg.flags; P.scoring = prof ? (int)kProfile : b->cfg.scoring;
+  P.flags = b->kflags; P.scoring = prof ? (int)kProfile : b->cfg.scoring;
+  P.ext_flags = (uint32_t)(b->cfg.flags & (BA_LOCAL_START | BA_FREE_QUERY_START_GAPS)); P.trace_zwords = b->d_zwords;
   P.out = b->d_out; P.ticket = b->d_ticket;
   P.ckpt = b->d_ckpt; P.slots_per_warp = b->slots_per_warp; P.fast_block = (uint32_t)(8 * b->fast_rows);
   P.trace_words = b->d_trace; P.trace_words_per_warp = b->trace_words_per_warp;
@@ -708,6 +720,10 @@ static int batch_wait(BaBatch* b, BaStats* stats) {
         pool_release(al, b->d_trace); b->d_trace = nullptr;
         pool_release(al, b->d_rects); b->d_rects = nullptr;
         if (pool_alloc(al, (void**)&b->d_trace, nslots2 * b->trace_words_bound * 4)) return BA_ERR_NOMEM;
+        if (b->d_zwords) {
+          pool_release(al, b->d_zwords); b->d_zwords = nullptr;
+          if (pool_alloc(al, (void**)&b->d_zwords, nslots2 * b->trace_words_bound * 4)) return BA_ERR_NOMEM;
+        }
         if (pool_alloc(al, (void**)&b->d_rects, nslots2 * (uint64_t)b->rects_per_warp * sizeof(Rect))) return BA_ERR_NOMEM;
         if ((uint64_t)b->blocks < blocks2) {   // per-slot / per-warp scratch of the first pass is too small: regrow
           const size_t msz = b->max_size < 32 ? 32 : b->max_size;

@@ -15,6 +15,8 @@ constexpr int kMaxBlock = 8192;    // our cap (reference allows < 65535; > 16384
 
 // Block<TRACE, X_DROP, ...> const generics as bit flags (reference: src/scan_block.rs:89)
 enum Flags : int { kTrace = 1, kXDrop = 2, kLocalStart = 4, kFreeQueryStartGaps = 8, kFreeQueryEndGaps = 16 };
+// template-only flag: the instantiation consults Params::ext_flags (LOCAL_START / FREE_QUERY_START_GAPS) at run time
+constexpr int kExt = 4;
 // scoring kinds
 enum Scoring : int { kNuc = 0, kAA = 1, kByte = 2, kProfile = 3 };
 enum Dir : int { kRight = 0, kDown = 1, kGrow = 2 };
@@ -69,6 +71,8 @@ struct Params {
   uint32_t min_size, max_size;   // already clamped to >= kL, powers of two
   int32_t x_drop;
   int32_t flags, scoring;
+  uint32_t ext_flags;            // kLocalStart | kFreeQueryStartGaps (only honoured by kernels instantiated with kExt)
+  uint32_t* trace_zwords;        // zero-mask words per slot (TRACE && LOCAL_START), same stride as trace_words
   DevResult* out;
   uint32_t* ticket;              // work counter
   // per-warp scratch in global memory

@@ -133,3 +133,41 @@ def test_trace_arena_overflow_is_retried(env):
     assert got[3].kernel_launches == 2, "expected the overflow retry pass to run"
     exp = parity.oracle_batch(w["scoring"], m, w["gaps"], w["size"], 0, api.TRACE, True, qa, qo, ra, ro)
     assert parity.compare("overflow-retry", got, exp) == 0
+
+
+@pytest.mark.parametrize("mode", [api.LOCAL_START, api.FREE_QUERY_START_GAPS])
+@pytest.mark.parametrize("flags", [0, api.XDROP, api.TRACE, api.TRACE | api.XDROP])
+@pytest.mark.parametrize("size", [(32, 32), (32, 256), (64, 512)])
+def test_local_start_and_free_query_start_gaps(env, mode, flags, size):
+    """Block<_, _, LOCAL_START> / Block<_, _, false, FREE_QUERY_START_GAPS> (scan_block.rs:1130-1136, 1597-1612)"""
+    w = dict(scoring=api.SCORING_NUC, matrix="NW1", gaps=(-2, -1), size=size, x_drop=60, flags=flags | mode, stream=41,
+             gen=P(alphabet=0, len_dist=0, len_min=200, len_max=1500, suffix_len=120, **NOISY))
+    assert parity.check_workload(*env, w, 300, seed=17 + flags) == 0
+
+
+def test_extended_mode_golden_vectors(env):
+    """scan_block.rs:2171-2211 (the FREE_QUERY_END_GAPS cases of that test are not implemented yet)"""
+    lib, al = env
+    nw1 = lib.builtin_matrix("NW1")[1]
+    T, X, L, F = api.TRACE, api.XDROP, api.LOCAL_START, api.FREE_QUERY_START_GAPS
+    for fl, q, r, xd, exp, cig in [
+            (T | L, b"CCCCCCCCCCAAAAAA", b"TTTTAAAAAA", 0, (6, 16, 10), "6="),
+            (T | X | L, b"CCCCCCCCCCAAAAAACCCCCCCCCCCC", b"TTTTAAAAAATTTTTTT", 100, (6, 16, 10), "6="),
+            (T | F, b"AAAAAA", b"CCCCCCCCCCAAAAAA", 0, (6, 6, 16), "6="),
+            (T | F, b"AAAAAA", b"CCCCCCCCCCAAATAA", 0, (4, 6, 16), "3=1X2=")]:
+        res, cigs, _ = al.align_batch([q], [r], api.SCORING_NUC, nw1, (-2, -1), (32, 32), xd, fl, True)
+        assert res[0] == exp and cigs[0] == cig
+    with pytest.raises(api.BlockAlignerError, match="not implemented"):
+        al.align_batch([b"AAAA"], [b"AAAA"], api.SCORING_NUC, nw1, (-2, -1), (32, 32), 0, api.FREE_QUERY_END_GAPS, False)
+    with pytest.raises(api.BlockAlignerError, match="both"):
+        al.align_batch([b"AAAA"], [b"AAAA"], api.SCORING_NUC, nw1, (-2, -1), (32, 32), 0, L | F, False)
+
+
+@pytest.mark.parametrize("mode", [api.LOCAL_START, api.FREE_QUERY_START_GAPS])
+def test_extended_modes_protein_and_profile(env, mode):
+    w = dict(workloads.WORKLOADS["C3_uniclust_protein_global"])
+    w["flags"], w["x_drop"] = api.TRACE | api.XDROP | mode, 40
+    assert parity.check_workload(*env, w, 300, seed=23) == 0
+    w = dict(workloads.WORKLOADS["C4_seq_to_profile_xdrop"])
+    w["flags"] = api.TRACE | mode
+    assert parity.check_workload(*env, w, 150, size=(32, 128), seed=29) == 0
