@@ -83,7 +83,7 @@ PART1_DATA = ["NW1", "BLOSUM45", "BLOSUM50", "BLOSUM62", "BLOSUM80", "BLOSUM90",
 PART2_FUNCTIONS = ["ba_error_string", "ba_last_error_message", "ba_create", "ba_destroy", "ba_batch_upload",
                    "ba_batch_upload_profiles", "ba_batch_run", "ba_batch_download", "ba_batch_cigar",
                    "ba_batch_traceback", "ba_batch_total_stats", "ba_batch_pair_stats", "ba_batch_free",
-                   "ba_align_batch", "ba_align_batch_profiles", "ba_new_simple_nucmatrix", "ba_set_nucmatrix", "ba_free_nucmatrix",
+                   "ba_align_batch", "ba_align_batch_exp", "ba_align_batch_profiles", "ba_new_simple_nucmatrix", "ba_set_nucmatrix", "ba_free_nucmatrix",
                    "ba_percent_len", "ba_cigar_format", "ba_measure_int_peak"]
 
 
@@ -114,6 +114,7 @@ class Library:
         L.ba_batch_pair_stats.argtypes = [vp, sz, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.ba_batch_free.argtypes = [vp]
         L.ba_align_batch.argtypes = [vp, C.POINTER(BaConfig), sz, vp, vp, vp, vp, vp, C.POINTER(BaStats)]
+        L.ba_align_batch_exp.argtypes = [vp, C.POINTER(BaConfig), sz, vp, vp, vp, vp, vp, vp, vp, C.POINTER(BaStats)]
         L.ba_align_batch_profiles.argtypes = [vp, C.POINTER(BaConfig), sz, vp, vp, vp, vp, C.POINTER(BaStats)]
         L.ba_new_simple_nucmatrix.restype = vp
         L.ba_new_simple_nucmatrix.argtypes = [i8, i8]
@@ -273,6 +274,22 @@ class Aligner:
             return out, cig, b.total_stats()
         finally:
             b.free()
+
+
+def align_batch_exp(al, queries, references, scoring, matrix, gaps, size, target_scores, x_drop=0, flags=0):
+    """Block::align_exp for a batch -> (results, min_size_used with None where the target was never reached)"""
+    qa, qo = concat(queries)
+    ra, ro = concat(references)
+    n = len(queries)
+    cfg = al.config(scoring, matrix, gaps, size, x_drop, flags, False)
+    out = np.zeros(n, dtype=np.dtype([("score", np.int32), ("query_idx", np.uint64), ("reference_idx", np.uint64)], align=True))
+    used = np.zeros(n, dtype=np.uint64)
+    tgt = np.ascontiguousarray(target_scores, dtype=np.int32)
+    st = BaStats()
+    al.lib.check(al.lib.L.ba_align_batch_exp(al.h, C.byref(cfg), n, qa.ctypes.data, qo.ctypes.data, ra.ctypes.data, ro.ctypes.data,
+                                             tgt.ctypes.data, out.ctypes.data, used.ctypes.data, C.byref(st)))
+    res = [(int(r["score"]), int(r["query_idx"]), int(r["reference_idx"])) for r in out]
+    return res, [int(u) if u else None for u in used]
 
 
 class Batch:

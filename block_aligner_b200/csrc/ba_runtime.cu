@@ -870,6 +870,52 @@ extern "C" int ba_align_batch(BaAligner* a, const BaConfig* cfg, size_t n, const
   return rc;
 }
 
+// Block::align_exp (scan_block.rs:884-902) for a batch: every pair is aligned with min block size s = min, 2 min, ...
+// <= max until its score reaches target_score[k]. min_size_used[k] = the size that reached it, 0 = the reference's
+// None; out[k] = the result of the last attempt (what Block::res() returns afterwards).
+extern "C" int ba_align_batch_exp(BaAligner* a, const BaConfig* cfg, size_t n, const uint8_t* q_bytes, const uint64_t* q_off,
+                                  const uint8_t* r_bytes, const uint64_t* r_off, const int32_t* target_score,
+                                  AlignResult* out, uintptr_t* min_size_used, BaStats* stats) {
+  if (!cfg || !target_score || !out || !min_size_used) return fail(BA_ERR_ARG, "null argument");
+  uint32_t mn = 0, mx = 0;
+  int rc = check_config(cfg, &mn, &mx);
+  if (rc) return rc;
+  std::vector<size_t> active(n);
+  for (size_t k = 0; k < n; k++) { active[k] = k; min_size_used[k] = 0; }
+  BaStats tot; memset(&tot, 0, sizeof(tot));
+  for (uint64_t sz = mn; sz <= mx && !active.empty(); sz *= 2) {
+    // compact copy of the still-active pairs
+    const size_t m = active.size();
+    std::vector<uint64_t> qo(m + 1, 0), ro(m + 1, 0);
+    for (size_t t = 0; t < m; t++) {
+      qo[t + 1] = qo[t] + (q_off[active[t] + 1] - q_off[active[t]]);
+      ro[t + 1] = ro[t] + (r_off[active[t] + 1] - r_off[active[t]]);
+    }
+    std::vector<uint8_t> qa(qo[m] + 1), ra(ro[m] + 1);
+    for (size_t t = 0; t < m; t++) {
+      memcpy(qa.data() + qo[t], q_bytes + q_off[active[t]], qo[t + 1] - qo[t]);
+      memcpy(ra.data() + ro[t], r_bytes + r_off[active[t]], ro[t + 1] - ro[t]);
+    }
+    BaConfig c2 = *cfg;
+    c2.size.min = sz; c2.size.max = mx;
+    std::vector<AlignResult> res(m);
+    BaStats st1;
+    rc = ba_align_batch(a, &c2, m, qa.data(), qo.data(), ra.data(), ro.data(), res.data(), &st1);
+    if (rc) return rc;
+    tot.cells += st1.cells; tot.steps += st1.steps; tot.kernel_ms += st1.kernel_ms; tot.pack_ms += st1.pack_ms;
+    tot.kernel_launches += st1.kernel_launches; tot.n_failed += st1.n_failed;
+    std::vector<size_t> next;
+    for (size_t t = 0; t < m; t++) {
+      out[active[t]] = res[t];
+      if (res[t].score >= target_score[active[t]]) min_size_used[active[t]] = (uintptr_t)sz;
+      else next.push_back(active[t]);
+    }
+    active.swap(next);
+  }
+  if (stats) *stats = tot;
+  return BA_OK;
+}
+
 // sequence-to-profile counterpart of ba_align_batch (no chunking: profiles are uploaded as one arena)
 extern "C" int ba_align_batch_profiles(BaAligner* a, const BaConfig* cfg, size_t n, const uint8_t* q_bytes, const uint64_t* q_off,
                                        const AAProfile* const* profiles, AlignResult* out, BaStats* stats) {

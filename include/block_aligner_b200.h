@@ -185,6 +185,11 @@ int ba_align_batch(BaAligner* a, const BaConfig* cfg, size_t n,
                    const uint8_t* r_bytes, const uint64_t* r_off,
                    AlignResult* out, BaStats* stats);
 
+/* Block::align_exp (src/scan_block.rs:884-902) for a batch: retry with doubled min block size until
+ * score >= target_score[k]. min_size_used[k] = the min size that reached the target, 0 = None. */
+int ba_align_batch_exp(BaAligner* a, const BaConfig* cfg, size_t n,
+                       const uint8_t* q_bytes, const uint64_t* q_off, const uint8_t* r_bytes, const uint64_t* r_off,
+                       const int32_t* target_score, AlignResult* out, uintptr_t* min_size_used, BaStats* stats);
 int ba_align_batch_profiles(BaAligner* a, const BaConfig* cfg, size_t n,
                             const uint8_t* q_bytes, const uint64_t* q_off,
                             const struct AAProfile* const* profiles, AlignResult* out, BaStats* stats);

@@ -100,3 +100,32 @@ def test_align_batch_pipelined_chunks(env, monkeypatch):
                                        out.ctypes.data, C.byref(st)))
         assert (out["score"] == ref[0][:, 0]).all() and (out["q"] == ref[0][:, 1]).all() and (out["r"] == ref[0][:, 2]).all()
         assert st.cells == int(ref[1].sum()) and st.n_failed == 0
+
+
+def test_align_exp_matches_reference_loop(env):
+    """ba_align_batch_exp vs the reference's align_exp loop (scan_block.rs:884-902) run on the oracle."""
+    import ora
+    from block_aligner_b200 import workloads
+    lib, al = env
+    gen = workloads.params(alphabet=0, len_dist=0, len_min=300, len_max=1200, sub_rate=0.05, ins_rate=0.03, del_rate=0.03,
+                           big_indel_prob=0.9, big_indel_min=40, big_indel_max=150)
+    qa, qo, ra, ro = workloads.generate(gen, 16, stream=51)
+    qs = [qa[int(qo[k]):int(qo[k + 1])].tobytes() for k in range(16)]
+    rs = [ra[int(ro[k]):int(ro[k + 1])].tobytes() for k in range(16)]
+    nw1 = lib.builtin_matrix("NW1")[1]
+    # targets: the score a 256-wide block finds (so small blocks often miss it)
+    full, _, _ = al.align_batch(qs, rs, api.SCORING_NUC, nw1, (-2, -1), (256, 256))
+    targets = [f[0] for f in full]
+    res, used = api.align_batch_exp(al, qs, rs, api.SCORING_NUC, nw1, (-2, -1), (32, 256), targets)
+    for k in range(16):
+        ob = ora.Block(len(qs[k]), len(rs[k]), 256, 0)
+        q, r = ora.Padded(ora.NUC, qs[k], 256), ora.Padded(ora.NUC, rs[k], 256)
+        exp_used, exp_res, mn = None, None, 32
+        while mn <= 256:
+            exp_res = ob.align(q, r, ora.NUC, ora.nw1(), (-2, -1), (mn, 256), 0)
+            if exp_res[0] >= targets[k]:
+                exp_used = mn
+                break
+            mn *= 2
+        assert res[k] == exp_res and used[k] == exp_used, (k, res[k], exp_res, used[k], exp_used)
+    assert any(u != 32 for u in used), "test inputs should need at least one retry"
