@@ -26,6 +26,11 @@
 #include "ba_types.h"
 #include "ba_warp.cuh"
 
+#ifdef BA_EMU
+// coverage counters of the emulated build (tests assert that the packed path really ran)
+namespace emu_stats { inline uint64_t pk_cells = 0, exact_cells = 0, fast_steps = 0; }
+#endif
+
 namespace ba {
 
 constexpr int kNegBig = -(1 << 28);
@@ -45,6 +50,8 @@ struct WarpMem {
   int32_t *misc;                    // [0..1]: A_old at the row above a chunk (double buffered)
   uint8_t *ecarry;                  // trace bit carried across chunks    [max_size] (only blocks > 256)
   const int8_t *mat;                // staged matrix (smem)
+  const unsigned char* smem0;       // start of the CTA's shared memory (matrix + packed-path tables)
+  uint32_t* fr;                     // packed path: bottom-row staging, 8 words per alignment group [64]
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -325,6 +332,10 @@ BA_DEV void place_rect(const SeqScorer<(SCORING == kProfile ? kAA : SCORING)>& s
   else place_rect_r<SCORING, RT, 1, TRACE, XDROP, EXT>(sc, pa, a, w, bv, bkey);
 }
 
+}  // namespace ba
+#include "ba_packed.cuh"
+namespace ba {
+
 // ---------------------------------------------------------------------------------------------
 // Border helpers
 // ---------------------------------------------------------------------------------------------
@@ -575,6 +586,26 @@ BA_DEV bool fast_eligible(const Params& P, const AlnState& st) {
   return true;
 }
 
+// Are the borders (shared memory, generic phase) inside the range the next packed shift step needs?
+BA_DEV bool pk_borders_ok(const Params& P, const AlnState& st, const WarpMem& w) {
+  const int lane = wp::lane_id();
+  int GL, GH;
+  pk_bounds(kStep, P.gap_open, P.gap_extend, P.pk_smax, GL, GH);
+  const int noa = clamp16(st.off - st.off_max);
+  const int lo_b = wp::imax(GL - noa, kI16Min), hi_b = wp::imin(GH - noa, kI16Max);
+  bool ok = lo_b <= hi_b;
+  for (int idx = lane; idx < st.B; idx += 32) {
+    const int a = w.Dc[idx], b = w.Cc[idx], c = w.Dr[idx], d = w.Rr[idx];
+    const int mn = wp::imin(wp::imin(a, b), wp::imin(c, d)), mx = wp::imax(wp::imax(a, b), wp::imax(c, d));
+    ok = ok && mn >= lo_b && mx <= hi_b;
+  }
+  if (st.prev_dir != kGrow && st.prev_dir != st.dir) {
+    const int cv = sat_add(st.D_corner, noa);
+    ok = ok && cv >= 0 && cv <= GH;
+  }
+  return wp::ballot(!ok) == 0u;
+}
+
 template <int SCORING, int FLAGS>
 BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const SlotMem& sm) {
   constexpr bool TRACE = (FLAGS & kTrace) != 0, XDROP = (FLAGS & kXDrop) != 0, EXT = (FLAGS & kExt) != 0;
@@ -595,7 +626,7 @@ BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const Sl
   const int min_size = (int)P.min_size, max_size = (int)P.max_size;
 
   for (;;) {
-    if (fast_eligible<SCORING, XDROP>(P, st)) return kRunFast;
+    if (fast_eligible<SCORING, XDROP>(P, st) && (!P.pk_fast || pk_borders_ok(P, st, w))) return kRunFast;
     const int prev_off = st.off;
     int bv = 0, gbv = 0; unsigned bkey = 15u << 27, gbkey = 15u << 27;
     int right_max, down_max;
@@ -650,7 +681,14 @@ BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const Sl
       sc.vec = rect_right ? q : r; sc.col = rect_right ? r : q;
       int pbv = 0; unsigned pkey = 15u << 27;
       if (!st.overflow) {
-        if (PROF && !rect_right) place_rect<SCORING, false, TRACE, XDROP, EXT>(sc, pa, a, w, pbv, pkey);
+        bool done = false;
+        if (!PROF && !TRACE && !EXT && P.pk_enable)
+          done = place_rect_pk<(PROF ? kAA : SCORING), XDROP>(w.smem0, P, sc.vec, sc.col, a, w.fr, pbv, pkey);
+#ifdef BA_EMU
+        if (wp::lane_id() == 0) { if (done) emu_stats::pk_cells += (uint64_t)a.W * a.H; else emu_stats::exact_cells += (uint64_t)a.W * a.H; }
+#endif
+        if (done) {}
+        else if (PROF && !rect_right) place_rect<SCORING, false, TRACE, XDROP, EXT>(sc, pa, a, w, pbv, pkey);
         else place_rect<SCORING, true, TRACE, XDROP, EXT>(sc, pa, a, w, pbv, pkey);
       }
       if (st.dir == kGrow && part == 0) { gbv = pbv; gbkey = pkey; }
@@ -1131,6 +1169,201 @@ BA_DEV void fast_step(const Params& P, const int8_t* mat, const FastConst<FR>& f
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Packed fast phase: 32 >> LGT alignments per warp, G = 1 << LGT lanes each (block size 8 * G == min_size),
+// borders in registers in the packed layout of ba_packed.cuh (entry e of a border: lane (e mod 4G) / 4,
+// register e mod 4, halfword e / 4G). Same step and the same decisions as fast_step, computed with
+// pk_cols8; a group whose values leave the packed path's exact range is parked for the generic phase.
+// ---------------------------------------------------------------------------------------------
+struct PkFast { uint32_t aD[4], aC[4], oD[4], oR[4]; };
+
+template <int LGT>
+BA_DEV void pk_fast_load(PkFast& f, const WarpMem& w, int dir, bool mine) {
+  constexpr int G = 1 << LGT;
+  const int lg = wp::lane_id() & (G - 1);
+  const int16_t *ad = dir == kRight ? w.Dc : w.Dr, *ac = dir == kRight ? w.Cc : w.Rr;
+  const int16_t *od = dir == kRight ? w.Dr : w.Dc, *orr = dir == kRight ? w.Rr : w.Cc;
+  if (mine) { pk_load4(ad, lg, G, f.aD); pk_load4(ac, lg, G, f.aC); pk_load4(od, lg, G, f.oD); pk_load4(orr, lg, G, f.oR); }
+}
+template <int LGT>
+BA_DEV void pk_fast_spill(const PkFast& f, const WarpMem& w, int dir, bool mine) {
+  constexpr int G = 1 << LGT;
+  const int lg = wp::lane_id() & (G - 1);
+  int16_t *ad = dir == kRight ? w.Dc : w.Dr, *ac = dir == kRight ? w.Cc : w.Rr;
+  int16_t *od = dir == kRight ? w.Dr : w.Dc, *orr = dir == kRight ? w.Rr : w.Cc;
+  wp::syncwarp();
+  if (mine) {
+    pk_store4(ad, lg, G, f.aD); pk_store4(ac, lg, G, f.aC); pk_store4(od, lg, G, f.oD); pk_store4(orr, lg, G, f.oR);
+    // temp_buf1/2 hold the 8 fresh values of the last shift = the last 8 entries of the orthogonal border
+    if (lg >= G - 2) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        w.t1[4 * (lg - (G - 2)) + k] = (int16_t)wp::h_hi(f.oD[k]);
+        w.t2[4 * (lg - (G - 2)) + k] = (int16_t)wp::h_hi(f.oR[k]);
+      }
+    }
+  }
+  wp::syncwarp();
+}
+
+template <int SCORING, int FLAGS, int LGT>
+BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, const PkConst& kc, AlnState& st, PkFast& f, int& status,
+                         const uint8_t* qp, const uint8_t* rp, const SlotMem& sm) {
+  constexpr bool XDROP = (FLAGS & kXDrop) != 0;
+  constexpr int KIND = (SCORING == kProfile) ? kAA : SCORING;
+  constexpr int G = 1 << LGT;
+  constexpr int B = 8 * G;
+  const int lane = wp::lane_id(), lg = lane & (G - 1), grp = lane >> LGT;
+  const bool active = status == kStFast;
+  const bool right = st.dir == kRight;
+  const uint32_t si = st.si, sj = st.sj;
+  const uint8_t* vec = right ? qp : rp;
+  const uint8_t* col = right ? rp : qp;
+  const uint32_t vec_base = right ? si : sj;
+  const uint32_t col_base = (right ? sj : si) + (B - kStep);
+
+  // ---- step prologue (scan_block.rs:148-158) ----
+  const int off = st.off_max;
+  const int off_add = clamp16(st.off - off);
+  const int corner = (st.prev_dir == (right ? kDown : kRight)) ? sat_add(st.D_corner, off_add) : 0;
+  const uint32_t oa2 = pk2(off_add);
+
+  PkScorer<KIND> sc;
+  sc.init(w.smem0, P);
+  sc.rows(*(const uint32_t*)(vec + vec_base + 4 * lg), *(const uint32_t*)(vec + vec_base + 4 * G + 4 * lg));
+  const uint2 cw = *(const uint2*)(col + col_base);
+
+  uint32_t D[4], C[4], m[4], mc[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) { D[k] = wp::vadd2(f.aD[k], oa2); C[k] = wp::vadd2(f.aC[k], oa2); m[k] = 0u; mc[k] = 0u; }
+  uint32_t* fr = w.fr + grp * 8;
+  pk_cols8<KIND, XDROP, LGT>(sc, kc, LGT, lg, cw.x, cw.y, D, C, (uint32_t)corner & 0xffffu, 0, m, mc, fr, lg == G - 1);
+  wp::syncwarp();
+
+  // ---- borders after the step ----
+  // D_corner = old orthogonal[STEP-1] + off_add (scan_block.rs:1041-1042): entry 7 = lane 1, register 3, low half
+  const int d_corner = sat_add(wp::h_lo((uint32_t)wp::shfl_idx_w((int)f.oD[3], 1, G)), off_add);
+  const bool last2 = lg >= G - 2;
+  const uint4 fv = *(const uint4*)(fr + (last2 ? 4 * (lg - (G - 2)) : 0));
+  const uint32_t fvv[4] = {fv.x, fv.y, fv.z, fv.w};
+  const uint32_t selD = last2 ? 0x7632u : 0x3210u, selR = last2 ? 0x5432u : 0x3210u;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    f.aD[k] = D[k]; f.aC[k] = C[k];
+    // slide by 8 entries = two lanes; the last two lanes take their high halves from the fresh bottom row
+    const uint32_t nd = wp::vadd2((uint32_t)wp::shfl_idx_w((int)f.oD[k], lg + 2, G), oa2);
+    const uint32_t nr = wp::vadd2((uint32_t)wp::shfl_idx_w((int)f.oR[k], lg + 2, G), oa2);
+    f.oD[k] = wp::prmt(nd, fvv[k], selD);
+    f.oR[k] = wp::prmt(nr, fvv[k], selR);
+  }
+  wp::syncwarp();
+
+  // ---- reductions (scan_block.rs:332-345) ----
+  uint32_t lv2 = XDROP ? wp::vmax2(wp::vmax3_2(m[0], m[1], m[2]), m[3]) : m[0];
+  int mxv = wp::imax(wp::h_lo(lv2), wp::h_hi(lv2));
+#pragma unroll
+  for (int s = 0; s < LGT; s++) mxv = wp::imax(mxv, wp::shfl_xor_w(mxv, 1 << s, G));
+  // prefix_max over entries 0..7 of both borders (scan_block.rs:1020-1022): low halves of lanes 0 and 1
+  const uint32_t a_loc = wp::vmax2(wp::vmax2(f.aD[0], f.aD[1]), wp::vmax2(f.aD[2], f.aD[3]));
+  const uint32_t o_loc = wp::vmax2(wp::vmax2(f.oD[0], f.oD[1]), wp::vmax2(f.oD[2], f.oD[3]));
+  const uint32_t pm = wp::prmt(a_loc, o_loc, 0x5410u);
+  const uint32_t pmm = wp::vmax2((uint32_t)wp::shfl_idx_w((int)pm, 0, G), (uint32_t)wp::shfl_idx_w((int)pm, 1, G));
+  const int a_max = wp::h_lo(pmm), o_max = wp::h_hi(pmm);
+  const int right_max = right ? a_max : o_max, down_max = right ? o_max : a_max;
+  unsigned key = 0;
+  if (XDROP) {
+    int bv = 0; unsigned bkey = 15u << 27;
+    pk_lane_best(m, mc, lg, G, bv, bkey);
+    key = bv == mxv ? bkey : 0u;
+#pragma unroll
+    for (int s = 0; s < LGT; s++) { const unsigned u = (unsigned)wp::shfl_xor_w((int)key, 1 << s, G); key = u > key ? u : key; }
+  }
+
+  if (P.step_log && active && lg == 0) {
+    const uint32_t n = *P.step_log_n;
+    if (n < P.step_log_cap) {
+      StepLog sl; sl.dir = st.dir; sl.i = si; sl.j = sj; sl.block_size = (uint32_t)B; sl.off = off;
+      sl.max = (int16_t)mxv; sl.right_max = (int16_t)right_max; sl.down_max = (int16_t)down_max;
+      P.step_log[n] = sl;
+    }
+    *P.step_log_n = n + 1;
+  }
+
+  // ---- post-step decisions (scan_block.rs:332-558 restricted to B == min_size, shift steps) ----
+  if (active) {
+#ifdef BA_EMU
+    if (lg == 0) emu_stats::fast_steps++;
+#endif
+    st.off = off;
+    st.steps++;
+    add_cells(st, (uint32_t)(kStep * B));
+    st.prev_dir = st.dir;
+    st.D_corner = d_corner;
+    st.off_max = off + mxv - kZero;
+    st.y_drop_iter++;
+    if (st.off_max > st.best_max) {
+      if (XDROP) {
+        const unsigned cp1 = (key >> 13) & 0x3fffu;
+        uint32_t v = key & 0x1fffu, c = 0;
+        if (cp1 == 0) v = 0; else c = cp1 - 1;
+        if (right) { st.best_i = si + v; st.best_j = sj + (B - kStep) + c; }
+        else { st.best_i = si + (B - kStep) + c; st.best_j = sj + v; }
+      }
+      if (B < (int)P.max_size) {
+        st.i_ckpt = si; st.j_ckpt = sj; st.off_ckpt = off;
+        // checkpoint copy of all four borders (scan_block.rs:413-420)
+        pk_store4(right ? sm.kDc : sm.kDr, lg, G, f.aD); pk_store4(right ? sm.kCc : sm.kRr, lg, G, f.aC);
+        pk_store4(right ? sm.kDr : sm.kDc, lg, G, f.oD); pk_store4(right ? sm.kRr : sm.kCc, lg, G, f.oR);
+      }
+      st.best_max = st.off_max;
+      st.y_drop_iter = 0;
+    }
+    int nstatus = kStFast;
+    if (XDROP) {
+      if (st.off_max < st.best_max - P.x_drop) {
+        if (st.x_drop_iter < kXDropIter - 1) st.x_drop_iter++;
+        else nstatus = kStDone;
+      } else {
+        st.x_drop_iter = 0;
+      }
+    }
+    if (nstatus == kStFast) {
+      if (si + B > st.qlen && sj + B > st.rlen) nstatus = kStDone;
+      else if (sj + B > st.rlen) { st.si = si + kStep; st.dir = kDown; }
+      else if (si + B > st.qlen) { st.sj = sj + kStep; st.dir = kRight; }
+      else if (2 * B <= (int)P.max_size && st.y_drop_iter > (B / kStep) - 1) nstatus = kStNeedGrow;   // state left untouched
+      else if (down_max > right_max) { st.si = si + kStep; st.dir = kDown; }
+      else { st.sj = sj + kStep; st.dir = kRight; }
+      if (nstatus == kStFast && !fast_eligible<SCORING, XDROP>(P, st)) nstatus = kStNeedGeneric;
+    }
+    status = nstatus;
+  }
+  // ---- range guard for the next packed step (ba_packed.cuh): all borders + next off_add inside [GL, GH] ----
+  {
+    int GL, GH;
+    pk_bounds(kStep, P.gap_open, P.gap_extend, P.pk_smax, GL, GH);
+    const int noa = clamp16(st.off - st.off_max);
+    const int lo_b = wp::imax(GL - noa, kI16Min), hi_b = wp::imin(GH - noa, kI16Max);
+    bool ok = lo_b <= hi_b && pk_in_range<4>(f.aD, f.aC, lo_b, hi_b) && pk_in_range<4>(f.oD, f.oR, lo_b, hi_b);
+    if (st.prev_dir != kGrow && st.prev_dir != st.dir) {
+      const int cv = sat_add(st.D_corner, noa);
+      ok = ok && cv >= 0 && cv <= GH;
+    }
+    const unsigned badm = wp::ballot(!ok);
+    if (status == kStFast && ((badm >> (lane & ~(G - 1))) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u))) != 0u) status = kStNeedGeneric;
+  }
+  // the registers are laid out for the executed direction; if the next fast step goes the other way the
+  // borders swap roles
+  if (status == kStFast && st.dir != st.prev_dir) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      uint32_t t = f.aD[k]; f.aD[k] = f.oD[k]; f.oD[k] = t;
+      t = f.aC[k]; f.aC[k] = f.oR[k]; f.oR[k] = t;
+    }
+  }
+}
+
 BA_DEV void bcast_state(AlnState& d, const AlnState& s, int src) {
 #define BA_BC(F) d.F = (decltype(d.F))wp::shfl_idx((int)s.F, src)
   BA_BC(pair); BA_BC(qlen); BA_BC(rlen); BA_BC(si); BA_BC(sj); BA_BC(B); BA_BC(prev_size); BA_BC(dir); BA_BC(prev_dir);
@@ -1146,7 +1379,7 @@ BA_DEV void bcast_state(AlnState& d, const AlnState& s, int src) {
 // ---------------------------------------------------------------------------------------------
 BA_HD size_t warp_smem_bytes(uint32_t max_size) {
   const size_t ms = max_size < 32 ? 32 : max_size;
-  size_t b = 4 * ms * sizeof(int16_t) + 2 * 16 * sizeof(int16_t) + 4 * sizeof(int32_t);
+  size_t b = 4 * ms * sizeof(int16_t) + 2 * 16 * sizeof(int16_t) + 4 * sizeof(int32_t) + 64 * sizeof(uint32_t);
   if (max_size > 32) b += ms;   // ecarry (rectangles swept in several chunks, TRACE)
   return (b + 15) & ~(size_t)15;
 }
@@ -1166,48 +1399,61 @@ BA_DEV void bind_slot(const Params& P, uint32_t slot, WarpMem& w, SlotMem& sm, b
   }
 }
 
-template <int SCORING, int FLAGS, int FR>
+// FM selects the fast phase: 0 = none (every step in the generic phase), 4 / 8 = s32 fast phase with that many
+// rows per lane (fast_step; the TRACE kernels), 16 + LGT = packed fast phase with 1 << LGT lanes per alignment.
+template <int SCORING, int FLAGS, int FM>
 BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, uint32_t warp_global) {
   constexpr bool TRACE = (FLAGS & kTrace) != 0;
+  constexpr bool PKF = FM >= 16;
+  constexpr int LGT = PKF ? FM - 16 : 3;       // log2(lanes per alignment group)
+  constexpr int GW = 1 << LGT;
+  constexpr int FR = PKF ? 0 : FM;
   const int lane = wp::lane_id();
   const size_t ms = P.max_size < 32 ? 32 : P.max_size;
   WarpMem w;
-  w.mat = (const int8_t*)smem;                     // first 1 KB: matrix
-  unsigned char* base = smem + 1024 + (size_t)warp_in_block * warp_smem_bytes(P.max_size);
+  w.mat = (const int8_t*)smem;                     // header: matrix, then the packed-path tables
+  w.smem0 = smem;
+  unsigned char* base = smem + kSmemHeader + (size_t)warp_in_block * warp_smem_bytes(P.max_size);
   int16_t* p16 = (int16_t*)base;
   w.Dc = p16; p16 += ms; w.Cc = p16; p16 += ms; w.Dr = p16; p16 += ms; w.Rr = p16; p16 += ms;
   w.t1 = p16; p16 += 16; w.t2 = p16; p16 += 16;
   w.misc = (int32_t*)p16; p16 += 8;
+  w.fr = (uint32_t*)p16; p16 += 128;
   w.ecarry = (uint8_t*)p16;
   w.kDc = w.kCc = w.kDr = w.kRr = nullptr;
   const uint32_t spw = P.slots_per_warp;
 
-  // Four groups of eight lanes; every lane carries the state of its group's alignment. Without the fast
-  // phase (profiles, min block size != 32) only group 0 is used and every alignment runs start to end in
-  // the generic phase.
-  const int my_g = lane >> 3;
+  // Groups of GW lanes; every lane carries the state of its group's alignment. Without a fast phase
+  // (profiles, extended modes, min block size the fast phases do not serve) only group 0 is used and every
+  // alignment runs start to end in the generic phase.
+  const int my_g = lane >> LGT;
   AlnState st;
   st.pair = 0; st.qlen = 0; st.rlen = 0; st.si = 0; st.sj = 0; st.B = 32; st.prev_size = 0; st.dir = kRight; st.prev_dir = kGrow;
   st.off = 0; st.off_max = 0; st.best_max = 0; st.best_i = 0; st.best_j = 0; st.i_ckpt = 0; st.j_ckpt = 0; st.off_ckpt = 0;
   st.y_drop_iter = 0; st.x_drop_iter = 0; st.D_corner = 0; st.cells_lo = 0; st.cells_hi = 0; st.steps = 0;
   st.widx = 0; st.ridx = 0; st.ck_widx = 0; st.ck_ridx = 0; st.overflow = 0;
-  constexpr int FRR = FR ? FR : 4;   // FR == 0: no fast phase (the fast code below is never reached)
+  constexpr int FRR = FR ? FR : 4;   // FR == 0: no s32 fast phase (that code is never reached)
   FastRegs<FRR> f;
+  PkFast pf;
 #pragma unroll
   for (int k = 0; k < FRR; k++) { f.aD[k] = 0; f.aC[k] = 0; f.oD[k] = 0; f.oR[k] = 0; }
+#pragma unroll
+  for (int k = 0; k < 4; k++) { pf.aD[k] = 0; pf.aC[k] = 0; pf.oD[k] = 0; pf.oR[k] = 0; }
   int status = kStEmpty;
   const uint8_t* qp = P.seq;
   const uint8_t* rp = P.seq;
   SlotMem my_sm;
-  { WarpMem tmpw = w; bind_slot(P, warp_global * spw + my_g, tmpw, my_sm, TRACE); }
+  { WarpMem tmpw = w; bind_slot(P, warp_global * spw + ((uint32_t)my_g < spw ? my_g : 0), tmpw, my_sm, TRACE); }
   bool tickets_left = true;
   FastConst<FRR> fc;
   fast_consts(fc, P.gap_extend);
+  PkConst kc;
+  pk_consts(kc, P.gap_open, P.gap_extend);
 
   for (;;) {
     // ---- service: refill empty groups, run the generic phase for parked ones ----
     for (int g = 0; g < (int)spw; g++) {
-      const int sg = wp::shfl_idx(status, g * 8);
+      const int sg = wp::shfl_idx(status, g * GW);
       if (sg == kStFast) continue;
       if (sg == kStEmpty && !tickets_left) continue;
       SlotMem sm;
@@ -1222,9 +1468,10 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
         if (t >= P.n_pairs) { tickets_left = false; continue; }
         init_alignment<SCORING, FLAGS>(P, gs, P.order ? P.order[t] : t, w);
       } else {
-        bcast_state(gs, st, g * 8);
+        bcast_state(gs, st, g * GW);
         // a parked group's registers are still laid out for the step it executed last (= prev_dir)
-        fast_spill(f, w, gs.prev_dir, mine);
+        if (PKF) pk_fast_spill<LGT>(pf, w, gs.prev_dir, mine);
+        else fast_spill(f, w, gs.prev_dir, mine);
         if (sg == kStNeedGrow) apply_grow(gs, w, TRACE);
       }
       int r = kRunDone;
@@ -1236,7 +1483,8 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
         continue;
       }
       wp::syncwarp();
-      fast_load(f, w, gs.dir, mine);
+      if (PKF) pk_fast_load<LGT>(pf, w, gs.dir, mine);
+      else fast_load(f, w, gs.dir, mine);
       if (mine) {
         st = gs; status = kStFast;
         qp = P.seq + P.q_off[gs.pair];
@@ -1247,7 +1495,8 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
     if (wp::ballot(status == kStFast) == 0u) break;
     // ---- fast phase: run until some group needs the generic phase ----
     for (;;) {
-      if (FR) fast_step<SCORING, FLAGS, FRR>(P, w.mat, fc, st, f, status, qp, rp, my_sm);
+      if (PKF) pk_fast_step<SCORING, FLAGS, LGT>(P, w, kc, st, pf, status, qp, rp, my_sm);
+      else if (FR) fast_step<SCORING, FLAGS, FRR>(P, w.mat, fc, st, f, status, qp, rp, my_sm);
       else break;
       if (wp::ballot(status != kStFast && status != kStEmpty) != 0u) break;
       if (wp::ballot(status == kStFast) == 0u) break;

@@ -1,0 +1,281 @@
+// ba_packed.cuh -- the DP of one rectangle on packed 2 x i16 DPX instructions.
+//
+// Included by ba_kernel.cuh. Same recurrence as place_rect_r (reference: place_block, scan_block.rs:1083-1228;
+// prefix scan avx2.rs:297-338), but two rows per 32-bit register: a group of G lanes (G = H / 8, H = 32..256 rows)
+// owns one rectangle; lane lg keeps rows 4*lg + k in the low halfword and rows 4*G + 4*lg + k in the high
+// halfword of register k (k = 0..3). Every add/max of the recurrence is one VIADDMNMX.S16x2 / VIMNMX.S16x2,
+// i.e. two cells per ALU instruction.
+//
+// Exactness. The reference computes with *saturating* i16 adds (_mm256_adds_epi16); the packed DPX adds wrap.
+// The two agree whenever no intermediate leaves the i16 range, and the reference's scan "phantoms" (negative
+// constants, avx2.rs:321-337) and its T[top-1] = 0 carry-in cannot win whenever every scanned value is >= 0.
+// Both are guaranteed by a range guard on the rectangle's inputs (pk_bounds): with every input D/C value in
+// [GL, GH], GL = -(W*open + open - extend) and GH = 32767 - W*max(matrix), every cell of a W-column rectangle
+// obeys 0 <= D + (open - extend) and D <= 32767 (D falls by at most |open| and rises by at most max(matrix) per
+// column). A rectangle whose inputs fail the guard is computed by the exact 32-bit path (place_rect_r) instead;
+// in practice that is the first block of an alignment (borders start at MIN = 0) and little else.
+//
+// The vertical-gap scan is kept in "U space", U = T - (open - extend): U[r] = max(U[r-1] + ext, D'[r]) needs no
+// add for x = D' + (open - extend), and D = max(D', U + (open - extend)) is one add-max.
+#pragma once
+
+namespace ba {
+
+BA_DEV uint32_t pk2(int v) { return wp::h_pack(v, v); }
+
+// shared-memory scoring tables of the packed path (one copy per CTA, built by stage_tables)
+constexpr int kMatBytes = 1024;            // raw matrix (exact path)
+constexpr int kPkTabBytes = 8192;          // kNuc: [8 classes][16][16] packed score pairs; kAA: [27][32] i16
+constexpr int kSmemHeader = kMatBytes + kPkTabBytes;
+
+template <int KIND> struct PkScorer;
+// NucMatrix (scores.rs:195-209): row (c & 7) * 16, column b & 15
+template <> struct PkScorer<kNuc> {
+  const unsigned char* tab; uint32_t rt[4];
+  BA_DEV void init(const unsigned char* smem, const Params&) { tab = smem + kMatBytes; }
+  BA_DEV void rows(uint32_t wlo, uint32_t whi) {
+    const uint32_t t = ((wlo & 0x0f0f0f0fu) << 4) | (whi & 0x0f0f0f0fu);
+#pragma unroll
+    for (int k = 0; k < 4; k++) rt[k] = ((t >> (8 * k)) & 0xffu) << 2;
+  }
+  BA_DEV uint32_t colh(uint32_t cb) const { return (cb & 7u) << 10; }
+  BA_DEV uint32_t score(uint32_t ch, int k) const { return *(const uint32_t*)(tab + (ch | rt[k])); }
+};
+// AAMatrix (scores.rs:110-127): row c * 32, column b & 31
+template <> struct PkScorer<kAA> {
+  const unsigned char* tab; uint32_t rt[4];
+  BA_DEV void init(const unsigned char* smem, const Params&) { tab = smem + kMatBytes; }
+  BA_DEV void rows(uint32_t wlo, uint32_t whi) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) rt[k] = (((wlo >> (8 * k)) & 31u) << 1) | ((((whi >> (8 * k)) & 31u) << 1) << 16);
+  }
+  BA_DEV uint32_t colh(uint32_t cb) const { return cb << 6; }
+  BA_DEV uint32_t score(uint32_t ch, int k) const {
+    const uint32_t lo = *(const uint16_t*)(tab + ch + (rt[k] & 0xffffu));
+    const uint32_t hi = *(const uint16_t*)(tab + ch + (rt[k] >> 16));
+    return lo | (hi << 16);
+  }
+};
+// ByteMatrix (scores.rs:263-267)
+template <> struct PkScorer<kByte> {
+  uint32_t rt[4]; uint32_t match, mismatch;
+  BA_DEV void init(const unsigned char*, const Params& P) { match = (uint32_t)(int)P.matrix[0] & 0xffffu; mismatch = (uint32_t)(int)P.matrix[1] & 0xffffu; }
+  BA_DEV void rows(uint32_t wlo, uint32_t whi) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) rt[k] = ((wlo >> (8 * k)) & 0xffu) | (((whi >> (8 * k)) & 0xffu) << 16);
+  }
+  BA_DEV uint32_t colh(uint32_t cb) const { return cb; }
+  BA_DEV uint32_t score(uint32_t ch, int k) const {
+    const uint32_t lo = ((rt[k] & 0xffffu) == ch) ? match : mismatch;
+    const uint32_t hi = ((rt[k] >> 16) == ch) ? match : mismatch;
+    return lo | (hi << 16);
+  }
+};
+
+// Build the packed-path tables from the staged matrix. tid / nthreads: the calling thread's share.
+template <int SCORING>
+BA_DEV void stage_tables(unsigned char* smem, int tid, int nthreads) {
+  const int8_t* mat = (const int8_t*)smem;
+  if (SCORING == kNuc) {
+    uint32_t* t = (uint32_t*)(smem + kMatBytes);
+    for (int i = tid; i < 2048; i += nthreads) {
+      const int cls = i >> 8, a = (i >> 4) & 15, b = i & 15;
+      t[i] = wp::h_pack((int)mat[cls * 16 + a], (int)mat[cls * 16 + b]);
+    }
+  } else if (SCORING == kAA) {
+    int16_t* t = (int16_t*)(smem + kMatBytes);
+    for (int i = tid; i < 27 * 32; i += nthreads) t[i] = (int16_t)mat[i];
+  }
+}
+
+// per-lane constants of the packed recurrence
+struct PkConst {
+  uint32_t ge2, go1, or2;   // packed gap_extend, gap_open * 65537 (see pk_cols8), packed gap_open - gap_extend
+  uint32_t kge[4];          // packed (k + 1) * gap_extend
+};
+BA_DEV void pk_consts(PkConst& c, int go, int ge) {
+  c.ge2 = pk2(ge); c.go1 = (uint32_t)go * 65537u; c.or2 = pk2(go - ge);
+#pragma unroll
+  for (int k = 0; k < 4; k++) c.kge[k] = pk2((k + 1) * ge);
+}
+
+// input range [GL, GH] under which a W-column packed rectangle is exact (see the header comment)
+BA_DEV void pk_bounds(int W, int go, int ge, int smax, int& GL, int& GH) {
+  GL = -(W * go + (go - ge));
+  GH = kI16Max - W * smax;
+}
+
+// Eight consecutive columns of a packed rectangle. D/C: the previous column on entry, the last column on exit.
+// m / mc: per-row running maximum and the (column + 1) of its last occurrence (X-drop argmax, scan_block.rs:
+// 1194-1201); without XDROP only m[0] is kept (block maximum). fr[c] receives the bottom row of column c
+// (row 8G - 1) as T | D << 16 from the group's last lane.
+template <int KIND, bool XDROP, int LGT>
+BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int LGr, int lg, uint32_t cw0, uint32_t cw1,
+                     uint32_t (&D)[4], uint32_t (&C)[4], uint32_t corner_lo, int cbase, uint32_t (&m)[4], uint32_t (&mc)[4],
+                     uint32_t* fr, bool writer) {
+  const int LG = LGT ? LGT : LGr;
+  const int G = 1 << LG;
+  const uint32_t lanedec = pk2(4 * lg * wp::h_lo(kc.ge2));
+#pragma unroll 1
+  for (int h = 0; h < 2; h++) {
+    const uint32_t cwh = h ? cw1 : cw0;
+#pragma unroll
+    for (int cc = 0; cc < 4; cc++) {
+      const int cidx = h * 4 + cc;
+      const uint32_t ch = sc.colh((cwh >> (8 * cc)) & 0xffu);
+      // diagonal input of the lane's first rows: the previous column of the row above. Lane 0: low half = the
+      // rectangle's corner (first column only; MIN = 0 afterwards, scan_block.rs:1211), high half = row 4G - 1,
+      // which is the low half of the last lane's register 3.
+      uint32_t up = (uint32_t)wp::shfl_idx_w((int)D[3], lg - 1, G);
+      if (lg == 0) up = (up << 16) | ((cbase + cidx == 0) ? corner_lo : 0u);
+      uint32_t dd[4], c11[4], uu[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t s2 = sc.score(ch, k);
+        const uint32_t d00 = k ? D[k - 1] : up;
+        const uint32_t c11o = D[k] + kc.go1;      // packed add as one 32-bit add: no borrow, both halves >= |open| (guard)
+        c11[k] = wp::viaddmax2(C[k], kc.ge2, c11o);
+        dd[k] = wp::viaddmax2(d00, s2, c11[k]);
+        uu[k] = k ? wp::viaddmax2(uu[k - 1], kc.ge2, dd[k]) : dd[0];
+      }
+      // Kogge-Stone over the lane aggregates, both half-blocks at once
+      uint32_t inc = uu[3];
+      uint32_t dec = kc.kge[3];
+      if (LGT) {
+#pragma unroll
+        for (int s = 0; s < (LGT ? LGT : 1); s++) {
+          const uint32_t u = (uint32_t)wp::shfl_up_w((int)inc, 1 << s, G);
+          inc = wp::viaddmax2(u, dec, inc);
+          dec = wp::vadd2(dec, dec);
+        }
+      } else {
+        for (int s = 0; s < LG; s++) {
+          const uint32_t u = (uint32_t)wp::shfl_up_w((int)inc, 1 << s, G);
+          inc = wp::viaddmax2(u, dec, inc);
+          dec = wp::vadd2(dec, dec);
+        }
+      }
+      // carry into the lane: the lanes above (same half) and, for the high half, the whole low half-block
+      const uint32_t tl = (uint32_t)wp::shfl_idx_w((int)inc, G - 1, G);
+      uint32_t ex = (uint32_t)wp::shfl_up_w((int)inc, 1, G);
+      if (lg == 0) ex = 0u;
+      const uint32_t cin = wp::viaddmax2(tl << 16, lanedec, ex);
+      uint32_t Un3 = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t Un = wp::viaddmax2(cin, kc.kge[k], uu[k]);
+        const uint32_t Dn = wp::viaddmax2(Un, kc.or2, dd[k]);
+        if (k == 3) Un3 = Un;
+        if (XDROP) {
+          bool ph, pl;
+          m[k] = wp::vibmax2(Dn, m[k], ph, pl);
+          const uint32_t c1 = (uint32_t)(cbase + cidx + 1);
+          if (pl) mc[k] = wp::prmt(mc[k], c1, 0x3254u);
+          if (ph) mc[k] = wp::prmt(mc[k], c1, 0x5410u);
+        } else {
+          m[0] = wp::vmax2(m[0], Dn);
+        }
+        D[k] = Dn; C[k] = c11[k];
+      }
+      if (writer) fr[cidx] = wp::prmt(wp::vadd2(Un3, kc.or2), D[3], 0x7632u);   // T.hi | D.hi << 16
+    }
+  }
+}
+
+// best cell of the lane under the reference's order: value desc, AVX lane (row mod 16) asc, column desc, row desc
+// (scan_block.rs:1194-1201, avx2.rs:271-274). Same (bv, bkey) format as place_rect_r.
+BA_DEV void pk_lane_best(const uint32_t (&m)[4], const uint32_t (&mc)[4], int lg, int G, int& bv, unsigned& bkey) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const unsigned cls = (unsigned)((4 * lg + k) & 15);
+#pragma unroll
+    for (int hf = 0; hf < 2; hf++) {
+      const int v = hf ? wp::h_hi(m[k]) : wp::h_lo(m[k]);
+      const unsigned c1 = hf ? (mc[k] >> 16) : (mc[k] & 0xffffu);
+      const unsigned row = (unsigned)(4 * lg + k + hf * 4 * G);
+      const unsigned key = ((15u - cls) << 27) | (c1 << 13) | row;
+      if (c1 != 0 && (v > bv || (v == bv && key > bkey))) { bv = v; bkey = key; }
+    }
+  }
+}
+
+// borders in shared memory <-> packed registers of lane lg (rows 4lg.. and 4G + 4lg..)
+BA_DEV void pk_load4(const int16_t* p, int lg, int G, uint32_t (&r)[4]) {
+  const uint2 lo = *(const uint2*)(p + 4 * lg);
+  const uint2 hi = *(const uint2*)(p + 4 * G + 4 * lg);
+  r[0] = wp::prmt(lo.x, hi.x, 0x5410u); r[1] = wp::prmt(lo.x, hi.x, 0x7632u);
+  r[2] = wp::prmt(lo.y, hi.y, 0x5410u); r[3] = wp::prmt(lo.y, hi.y, 0x7632u);
+}
+BA_DEV void pk_store4(int16_t* p, int lg, int G, const uint32_t (&r)[4]) {
+  uint2 lo, hi;
+  lo.x = wp::prmt(r[0], r[1], 0x5410u); lo.y = wp::prmt(r[2], r[3], 0x5410u);
+  hi.x = wp::prmt(r[0], r[1], 0x7632u); hi.y = wp::prmt(r[2], r[3], 0x7632u);
+  *(uint2*)(p + 4 * lg) = lo;
+  *(uint2*)(p + 4 * G + 4 * lg) = hi;
+}
+
+// lane-local range test of packed values: every halfword of every register within [lo, hi]
+template <int N>
+BA_DEV bool pk_in_range(const uint32_t (&a)[N], const uint32_t (&b)[N], int lo, int hi) {
+  uint32_t mn = a[0], mx = a[0];
+#pragma unroll
+  for (int k = 1; k < N; k++) { mn = wp::vmin2(mn, a[k]); mx = wp::vmax2(mx, a[k]); }
+#pragma unroll
+  for (int k = 0; k < N; k++) { mn = wp::vmin2(mn, b[k]); mx = wp::vmax2(mx, b[k]); }
+  bool p0, p1, p2, p3;
+  wp::vibmax2(mn, pk2(lo), p0, p1);     // mn >= lo per half
+  wp::vibmax2(pk2(hi), mx, p2, p3);     // hi >= mx per half
+  return p0 && p1 && p2 && p3;
+}
+
+// Packed replacement of place_rect for sequence-sequence rectangles with borders in shared memory (generic
+// phase, one alignment per warp; lanes >= G mirror lanes < G). Returns false -- with nothing modified -- when the
+// rectangle's shape or value range is outside what the packed path covers; the caller then runs place_rect.
+template <int KIND, bool XDROP>
+BA_DEV bool place_rect_pk(const unsigned char* smem, const Params& P, const uint8_t* vec, const uint8_t* col,
+                          const RectArgs& a, uint32_t* fr, int& bv, unsigned& bkey) {
+  const int lane = wp::lane_id();
+  const int H = a.H, W = a.W;
+  if (!(H == 32 || H == 64 || H == 128 || H == 256) || W <= 0 || (W & 7) || W > 256 || a.ncols != W) return false;
+  if (a.vec_base == 0 && a.col_base == 0) return false;        // forced origin cell (scan_block.rs:1130-1132)
+  const int G = H >> 3;
+  const int LG = H == 32 ? 2 : (H == 64 ? 3 : (H == 128 ? 4 : 5));
+  const int lg = lane & (G - 1);
+  const int go = P.gap_open, ge = P.gap_extend;
+  int GL, GH;
+  pk_bounds(W, go, ge, P.pk_smax, GL, GH);
+  // raw border values v become v + off_add (saturating in the reference): exact and inside [GL, GH] iff
+  // v is inside [GL - off_add, GH - off_add] (clipped to i16)
+  const int lo_b = wp::imax(GL - a.off_add, kI16Min), hi_b = wp::imin(GH - a.off_add, kI16Max);
+  uint32_t D[4], C[4];
+  pk_load4(a.AD, lg, G, D);
+  pk_load4(a.AC, lg, G, C);
+  bool ok = lo_b <= hi_b && a.corner >= 0 && a.corner <= GH && pk_in_range<4>(D, C, lo_b, hi_b);
+  if (wp::ballot(!ok) != 0u) return false;
+  bv = 0; bkey = 15u << 27;
+  const uint32_t oa2 = pk2(a.off_add);
+#pragma unroll
+  for (int k = 0; k < 4; k++) { D[k] = wp::vadd2(D[k], oa2); C[k] = wp::vadd2(C[k], oa2); }
+
+  PkScorer<KIND> sc;
+  sc.init(smem, P);
+  sc.rows(*(const uint32_t*)(vec + a.vec_base + 4 * lg), *(const uint32_t*)(vec + a.vec_base + 4 * G + 4 * lg));
+  PkConst kc;
+  pk_consts(kc, go, ge);
+  uint32_t m[4] = {0u, 0u, 0u, 0u}, mc[4] = {0u, 0u, 0u, 0u};
+  const bool writer = lane == G - 1;
+  for (int cb = 0; cb < W; cb += 8) {
+    const uint2 cw = *(const uint2*)(col + a.col_base + cb);
+    pk_cols8<KIND, XDROP, 0>(sc, kc, LG, lg, cw.x, cw.y, D, C, (uint32_t)a.corner & 0xffffu, cb, m, mc, fr, writer);
+    wp::syncwarp();
+    if (lane < 8) { const uint32_t v = fr[lane]; a.OD[cb + lane] = (int16_t)(v >> 16); a.OR_[cb + lane] = (int16_t)(v & 0xffffu); }
+    wp::syncwarp();
+  }
+  if (lane < G) { pk_store4(a.AD, lg, G, D); pk_store4(a.AC, lg, G, C); }
+  if (XDROP) pk_lane_best(m, mc, lg, G, bv, bkey);
+  else bv = wp::imax(bv, wp::imax(wp::h_lo(m[0]), wp::h_hi(m[0])));
+  wp::syncwarp();
+  return true;
+}
+
+}  // namespace ba

@@ -97,6 +97,7 @@ static int launch_align(const Params& P, int blocks, int wpb, size_t smem_bytes,
     std::vector<unsigned char> smem(smem_bytes + 64, 0xAB);
     const int nm = SCORING == kNuc ? 128 : (SCORING == kAA ? 864 : 0);
     for (int i = 0; i < nm; i++) smem[i] = (unsigned char)P.matrix[i];
+    stage_tables<SCORING>(smem.data(), 0, 1);
     EmuLaunch l{&P, smem.data(), (uint32_t)b};
     emu::run_warp(&emu_warp_entry<SCORING, FLAGS, FR>, &l);
     // guard: the device code must stay inside the shared memory it was given
@@ -142,6 +143,8 @@ __global__ void __launch_bounds__(128, 4) ba_align_kernel(const __grid_constant_
   const int nm = SCORING == kNuc ? 128 : (SCORING == kAA ? 864 : 0);
   for (int i = threadIdx.x; i < nm; i += blockDim.x) ba_smem[i] = (unsigned char)P.matrix[i];
   __syncthreads();
+  stage_tables<SCORING>(ba_smem, (int)threadIdx.x, (int)blockDim.x);
+  __syncthreads();
   const int wib = threadIdx.x >> 5;
   warp_main<SCORING, FLAGS, FR>(P, ba_smem, wib, blockIdx.x * (blockDim.x >> 5) + wib);
 }
@@ -173,7 +176,8 @@ static int occupancy(int wpb, size_t smem_bytes, int* blocks_per_sm) {
 // kernel instantiations: scoring x flags x rows-per-lane of the fast phase (0 = generic phase only)
 // flags 4..7 = kExt | {TRACE, X_DROP}: LOCAL_START / FREE_QUERY_START_GAPS selected at run time, generic phase only
 #define BA_FOR_SEQ(X, S) X(S, 0, 0) X(S, 1, 0) X(S, 2, 0) X(S, 3, 0) X(S, 0, 4) X(S, 1, 4) X(S, 2, 4) X(S, 3, 4) \
-                         X(S, 0, 8) X(S, 1, 8) X(S, 2, 8) X(S, 3, 8) X(S, 4, 0) X(S, 5, 0) X(S, 6, 0) X(S, 7, 0)
+                         X(S, 0, 8) X(S, 1, 8) X(S, 2, 8) X(S, 3, 8) X(S, 4, 0) X(S, 5, 0) X(S, 6, 0) X(S, 7, 0) \
+                         X(S, 0, 18) X(S, 2, 18) X(S, 0, 19) X(S, 2, 19)
 #define BA_FOR_KERNELS(X) BA_FOR_SEQ(X, kNuc) BA_FOR_SEQ(X, kAA) BA_FOR_SEQ(X, kByte) \
   X(kProfile, 0, 0) X(kProfile, 1, 0) X(kProfile, 2, 0) X(kProfile, 3, 0) \
   X(kProfile, 4, 0) X(kProfile, 5, 0) X(kProfile, 6, 0) X(kProfile, 7, 0)
@@ -294,6 +298,7 @@ struct BaBatch {
   uint32_t* d_overflow_list = nullptr; uint32_t* d_overflow_n = nullptr;
   uint32_t* d_zwords = nullptr;     // zero masks (TRACE && LOCAL_START)
   int kflags = 0;                   // template FLAGS of the kernel: (flags & 3) | kExt
+  int pk_smax = 0; uint32_t pk_enable = 0;   // packed 2 x i16 path (ba_packed.cuh): largest matrix entry, on/off
   uint64_t trace_words_bound = 0;   // worst case per alignment (the reference's Trace::new size)
   uint64_t mem_budget = 0; uint64_t max_blocks_hw = 1;
   // launch geometry
@@ -502,6 +507,10 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
   // scoring data
   if (!prof) {
     const size_t mb = cfg->scoring == BA_SCORING_NUC ? 128 : (cfg->scoring == BA_SCORING_AA ? 864 : 2);
+    int smax = 0;
+    for (size_t i = 0; i < mb; i++) smax = std::max(smax, (int)((const int8_t*)cfg->matrix)[i]);
+    b->pk_smax = smax;
+    b->pk_enable = getenv("BA_NO_PACKED") ? 0u : 1u;
     TRY2(pool_alloc(al, (void**)&b->d_matrix, mb));
     TRY2(h2d(b->d_matrix, cfg->matrix, mb, st));
   } else {
@@ -569,13 +578,19 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
   // fast phase: four alignments per warp while the block sits at its minimum size (32 or 64)
   const bool ext = (cfg->flags & (BA_LOCAL_START | BA_FREE_QUERY_START_GAPS)) != 0;
   b->kflags = (cfg->flags & 3) | (ext ? kExt : 0);
+  // fast-phase mode (third kernel template argument): 4 / 8 = s32 rows per lane (TRACE), 16 + LGT = packed, 0 = none
   b->fast_rows = (!prof && !ext && !getenv("BA_NO_FAST")) ? (mn == 32 ? 4 : (mn == 64 ? 8 : 0)) : 0;
   b->slots_per_warp = b->fast_rows ? 4 : 1;
+  if (b->fast_rows && b->pk_enable && !(cfg->flags & BA_TRACE)) {
+    const int lgt = mn == 32 ? 2 : 3;
+    b->fast_rows = 16 + lgt;
+    b->slots_per_warp = 32u >> lgt;
+  }
   const size_t wbytes = warp_smem_bytes(mx);
   int wpb = 4;
-  while (wpb > 1 && 1024 + wpb * wbytes > al->smem_optin - 1024) wpb >>= 1;
-  if (1024 + wpb * wbytes > al->smem_optin) { ba_batch_free(b); return fail(BA_ERR_SIZE, "max block size does not fit in shared memory"); }
-  b->wpb = wpb; b->smem_bytes = 1024 + wpb * wbytes;
+  while (wpb > 1 && kSmemHeader + wpb * wbytes > al->smem_optin - 1024) wpb >>= 1;
+  if (kSmemHeader + wpb * wbytes > al->smem_optin) { ba_batch_free(b); return fail(BA_ERR_SIZE, "max block size does not fit in shared memory"); }
+  b->wpb = wpb; b->smem_bytes = kSmemHeader + wpb * wbytes;
   int bps = 1;
   TRY(occupancy_dispatch(prof ? (int)kProfile : cfg->scoring, b->kflags, b->fast_rows, wpb, b->smem_bytes, &bps));
   if (bps < 1) bps = 1;
@@ -658,9 +673,12 @@ static Params make_params(const BaBatch* b) {
   P.gap_open = b->cfg.gaps.open; P.gap_extend = b->cfg.gaps.extend;
   P.min_size = b->min_size; P.max_size = b->max_size; P.x_drop = b->cfg.x_drop;
   P.flags = b->kflags; P.scoring = prof ? (int)kProfile : b->cfg.scoring;
+  P.pk_smax = b->pk_smax; P.pk_enable = b->pk_enable;
   P.ext_flags = (uint32_t)(b->cfg.flags & (BA_LOCAL_START | BA_FREE_QUERY_START_GAPS)); P.trace_zwords = b->d_zwords;
   P.out = b->d_out; P.ticket = b->d_ticket;
-  P.ckpt = b->d_ckpt; P.slots_per_warp = b->slots_per_warp; P.fast_block = (uint32_t)(8 * b->fast_rows);
+  P.ckpt = b->d_ckpt; P.slots_per_warp = b->slots_per_warp;
+  P.fast_block = b->fast_rows >= 16 ? (8u << (b->fast_rows - 16)) : (uint32_t)(8 * b->fast_rows);
+  P.pk_fast = b->fast_rows >= 16 ? 1u : 0u;
   P.trace_words = b->d_trace; P.trace_words_per_warp = b->trace_words_per_warp;
   P.rects = b->d_rects; P.rects_per_warp = b->rects_per_warp;
   P.run_scratch = b->d_runs; P.runs_per_warp = b->runs_per_warp;
@@ -808,6 +826,13 @@ extern "C" int ba_batch_pair_stats(const BaBatch* b, size_t k, uint64_t* cells, 
   if (status) *status = b->h_out[k].status;
   return BA_OK;
 }
+
+#ifdef BA_EMU
+extern "C" void ba_emu_stats(uint64_t* out3, int reset) {
+  out3[0] = emu_stats::pk_cells; out3[1] = emu_stats::exact_cells; out3[2] = emu_stats::fast_steps;
+  if (reset) { emu_stats::pk_cells = 0; emu_stats::exact_cells = 0; emu_stats::fast_steps = 0; }
+}
+#endif
 
 // debug: fetch the per-step log of a single-pair batch run with BA_STEP_LOG=1
 extern "C" size_t ba_debug_step_log(BaBatch* b, StepLog* out, size_t cap) {

@@ -71,6 +71,9 @@ struct Params {
   uint32_t min_size, max_size;   // already clamped to >= kL, powers of two
   int32_t x_drop;
   int32_t flags, scoring;
+  int32_t pk_smax;               // max(0, largest matrix entry): growth bound of the packed path's range guard
+  uint32_t pk_enable;            // packed 2 x i16 DP path on (sequence-sequence)
+  uint32_t pk_fast;              // the fast phase is the packed one (pk_fast_step): entering it needs pk_borders_ok
   uint32_t ext_flags;            // kLocalStart | kFreeQueryStartGaps (only honoured by kernels instantiated with kExt)
   uint32_t* trace_zwords;        // zero-mask words per slot (TRACE && LOCAL_START), same stride as trace_words
   DevResult* out;

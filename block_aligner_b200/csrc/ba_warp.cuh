@@ -24,6 +24,25 @@ inline int shfl_up8(int v, int d) { const uint32_t* a = emu::exchange((uint32_t)
 inline int shfl_down8(int v, int d) { const uint32_t* a = emu::exchange((uint32_t)v); int l = emu::lane(); return (l & 7) + d < 8 ? (int)a[l + d] : v; }
 inline int shfl_idx8(int v, int src) { const uint32_t* a = emu::exchange((uint32_t)v); int l = emu::lane(); return (int)a[(l & ~7) | (src & 7)]; }
 inline int shfl_xor8(int v, int m) { const uint32_t* a = emu::exchange((uint32_t)v); int l = emu::lane(); return (int)a[(l & ~7) | ((l ^ m) & 7)]; }
+inline int shfl_up_w(int v, int d, int w) { const uint32_t* a = emu::exchange((uint32_t)v); int l = emu::lane(); return (l & (w - 1)) >= d ? (int)a[l - d] : v; }
+inline int shfl_idx_w(int v, int src, int w) { const uint32_t* a = emu::exchange((uint32_t)v); int l = emu::lane(); return (int)a[(l & ~(w - 1)) | (src & (w - 1))]; }
+inline int shfl_xor_w(int v, int m, int w) { const uint32_t* a = emu::exchange((uint32_t)v); int l = emu::lane(); return (int)a[(l & ~(w - 1)) | ((l ^ m) & (w - 1))]; }
+// packed 2 x i16 (DPX / SIMD-in-a-word) operations: lane-wise on the two halfwords, wrapping adds
+inline int h_lo(uint32_t p) { return (int)(int16_t)(p & 0xffffu); }
+inline int h_hi(uint32_t p) { return (int)(int16_t)(p >> 16); }
+inline uint32_t h_pack(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+inline uint32_t vadd2(uint32_t a, uint32_t b) { return h_pack(h_lo(a) + h_lo(b), h_hi(a) + h_hi(b)); }
+inline uint32_t vmax2(uint32_t a, uint32_t b) { return h_pack(h_lo(a) > h_lo(b) ? h_lo(a) : h_lo(b), h_hi(a) > h_hi(b) ? h_hi(a) : h_hi(b)); }
+inline uint32_t vmin2(uint32_t a, uint32_t b) { return h_pack(h_lo(a) < h_lo(b) ? h_lo(a) : h_lo(b), h_hi(a) < h_hi(b) ? h_hi(a) : h_hi(b)); }
+inline uint32_t vmax3_2(uint32_t a, uint32_t b, uint32_t c) { return vmax2(vmax2(a, b), c); }
+inline uint32_t vmin3_2(uint32_t a, uint32_t b, uint32_t c) { return vmin2(vmin2(a, b), c); }
+inline uint32_t viaddmax2(uint32_t a, uint32_t b, uint32_t c) { return vmax2(vadd2(a, b), c); }
+inline uint32_t vibmax2(uint32_t a, uint32_t b, bool& ph, bool& pl) { pl = h_lo(a) >= h_lo(b); ph = h_hi(a) >= h_hi(b); return vmax2(a, b); }
+inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  const uint64_t src = ((uint64_t)b << 32) | a; uint32_t r = 0;
+  for (int i = 0; i < 4; i++) { const uint32_t n = (sel >> (4 * i)) & 0xfu; uint32_t byte = (uint32_t)(src >> (8 * (n & 7))) & 0xffu; if (n & 8) byte = (byte & 0x80u) ? 0xffu : 0u; r |= byte << (8 * i); }
+  return r;
+}
 inline int red_max(int v) { const uint32_t* a = emu::exchange((uint32_t)v); int m = (int)a[0]; for (int i = 1; i < 32; i++) m = (int)a[i] > m ? (int)a[i] : m; return m; }
 inline unsigned red_max_u(unsigned v) { const uint32_t* a = emu::exchange(v); unsigned m = a[0]; for (int i = 1; i < 32; i++) m = a[i] > m ? a[i] : m; return m; }
 inline unsigned ballot(bool p) { const uint32_t* a = emu::exchange(p ? 1u : 0u); unsigned m = 0; for (int i = 0; i < 32; i++) m |= (a[i] & 1u) << i; return m; }
@@ -50,6 +69,21 @@ BA_DEV int shfl_up8(int v, int d) { return __shfl_up_sync(kFull, v, d, 8); }
 BA_DEV int shfl_down8(int v, int d) { return __shfl_down_sync(kFull, v, d, 8); }
 BA_DEV int shfl_idx8(int v, int src) { return __shfl_sync(kFull, v, src, 8); }
 BA_DEV int shfl_xor8(int v, int m) { return __shfl_xor_sync(kFull, v, m, 8); }
+BA_DEV int shfl_up_w(int v, int d, int w) { return __shfl_up_sync(kFull, v, d, w); }
+BA_DEV int shfl_idx_w(int v, int src, int w) { return __shfl_sync(kFull, v, src, w); }
+BA_DEV int shfl_xor_w(int v, int m, int w) { return __shfl_xor_sync(kFull, v, m, w); }
+// packed 2 x i16 DPX operations (VIADD.16x2, VIMNMX.S16x2, VIMNMX3.S16x2, VIADDMNMX.S16x2 on sm_100a)
+BA_DEV int h_lo(uint32_t p) { return (int)(int16_t)(p & 0xffffu); }
+BA_DEV int h_hi(uint32_t p) { return (int)p >> 16; }
+BA_DEV uint32_t h_pack(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+BA_DEV uint32_t vadd2(uint32_t a, uint32_t b) { return __vadd2(a, b); }
+BA_DEV uint32_t vmax2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
+BA_DEV uint32_t vmin2(uint32_t a, uint32_t b) { return __vmins2(a, b); }
+BA_DEV uint32_t vmax3_2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
+BA_DEV uint32_t vmin3_2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s16x2(a, b, c); }
+BA_DEV uint32_t viaddmax2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }
+BA_DEV uint32_t vibmax2(uint32_t a, uint32_t b, bool& ph, bool& pl) { return __vibmax_s16x2(a, b, &ph, &pl); }
+BA_DEV uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
 BA_DEV int red_max(int v) { return __reduce_max_sync(kFull, v); }
 BA_DEV unsigned red_max_u(unsigned v) { return __reduce_max_sync(kFull, v); }
 BA_DEV unsigned ballot(bool p) { return __ballot_sync(kFull, p); }
