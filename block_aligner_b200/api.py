@@ -84,7 +84,7 @@ PART2_FUNCTIONS = ["ba_error_string", "ba_last_error_message", "ba_create", "ba_
                    "ba_batch_upload_profiles", "ba_batch_run", "ba_batch_download", "ba_batch_cigar",
                    "ba_batch_traceback", "ba_batch_total_stats", "ba_batch_pair_stats", "ba_batch_free",
                    "ba_align_batch", "ba_align_batch_exp", "ba_align_batch_profiles", "ba_new_simple_nucmatrix", "ba_set_nucmatrix", "ba_free_nucmatrix",
-                   "ba_percent_len", "ba_cigar_format", "ba_measure_int_peak"]
+                   "ba_percent_len", "ba_cigar_format", "ba_measure_int_peak", "ba_measure_int_peak_packed"]
 
 
 class Library:
@@ -125,6 +125,7 @@ class Library:
         L.ba_cigar_format.restype = sz
         L.ba_cigar_format.argtypes = [vp, sz, C.c_char_p, sz]
         L.ba_measure_int_peak.argtypes = [vp, C.POINTER(C.c_double)]
+        L.ba_measure_int_peak_packed.argtypes = [vp, C.POINTER(C.c_double)]
         if hasattr(L, "ba_debug_step_log"):
             L.ba_debug_step_log.restype = sz
             L.ba_debug_step_log.argtypes = [vp, vp, sz]
@@ -242,9 +243,10 @@ class Aligner:
         except Exception:
             pass
 
-    def int_peak_gops(self):
+    def int_peak_gops(self, packed=False):
         v = C.c_double()
-        self.lib.check(self.lib.L.ba_measure_int_peak(self.h, C.byref(v)))
+        fn = self.lib.L.ba_measure_int_peak_packed if packed else self.lib.L.ba_measure_int_peak
+        self.lib.check(fn(self.h, C.byref(v)))
         return v.value
 
     def config(self, scoring, matrix, gaps, size, x_drop=0, flags=0, cigar_eq=False):

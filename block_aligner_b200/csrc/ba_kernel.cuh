@@ -52,6 +52,7 @@ struct WarpMem {
   const int8_t *mat;                // staged matrix (smem)
   const unsigned char* smem0;       // start of the CTA's shared memory (matrix + packed-path tables)
   uint32_t* fr;                     // packed path: bottom-row staging, 8 words per alignment group [64]
+  uint32_t* ck;                     // packed fast phase: checkpoint borders in the packed layout, 64 words per group [512]
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -412,6 +413,7 @@ struct AlnState {
   int off_ckpt, y_drop_iter, x_drop_iter, D_corner;
   uint32_t cells_lo, cells_hi, steps;
   uint32_t widx, ridx, ck_widx, ck_ridx, overflow;   // trace stack (scan_block.rs:1351-1354)
+  uint32_t ck_pk;                                    // the newest checkpoint borders are in WarpMem::ck (packed fast phase)
 };
 
 // per-slot scratch in global memory (slot = one alignment in flight)
@@ -559,7 +561,7 @@ BA_DEV void init_alignment(const Params& P, AlnState& st, uint32_t pair, const W
   st.i_ckpt = 0; st.j_ckpt = 0; st.off_ckpt = 0;
   st.y_drop_iter = 0; st.x_drop_iter = 0; st.D_corner = 0;
   st.cells_lo = 0; st.cells_hi = 0; st.steps = 0;
-  st.widx = 0; st.ridx = 0; st.ck_widx = 0; st.ck_ridx = 0; st.overflow = 0;
+  st.widx = 0; st.ridx = 0; st.ck_widx = 0; st.ck_ridx = 0; st.overflow = 0; st.ck_pk = 0;
 }
 
 // grow transition (scan_block.rs:477-500): back to the checkpoint with a doubled block
@@ -586,6 +588,25 @@ BA_DEV bool fast_eligible(const Params& P, const AlnState& st) {
   return true;
 }
 
+// The packed fast phase keeps its newest checkpoint in shared memory (pk_fast_step); the generic phase reads and
+// writes the slot's checkpoint in global memory in the plain layout. Called when a group parks.
+template <int LGT>
+BA_DEV void pk_ckpt_flush(const WarpMem& w, const SlotMem& sm, int g, bool mine) {
+  constexpr int G = 1 << LGT;
+  const int lg = wp::lane_id() & (G - 1);
+  if (mine) {
+    const uint4* ck = (const uint4*)w.ck + (g * 4) * G + lg;
+    int16_t* dst[4] = {sm.kDc, sm.kCc, sm.kDr, sm.kRr};
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const uint4 v = ck[a * G];
+      const uint32_t r[4] = {v.x, v.y, v.z, v.w};
+      pk_store4(dst[a], lg, G, r);
+    }
+  }
+  wp::syncwarp();
+}
+
 // Are the borders (shared memory, generic phase) inside the range the next packed shift step needs?
 BA_DEV bool pk_borders_ok(const Params& P, const AlnState& st, const WarpMem& w) {
   const int lane = wp::lane_id();
@@ -593,7 +614,7 @@ BA_DEV bool pk_borders_ok(const Params& P, const AlnState& st, const WarpMem& w)
   pk_bounds(kStep, P.gap_open, P.gap_extend, P.pk_smax, GL, GH);
   const int noa = clamp16(st.off - st.off_max);
   const int lo_b = wp::imax(GL - noa, kI16Min), hi_b = wp::imin(GH - noa, kI16Max);
-  bool ok = lo_b <= hi_b;
+  bool ok = lo_b <= hi_b && noa >= -1024 && noa <= 1024;
   for (int idx = lane; idx < st.B; idx += 32) {
     const int a = w.Dc[idx], b = w.Cc[idx], c = w.Dr[idx], d = w.Rr[idx];
     const int mn = wp::imin(wp::imin(a, b), wp::imin(c, d)), mx = wp::imax(wp::imax(a, b), wp::imax(c, d));
@@ -607,7 +628,7 @@ BA_DEV bool pk_borders_ok(const Params& P, const AlnState& st, const WarpMem& w)
 }
 
 template <int SCORING, int FLAGS>
-BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const SlotMem& sm) {
+BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const SlotMem& sm, const PkConst& kc) {
   constexpr bool TRACE = (FLAGS & kTrace) != 0, XDROP = (FLAGS & kXDrop) != 0, EXT = (FLAGS & kExt) != 0;
   constexpr bool PROF = SCORING == kProfile;
   const bool m_local = EXT && (P.ext_flags & kLocalStart), m_fqs = EXT && (P.ext_flags & kFreeQueryStartGaps);
@@ -683,7 +704,7 @@ BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const Sl
       if (!st.overflow) {
         bool done = false;
         if (!PROF && !TRACE && !EXT && P.pk_enable)
-          done = place_rect_pk<(PROF ? kAA : SCORING), XDROP>(w.smem0, P, sc.vec, sc.col, a, w.fr, pbv, pkey);
+          done = place_rect_pk<(PROF ? kAA : SCORING), XDROP>(w.smem0, P, kc, sc.vec, sc.col, a, w.fr, pbv, pkey);
 #ifdef BA_EMU
         if (wp::lane_id() == 0) { if (done) emu_stats::pk_cells += (uint64_t)a.W * a.H; else emu_stats::exact_cells += (uint64_t)a.W * a.H; }
 #endif
@@ -1273,9 +1294,7 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, const PkConst& kc, A
   const int right_max = right ? a_max : o_max, down_max = right ? o_max : a_max;
   unsigned key = 0;
   if (XDROP) {
-    int bv = 0; unsigned bkey = 15u << 27;
-    pk_lane_best(m, mc, lg, G, bv, bkey);
-    key = bv == mxv ? bkey : 0u;
+    key = pk_lane_key(m, mc, lg, G, mxv);
 #pragma unroll
     for (int s = 0; s < LGT; s++) { const unsigned u = (unsigned)wp::shfl_xor_w((int)key, 1 << s, G); key = u > key ? u : key; }
   }
@@ -1312,9 +1331,13 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, const PkConst& kc, A
       }
       if (B < (int)P.max_size) {
         st.i_ckpt = si; st.j_ckpt = sj; st.off_ckpt = off;
-        // checkpoint copy of all four borders (scan_block.rs:413-420)
-        pk_store4(right ? sm.kDc : sm.kDr, lg, G, f.aD); pk_store4(right ? sm.kCc : sm.kRr, lg, G, f.aC);
-        pk_store4(right ? sm.kDr : sm.kDc, lg, G, f.oD); pk_store4(right ? sm.kRr : sm.kCc, lg, G, f.oR);
+        // checkpoint copy of all four borders (scan_block.rs:413-420): kept in shared memory in the packed
+        // layout, array order D_col, C_col, D_row, R_row; moved to the slot's global checkpoint when the group parks
+        uint4* ck = (uint4*)w.ck + (grp * 4) * G + lg;
+        const int ia = right ? 0 : 2 * G, io = right ? 2 * G : 0;
+        ck[ia] = make_uint4(f.aD[0], f.aD[1], f.aD[2], f.aD[3]); ck[ia + G] = make_uint4(f.aC[0], f.aC[1], f.aC[2], f.aC[3]);
+        ck[io] = make_uint4(f.oD[0], f.oD[1], f.oD[2], f.oD[3]); ck[io + G] = make_uint4(f.oR[0], f.oR[1], f.oR[2], f.oR[3]);
+        st.ck_pk = 1u;
       }
       st.best_max = st.off_max;
       st.y_drop_iter = 0;
@@ -1345,7 +1368,11 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, const PkConst& kc, A
     pk_bounds(kStep, P.gap_open, P.gap_extend, P.pk_smax, GL, GH);
     const int noa = clamp16(st.off - st.off_max);
     const int lo_b = wp::imax(GL - noa, kI16Min), hi_b = wp::imin(GH - noa, kI16Max);
-    bool ok = lo_b <= hi_b && pk_in_range<4>(f.aD, f.aC, lo_b, hi_b) && pk_in_range<4>(f.oD, f.oR, lo_b, hi_b);
+    // Only the D registers need the test: C <= D and R <= D bound the gap tables from above, and from below they
+    // only have to stay clear of i16 wrap-around, which holds by induction: every C / R value is >= 0 when it is
+    // produced (or checked by pk_borders_ok on entry) and then moves by at most |noa| <= 1024 per step for the
+    // at most G <= 8 steps it stays in a border.
+    bool ok = lo_b <= hi_b && noa >= -1024 && noa <= 1024 && pk_in_range_d(f.aD, f.oD, lo_b, hi_b);
     if (st.prev_dir != kGrow && st.prev_dir != st.dir) {
       const int cv = sat_add(st.D_corner, noa);
       ok = ok && cv >= 0 && cv <= GH;
@@ -1355,11 +1382,12 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, const PkConst& kc, A
   }
   // the registers are laid out for the executed direction; if the next fast step goes the other way the
   // borders swap roles
-  if (status == kStFast && st.dir != st.prev_dir) {
+  {
+    const uint32_t flip = (status == kStFast && st.dir != st.prev_dir) ? 0xffffffffu : 0u;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      uint32_t t = f.aD[k]; f.aD[k] = f.oD[k]; f.oD[k] = t;
-      t = f.aC[k]; f.aC[k] = f.oR[k]; f.oR[k] = t;
+      uint32_t t = (f.aD[k] ^ f.oD[k]) & flip; f.aD[k] ^= t; f.oD[k] ^= t;
+      t = (f.aC[k] ^ f.oR[k]) & flip; f.aC[k] ^= t; f.oR[k] ^= t;
     }
   }
 }
@@ -1369,7 +1397,7 @@ BA_DEV void bcast_state(AlnState& d, const AlnState& s, int src) {
   BA_BC(pair); BA_BC(qlen); BA_BC(rlen); BA_BC(si); BA_BC(sj); BA_BC(B); BA_BC(prev_size); BA_BC(dir); BA_BC(prev_dir);
   BA_BC(off); BA_BC(off_max); BA_BC(best_max); BA_BC(best_i); BA_BC(best_j); BA_BC(i_ckpt); BA_BC(j_ckpt);
   BA_BC(off_ckpt); BA_BC(y_drop_iter); BA_BC(x_drop_iter); BA_BC(D_corner); BA_BC(cells_lo); BA_BC(cells_hi); BA_BC(steps);
-  BA_BC(widx); BA_BC(ridx); BA_BC(ck_widx); BA_BC(ck_ridx); BA_BC(overflow);
+  BA_BC(widx); BA_BC(ridx); BA_BC(ck_widx); BA_BC(ck_ridx); BA_BC(overflow); BA_BC(ck_pk);
 #undef BA_BC
 }
 
@@ -1379,7 +1407,7 @@ BA_DEV void bcast_state(AlnState& d, const AlnState& s, int src) {
 // ---------------------------------------------------------------------------------------------
 BA_HD size_t warp_smem_bytes(uint32_t max_size) {
   const size_t ms = max_size < 32 ? 32 : max_size;
-  size_t b = 4 * ms * sizeof(int16_t) + 2 * 16 * sizeof(int16_t) + 4 * sizeof(int32_t) + 64 * sizeof(uint32_t);
+  size_t b = 4 * ms * sizeof(int16_t) + 2 * 16 * sizeof(int16_t) + 4 * sizeof(int32_t) + 64 * sizeof(uint32_t) + 512 * sizeof(uint32_t);
   if (max_size > 32) b += ms;   // ecarry (rectangles swept in several chunks, TRACE)
   return (b + 15) & ~(size_t)15;
 }
@@ -1419,6 +1447,7 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
   w.t1 = p16; p16 += 16; w.t2 = p16; p16 += 16;
   w.misc = (int32_t*)p16; p16 += 8;
   w.fr = (uint32_t*)p16; p16 += 128;
+  w.ck = (uint32_t*)p16; p16 += 1024;
   w.ecarry = (uint8_t*)p16;
   w.kDc = w.kCc = w.kDr = w.kRr = nullptr;
   const uint32_t spw = P.slots_per_warp;
@@ -1431,7 +1460,7 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
   st.pair = 0; st.qlen = 0; st.rlen = 0; st.si = 0; st.sj = 0; st.B = 32; st.prev_size = 0; st.dir = kRight; st.prev_dir = kGrow;
   st.off = 0; st.off_max = 0; st.best_max = 0; st.best_i = 0; st.best_j = 0; st.i_ckpt = 0; st.j_ckpt = 0; st.off_ckpt = 0;
   st.y_drop_iter = 0; st.x_drop_iter = 0; st.D_corner = 0; st.cells_lo = 0; st.cells_hi = 0; st.steps = 0;
-  st.widx = 0; st.ridx = 0; st.ck_widx = 0; st.ck_ridx = 0; st.overflow = 0;
+  st.widx = 0; st.ridx = 0; st.ck_widx = 0; st.ck_ridx = 0; st.overflow = 0; st.ck_pk = 0;
   constexpr int FRR = FR ? FR : 4;   // FR == 0: no s32 fast phase (that code is never reached)
   FastRegs<FRR> f;
   PkFast pf;
@@ -1470,12 +1499,16 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
       } else {
         bcast_state(gs, st, g * GW);
         // a parked group's registers are still laid out for the step it executed last (= prev_dir)
-        if (PKF) pk_fast_spill<LGT>(pf, w, gs.prev_dir, mine);
-        else fast_spill(f, w, gs.prev_dir, mine);
+        if (PKF) {
+          pk_fast_spill<LGT>(pf, w, gs.prev_dir, mine);
+          if (gs.ck_pk) { pk_ckpt_flush<LGT>(w, sm, g, mine); gs.ck_pk = 0u; }
+        } else {
+          fast_spill(f, w, gs.prev_dir, mine);
+        }
         if (sg == kStNeedGrow) apply_grow(gs, w, TRACE);
       }
       int r = kRunDone;
-      if (sg != kStDone) r = run_generic<SCORING, FLAGS>(P, gs, w, sm);
+      if (sg != kStDone) r = run_generic<SCORING, FLAGS>(P, gs, w, sm, kc);
       if (r == kRunDone) {
         finish_alignment<SCORING, FLAGS>(P, gs, w, sm, slot, warp_global);
         if (mine) status = kStEmpty;

@@ -23,6 +23,11 @@ namespace ba {
 
 BA_DEV uint32_t pk2(int v) { return wp::h_pack(v, v); }
 
+#ifndef BA_PK_UNROLL
+#define BA_PK_UNROLL 1
+#endif
+constexpr int kPkUnroll = BA_PK_UNROLL;    // 1, 2 or 4
+
 // shared-memory scoring tables of the packed path (one copy per CTA, built by stage_tables)
 constexpr int kMatBytes = 1024;            // raw matrix (exact path)
 constexpr int kPkTabBytes = 8192;          // kNuc: [8 classes][16][16] packed score pairs; kAA: [27][32] i16
@@ -116,12 +121,16 @@ BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int LGr, int l
   const int LG = LGT ? LGT : LGr;
   const int G = 1 << LG;
   const uint32_t lanedec = pk2(4 * lg * wp::h_lo(kc.ge2));
+  // kPkUnroll columns per iteration of the rolled loop: the kernel's hot code has to stay inside the SM's
+  // instruction cache (ncu: sm__icc_request_hit_rate), which a fully unrolled 8-column body does not
+  uint64_t cwq = ((uint64_t)cw1 << 32) | cw0;
 #pragma unroll 1
-  for (int h = 0; h < 2; h++) {
-    const uint32_t cwh = h ? cw1 : cw0;
+  for (int h = 0; h < 8 / kPkUnroll; h++) {
+    const uint32_t cwh = (uint32_t)cwq;
+    cwq >>= 8 * kPkUnroll;
 #pragma unroll
-    for (int cc = 0; cc < 4; cc++) {
-      const int cidx = h * 4 + cc;
+    for (int cc = 0; cc < kPkUnroll; cc++) {
+      const int cidx = h * kPkUnroll + cc;
       const uint32_t ch = sc.colh((cwh >> (8 * cc)) & 0xffu);
       // diagonal input of the lane's first rows: the previous column of the row above. Lane 0: low half = the
       // rectangle's corner (first column only; MIN = 0 afterwards, scan_block.rs:1211), high half = row 4G - 1,
@@ -182,21 +191,29 @@ BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int LGr, int l
   }
 }
 
-// best cell of the lane under the reference's order: value desc, AVX lane (row mod 16) asc, column desc, row desc
-// (scan_block.rs:1194-1201, avx2.rs:271-274). Same (bv, bkey) format as place_rect_r.
-BA_DEV void pk_lane_best(const uint32_t (&m)[4], const uint32_t (&mc)[4], int lg, int G, int& bv, unsigned& bkey) {
+// Best cell of the lane under the reference's order: value desc, AVX lane (row mod 16) asc, column desc, row desc
+// (scan_block.rs:1194-1201, avx2.rs:271-274). pk_lane_key: key of the lane's best cell among those equal to M
+// (0 if none); key format as in place_rect_r: (15 - class) << 27 | (column + 1) << 13 | row. Every row has seen
+// a cell >= 0 (guard), so there is no "no cell" case.
+BA_DEV unsigned pk_lane_key(const uint32_t (&m)[4], const uint32_t (&mc)[4], int lg, int G, int M) {
+  const uint32_t M2 = pk2(M);
+  const unsigned base0 = ((15u - (unsigned)((4 * lg) & 15)) << 27) | (unsigned)(4 * lg);
+  unsigned key = 0;
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    const unsigned cls = (unsigned)((4 * lg + k) & 15);
-#pragma unroll
-    for (int hf = 0; hf < 2; hf++) {
-      const int v = hf ? wp::h_hi(m[k]) : wp::h_lo(m[k]);
-      const unsigned c1 = hf ? (mc[k] >> 16) : (mc[k] & 0xffffu);
-      const unsigned row = (unsigned)(4 * lg + k + hf * 4 * G);
-      const unsigned key = ((15u - cls) << 27) | (c1 << 13) | row;
-      if (c1 != 0 && (v > bv || (v == bv && key > bkey))) { bv = v; bkey = key; }
-    }
+    bool ph, pl;
+    wp::vibmax2(m[k], M2, ph, pl);            // m >= M, i.e. m == M for M = the maximum
+    const unsigned base = base0 - ((unsigned)k << 27) + (unsigned)k;
+    const unsigned klo = base | ((mc[k] & 0xffffu) << 13);
+    const unsigned khi = (base + (unsigned)(4 * G)) | ((mc[k] >> 16) << 13);
+    if (pl && klo > key) key = klo;
+    if (ph && khi > key) key = khi;
   }
+  return key;
+}
+BA_DEV int pk_lane_max(const uint32_t (&m)[4]) {
+  const uint32_t v = wp::vmax2(wp::vmax3_2(m[0], m[1], m[2]), m[3]);
+  return wp::imax(wp::h_lo(v), wp::h_hi(v));
 }
 
 // borders in shared memory <-> packed registers of lane lg (rows 4lg.. and 4G + 4lg..)
@@ -212,6 +229,18 @@ BA_DEV void pk_store4(int16_t* p, int lg, int G, const uint32_t (&r)[4]) {
   hi.x = wp::prmt(r[0], r[1], 0x7632u); hi.y = wp::prmt(r[2], r[3], 0x7632u);
   *(uint2*)(p + 4 * lg) = lo;
   *(uint2*)(p + 4 * G + 4 * lg) = hi;
+}
+
+// lane-local range test of the D registers of both borders (the packed fast phase's per-step guard)
+BA_DEV bool pk_in_range_d(const uint32_t (&a)[4], const uint32_t (&b)[4], int lo, int hi) {
+  uint32_t mn = wp::vmin3_2(a[0], a[1], a[2]), mx = wp::vmax3_2(a[0], a[1], a[2]);
+  mn = wp::vmin3_2(mn, a[3], b[0]); mx = wp::vmax3_2(mx, a[3], b[0]);
+  mn = wp::vmin3_2(mn, b[1], b[2]); mx = wp::vmax3_2(mx, b[1], b[2]);
+  mn = wp::vmin2(mn, b[3]); mx = wp::vmax2(mx, b[3]);
+  bool p0, p1, p2, p3;
+  wp::vibmax2(mn, pk2(lo), p0, p1);
+  wp::vibmax2(pk2(hi), mx, p2, p3);
+  return p0 && p1 && p2 && p3;
 }
 
 // lane-local range test of packed values: every halfword of every register within [lo, hi]
@@ -232,7 +261,7 @@ BA_DEV bool pk_in_range(const uint32_t (&a)[N], const uint32_t (&b)[N], int lo, 
 // phase, one alignment per warp; lanes >= G mirror lanes < G). Returns false -- with nothing modified -- when the
 // rectangle's shape or value range is outside what the packed path covers; the caller then runs place_rect.
 template <int KIND, bool XDROP>
-BA_DEV bool place_rect_pk(const unsigned char* smem, const Params& P, const uint8_t* vec, const uint8_t* col,
+BA_DEV bool place_rect_pk(const unsigned char* smem, const Params& P, const PkConst& kc, const uint8_t* vec, const uint8_t* col,
                           const RectArgs& a, uint32_t* fr, int& bv, unsigned& bkey) {
   const int lane = wp::lane_id();
   const int H = a.H, W = a.W;
@@ -260,19 +289,21 @@ BA_DEV bool place_rect_pk(const unsigned char* smem, const Params& P, const uint
   PkScorer<KIND> sc;
   sc.init(smem, P);
   sc.rows(*(const uint32_t*)(vec + a.vec_base + 4 * lg), *(const uint32_t*)(vec + a.vec_base + 4 * G + 4 * lg));
-  PkConst kc;
-  pk_consts(kc, go, ge);
   uint32_t m[4] = {0u, 0u, 0u, 0u}, mc[4] = {0u, 0u, 0u, 0u};
   const bool writer = lane == G - 1;
   for (int cb = 0; cb < W; cb += 8) {
     const uint2 cw = *(const uint2*)(col + a.col_base + cb);
+#ifndef BA_PK_NO_LG5
+    if (LG == 5) pk_cols8<KIND, XDROP, 5>(sc, kc, 5, lg, cw.x, cw.y, D, C, (uint32_t)a.corner & 0xffffu, cb, m, mc, fr, writer);
+    else
+#endif
     pk_cols8<KIND, XDROP, 0>(sc, kc, LG, lg, cw.x, cw.y, D, C, (uint32_t)a.corner & 0xffffu, cb, m, mc, fr, writer);
     wp::syncwarp();
     if (lane < 8) { const uint32_t v = fr[lane]; a.OD[cb + lane] = (int16_t)(v >> 16); a.OR_[cb + lane] = (int16_t)(v & 0xffffu); }
     wp::syncwarp();
   }
   if (lane < G) { pk_store4(a.AD, lg, G, D); pk_store4(a.AC, lg, G, C); }
-  if (XDROP) pk_lane_best(m, mc, lg, G, bv, bkey);
+  if (XDROP) { bv = pk_lane_max(m); bkey = pk_lane_key(m, mc, lg, G, bv); }
   else bv = wp::imax(bv, wp::imax(wp::h_lo(m[0]), wp::h_hi(m[0])));
   wp::syncwarp();
   return true;

@@ -137,8 +137,11 @@ __global__ void ba_pack_kernel(PackArgs a) {
 
 // 128 threads per block, at least 4 blocks per SM: caps the kernel at 128 registers/thread. Measured on
 // B200 (C2 workload): uncapped (207 regs, 8 warps/SM) 476 GCUPS, 160 regs 580, 128 regs 634, 96 regs 596.
+#ifndef BA_LB_BLOCKS
+#define BA_LB_BLOCKS 4
+#endif
 template <int SCORING, int FLAGS, int FR>
-__global__ void __launch_bounds__(128, 4) ba_align_kernel(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(128, BA_LB_BLOCKS) ba_align_kernel(const __grid_constant__ Params P) {
   extern __shared__ __align__(16) unsigned char ba_smem[];
   const int nm = SCORING == kNuc ? 128 : (SCORING == kAA ? 864 : 0);
   for (int i = threadIdx.x; i < nm; i += blockDim.x) ba_smem[i] = (unsigned char)P.matrix[i];
@@ -178,9 +181,13 @@ static int occupancy(int wpb, size_t smem_bytes, int* blocks_per_sm) {
 #define BA_FOR_SEQ(X, S) X(S, 0, 0) X(S, 1, 0) X(S, 2, 0) X(S, 3, 0) X(S, 0, 4) X(S, 1, 4) X(S, 2, 4) X(S, 3, 4) \
                          X(S, 0, 8) X(S, 1, 8) X(S, 2, 8) X(S, 3, 8) X(S, 4, 0) X(S, 5, 0) X(S, 6, 0) X(S, 7, 0) \
                          X(S, 0, 18) X(S, 2, 18) X(S, 0, 19) X(S, 2, 19)
+#ifdef BA_MINIMAL   // tuning builds (tools/build_variant.sh): only the kernels of the C2 workload
+#define BA_FOR_KERNELS(X) X(kNuc, 2, 0) X(kNuc, 2, 18)
+#else
 #define BA_FOR_KERNELS(X) BA_FOR_SEQ(X, kNuc) BA_FOR_SEQ(X, kAA) BA_FOR_SEQ(X, kByte) \
   X(kProfile, 0, 0) X(kProfile, 1, 0) X(kProfile, 2, 0) X(kProfile, 3, 0) \
   X(kProfile, 4, 0) X(kProfile, 5, 0) X(kProfile, 6, 0) X(kProfile, 7, 0)
+#endif
 
 static int launch_dispatch(int scoring, int flags, int fr, const Params& P, int blocks, int wpb, size_t smem, dev_stream_t st) {
 #define X(S, F, R) if (scoring == S && flags == F && fr == R) return launch_align<S, F, R>(P, blocks, wpb, smem, st);
@@ -219,6 +226,7 @@ struct BaAligner {
 #ifndef BA_EMU
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
 #endif
+  double budget_frac = 0.55;   // share of device memory one batch may take for per-slot trace arenas
   int emu_warps = 3;   // emulation: number of (sequentially executed) warps, to exercise per-warp scratch
   // Device-buffer pool: cudaMalloc / cudaFree cost tens to hundreds of milliseconds for GB-sized buffers
   // (measured: 26-257 ms and 8-613 ms per call on B200), far more than the 40 ms H2D copy of a 2 GB batch,
@@ -619,7 +627,7 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
     b->runs_per_warp = (uint32_t)std::min<uint64_t>(len + 8, 0x7fffffffu);
     const uint64_t zmul = (cfg->flags & BA_LOCAL_START) ? 2 : 1;
     const uint64_t per_warp = spw * (zmul * b->trace_words_per_warp * 4 + (uint64_t)b->rects_per_warp * sizeof(Rect)) + (uint64_t)b->runs_per_warp * 4;
-    b->mem_budget = (uint64_t)(al->mem_total * 0.55);
+    b->mem_budget = (uint64_t)(al->mem_total * al->budget_frac);
     const uint64_t fit_warps = std::max<uint64_t>(1, b->mem_budget / std::max<uint64_t>(per_warp, 1));
     max_blocks = std::max<uint64_t>(1, std::min<uint64_t>(max_blocks, fit_warps / wpb));
   }
@@ -857,7 +865,11 @@ extern "C" int ba_align_batch(BaAligner* a, const BaConfig* cfg, size_t n, const
   const uint64_t bytes = n ? (q_off[n] - q_off[0]) + (r_off[n] - r_off[0]) : 0;
   if (n >= 8192 && bytes >= ((uint64_t)32 << 20)) K = 4;
   if (const char* e = getenv("BA_PIPELINE_CHUNKS")) K = std::max<size_t>(1, std::min<size_t>((size_t)atoi(e), 64));
+  // TRACE: every chunk in flight owns trace arenas, so fewer chunks and a split memory budget
+  if (cfg && (cfg->flags & BA_TRACE) && K > 2) K = 2;
   if (K > n) K = n ? n : 1;
+  const double budget_saved = a->budget_frac;
+  a->budget_frac = budget_saved / (double)K;
   // chunk boundaries with roughly equal input bytes
   std::vector<size_t> cut(K + 1, 0);
   cut[K] = n;
@@ -889,6 +901,7 @@ extern "C" int ba_align_batch(BaAligner* a, const BaConfig* cfg, size_t n, const
     }
     ba_batch_free(bs[c]);
   }
+  a->budget_frac = budget_saved;
   if (stats) *stats = tot;
   if (timing) fprintf(stderr, "ba_align_batch: %zu chunk(s), %.1f ms wall\n", K,
                       std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
@@ -996,27 +1009,33 @@ extern "C" int ba_batch_total_stats(const BaBatch* b, BaStats* stats) {
 // how the 13-ops-per-cell figure of the recurrence is counted.
 // -------------------------------------------------------------------------------------------------
 #ifndef BA_EMU
+template <bool PACKED>
 __global__ void ba_int_peak_kernel(int* out, int iters, int seed) {
-  int a[8];
+  unsigned a[8];
 #pragma unroll
-  for (int k = 0; k < 8; k++) a[k] = seed + k * 7 + threadIdx.x;
-  const int g = -(seed & 3) - 1;
+  for (int k = 0; k < 8; k++) a[k] = (unsigned)(seed + k * 7 + threadIdx.x);
+  const unsigned g = PACKED ? 0xfffefffeu : (unsigned)(-(seed & 3) - 1);
   for (int it = 0; it < iters; it++) {
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      a[k] = __viaddmax_s32(a[k], g, a[(k + 1) & 7]);
-      a[k] = __vimax3_s32(a[k], a[(k + 3) & 7], g);
+      if (PACKED) {
+        a[k] = __viaddmax_s16x2(a[k], g, a[(k + 1) & 7]);
+        a[k] = __vimax3_s16x2(a[k], a[(k + 3) & 7], g);
+      } else {
+        a[k] = (unsigned)__viaddmax_s32((int)a[k], (int)g, (int)a[(k + 1) & 7]);
+        a[k] = (unsigned)__vimax3_s32((int)a[k], (int)a[(k + 3) & 7], (int)g);
+      }
     }
   }
-  int r = 0;
+  unsigned r = 0;
 #pragma unroll
   for (int k = 0; k < 8; k++) r ^= a[k];
-  if (r == 0x7fffffff) out[0] = r;
+  if (r == 0x7fffffffu) out[0] = (int)r;
 }
 #endif
-extern "C" int ba_measure_int_peak(BaAligner* al, double* giga_ops_per_s) {
+static int measure_int_peak(BaAligner* al, bool packed, double* giga_ops_per_s) {
 #ifdef BA_EMU
-  (void)al; *giga_ops_per_s = 0; return BA_OK;
+  (void)al; (void)packed; *giga_ops_per_s = 0; return BA_OK;
 #else
   if (!al || !giga_ops_per_s) return fail(BA_ERR_ARG, "null");
   if (cudaSetDevice(al->device) != cudaSuccess) return fail(BA_ERR_CUDA, "cudaSetDevice failed");
@@ -1026,15 +1045,21 @@ extern "C" int ba_measure_int_peak(BaAligner* al, double* giga_ops_per_s) {
   float best = 1e30f;
   for (int rep = 0; rep < 5; rep++) {
     cudaEventRecord(al->ev0, al->stream);
-    ba_int_peak_kernel<<<blocks, threads, 0, al->stream>>>(d, iters, 12345 + rep);
+    if (packed) ba_int_peak_kernel<true><<<blocks, threads, 0, al->stream>>>(d, iters, 12345 + rep);
+    else ba_int_peak_kernel<false><<<blocks, threads, 0, al->stream>>>(d, iters, 12345 + rep);
     cudaEventRecord(al->ev1, al->stream);
     if (cudaEventSynchronize(al->ev1) != cudaSuccess) { dfree(d); return fail(BA_ERR_CUDA, "int peak kernel failed"); }
     float ms = 0; cudaEventElapsedTime(&ms, al->ev0, al->ev1);
     if (rep > 0 && ms < best) best = ms;
   }
   dfree(d);
-  const double ops = (double)blocks * threads * (double)iters * 8 * 4;   // 2 instr x 2 ops each per chain step
+  // per chain step: 2 instructions x 2 ops (add + max / two max) x 1 (s32) or 2 (s16x2) values each
+  const double ops = (double)blocks * threads * (double)iters * 8 * 4 * (packed ? 2 : 1);
   *giga_ops_per_s = ops / (best * 1e-3) / 1e9;
   return BA_OK;
 #endif
 }
+// issue rate of the DPX add-max / max3 instructions the DP is made of: one 32-bit value per lane and instruction ...
+extern "C" int ba_measure_int_peak(BaAligner* al, double* giga_ops_per_s) { return measure_int_peak(al, false, giga_ops_per_s); }
+// ... and two 16-bit values per lane and instruction (VIADDMNMX.S16x2 / VIMNMX3.S16x2), the packed path's peak
+extern "C" int ba_measure_int_peak_packed(BaAligner* al, double* giga_ops_per_s) { return measure_int_peak(al, true, giga_ops_per_s); }

@@ -194,8 +194,11 @@ int ba_align_batch_profiles(BaAligner* a, const BaConfig* cfg, size_t n,
                             const uint8_t* q_bytes, const uint64_t* q_off,
                             const struct AAProfile* const* profiles, AlignResult* out, BaStats* stats);
 
-/* Measured integer-ALU roofline denominator (giga i16-cell ops / s) for this device; see DESIGN.md. */
+/* Measured integer-ALU roofline denominators for this device (giga add/max operations per second); see DESIGN.md.
+ * ba_measure_int_peak: DPX add-max / max3 on one 32-bit value per lane (the exact path);
+ * ba_measure_int_peak_packed: the same instructions on two i16 values per lane (VIADDMNMX.S16x2, the packed path). */
 int ba_measure_int_peak(BaAligner* a, double* giga_ops_per_s);
+int ba_measure_int_peak_packed(BaAligner* a, double* giga_ops_per_s);
 
 /* helpers mirroring the Rust API that the C header of the reference lacks */
 struct NucMatrix* ba_new_simple_nucmatrix(int8_t match_score, int8_t mismatch_score); /* src/scores.rs:150-164 */
