@@ -628,7 +628,7 @@ BA_DEV bool pk_borders_ok(const Params& P, const AlnState& st, const WarpMem& w)
 }
 
 template <int SCORING, int FLAGS>
-BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const SlotMem& sm, const PkConst& kc) {
+BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const SlotMem& sm) {
   constexpr bool TRACE = (FLAGS & kTrace) != 0, XDROP = (FLAGS & kXDrop) != 0, EXT = (FLAGS & kExt) != 0;
   constexpr bool PROF = SCORING == kProfile;
   const bool m_local = EXT && (P.ext_flags & kLocalStart), m_fqs = EXT && (P.ext_flags & kFreeQueryStartGaps);
@@ -704,7 +704,7 @@ BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const Sl
       if (!st.overflow) {
         bool done = false;
         if (!PROF && !TRACE && !EXT && P.pk_enable)
-          done = place_rect_pk<(PROF ? kAA : SCORING), XDROP>(w.smem0, P, kc, sc.vec, sc.col, a, w.fr, pbv, pkey);
+          done = place_rect_pk<(PROF ? kAA : SCORING), XDROP>(w.smem0, P, P.kc, sc.vec, sc.col, a, w.fr, pbv, pkey);
 #ifdef BA_EMU
         if (wp::lane_id() == 0) { if (done) emu_stats::pk_cells += (uint64_t)a.W * a.H; else emu_stats::exact_cells += (uint64_t)a.W * a.H; }
 #endif
@@ -1229,7 +1229,7 @@ BA_DEV void pk_fast_spill(const PkFast& f, const WarpMem& w, int dir, bool mine)
 }
 
 template <int SCORING, int FLAGS, int LGT>
-BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, const PkConst& kc, AlnState& st, PkFast& f, int& status,
+BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast& f, int& status,
                          const uint8_t* qp, const uint8_t* rp, const SlotMem& sm) {
   constexpr bool XDROP = (FLAGS & kXDrop) != 0;
   constexpr int KIND = (SCORING == kProfile) ? kAA : SCORING;
@@ -1259,7 +1259,7 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, const PkConst& kc, A
 #pragma unroll
   for (int k = 0; k < 4; k++) { D[k] = wp::vadd2(f.aD[k], oa2); C[k] = wp::vadd2(f.aC[k], oa2); m[k] = 0u; mc[k] = 0u; }
   uint32_t* fr = w.fr + grp * 8;
-  pk_cols8<KIND, XDROP, LGT>(sc, kc, LGT, lg, cw.x, cw.y, D, C, (uint32_t)corner & 0xffffu, 0, m, mc, fr, lg == G - 1);
+  pk_cols8<KIND, XDROP, LGT>(sc, P.kc, LGT, lg, cw.x, cw.y, D, C, (uint32_t)corner & 0xffffu, 0, m, mc, fr, lg == G - 1);
   wp::syncwarp();
 
   // ---- borders after the step ----
@@ -1476,8 +1476,6 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
   bool tickets_left = true;
   FastConst<FRR> fc;
   fast_consts(fc, P.gap_extend);
-  PkConst kc;
-  pk_consts(kc, P.gap_open, P.gap_extend);
 
   for (;;) {
     // ---- service: refill empty groups, run the generic phase for parked ones ----
@@ -1508,7 +1506,7 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
         if (sg == kStNeedGrow) apply_grow(gs, w, TRACE);
       }
       int r = kRunDone;
-      if (sg != kStDone) r = run_generic<SCORING, FLAGS>(P, gs, w, sm, kc);
+      if (sg != kStDone) r = run_generic<SCORING, FLAGS>(P, gs, w, sm);
       if (r == kRunDone) {
         finish_alignment<SCORING, FLAGS>(P, gs, w, sm, slot, warp_global);
         if (mine) status = kStEmpty;
@@ -1528,7 +1526,7 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
     if (wp::ballot(status == kStFast) == 0u) break;
     // ---- fast phase: run until some group needs the generic phase ----
     for (;;) {
-      if (PKF) pk_fast_step<SCORING, FLAGS, LGT>(P, w, kc, st, pf, status, qp, rp, my_sm);
+      if (PKF) pk_fast_step<SCORING, FLAGS, LGT>(P, w, st, pf, status, qp, rp, my_sm);
       else if (FR) fast_step<SCORING, FLAGS, FRR>(P, w.mat, fc, st, f, status, qp, rp, my_sm);
       else break;
       if (wp::ballot(status != kStFast && status != kStEmpty) != 0u) break;

@@ -93,17 +93,6 @@ BA_DEV void stage_tables(unsigned char* smem, int tid, int nthreads) {
   }
 }
 
-// per-lane constants of the packed recurrence
-struct PkConst {
-  uint32_t ge2, go1, or2;   // packed gap_extend, gap_open * 65537 (see pk_cols8), packed gap_open - gap_extend
-  uint32_t kge[4];          // packed (k + 1) * gap_extend
-};
-BA_DEV void pk_consts(PkConst& c, int go, int ge) {
-  c.ge2 = pk2(ge); c.go1 = (uint32_t)go * 65537u; c.or2 = pk2(go - ge);
-#pragma unroll
-  for (int k = 0; k < 4; k++) c.kge[k] = pk2((k + 1) * ge);
-}
-
 // input range [GL, GH] under which a W-column packed rectangle is exact (see the header comment)
 BA_DEV void pk_bounds(int W, int go, int ge, int smax, int& GL, int& GH) {
   GL = -(W * go + (go - ge));
@@ -120,7 +109,12 @@ BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int LGr, int l
                      uint32_t* fr, bool writer) {
   const int LG = LGT ? LGT : LGr;
   const int G = 1 << LG;
-  const uint32_t lanedec = pk2(4 * lg * wp::h_lo(kc.ge2));
+  // The uniform constants are copied into vector registers once per call (opaque_zero): ptxas otherwise rebuilds
+  // every packed constant from its 16-bit halves at each use.
+  const uint32_t z = wp::opaque_zero();
+  const uint32_t ge2 = kc.ge2 + z, or2 = kc.or2 + z;
+  const uint32_t kge1 = kc.kge[1] + z, kge2 = kc.kge[2] + z, kge3 = kc.kge[3] + z;
+  const uint32_t lanedec = (uint32_t)lg * kc.lane1 + (lg ? 0x10000u : 0u);   // packed 4 * lg * gap_extend
   // kPkUnroll columns per iteration of the rolled loop: the kernel's hot code has to stay inside the SM's
   // instruction cache (ncu: sm__icc_request_hit_rate), which a fully unrolled 8-column body does not
   uint64_t cwq = ((uint64_t)cw1 << 32) | cw0;
@@ -143,25 +137,22 @@ BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int LGr, int l
         const uint32_t s2 = sc.score(ch, k);
         const uint32_t d00 = k ? D[k - 1] : up;
         const uint32_t c11o = D[k] + kc.go1;      // packed add as one 32-bit add: no borrow, both halves >= |open| (guard)
-        c11[k] = wp::viaddmax2(C[k], kc.ge2, c11o);
+        c11[k] = wp::viaddmax2(C[k], ge2, c11o);
         dd[k] = wp::viaddmax2(d00, s2, c11[k]);
-        uu[k] = k ? wp::viaddmax2(uu[k - 1], kc.ge2, dd[k]) : dd[0];
+        uu[k] = k ? wp::viaddmax2(uu[k - 1], ge2, dd[k]) : dd[0];
       }
       // Kogge-Stone over the lane aggregates, both half-blocks at once
       uint32_t inc = uu[3];
-      uint32_t dec = kc.kge[3];
       if (LGT) {
 #pragma unroll
         for (int s = 0; s < (LGT ? LGT : 1); s++) {
           const uint32_t u = (uint32_t)wp::shfl_up_w((int)inc, 1 << s, G);
-          inc = wp::viaddmax2(u, dec, inc);
-          dec = wp::vadd2(dec, dec);
+          inc = wp::viaddmax2(u, s == 0 ? kge3 : kc.dec[s] + z, inc);
         }
       } else {
         for (int s = 0; s < LG; s++) {
           const uint32_t u = (uint32_t)wp::shfl_up_w((int)inc, 1 << s, G);
-          inc = wp::viaddmax2(u, dec, inc);
-          dec = wp::vadd2(dec, dec);
+          inc = wp::viaddmax2(u, kc.dec[s] + z, inc);
         }
       }
       // carry into the lane: the lanes above (same half) and, for the high half, the whole low half-block
@@ -172,13 +163,14 @@ BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int LGr, int l
       uint32_t Un3 = 0;
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        const uint32_t Un = wp::viaddmax2(cin, kc.kge[k], uu[k]);
-        const uint32_t Dn = wp::viaddmax2(Un, kc.or2, dd[k]);
+        const uint32_t Un = wp::viaddmax2(cin, k == 0 ? ge2 : (k == 1 ? kge1 : (k == 2 ? kge2 : kge3)), uu[k]);
+        const uint32_t Dn = wp::viaddmax2(Un, or2, dd[k]);
         if (k == 3) Un3 = Un;
         if (XDROP) {
           bool ph, pl;
           m[k] = wp::vibmax2(Dn, m[k], ph, pl);
-          const uint32_t c1 = (uint32_t)(cbase + cidx + 1);
+          // kept in a vector register (opaque_zero) so that PRMT can take its selector as an immediate
+          const uint32_t c1 = (uint32_t)(cbase + cidx + 1) + wp::opaque_zero();
           if (pl) mc[k] = wp::prmt(mc[k], c1, 0x3254u);
           if (ph) mc[k] = wp::prmt(mc[k], c1, 0x5410u);
         } else {
@@ -186,7 +178,7 @@ BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int LGr, int l
         }
         D[k] = Dn; C[k] = c11[k];
       }
-      if (writer) fr[cidx] = wp::prmt(wp::vadd2(Un3, kc.or2), D[3], 0x7632u);   // T.hi | D.hi << 16
+      if (writer) fr[cidx] = wp::prmt(wp::vadd2(Un3, or2), D[3], 0x7632u);   // T.hi | D.hi << 16
     }
   }
 }

@@ -682,6 +682,14 @@ static Params make_params(const BaBatch* b) {
   P.min_size = b->min_size; P.max_size = b->max_size; P.x_drop = b->cfg.x_drop;
   P.flags = b->kflags; P.scoring = prof ? (int)kProfile : b->cfg.scoring;
   P.pk_smax = b->pk_smax; P.pk_enable = b->pk_enable;
+  {
+    auto pk2h = [](int v) { return ((uint32_t)v & 0xffffu) | ((uint32_t)v << 16); };
+    const int go = b->cfg.gaps.open, ge = b->cfg.gaps.extend;
+    P.kc.ge2 = pk2h(ge); P.kc.go1 = (uint32_t)go * 65537u; P.kc.or2 = pk2h(go - ge);
+    for (int k = 0; k < 4; k++) P.kc.kge[k] = pk2h((k + 1) * ge);
+    for (int s2 = 0; s2 < 5; s2++) P.kc.dec[s2] = pk2h((4 << s2) * ge);
+    P.kc.lane1 = (uint32_t)(4 * ge) * 65537u;
+  }
   P.ext_flags = (uint32_t)(b->cfg.flags & (BA_LOCAL_START | BA_FREE_QUERY_START_GAPS)); P.trace_zwords = b->d_zwords;
   P.out = b->d_out; P.ticket = b->d_ticket;
   P.ckpt = b->d_ckpt; P.slots_per_warp = b->slots_per_warp;

@@ -59,6 +59,15 @@ struct DevResult {
 // one record per step, debug builds only (mirrors ora_step in oracle/ba_oracle.h)
 struct StepLog { int32_t dir; uint32_t i, j, block_size; int32_t off; int16_t max, right_max, down_max; };
 
+// Uniform constants of the packed recurrence (ba_packed.cuh), filled in by the host so that the kernel reads them
+// as constant-bank operands instead of keeping (or recomputing) them in registers.
+struct PkConst {
+  uint32_t ge2, go1, or2;   // packed gap_extend; gap_open * 65537 (one 32-bit add = packed add, see pk_cols8); packed open - extend
+  uint32_t kge[4];          // packed (k + 1) * gap_extend
+  uint32_t dec[5];          // Kogge-Stone decays: packed (4 << s) * gap_extend
+  uint32_t lane1;           // 4 * gap_extend * 65537: lane lg's packed decay 4 * lg * gap_extend = lg * lane1 + (lg ? 65536 : 0)
+};
+
 struct Params {
   uint32_t n_pairs;
   const uint32_t* order;         // optional processing order (pair ids), longest first
@@ -73,6 +82,7 @@ struct Params {
   int32_t flags, scoring;
   int32_t pk_smax;               // max(0, largest matrix entry): growth bound of the packed path's range guard
   uint32_t pk_enable;            // packed 2 x i16 DP path on (sequence-sequence)
+  PkConst kc;
   uint32_t pk_fast;              // the fast phase is the packed one (pk_fast_step): entering it needs pk_borders_ok
   uint32_t ext_flags;            // kLocalStart | kFreeQueryStartGaps (only honoured by kernels instantiated with kExt)
   uint32_t* trace_zwords;        // zero-mask words per slot (TRACE && LOCAL_START), same stride as trace_words

@@ -44,6 +44,7 @@ inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   for (int i = 0; i < 4; i++) { const uint32_t n = (sel >> (4 * i)) & 0xfu; uint32_t byte = (uint32_t)(src >> (8 * (n & 7))) & 0xffu; if (n & 8) byte = (byte & 0x80u) ? 0xffu : 0u; r |= byte << (8 * i); }
   return r;
 }
+inline uint32_t opaque_zero() { return 0u; }
 inline int red_max(int v) { const uint32_t* a = emu::exchange((uint32_t)v); int m = (int)a[0]; for (int i = 1; i < 32; i++) m = (int)a[i] > m ? (int)a[i] : m; return m; }
 inline unsigned red_max_u(unsigned v) { const uint32_t* a = emu::exchange(v); unsigned m = a[0]; for (int i = 1; i < 32; i++) m = a[i] > m ? a[i] : m; return m; }
 inline unsigned ballot(bool p) { const uint32_t* a = emu::exchange(p ? 1u : 0u); unsigned m = 0; for (int i = 0; i < 32; i++) m |= (a[i] & 1u) << i; return m; }
@@ -85,6 +86,8 @@ BA_DEV uint32_t vmin3_2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s1
 BA_DEV uint32_t viaddmax2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }
 BA_DEV uint32_t vibmax2(uint32_t a, uint32_t b, bool& ph, bool& pl) { return __vibmax_s16x2(a, b, &ph, &pl); }
 BA_DEV uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+// always 0 (blocks are one-dimensional) but thread-varying for the compiler: keeps a value out of the uniform datapath
+BA_DEV uint32_t opaque_zero() { return threadIdx.y; }
 BA_DEV int red_max(int v) { return __reduce_max_sync(kFull, v); }
 BA_DEV unsigned red_max_u(unsigned v) { return __reduce_max_sync(kFull, v); }
 BA_DEV unsigned ballot(bool p) { return __ballot_sync(kFull, p); }
