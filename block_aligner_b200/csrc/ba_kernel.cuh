@@ -100,6 +100,9 @@ struct RectArgs {
   bool local;                    // LOCAL_START: every cell is floored at relative_zero (scan_block.rs:1134-1136)
   bool fqs0;                     // FREE_QUERY_START_GAPS and this rectangle's vectors start at row 0 (:1130)
   uint32_t* tz;                  // zero-mask words (TRACE && LOCAL_START, scan_block.rs:1184-1187), same indexing as tw
+  // FREE_QUERY_END_GAPS (scan_block.rs:333-368, 1194-1201): the block maximum is the running maximum of AVX lane
+  // |q| % 16 only, and the argmax column is tracked for the vectors that reach row |q| or lie below it
+  bool fqe; int fq_cls, fq_row0;  // lane class |q| % 16; first eligible row relative to the rectangle's top (= |q| - vec_base)
 };
 
 // profile context handed to the rectangle (scan_block.rs:612-783)
@@ -137,6 +140,7 @@ BA_DEV void place_rect_r(const SeqScorer<(SCORING == kProfile ? kAA : SCORING)>&
   const int ngroups = a.W >> 3;
   const bool origin = (a.vec_base == 0 && a.col_base == 0);  // scan_block.rs:1130
 
+  int fq_m = 0, fq_j = 0;      // D_max lane starts at MIN = 0, D_argmax_j at 0
   for (int ch = 0; ch < nchunks; ch++) {
     const int v0 = ch * CH + lane * R;
     const bool act = v0 < a.H;
@@ -263,6 +267,18 @@ BA_DEV void place_rect_r(const SeqScorer<(SCORING == kProfile ? kAA : SCORING)>&
         if (XDROP) trk[k] = wp::imax(trk[k], Dn[k] * 16384 + (cidx + 1));
         else trk[0] = wp::imax(trk[0], act ? Dn[k] : 0);
       }
+      if (EXT && a.fqe) {
+        // The reference visits the cells of one AVX lane column by column, top vector first, and records the column
+        // whenever an eligible cell is >= everything that lane has seen so far (D_max == D11 after the update).
+        // Rows of one class sit in the same register slot (16 = 0 mod R) of every second lane.
+        int vloc = Dn[0];
+#pragma unroll
+        for (int k = 1; k < R; k++) if ((a.fq_cls & (R - 1)) == k) vloc = Dn[k];
+        for (int r0 = a.fq_cls; r0 < rows_here; r0 += 16) {
+          const int v = wp::shfl_idx(vloc, r0 / R);
+          if (v >= fq_m) { fq_m = v; if (ch * CH + r0 >= a.fq_row0) fq_j = cidx; }
+        }
+      }
       if (TRACE) {
         // "R gap at this row was opened at the row above" = e of the row above (scan_block.rs:1179-1181)
         const unsigned eb = wp::ballot(((ebits >> (R - 1)) & 1u) != 0);
@@ -317,6 +333,7 @@ BA_DEV void place_rect_r(const SeqScorer<(SCORING == kProfile ? kAA : SCORING)>&
     }
     if (multi) wp::syncwarp();
   }
+  if (EXT && a.fqe) { bv = fq_m; bkey = (unsigned)fq_j; }
   wp::syncwarp();
 }
 
@@ -329,7 +346,8 @@ BA_DEV void place_rect(const SeqScorer<(SCORING == kProfile ? kAA : SCORING)>& s
   bv = 0;                // D_max starts at MIN = 0 (scan_block.rs:1101)
   bkey = 15u << 27;      // "no cell": AVX lane 0 with argmax (0, 0)
   if (a.W == 0 || a.H == 0) return;   // scan_block.rs:1105-1107
-  if (a.H >= 256) place_rect_r<SCORING, RT, 8, TRACE, XDROP, EXT>(sc, pa, a, w, bv, bkey);
+  // FREE_QUERY_END_GAPS needs the whole rectangle in one chunk (cell order matters): 8 rows per lane up to 256 rows
+  if (a.H >= 256 || (EXT && a.fqe)) place_rect_r<SCORING, RT, 8, TRACE, XDROP, EXT>(sc, pa, a, w, bv, bkey);
   else place_rect_r<SCORING, RT, 1, TRACE, XDROP, EXT>(sc, pa, a, w, bv, bkey);
 }
 
@@ -430,21 +448,24 @@ BA_DEV void add_cells(AlnState& st, uint32_t n) {
   st.cells_lo = lo;
 }
 
-BA_HD uint64_t rect_words(int H, int W) {
-  const int R = rect_rows_per_lane(H);
+BA_HD uint64_t rect_words(int H, int W, bool force8 = false) {
+  const int R = force8 ? 8 : rect_rows_per_lane(H);
   const int CH = 32 * R;
   const int nch = (H + CH - 1) / CH;
   return (uint64_t)nch * (uint64_t)(W >> 3) * R * 32;
 }
 // Trace::add_block (scan_block.rs:1428-1443); returns where this rectangle's words go
-BA_DEV uint32_t* trace_push(AlnState& st, const SlotMem& sm, uint32_t row, uint32_t col, int W, int H, bool right, bool writer) {
-  const uint64_t need = rect_words(H, W);
+// force8: the rectangle is computed with 8 rows per lane whatever its height (FREE_QUERY_END_GAPS); recorded in bit 1
+// of Rect::right so that the walk-back indexes the words the same way
+BA_DEV uint32_t* trace_push(AlnState& st, const SlotMem& sm, uint32_t row, uint32_t col, int W, int H, bool right, bool writer,
+                            bool force8 = false) {
+  const uint64_t need = rect_words(H, W, force8);
   if (st.ridx >= sm.rects_cap || (uint64_t)st.widx + need > sm.words_cap || ((uint64_t)st.widx + need) >> 32) {
     st.overflow = 1u;
     return sm.words;
   }
   if (writer) {
-    Rect r; r.row = row; r.col = col; r.h = (uint16_t)H; r.w = (uint16_t)W; r.right = right ? 1u : 0u; r.word_off = st.widx;
+    Rect r; r.row = row; r.col = col; r.h = (uint16_t)H; r.w = (uint16_t)W; r.right = (right ? 1u : 0u) | (force8 ? 2u : 0u); r.word_off = st.widx;
     sm.rects[st.ridx] = r;
   }
   uint32_t* p = sm.words + st.widx;
@@ -475,20 +496,21 @@ BA_DEV void traceback_walk(const uint32_t* words, const uint32_t* zwords, bool f
     }
     if (bad) break;
     const int H = rc.h, W = rc.w;
-    const int R = rect_rows_per_lane(H);
+    const bool rc_right = (rc.right & 1u) != 0;
+    const int R = (rc.right & 2u) ? 8 : rect_rows_per_lane(H);
     const int CH = 32 * R;
     const int ngroups = W >> 3;
     const uint32_t* tw = words + rc.word_off;
     // The 64-entry OP_LUT (scan_block.rs:1508-1572) folded into branches. Bit 0 of trace/trace2
     // talks about the gap table that runs along the rectangle's sequential columns (C for a right
     // rectangle, R for a down rectangle), bit 1 about the table along its vectors.
-    const int tabA = rc.right ? 1 : 2, tabB = rc.right ? 2 : 1;
-    const uint32_t opA = rc.right ? 5u : 4u, opB = rc.right ? 4u : 5u;   // D : I
+    const int tabA = rc_right ? 1 : 2, tabB = rc_right ? 2 : 1;
+    const uint32_t opA = rc_right ? 5u : 4u, opB = rc_right ? 4u : 5u;   // D : I
     while (i >= rc.row && j >= rc.col && (i > 0 || j > 0)) {
       // FREE_QUERY_START_GAPS: stop on row 0, which always lies in right rectangles (scan_block.rs:1597-1600)
-      if (fqs && rc.right && i == 0) { stop = true; break; }
-      const uint32_t v = rc.right ? i - rc.row : j - rc.col;
-      const uint32_t c = rc.right ? j - rc.col : i - rc.row;
+      if (fqs && rc_right && i == 0) { stop = true; break; }
+      const uint32_t v = rc_right ? i - rc.row : j - rc.col;
+      const uint32_t c = rc_right ? j - rc.col : i - rc.row;
       const uint32_t ch = v / CH, ln = (v % CH) / R, k = v % R;
       const size_t widx = (((size_t)ch * ngroups + (c >> 3)) * R + k) * 32 + ln;
       // LOCAL_START: the alignment starts at a cell equal to relative_zero (scan_block.rs:1606-1612)
@@ -632,6 +654,7 @@ BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const Sl
   constexpr bool TRACE = (FLAGS & kTrace) != 0, XDROP = (FLAGS & kXDrop) != 0, EXT = (FLAGS & kExt) != 0;
   constexpr bool PROF = SCORING == kProfile;
   const bool m_local = EXT && (P.ext_flags & kLocalStart), m_fqs = EXT && (P.ext_flags & kFreeQueryStartGaps);
+  const bool m_fqe = EXT && (P.ext_flags & kFreeQueryEndGaps);
   const int lane = wp::lane_id();
   const uint8_t* q = P.seq + P.q_off[st.pair];
   const uint8_t* r = nullptr;
@@ -686,17 +709,18 @@ BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const Sl
       }
       const uint32_t vec_len = rect_right ? qlen : rlen, col_len = rect_right ? rlen : qlen;
       a.ncols = a.W;
-      if (!XDROP && a.vec_base + a.H > vec_len) {   // early break (scan_block.rs:1216-1224)
+      if (!XDROP && !m_fqe && a.vec_base + a.H > vec_len) {   // early break (scan_block.rs:1216-1224)
         int lim = (int)col_len - (int)a.col_base;
         if (lim < 0) lim = 0;
         if (lim + 1 < a.ncols) a.ncols = lim + 1;
       }
       a.tw = nullptr; a.tz = nullptr;
       a.local = m_local; a.fqs0 = m_fqs && rect_right && a.vec_base == 0;
+      a.fqe = m_fqe; a.fq_cls = (int)(qlen % kL); a.fq_row0 = (int)qlen - (int)a.vec_base;
       if (TRACE && a.W > 0 && a.H >= 0) {
         const uint32_t woff = st.widx;
         if (m_local && sm.zwords) a.tz = sm.zwords + woff;
-        a.tw = trace_push(st, sm, rect_right ? a.vec_base : a.col_base, rect_right ? a.col_base : a.vec_base, a.W, a.H, rect_right, lane == 0);
+        a.tw = trace_push(st, sm, rect_right ? a.vec_base : a.col_base, rect_right ? a.col_base : a.vec_base, a.W, a.H, rect_right, lane == 0, m_fqe);
       }
       add_cells(st, (uint32_t)(a.W * a.H));
       sc.vec = rect_right ? q : r; sc.col = rect_right ? r : q;
@@ -746,6 +770,10 @@ BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const Sl
     }
 
     if (st.off_max > st.best_max) {
+      if (m_fqe) {   // scan_block.rs:354-368: always in row |q|; the block only grows (first block) or shifts right
+        st.best_i = qlen;
+        st.best_j = sj + (uint32_t)(this_dir == kRight ? B - kStep : st.prev_size) + (uint32_t)bkey;
+      }
       if (XDROP) {
         // decode the argmax (scan_block.rs:370-404)
         const bool use_right = (this_dir != kGrow) || (D_max_max >= grow_max);
@@ -821,7 +849,7 @@ BA_DEV void finish_alignment(const Params& P, const AlnState& st, const WarpMem&
   DevResult res;
   res.status = st.overflow ? (uint32_t)kTraceOverflow : (uint32_t)kOk;
   res.cells = ((uint64_t)st.cells_hi << 32) | st.cells_lo; res.steps = st.steps; res.cigar_n = 0; res.cigar_off = 0;
-  if (XDROP) {
+  if (XDROP || (P.ext_flags & kFreeQueryEndGaps)) {   // scan_block.rs:567-573
     res.score = st.best_max; res.query_idx = st.best_i; res.reference_idx = st.best_j;
   } else if (st.overflow) {
     // aborted mid-way (trace arena full): the block is not at the end of the sequences, there is no result yet

@@ -407,8 +407,9 @@ extern "C" void ba_batch_free(BaBatch* b) {
 static int check_config(const BaConfig* cfg, uint32_t* mn, uint32_t* mx) {
   if (!cfg) return fail(BA_ERR_ARG, "cfg is null");
   if (cfg->scoring < 0 || cfg->scoring > 3) return fail(BA_ERR_ARG, "bad scoring kind");
-  if (cfg->flags & BA_FREE_QUERY_END_GAPS) return fail(BA_ERR_ARG, "FREE_QUERY_END_GAPS is not implemented yet");
-  if (cfg->flags & ~(BA_TRACE | BA_XDROP | BA_LOCAL_START | BA_FREE_QUERY_START_GAPS)) return fail(BA_ERR_ARG, "unsupported flags");
+  if (cfg->flags & ~(BA_TRACE | BA_XDROP | BA_LOCAL_START | BA_FREE_QUERY_START_GAPS | BA_FREE_QUERY_END_GAPS)) return fail(BA_ERR_ARG, "unsupported flags");
+  if ((cfg->flags & BA_XDROP) && (cfg->flags & BA_FREE_QUERY_END_GAPS))
+    return fail(BA_ERR_ARG, "Cannot set both X_DROP and FREE_QUERY_END_GAPS!");   // scan_block.rs:861
   if ((cfg->flags & BA_LOCAL_START) && (cfg->flags & BA_FREE_QUERY_START_GAPS))
     return fail(BA_ERR_ARG, "Cannot set both LOCAL_START and FREE_QUERY_START_GAPS!");   // scan_block.rs:860
   if (cfg->scoring != BA_SCORING_PROFILE) {
@@ -422,6 +423,8 @@ static int check_config(const BaConfig* cfg, uint32_t* mn, uint32_t* mx) {
   if (b > (uint64_t)kMaxBlock) return fail(BA_ERR_SIZE, "max block size above 8192 is not supported by this build");
   if ((cfg->flags & BA_XDROP) && cfg->x_drop < 0) return fail(BA_ERR_XDROP, "X-drop threshold amount must be nonnegative!");
   if (cfg->scoring == BA_SCORING_PROFILE && cfg->cigar_eq) return fail(BA_ERR_ARG, "cigar_eq needs a reference sequence");
+  // our limit: the lane-ordered argmax of this mode is computed with the whole block in one 256-row chunk
+  if ((cfg->flags & BA_FREE_QUERY_END_GAPS) && a > 256) return fail(BA_ERR_SIZE, "FREE_QUERY_END_GAPS supports min block sizes up to 256");
   *mn = (uint32_t)a; *mx = (uint32_t)b;
   return BA_OK;
 }
@@ -467,6 +470,9 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
       c = r_off[k + 1] - r_off[k];
     }
     if (a >= ((uint64_t)1 << 31) || c >= ((uint64_t)1 << 31)) { ba_batch_free(b); return fail(BA_ERR_ARG, "sequence too long"); }
+    if ((cfg->flags & BA_FREE_QUERY_END_GAPS) && !(mn > a)) {   // scan_block.rs:862
+      ba_batch_free(b); return fail(BA_ERR_SIZE, "Min block size must be larger than the query length for FREE_QUERY_END_GAPS!");
+    }
     ql[k] = (uint32_t)a; rl[k] = (uint32_t)c;
     pq[k] = pos; pos += (1 + a + pad + 15) & ~(uint64_t)15;
     if (!prof) { pr[k] = pos; pos += (1 + c + pad + 15) & ~(uint64_t)15; }
@@ -584,7 +590,7 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
 
   // launch geometry and per-slot scratch
   // fast phase: four alignments per warp while the block sits at its minimum size (32 or 64)
-  const bool ext = (cfg->flags & (BA_LOCAL_START | BA_FREE_QUERY_START_GAPS)) != 0;
+  const bool ext = (cfg->flags & (BA_LOCAL_START | BA_FREE_QUERY_START_GAPS | BA_FREE_QUERY_END_GAPS)) != 0;
   b->kflags = (cfg->flags & 3) | (ext ? kExt : 0);
   // fast-phase mode (third kernel template argument): 4 / 8 = s32 rows per lane (TRACE), 16 + LGT = packed, 0 = none
   b->fast_rows = (!prof && !ext && !getenv("BA_NO_FAST")) ? (mn == 32 ? 4 : (mn == 64 ? 8 : 0)) : 0;
@@ -618,10 +624,12 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
     const uint64_t len = (uint64_t)b->max_pair_len + 2;
     uint64_t words = 2 * (uint64_t)(mx / 16) * (len + 2 * (uint64_t)mx);
     if (mn == 16) words *= 2;   // 16-row rectangles still occupy a 32-lane word group
+    // FREE_QUERY_END_GAPS: every rectangle is laid out with 8 rows per lane (one 256-row chunk): 32 words per column
+    if (cfg->flags & BA_FREE_QUERY_END_GAPS) words = std::max<uint64_t>(words, 32 * (len + 2 * (uint64_t)mx));
     if (words + 64 >= ((uint64_t)1 << 32)) { ba_batch_free(b); return fail(BA_ERR_SIZE, "trace arena of one alignment exceeds 2^32 words"); }
     b->trace_words_bound = words + 64;
     uint64_t first = 4 * len * (uint64_t)std::max<uint32_t>(mn, 32) / 8 + (uint64_t)mx * mx / 4 + 4096;
-    if (getenv("BA_TRACE_WORST_CASE")) first = b->trace_words_bound;
+    if (getenv("BA_TRACE_WORST_CASE") || (cfg->flags & BA_FREE_QUERY_END_GAPS)) first = b->trace_words_bound;
     b->trace_words_per_warp = std::min<uint64_t>(b->trace_words_bound, first);
     b->rects_per_warp = (uint32_t)std::min<uint64_t>(len * 2 + 8, 0x7fffffffu);
     b->runs_per_warp = (uint32_t)std::min<uint64_t>(len + 8, 0x7fffffffu);
@@ -690,7 +698,7 @@ static Params make_params(const BaBatch* b) {
     for (int s2 = 0; s2 < 5; s2++) P.kc.dec[s2] = pk2h((4 << s2) * ge);
     P.kc.lane1 = (uint32_t)(4 * ge) * 65537u;
   }
-  P.ext_flags = (uint32_t)(b->cfg.flags & (BA_LOCAL_START | BA_FREE_QUERY_START_GAPS)); P.trace_zwords = b->d_zwords;
+  P.ext_flags = (uint32_t)(b->cfg.flags & (BA_LOCAL_START | BA_FREE_QUERY_START_GAPS | BA_FREE_QUERY_END_GAPS)); P.trace_zwords = b->d_zwords;
   P.out = b->d_out; P.ticket = b->d_ticket;
   P.ckpt = b->d_ckpt; P.slots_per_warp = b->slots_per_warp;
   P.fast_block = b->fast_rows >= 16 ? (8u << (b->fast_rows - 16)) : (uint32_t)(8 * b->fast_rows);

@@ -122,7 +122,8 @@ enum { BA_OK = 0, BA_ERR_CUDA = 1, BA_ERR_GAPS = 2, BA_ERR_SIZE = 3, BA_ERR_XDRO
        BA_ERR_CHAR = 6, BA_ERR_NOMEM = 7, BA_ERR_OVERFLOW = 8 };
 enum { BA_SCORING_NUC = 0, BA_SCORING_AA = 1, BA_SCORING_BYTE = 2, BA_SCORING_PROFILE = 3 };
 /* Block<TRACE, X_DROP, LOCAL_START, FREE_QUERY_START_GAPS, FREE_QUERY_END_GAPS> const generics
- * (src/scan_block.rs:89) as flags. The last one is not implemented yet (BA_ERR_ARG). */
+ * (src/scan_block.rs:89) as flags. BA_FREE_QUERY_END_GAPS: min block size <= 256 (and, as in the reference, larger
+ * than every query and not combined with BA_XDROP). */
 enum { BA_TRACE = 1, BA_XDROP = 2, BA_LOCAL_START = 4, BA_FREE_QUERY_START_GAPS = 8, BA_FREE_QUERY_END_GAPS = 16 };
 
 typedef struct BaAligner BaAligner; /* one per GPU: stream + reusable device scratch */
@@ -130,7 +131,7 @@ typedef struct BaBatch BaBatch;     /* one uploaded batch: device-resident input
 
 typedef struct BaConfig {
   int32_t scoring;        /* BA_SCORING_* ; selects what `matrix` points at */
-  int32_t flags;          /* BA_TRACE | BA_XDROP | BA_LOCAL_START | BA_FREE_QUERY_START_GAPS */
+  int32_t flags;          /* BA_TRACE | BA_XDROP | BA_LOCAL_START | BA_FREE_QUERY_START_GAPS | BA_FREE_QUERY_END_GAPS */
   const void* matrix;     /* NucMatrix* (128 B) / AAMatrix* (864 B) / ByteMatrix* ; NULL for profiles */
   Gaps gaps;              /* src/scores.rs:335-338; ignored for profiles (per-position gaps) */
   SizeRange size;         /* min..=max block size, powers of two (clamped up to 16 like the reference) */

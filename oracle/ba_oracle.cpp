@@ -848,7 +848,7 @@ static void run_prof(OraBlock& B, View q, const OraProfile& p, size_t mn, size_t
 
 // flags -> instantiation. Valid combos: TRACE x XDROP x {plain, LOCAL, FQS, FQE (no XDROP)}.
 #define FOR_FLAGS(X) \
-  X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(16) X(17)
+  X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(16) X(17) X(20) X(21) X(24) X(25)
 
 template <class M>
 static int dispatch_seq(OraBlock& B, const M& m, Gaps g, View q, View r, size_t mn, size_t mx, int32_t x) {

@@ -1,6 +1,7 @@
 """Device source (emulated on the CPU) vs the oracle on seeded random inputs: every scoring kind, every
 TRACE/X_DROP combination, fixed and adaptive block ranges from 16 up to the multi-chunk (>256) path.
 Bit-exact bar: score, query_idx, reference_idx, CIGAR runs and the path-determined cell count."""
+import numpy as np
 import pytest
 
 import backend
@@ -104,8 +105,57 @@ def test_local_start_and_free_query_start_gaps(env, mode, flags, size):
     assert parity.check_workload(*env, w, 10, seed=17 + flags) == 0
 
 
+def _short_query_batch(n, qmax, rmin, rmax, seed, alphabet=b"ACGT"):
+    """Short queries (a mutated window of the reference) against longer references: the FREE_QUERY_END_GAPS shape."""
+    rng = np.random.default_rng(seed)
+    qs, rs = [], []
+    for _ in range(n):
+        rl = int(rng.integers(rmin, rmax + 1))
+        r = rng.choice(list(alphabet), rl).astype(np.uint8)
+        ql = int(rng.integers(0, qmax + 1))
+        st = int(rng.integers(0, max(1, rl - ql)))
+        q = r[st:st + ql].copy()
+        for k in range(len(q)):
+            if rng.random() < 0.08:
+                q[k] = rng.choice(list(alphabet))
+        if len(q) > 4 and rng.random() < 0.3:
+            cut = int(rng.integers(1, len(q) - 1))
+            q = np.concatenate([q[:cut], q[cut + 1:]])
+        qs.append(q)
+        rs.append(r)
+    qo = np.zeros(n + 1, dtype=np.uint64)
+    ro = np.zeros(n + 1, dtype=np.uint64)
+    qo[1:] = np.cumsum([len(x) for x in qs])
+    ro[1:] = np.cumsum([len(x) for x in rs])
+    return np.concatenate(qs + [np.zeros(0, np.uint8)]), qo, np.concatenate(rs), ro
+
+
+@pytest.mark.parametrize("flags", [0, api.TRACE, api.TRACE | api.LOCAL_START, api.FREE_QUERY_START_GAPS])
+@pytest.mark.parametrize("size", [(32, 32), (64, 64), (64, 256), (128, 128), (256, 256)])
+def test_free_query_end_gaps(env, flags, size):
+    """Block<_, false, _, _, FREE_QUERY_END_GAPS> (scan_block.rs:333-368, 1194-1201): the block maximum and its column
+    come from one AVX lane class only, in the reference's cell order."""
+    lib, al = env
+    fl = flags | api.FREE_QUERY_END_GAPS
+    qa, qo, ra, ro = _short_query_batch(24, size[0] - 1, 40, 700, seed=size[0] + flags)
+    m = lib.builtin_matrix("NW1")[1]
+    got = parity.run_lib(lib, al, api.SCORING_NUC, m, (-2, -1), size, 0, fl, bool(fl & api.TRACE), qa, qo, ra, ro)
+    exp = parity.oracle_batch(api.SCORING_NUC, m, (-2, -1), size, 0, fl, bool(fl & api.TRACE), qa, qo, ra, ro)
+    assert parity.compare(f"fqe/{flags}/{size}", got, exp) == 0
+
+
+def test_free_query_end_gaps_protein(env):
+    lib, al = env
+    fl = api.TRACE | api.FREE_QUERY_END_GAPS
+    qa, qo, ra, ro = _short_query_batch(24, 63, 80, 500, seed=77, alphabet=b"ACDEFGHIKLMNPQRSTVWY")
+    m = lib.builtin_matrix("BLOSUM62")[1]
+    got = parity.run_lib(lib, al, api.SCORING_AA, m, (-11, -1), (64, 64), 0, fl, True, qa, qo, ra, ro)
+    exp = parity.oracle_batch(api.SCORING_AA, m, (-11, -1), (64, 64), 0, fl, True, qa, qo, ra, ro)
+    assert parity.compare("fqe/protein", got, exp) == 0
+
+
 def test_extended_mode_golden_vectors(env):
-    """scan_block.rs:2171-2211 (the FREE_QUERY_END_GAPS cases of that test are not implemented yet)"""
+    """scan_block.rs:2171-2229"""
     lib, al = env
     nw1 = lib.builtin_matrix("NW1")[1]
     T, X, L, F = api.TRACE, api.XDROP, api.LOCAL_START, api.FREE_QUERY_START_GAPS
@@ -116,8 +166,14 @@ def test_extended_mode_golden_vectors(env):
             (T | F, b"AAAAAA", b"CCCCCCCCCCAAATAA", 0, (4, 6, 16), "3=1X2=")]:
         res, cigs, _ = al.align_batch([q], [r], api.SCORING_NUC, nw1, (-2, -1), (32, 32), xd, fl, True)
         assert res[0] == exp and cigs[0] == cig
-    with pytest.raises(api.BlockAlignerError, match="not implemented"):
-        al.align_batch([b"AAAA"], [b"AAAA"], api.SCORING_NUC, nw1, (-2, -1), (32, 32), 0, api.FREE_QUERY_END_GAPS, False)
+    E = api.FREE_QUERY_END_GAPS
+    for q, r, exp, cig in [(b"AAAAAA", b"AAAAAACCCCCCCCCC", (6, 6, 6), "6="), (b"AAAAAA", b"AAATAACCCCCCCCCC", (4, 6, 6), "3=1X2=")]:
+        res, cigs, _ = al.align_batch([q], [r], api.SCORING_NUC, nw1, (-2, -1), (32, 32), 0, T | E, True)
+        assert res[0] == exp and cigs[0] == cig
+    with pytest.raises(api.BlockAlignerError, match="larger than the query"):
+        al.align_batch([b"A" * 40], [b"AAAA"], api.SCORING_NUC, nw1, (-2, -1), (32, 32), 0, E, False)
+    with pytest.raises(api.BlockAlignerError, match="X_DROP and FREE_QUERY_END_GAPS"):
+        al.align_batch([b"AAAA"], [b"AAAA"], api.SCORING_NUC, nw1, (-2, -1), (32, 32), 0, E | X, False)
     with pytest.raises(api.BlockAlignerError, match="both"):
         al.align_batch([b"AAAA"], [b"AAAA"], api.SCORING_NUC, nw1, (-2, -1), (32, 32), 0, L | F, False)
 

@@ -146,7 +146,7 @@ def test_local_start_and_free_query_start_gaps(env, mode, flags, size):
 
 
 def test_extended_mode_golden_vectors(env):
-    """scan_block.rs:2171-2211 (the FREE_QUERY_END_GAPS cases of that test are not implemented yet)"""
+    """scan_block.rs:2171-2229"""
     lib, al = env
     nw1 = lib.builtin_matrix("NW1")[1]
     T, X, L, F = api.TRACE, api.XDROP, api.LOCAL_START, api.FREE_QUERY_START_GAPS
@@ -157,8 +157,14 @@ def test_extended_mode_golden_vectors(env):
             (T | F, b"AAAAAA", b"CCCCCCCCCCAAATAA", 0, (4, 6, 16), "3=1X2=")]:
         res, cigs, _ = al.align_batch([q], [r], api.SCORING_NUC, nw1, (-2, -1), (32, 32), xd, fl, True)
         assert res[0] == exp and cigs[0] == cig
-    with pytest.raises(api.BlockAlignerError, match="not implemented"):
-        al.align_batch([b"AAAA"], [b"AAAA"], api.SCORING_NUC, nw1, (-2, -1), (32, 32), 0, api.FREE_QUERY_END_GAPS, False)
+    E = api.FREE_QUERY_END_GAPS
+    for q, r, exp, cig in [(b"AAAAAA", b"AAAAAACCCCCCCCCC", (6, 6, 6), "6="), (b"AAAAAA", b"AAATAACCCCCCCCCC", (4, 6, 6), "3=1X2=")]:
+        res, cigs, _ = al.align_batch([q], [r], api.SCORING_NUC, nw1, (-2, -1), (32, 32), 0, T | E, True)
+        assert res[0] == exp and cigs[0] == cig
+    with pytest.raises(api.BlockAlignerError, match="larger than the query"):
+        al.align_batch([b"A" * 40], [b"AAAA"], api.SCORING_NUC, nw1, (-2, -1), (32, 32), 0, E, False)
+    with pytest.raises(api.BlockAlignerError, match="X_DROP and FREE_QUERY_END_GAPS"):
+        al.align_batch([b"AAAA"], [b"AAAA"], api.SCORING_NUC, nw1, (-2, -1), (32, 32), 0, E | X, False)
     with pytest.raises(api.BlockAlignerError, match="both"):
         al.align_batch([b"AAAA"], [b"AAAA"], api.SCORING_NUC, nw1, (-2, -1), (32, 32), 0, L | F, False)
 
@@ -171,3 +177,17 @@ def test_extended_modes_protein_and_profile(env, mode):
     w = dict(workloads.WORKLOADS["C4_seq_to_profile_xdrop"])
     w["flags"] = api.TRACE | mode
     assert parity.check_workload(*env, w, 150, size=(32, 128), seed=29) == 0
+
+
+@pytest.mark.parametrize("flags", [0, api.TRACE, api.TRACE | api.LOCAL_START, api.FREE_QUERY_START_GAPS])
+@pytest.mark.parametrize("size", [(32, 32), (64, 64), (64, 256), (128, 128), (256, 256)])
+def test_free_query_end_gaps(env, flags, size):
+    """Block<_, false, _, _, FREE_QUERY_END_GAPS> (scan_block.rs:333-368, 1194-1201) on short queries"""
+    from test_emu_parity import _short_query_batch
+    lib, al = env
+    fl = flags | api.FREE_QUERY_END_GAPS
+    qa, qo, ra, ro = _short_query_batch(400, size[0] - 1, 40, 900, seed=size[0] + flags)
+    m = lib.builtin_matrix("NW1")[1]
+    got = parity.run_lib(lib, al, api.SCORING_NUC, m, (-2, -1), size, 0, fl, bool(fl & api.TRACE), qa, qo, ra, ro)
+    exp = parity.oracle_batch(api.SCORING_NUC, m, (-2, -1), size, 0, fl, bool(fl & api.TRACE), qa, qo, ra, ro)
+    assert parity.compare(f"fqe/{flags}/{size}", got, exp) == 0
