@@ -448,24 +448,27 @@ BA_DEV void add_cells(AlnState& st, uint32_t n) {
   st.cells_lo = lo;
 }
 
-BA_HD uint64_t rect_words(int H, int W, bool force8 = false) {
-  const int R = force8 ? 8 : rect_rows_per_lane(H);
+// layout: 0 = rows-per-lane from the height, 1 = forced 8 rows per lane (FREE_QUERY_END_GAPS), 3 = packed path
+// (one word per lane and column, word index = column * H / 8 + lane; ba_packed.cuh)
+BA_HD uint64_t rect_words(int H, int W, int layout = 0) {
+  if (layout == 3) return (uint64_t)(H >> 3) * (uint64_t)W;
+  const int R = layout == 1 ? 8 : rect_rows_per_lane(H);
   const int CH = 32 * R;
   const int nch = (H + CH - 1) / CH;
   return (uint64_t)nch * (uint64_t)(W >> 3) * R * 32;
 }
 // Trace::add_block (scan_block.rs:1428-1443); returns where this rectangle's words go
-// force8: the rectangle is computed with 8 rows per lane whatever its height (FREE_QUERY_END_GAPS); recorded in bit 1
-// of Rect::right so that the walk-back indexes the words the same way
+// The word layout of the rectangle is recorded in bits 1-2 of Rect::right so that the walk-back indexes the words
+// the same way
 BA_DEV uint32_t* trace_push(AlnState& st, const SlotMem& sm, uint32_t row, uint32_t col, int W, int H, bool right, bool writer,
-                            bool force8 = false) {
-  const uint64_t need = rect_words(H, W, force8);
+                            int layout = 0) {
+  const uint64_t need = rect_words(H, W, layout);
   if (st.ridx >= sm.rects_cap || (uint64_t)st.widx + need > sm.words_cap || ((uint64_t)st.widx + need) >> 32) {
     st.overflow = 1u;
     return sm.words;
   }
   if (writer) {
-    Rect r; r.row = row; r.col = col; r.h = (uint16_t)H; r.w = (uint16_t)W; r.right = (right ? 1u : 0u) | (force8 ? 2u : 0u); r.word_off = st.widx;
+    Rect r; r.row = row; r.col = col; r.h = (uint16_t)H; r.w = (uint16_t)W; r.right = (right ? 1u : 0u) | ((uint32_t)layout << 1); r.word_off = st.widx;
     sm.rects[st.ridx] = r;
   }
   uint32_t* p = sm.words + st.widx;
@@ -497,7 +500,8 @@ BA_DEV void traceback_walk(const uint32_t* words, const uint32_t* zwords, bool f
     if (bad) break;
     const int H = rc.h, W = rc.w;
     const bool rc_right = (rc.right & 1u) != 0;
-    const int R = (rc.right & 2u) ? 8 : rect_rows_per_lane(H);
+    const uint32_t layout = (rc.right >> 1) & 3u;
+    const int R = layout == 1u ? 8 : rect_rows_per_lane(H);
     const int CH = 32 * R;
     const int ngroups = W >> 3;
     const uint32_t* tw = words + rc.word_off;
@@ -512,11 +516,16 @@ BA_DEV void traceback_walk(const uint32_t* words, const uint32_t* zwords, bool f
       const uint32_t v = rc_right ? i - rc.row : j - rc.col;
       const uint32_t c = rc_right ? j - rc.col : i - rc.row;
       const uint32_t ch = v / CH, ln = (v % CH) / R, k = v % R;
-      const size_t widx = (((size_t)ch * ngroups + (c >> 3)) * R + k) * 32 + ln;
-      // LOCAL_START: the alignment starts at a cell equal to relative_zero (scan_block.rs:1606-1612)
-      if (zwords && table == 0 && ((zwords[rc.word_off + widx] >> (c & 7)) & 1u)) { stop = true; break; }
-      const uint32_t word = tw[widx];
-      const uint32_t nib = (word >> (4 * (c & 7))) & 15u;
+      uint32_t nib;
+      if (layout == 3u) {     // packed path: word (column, lane in group), nibble (row mod 4) of the half-block's 16 bits
+        const uint32_t half = v >= (uint32_t)(H >> 1) ? 1u : 0u, vv = v - half * (uint32_t)(H >> 1);
+        nib = (tw[(size_t)c * (H >> 3) + (vv >> 2)] >> (16u * half + 4u * (vv & 3u))) & 15u;
+      } else {
+        const size_t widx = (((size_t)ch * ngroups + (c >> 3)) * R + k) * 32 + ln;
+        // LOCAL_START: the alignment starts at a cell equal to relative_zero (scan_block.rs:1606-1612)
+        if (zwords && table == 0 && ((zwords[rc.word_off + widx] >> (c & 7)) & 1u)) { stop = true; break; }
+        nib = (tw[widx] >> (4 * (c & 7))) & 15u;
+      }
       const uint32_t t = nib & 3u, t2 = nib >> 2;
       uint32_t op; int ntab;
       if (table == tabA) { op = opA; ntab = (t2 & 1u) ? 0 : tabA; }
@@ -717,18 +726,18 @@ BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const Sl
       a.tw = nullptr; a.tz = nullptr;
       a.local = m_local; a.fqs0 = m_fqs && rect_right && a.vec_base == 0;
       a.fqe = m_fqe; a.fq_cls = (int)(qlen % kL); a.fq_row0 = (int)qlen - (int)a.vec_base;
+      const bool pk_ok = !PROF && !EXT && P.pk_enable && !st.overflow && pk_rect_ok(P, a);
       if (TRACE && a.W > 0 && a.H >= 0) {
         const uint32_t woff = st.widx;
         if (m_local && sm.zwords) a.tz = sm.zwords + woff;
-        a.tw = trace_push(st, sm, rect_right ? a.vec_base : a.col_base, rect_right ? a.col_base : a.vec_base, a.W, a.H, rect_right, lane == 0, m_fqe);
+        a.tw = trace_push(st, sm, rect_right ? a.vec_base : a.col_base, rect_right ? a.col_base : a.vec_base, a.W, a.H, rect_right, lane == 0, pk_ok ? 3 : (m_fqe ? 1 : 0));
       }
       add_cells(st, (uint32_t)(a.W * a.H));
       sc.vec = rect_right ? q : r; sc.col = rect_right ? r : q;
       int pbv = 0; unsigned pkey = 15u << 27;
       if (!st.overflow) {
-        bool done = false;
-        if (!PROF && !TRACE && !EXT && P.pk_enable)
-          done = place_rect_pk<(PROF ? kAA : SCORING), XDROP>(w.smem0, P, P.kc, sc.vec, sc.col, a, w.fr, pbv, pkey);
+        const bool done = pk_ok;
+        if (pk_ok) place_rect_pk<(PROF ? kAA : SCORING), XDROP, TRACE>(w.smem0, P, P.kc, sc.vec, sc.col, a, w.fr, pbv, pkey);
 #ifdef BA_EMU
         if (wp::lane_id() == 0) { if (done) emu_stats::pk_cells += (uint64_t)a.W * a.H; else emu_stats::exact_cells += (uint64_t)a.W * a.H; }
 #endif
@@ -1259,7 +1268,7 @@ BA_DEV void pk_fast_spill(const PkFast& f, const WarpMem& w, int dir, bool mine)
 template <int SCORING, int FLAGS, int LGT>
 BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast& f, int& status,
                          const uint8_t* qp, const uint8_t* rp, const SlotMem& sm) {
-  constexpr bool XDROP = (FLAGS & kXDrop) != 0;
+  constexpr bool XDROP = (FLAGS & kXDrop) != 0, TRACE = (FLAGS & kTrace) != 0;
   constexpr int KIND = (SCORING == kProfile) ? kAA : SCORING;
   constexpr int G = 1 << LGT;
   constexpr int B = 8 * G;
@@ -1287,7 +1296,9 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast
 #pragma unroll
   for (int k = 0; k < 4; k++) { D[k] = wp::vadd2(f.aD[k], oa2); C[k] = wp::vadd2(f.aC[k], oa2); m[k] = 0u; mc[k] = 0u; }
   uint32_t* fr = w.fr + grp * 8;
-  pk_cols8<KIND, XDROP, LGT>(sc, P.kc, LGT, lg, cw.x, cw.y, D, C, (uint32_t)corner & 0xffffu, 0, m, mc, fr, lg == G - 1);
+  uint32_t* tw = nullptr;
+  if (TRACE && active) tw = trace_push(st, sm, right ? si : si + (B - kStep), right ? sj + (B - kStep) : sj, kStep, B, right, lg == 0, 3);
+  pk_cols8<KIND, XDROP, LGT, TRACE>(sc, P.kc, LGT, lg, cw.x, cw.y, D, C, (uint32_t)corner & 0xffffu, 0, m, mc, fr, lg == G - 1, tw, TRACE && active);
   wp::syncwarp();
 
   // ---- borders after the step ----
@@ -1366,6 +1377,7 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast
         ck[ia] = make_uint4(f.aD[0], f.aD[1], f.aD[2], f.aD[3]); ck[ia + G] = make_uint4(f.aC[0], f.aC[1], f.aC[2], f.aC[3]);
         ck[io] = make_uint4(f.oD[0], f.oD[1], f.oD[2], f.oD[3]); ck[io + G] = make_uint4(f.oR[0], f.oR[1], f.oR[2], f.oR[3]);
         st.ck_pk = 1u;
+        if (TRACE) { st.ck_widx = st.widx; st.ck_ridx = st.ridx; }
       }
       st.best_max = st.off_max;
       st.y_drop_iter = 0;
@@ -1379,6 +1391,7 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast
         st.x_drop_iter = 0;
       }
     }
+    if (TRACE && st.overflow) nstatus = kStDone;
     if (nstatus == kStFast) {
       if (si + B > st.qlen && sj + B > st.rlen) nstatus = kStDone;
       else if (sj + B > st.rlen) { st.si = si + kStep; st.dir = kDown; }

@@ -103,10 +103,19 @@ BA_DEV void pk_bounds(int W, int go, int ge, int smax, int& GL, int& GH) {
 // m / mc: per-row running maximum and the (column + 1) of its last occurrence (X-drop argmax, scan_block.rs:
 // 1194-1201); without XDROP only m[0] is kept (block maximum). fr[c] receives the bottom row of column c
 // (row 8G - 1) as T | D << 16 from the group's last lane.
-template <int KIND, bool XDROP, int LGT>
+//
+// TRACE: one word per lane and column (Rect layout 3, word index = column * G + lane in group): nibble k of the low
+// 16 bits belongs to row 4lg + k, nibble k of the high 16 bits to row 4G + 4lg + k; bit 0 D == C, bit 1 D == R,
+// bit 2 C opened in this cell, bit 3 the R gap of this row was opened at the row above (the reference's trace /
+// trace2 words, scan_block.rs:1166-1190). Every comparison is an equality between x <= y, computed without
+// predicates as a halfword mask (pk_eqmask).
+// per halfword 0xffff where y == x, else 0; needs x <= y (then y + ~x = y - x - 1 is -1 exactly for equal halves)
+BA_DEV uint32_t pk_eqmask(uint32_t y, uint32_t x) { return wp::viaddmin2(y, ~x, 0u); }
+
+template <int KIND, bool XDROP, int LGT, bool TRACE = false>
 BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int LGr, int lg, uint32_t cw0, uint32_t cw1,
                      uint32_t (&D)[4], uint32_t (&C)[4], uint32_t corner_lo, int cbase, uint32_t (&m)[4], uint32_t (&mc)[4],
-                     uint32_t* fr, bool writer) {
+                     uint32_t* fr, bool writer, uint32_t* tw = nullptr, bool tstore = false) {
   const int LG = LGT ? LGT : LGr;
   const int G = 1 << LG;
   // The uniform constants are copied into vector registers once per call (opaque_zero): ptxas otherwise rebuilds
@@ -132,12 +141,14 @@ BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int LGr, int l
       uint32_t up = (uint32_t)wp::shfl_idx_w((int)D[3], lg - 1, G);
       if (lg == 0) up = (up << 16) | ((cbase + cidx == 0) ? corner_lo : 0u);
       uint32_t dd[4], c11[4], uu[4];
+      uint32_t acc[4];                            // trace nibbles of the lane's rows (TRACE)
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         const uint32_t s2 = sc.score(ch, k);
         const uint32_t d00 = k ? D[k - 1] : up;
         const uint32_t c11o = D[k] + kc.go1;      // packed add as one 32-bit add: no borrow, both halves >= |open| (guard)
         c11[k] = wp::viaddmax2(C[k], ge2, c11o);
+        if (TRACE) acc[k] = pk_eqmask(c11[k], c11o) & 0x00040004u;       // C opened here <=> C == D10 + open
         dd[k] = wp::viaddmax2(d00, s2, c11[k]);
         uu[k] = k ? wp::viaddmax2(uu[k - 1], ge2, dd[k]) : dd[0];
       }
@@ -161,10 +172,21 @@ BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int LGr, int l
       if (lg == 0) ex = 0u;
       const uint32_t cin = wp::viaddmax2(tl << 16, lanedec, ex);
       uint32_t Un3 = 0;
+      uint32_t eprev = 0u;                        // "R gap opened at this row" (T == x) of the previous row of the lane
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         const uint32_t Un = wp::viaddmax2(cin, k == 0 ? ge2 : (k == 1 ? kge1 : (k == 2 ? kge2 : kge3)), uu[k]);
-        const uint32_t Dn = wp::viaddmax2(Un, or2, dd[k]);
+        uint32_t Dn;
+        if (TRACE) {
+          const uint32_t Rv = wp::vadd2(Un, or2);
+          Dn = wp::vmax2(Rv, dd[k]);
+          acc[k] |= pk_eqmask(Dn, c11[k]) & 0x00010001u;                 // D == C
+          acc[k] |= pk_eqmask(Dn, Rv) & 0x00020002u;                     // D == R
+          if (k > 0) acc[k] |= eprev & 0x00080008u;
+          eprev = pk_eqmask(Un, dd[k]);                                  // T == x  <=>  U == D'
+        } else {
+          Dn = wp::viaddmax2(Un, or2, dd[k]);
+        }
         if (k == 3) Un3 = Un;
         if (XDROP) {
           bool ph, pl;
@@ -177,6 +199,15 @@ BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int LGr, int l
           m[0] = wp::vmax2(m[0], Dn);
         }
         D[k] = Dn; C[k] = c11[k];
+      }
+      if (TRACE) {
+        // bit 3 of the lane's first rows comes from the last row of the lane above: lane 0's high half continues the
+        // last lane's low half, lane 0's low half is the top of the rectangle (no row above: R01 = MIN)
+        uint32_t eup = (uint32_t)wp::shfl_idx_w((int)eprev, lg - 1, G);
+        if (lg == 0) eup <<= 16;
+        acc[0] |= eup & 0x00080008u;
+        const uint32_t word = acc[0] | (acc[1] << 4) | (acc[2] << 8) | (acc[3] << 12);
+        if (tstore) tw[(size_t)(cbase + cidx) * G + lg] = word;
       }
       if (writer) fr[cidx] = wp::prmt(wp::vadd2(Un3, or2), D[3], 0x7632u);   // T.hi | D.hi << 16
     }
@@ -249,30 +280,41 @@ BA_DEV bool pk_in_range(const uint32_t (&a)[N], const uint32_t (&b)[N], int lo, 
   return p0 && p1 && p2 && p3;
 }
 
-// Packed replacement of place_rect for sequence-sequence rectangles with borders in shared memory (generic
-// phase, one alignment per warp; lanes >= G mirror lanes < G). Returns false -- with nothing modified -- when the
-// rectangle's shape or value range is outside what the packed path covers; the caller then runs place_rect.
-template <int KIND, bool XDROP>
-BA_DEV bool place_rect_pk(const unsigned char* smem, const Params& P, const PkConst& kc, const uint8_t* vec, const uint8_t* col,
-                          const RectArgs& a, uint32_t* fr, int& bv, unsigned& bkey) {
+// Can this rectangle go through the packed path? Shape (32..256 rows, whole 8-column groups, no early break, not
+// the forced origin cell) and value range of its inputs (pk_bounds). Nothing is modified.
+BA_DEV bool pk_rect_ok(const Params& P, const RectArgs& a) {
   const int lane = wp::lane_id();
   const int H = a.H, W = a.W;
   if (!(H == 32 || H == 64 || H == 128 || H == 256) || W <= 0 || (W & 7) || W > 256 || a.ncols != W) return false;
   if (a.vec_base == 0 && a.col_base == 0) return false;        // forced origin cell (scan_block.rs:1130-1132)
   const int G = H >> 3;
-  const int LG = H == 32 ? 2 : (H == 64 ? 3 : (H == 128 ? 4 : 5));
   const int lg = lane & (G - 1);
-  const int go = P.gap_open, ge = P.gap_extend;
   int GL, GH;
-  pk_bounds(W, go, ge, P.pk_smax, GL, GH);
+  pk_bounds(W, P.gap_open, P.gap_extend, P.pk_smax, GL, GH);
   // raw border values v become v + off_add (saturating in the reference): exact and inside [GL, GH] iff
   // v is inside [GL - off_add, GH - off_add] (clipped to i16)
   const int lo_b = wp::imax(GL - a.off_add, kI16Min), hi_b = wp::imin(GH - a.off_add, kI16Max);
   uint32_t D[4], C[4];
   pk_load4(a.AD, lg, G, D);
   pk_load4(a.AC, lg, G, C);
-  bool ok = lo_b <= hi_b && a.corner >= 0 && a.corner <= GH && pk_in_range<4>(D, C, lo_b, hi_b);
-  if (wp::ballot(!ok) != 0u) return false;
+  const bool ok = lo_b <= hi_b && a.corner >= 0 && a.corner <= GH && pk_in_range<4>(D, C, lo_b, hi_b);
+  return wp::ballot(!ok) == 0u;
+}
+
+// Packed replacement of place_rect for sequence-sequence rectangles with borders in shared memory (generic
+// phase, one alignment per warp; lanes >= G mirror lanes < G). Only for rectangles pk_rect_ok accepted.
+// TRACE: a.tw receives H / 8 words per column (Rect layout 3, see pk_cols8).
+template <int KIND, bool XDROP, bool TRACE>
+BA_DEV void place_rect_pk(const unsigned char* smem, const Params& P, const PkConst& kc, const uint8_t* vec, const uint8_t* col,
+                          const RectArgs& a, uint32_t* fr, int& bv, unsigned& bkey) {
+  const int lane = wp::lane_id();
+  const int H = a.H, W = a.W;
+  const int G = H >> 3;
+  const int LG = H == 32 ? 2 : (H == 64 ? 3 : (H == 128 ? 4 : 5));
+  const int lg = lane & (G - 1);
+  uint32_t D[4], C[4];
+  pk_load4(a.AD, lg, G, D);
+  pk_load4(a.AC, lg, G, C);
   bv = 0; bkey = 15u << 27;
   const uint32_t oa2 = pk2(a.off_add);
 #pragma unroll
@@ -286,10 +328,10 @@ BA_DEV bool place_rect_pk(const unsigned char* smem, const Params& P, const PkCo
   for (int cb = 0; cb < W; cb += 8) {
     const uint2 cw = *(const uint2*)(col + a.col_base + cb);
 #ifndef BA_PK_NO_LG5
-    if (LG == 5) pk_cols8<KIND, XDROP, 5>(sc, kc, 5, lg, cw.x, cw.y, D, C, (uint32_t)a.corner & 0xffffu, cb, m, mc, fr, writer);
+    if (LG == 5) pk_cols8<KIND, XDROP, 5, TRACE>(sc, kc, 5, lg, cw.x, cw.y, D, C, (uint32_t)a.corner & 0xffffu, cb, m, mc, fr, writer, a.tw, lane < G);
     else
 #endif
-    pk_cols8<KIND, XDROP, 0>(sc, kc, LG, lg, cw.x, cw.y, D, C, (uint32_t)a.corner & 0xffffu, cb, m, mc, fr, writer);
+    pk_cols8<KIND, XDROP, 0, TRACE>(sc, kc, LG, lg, cw.x, cw.y, D, C, (uint32_t)a.corner & 0xffffu, cb, m, mc, fr, writer, a.tw, lane < G);
     wp::syncwarp();
     if (lane < 8) { const uint32_t v = fr[lane]; a.OD[cb + lane] = (int16_t)(v >> 16); a.OR_[cb + lane] = (int16_t)(v & 0xffffu); }
     wp::syncwarp();
@@ -298,7 +340,6 @@ BA_DEV bool place_rect_pk(const unsigned char* smem, const Params& P, const PkCo
   if (XDROP) { bv = pk_lane_max(m); bkey = pk_lane_key(m, mc, lg, G, bv); }
   else bv = wp::imax(bv, wp::imax(wp::h_lo(m[0]), wp::h_hi(m[0])));
   wp::syncwarp();
-  return true;
 }
 
 }  // namespace ba

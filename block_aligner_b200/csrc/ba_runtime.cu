@@ -178,11 +178,10 @@ static int occupancy(int wpb, size_t smem_bytes, int* blocks_per_sm) {
 
 // kernel instantiations: scoring x flags x rows-per-lane of the fast phase (0 = generic phase only)
 // flags 4..7 = kExt | {TRACE, X_DROP}: LOCAL_START / FREE_QUERY_START_GAPS selected at run time, generic phase only
-#define BA_FOR_SEQ(X, S) X(S, 0, 0) X(S, 1, 0) X(S, 2, 0) X(S, 3, 0) X(S, 0, 4) X(S, 1, 4) X(S, 2, 4) X(S, 3, 4) \
-                         X(S, 0, 8) X(S, 1, 8) X(S, 2, 8) X(S, 3, 8) X(S, 4, 0) X(S, 5, 0) X(S, 6, 0) X(S, 7, 0) \
-                         X(S, 0, 18) X(S, 2, 18) X(S, 0, 19) X(S, 2, 19)
+#define BA_FOR_SEQ(X, S) X(S, 0, 0) X(S, 1, 0) X(S, 2, 0) X(S, 3, 0) X(S, 4, 0) X(S, 5, 0) X(S, 6, 0) X(S, 7, 0) \
+                         X(S, 0, 18) X(S, 1, 18) X(S, 2, 18) X(S, 3, 18) X(S, 0, 19) X(S, 1, 19) X(S, 2, 19) X(S, 3, 19)
 #ifdef BA_MINIMAL   // tuning builds (tools/build_variant.sh): only the kernels of the C2 workload
-#define BA_FOR_KERNELS(X) X(kNuc, 2, 0) X(kNuc, 2, 18)
+#define BA_FOR_KERNELS(X) X(kNuc, 2, 0) X(kNuc, 2, 18) X(kNuc, 3, 19)
 #else
 #define BA_FOR_KERNELS(X) BA_FOR_SEQ(X, kNuc) BA_FOR_SEQ(X, kAA) BA_FOR_SEQ(X, kByte) \
   X(kProfile, 0, 0) X(kProfile, 1, 0) X(kProfile, 2, 0) X(kProfile, 3, 0) \
@@ -595,7 +594,8 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
   // fast-phase mode (third kernel template argument): 4 / 8 = s32 rows per lane (TRACE), 16 + LGT = packed, 0 = none
   b->fast_rows = (!prof && !ext && !getenv("BA_NO_FAST")) ? (mn == 32 ? 4 : (mn == 64 ? 8 : 0)) : 0;
   b->slots_per_warp = b->fast_rows ? 4 : 1;
-  if (b->fast_rows && b->pk_enable && !(cfg->flags & BA_TRACE)) {
+  if (b->fast_rows && !b->pk_enable) b->fast_rows = 0;
+  if (b->fast_rows) {
     const int lgt = mn == 32 ? 2 : 3;
     b->fast_rows = 16 + lgt;
     b->slots_per_warp = 32u >> lgt;

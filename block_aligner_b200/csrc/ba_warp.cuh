@@ -38,6 +38,7 @@ inline uint32_t vmin2(uint32_t a, uint32_t b) { return h_pack(h_lo(a) < h_lo(b) 
 inline uint32_t vmax3_2(uint32_t a, uint32_t b, uint32_t c) { return vmax2(vmax2(a, b), c); }
 inline uint32_t vmin3_2(uint32_t a, uint32_t b, uint32_t c) { return vmin2(vmin2(a, b), c); }
 inline uint32_t viaddmax2(uint32_t a, uint32_t b, uint32_t c) { return vmax2(vadd2(a, b), c); }
+inline uint32_t viaddmin2(uint32_t a, uint32_t b, uint32_t c) { return vmin2(vadd2(a, b), c); }
 inline uint32_t vibmax2(uint32_t a, uint32_t b, bool& ph, bool& pl) { pl = h_lo(a) >= h_lo(b); ph = h_hi(a) >= h_hi(b); return vmax2(a, b); }
 inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   const uint64_t src = ((uint64_t)b << 32) | a; uint32_t r = 0;
@@ -84,6 +85,7 @@ BA_DEV uint32_t vmin2(uint32_t a, uint32_t b) { return __vmins2(a, b); }
 BA_DEV uint32_t vmax3_2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
 BA_DEV uint32_t vmin3_2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s16x2(a, b, c); }
 BA_DEV uint32_t viaddmax2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }
+BA_DEV uint32_t viaddmin2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_s16x2(a, b, c); }
 BA_DEV uint32_t vibmax2(uint32_t a, uint32_t b, bool& ph, bool& pl) { return __vibmax_s16x2(a, b, &ph, &pl); }
 BA_DEV uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
 // always 0 (blocks are one-dimensional) but thread-varying for the compiler: keeps a value out of the uniform datapath
