@@ -885,353 +885,18 @@ BA_DEV void finish_alignment(const Params& P, const AlnState& st, const WarpMem&
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fast phase: four alignments per warp, 8 lanes x 4 rows each, block size 32, borders in registers.
-// Lane g*8+l of group g owns border entries 4l..4l+3. One iteration = one Right/Down shift step
-// (scan_block.rs:147-246) of every group, followed by the post-step decisions (scan_block.rs:332-558)
-// as straight-line predicated code. Anything else (grow, early break, end of the alignment) parks
-// the group: its status changes and the generic phase services it with the whole warp.
+// Fast phase: several alignments per warp while their block sits at the minimum size (pk_fast_step below). One
+// iteration = one Right/Down shift step (scan_block.rs:147-246) of every group of lanes, followed by the post-step
+// decisions (scan_block.rs:332-558) as straight-line predicated code. Anything else (grow, early break, values
+// outside the packed path's exact range, end of the alignment) parks the group: its status changes and the generic
+// phase services it with the whole warp.
 // ---------------------------------------------------------------------------------------------
 enum { kStFast = 0, kStNeedGeneric = 1, kStNeedGrow = 2, kStDone = 3, kStEmpty = 4 };
-
-template <int FR> struct FastRegs {
-  int aD[FR], aC[FR];   // border that moves with the step (D_col/C_col for Right, D_row/R_row for Down)
-  int oD[FR], oR[FR];   // the orthogonal border
-};
-
-BA_DEV int pack16(int lo, int hi) { return (lo & 0xffff) | (hi << 16); }
-BA_DEV int lo16(int p) { return (int)(int16_t)(p & 0xffff); }
-BA_DEV int hi16(int p) { return p >> 16; }
-
-BA_DEV int group_max(int v) {
-  v = wp::imax(v, wp::shfl_xor8(v, 1));
-  v = wp::imax(v, wp::shfl_xor8(v, 2));
-  v = wp::imax(v, wp::shfl_xor8(v, 4));
-  return v;
-}
-BA_DEV unsigned group_max_u(unsigned v) {
-  unsigned u = (unsigned)wp::shfl_xor8((int)v, 1); v = u > v ? u : v;
-  u = (unsigned)wp::shfl_xor8((int)v, 2); v = u > v ? u : v;
-  u = (unsigned)wp::shfl_xor8((int)v, 4); v = u > v ? u : v;
-  return v;
-}
-
-// registers <-> shared-memory borders for the lanes of group g (laid out for direction `dir`)
-template <int FR>
-BA_DEV void fast_load(FastRegs<FR>& f, const WarpMem& w, int dir, bool mine) {
-  const int i0 = (wp::lane_id() & 7) * FR;
-  const int16_t *ad = dir == kRight ? w.Dc : w.Dr, *ac = dir == kRight ? w.Cc : w.Rr;
-  const int16_t *od = dir == kRight ? w.Dr : w.Dc, *orr = dir == kRight ? w.Rr : w.Cc;
-  if (mine) {
-#pragma unroll
-    for (int k = 0; k < FR; k++) { f.aD[k] = ad[i0 + k]; f.aC[k] = ac[i0 + k]; f.oD[k] = od[i0 + k]; f.oR[k] = orr[i0 + k]; }
-  }
-}
-template <int FR>
-BA_DEV void fast_spill(const FastRegs<FR>& f, const WarpMem& w, int dir, bool mine) {
-  constexpr int B = 8 * FR;
-  const int lg = wp::lane_id() & 7, i0 = lg * FR;
-  int16_t *ad = dir == kRight ? w.Dc : w.Dr, *ac = dir == kRight ? w.Cc : w.Rr;
-  int16_t *od = dir == kRight ? w.Dr : w.Dc, *orr = dir == kRight ? w.Rr : w.Cc;
-  wp::syncwarp();
-  if (mine) {
-#pragma unroll
-    for (int k = 0; k < FR; k++) {
-      ad[i0 + k] = (int16_t)f.aD[k]; ac[i0 + k] = (int16_t)f.aC[k]; od[i0 + k] = (int16_t)f.oD[k]; orr[i0 + k] = (int16_t)f.oR[k];
-      // temp_buf1/2 hold the 8 fresh values of the last shift = the last 8 entries of the orthogonal border
-      if (i0 + k >= B - kStep) { w.t1[i0 + k - (B - kStep)] = (int16_t)f.oD[k]; w.t2[i0 + k - (B - kStep)] = (int16_t)f.oR[k]; }
-    }
-  }
-  wp::syncwarp();
-}
-
-// per-lane constants of the fast phase (hoisted out of the step)
-template <int FR> struct FastConst {
-  int ph[FR];      // scan phantoms of the lane's rows (avx2.rs:321-337)
-  int lane_rg;     // (lane in group) * FR * gap_extend
-};
-template <int FR>
-BA_DEV void fast_consts(FastConst<FR>& fc, int ge) {
-  const int lg = wp::lane_id() & 7;
-#pragma unroll
-  for (int k = 0; k < FR; k++) {
-    const int m = (lg * FR + k) & 15;
-    fc.ph[k] = (m == 15) ? kI16Min : (m == 7 ? 12 * ge : ((m & 7) + 1) * ge);
-  }
-  fc.lane_rg = lg * FR * ge;
-}
-
-// One shift step of up to four alignments (one per 8-lane group) with block size B = 8 * FR.
-template <int SCORING, int FLAGS, int FR>
-BA_DEV void fast_step(const Params& P, const int8_t* mat, const FastConst<FR>& fc, AlnState& st, FastRegs<FR>& f, int& status,
-                      const uint8_t* qp, const uint8_t* rp, const SlotMem& sm) {
-  constexpr bool TRACE = (FLAGS & kTrace) != 0, XDROP = (FLAGS & kXDrop) != 0;
-  constexpr int KIND = (SCORING == kProfile) ? kAA : SCORING;
-  constexpr int B = 8 * FR;               // block size
-  constexpr int NEWL = kStep / FR;        // lanes that hold the 8 fresh entries of the orthogonal border (2 or 1)
-  constexpr int TM = 16;                  // tracker multiplier: value * TM + (column + 1), column + 1 <= 8
-  const int lane = wp::lane_id(), lg = lane & 7;
-  const bool active = status == kStFast;
-  const int ge = P.gap_extend, go = P.gap_open, open_r = go - ge;
-  SeqScorer<KIND> sc;
-  sc.mat = mat; sc.go = go; sc.ge = ge; sc.b_match = sc.b_mismatch = 0;
-  if (KIND == kByte) { sc.b_match = (int)P.matrix[0]; sc.b_mismatch = (int)P.matrix[1]; }
-
-  const bool right = st.dir == kRight;
-  const uint32_t si = st.si, sj = st.sj;
-  const uint8_t* vec = right ? qp : rp;
-  const uint8_t* col = right ? rp : qp;
-  const uint32_t vec_base = right ? si : sj;
-  const uint32_t col_base = (right ? sj : si) + (B - kStep);
-
-  // ---- step prologue (scan_block.rs:148-158) ----
-  const int off = st.off_max;
-  const int off_add = clamp16(st.off - off);
-  const int corner = (st.prev_dir == (right ? kDown : kRight)) ? sat_add(st.D_corner, off_add) : 0;
-
-  // tokens: FR bytes of the vector-direction sequence per lane, 8 bytes of the column sequence per group
-  uint32_t vw[FR / 4], cw0 = 0, cw1 = 0;
-#pragma unroll
-  for (int t = 0; t < FR / 4; t++) vw[t] = 0;
-  if (active) {
-#pragma unroll
-    for (int t = 0; t < FR / 4; t++) vw[t] = *(const uint32_t*)(vec + vec_base + lg * FR + 4 * t);
-    const uint2 cw = *(const uint2*)(col + col_base);
-    cw0 = cw.x; cw1 = cw.y;
-  }
-  int rtok[FR];
-#pragma unroll
-  for (int k = 0; k < FR; k++) {
-    const int b = (int)((vw[k / 4] >> (8 * (k & 3))) & 0xffu);
-    rtok[k] = KIND == kNuc ? (b & 15) : (KIND == kAA ? (b & 31) : b);
-  }
-
-  uint32_t* tw = nullptr;
-  if (TRACE && active) tw = trace_push(st, sm, right ? si : si + (B - kStep), right ? sj + (B - kStep) : sj, kStep, B, right, lg == 0);
-
-  int D10[FR], C10[FR];
-#pragma unroll
-  for (int k = 0; k < FR; k++) { D10[k] = sat_add(f.aD[k], off_add); C10[k] = sat_add(f.aC[k], off_add); }
-
-  // per-row tracker: max over the step of value * TM + (column + 1); 0 = "no cell >= 0" (D_max starts at 0)
-  int trk[FR];
-  unsigned twd[FR];
-#pragma unroll
-  for (int k = 0; k < FR; k++) { trk[k] = 0; twd[k] = 0; }
-  // fresh bottom-row values (packed D | T << 16). FR == 4: lanes 6 and 7 of the group keep 4 each (columns 0..3 /
-  // 4..7 = border entries 24..27 / 28..31); FR == 8: every lane keeps all 8, lane 7 uses them.
-  constexpr int NB = FR == 4 ? 4 : 8;
-  int nb[NB];
-#pragma unroll
-  for (int t = 0; t < NB; t++) nb[t] = 0;
-
-#pragma unroll 1
-  for (int h = 0; h < 2; h++) {
-    const uint32_t cwh = h ? cw1 : cw0;
-#pragma unroll
-    for (int cc = 0; cc < 4; cc++) {
-      const int cidx = h * 4 + cc;
-      const int cb = (int)((cwh >> (8 * cc)) & 0xffu);
-      const int ctok = KIND == kNuc ? ((cb & 7) * 16) : (KIND == kAA ? cb * 32 : cb);
-      int up = wp::shfl_up8(D10[FR - 1], 1);
-      if (lg == 0) up = (cidx == 0) ? corner : 0;
-      int dd[FR], xx[FR], c11[FR], c11o[FR], tt[FR];
-#pragma unroll
-      for (int k = 0; k < FR; k++) {
-        const int s = sc.score(ctok, rtok[k]);
-        const int d00 = (k == 0) ? up : D10[k - 1];
-        c11o[k] = sat_add_lo(D10[k], go);
-        c11[k] = wp::viaddmax(C10[k], ge, c11o[k]);
-        dd[k] = wp::imin(wp::viaddmax(d00, s, c11[k]), kI16Max);
-        xx[k] = sat_add_lo(dd[k], open_r);
-        tt[k] = (k == 0) ? xx[0] : wp::viaddmax(tt[k - 1], ge, xx[k]);
-      }
-      int inc = tt[FR - 1];
-#pragma unroll
-      for (int s = 0; s < 3; s++) {
-        const int u = wp::shfl_up8(inc, 1 << s);
-        inc = wp::viaddmax(u, (FR << s) * ge, inc);
-      }
-      int ex = wp::shfl_up8(inc, 1);
-      if (lg == 0) ex = kNegBig;
-      const int cin = wp::imax(fc.lane_rg, ex);
-      int Dn[FR], Tn[FR];
-      unsigned ebits = 0;
-#pragma unroll
-      for (int k = 0; k < FR; k++) {
-        Tn[k] = wp::viaddmax(cin, (k + 1) * ge, tt[k]);
-        if (TRACE) {
-          const int Rv = wp::imax(Tn[k], fc.ph[k]);
-          Dn[k] = wp::imax(dd[k], Rv);
-          unsigned nib = (Dn[k] == c11[k] ? 1u : 0u) | (Dn[k] == Rv ? 2u : 0u) | (c11[k] == c11o[k] ? 4u : 0u);
-          ebits |= (Rv == xx[k] ? 1u : 0u) << k;
-          twd[k] |= nib << (4 * cidx);
-        } else {
-          Dn[k] = wp::vimax3(dd[k], Tn[k], fc.ph[k]);
-        }
-        if (XDROP) trk[k] = wp::imax(trk[k], Dn[k] * TM + (cidx + 1));
-        else trk[0] = wp::imax(trk[0], Dn[k]);
-      }
-      if (TRACE) {
-        const unsigned eb = wp::ballot(((ebits >> (FR - 1)) & 1u) != 0);
-        const unsigned above = lg == 0 ? 0u : ((eb >> (lane - 1)) & 1u);
-#pragma unroll
-        for (int k = 0; k < FR; k++) {
-          const unsigned b3 = (k == 0) ? above : ((ebits >> (k - 1)) & 1u);
-          twd[k] |= (b3 << 3) << (4 * cidx);
-        }
-      }
-      const int bot = wp::shfl_idx8(pack16(Dn[FR - 1], Tn[FR - 1]), 7);
-      if (FR == 4) { if (lg == 6 + h) nb[cc] = bot; }
-      else { if (h == 0) nb[cc] = bot; else nb[(NB - 4) + cc] = bot; }
-#pragma unroll
-      for (int k = 0; k < FR; k++) { D10[k] = Dn[k]; C10[k] = c11[k]; }
-    }
-  }
-  if (TRACE && active) {
-    // same layout as a generic B x 8 rectangle with one row per lane: word index = row
-#pragma unroll
-    for (int t = 0; t < FR / 4; t++) {
-      uint4 wv; wv.x = twd[4 * t]; wv.y = twd[4 * t + 1]; wv.z = twd[4 * t + 2]; wv.w = twd[4 * t + 3];
-      *(uint4*)(tw + lg * FR + 4 * t) = wv;
-    }
-  }
-
-  // ---- borders after the step ----
-  // D_corner = old orthogonal[STEP-1] + off_add (scan_block.rs:1041-1042): entry 7
-  const int d_corner = sat_add(wp::shfl_idx8(f.oD[(kStep - 1) % FR], (kStep - 1) / FR), off_add);
-#pragma unroll
-  for (int k = 0; k < FR; k++) {
-    f.aD[k] = D10[k]; f.aC[k] = C10[k];
-    const int p = wp::shfl_down8(pack16(f.oD[k], f.oR[k]), NEWL);   // slide by 8 entries
-    if (lg < 8 - NEWL) { f.oD[k] = sat_add(lo16(p), off_add); f.oR[k] = sat_add(hi16(p), off_add); }
-    else {
-      // entry (lg * FR + k) - (B - 8) of the fresh values
-      const int v = nb[k & (NB - 1)];
-      f.oD[k] = lo16(v); f.oR[k] = hi16(v);
-    }
-  }
-
-  // ---- reductions (scan_block.rs:332-345) ----
-  // tie-break order of the reference: value desc, AVX lane (row mod 16) asc, column desc, row desc
-  int bv = 0; unsigned bkey = 15u << 27;
-  if (XDROP) {
-    // rows that saw no cell >= 0 (trk == 0) compare as -1 and never win
-    // (within a lane the rows have distinct, ascending AVX lanes, so among equal values the lowest k wins)
-    int bw = -1, bt = 0, bk = 0;
-#pragma unroll
-    for (int k = 0; k < FR; k++) {
-      const int wv = (trk[k] - 1) >> 4;
-      if (wv > bw) { bw = wv; bt = trk[k]; bk = k; }
-    }
-    if (bw >= 0) {
-      const unsigned row = (unsigned)(lg * FR + bk);
-      bv = bw;
-      bkey = ((15u - (row & 15u)) << 27) | ((unsigned)(bt & (TM - 1)) << 13) | row;
-    }
-  } else {
-    bv = trk[0];
-  }
-  const int mxv = group_max(bv);
-  // prefix_max over entries 0..7 of both borders (scan_block.rs:1020-1022)
-  int a_loc = f.aD[0], o_loc = f.oD[0];
-#pragma unroll
-  for (int k = 1; k < FR; k++) { a_loc = wp::imax(a_loc, f.aD[k]); o_loc = wp::imax(o_loc, f.oD[k]); }
-  const int pm = pack16(a_loc, o_loc);
-  int a_max, o_max;
-  if (FR == 4) {
-    const int pm0 = wp::shfl_idx8(pm, 0), pm1 = wp::shfl_idx8(pm, 1);
-    a_max = wp::imax(lo16(pm0), lo16(pm1)); o_max = wp::imax(hi16(pm0), hi16(pm1));
-  } else {
-    const int pm0 = wp::shfl_idx8(pm, 0);
-    a_max = lo16(pm0); o_max = hi16(pm0);
-  }
-  const int right_max = right ? a_max : o_max, down_max = right ? o_max : a_max;
-  unsigned key = 0;
-  if (XDROP) key = group_max_u(bv == mxv ? bkey : 0u);
-
-  if (P.step_log && active && lg == 0) {
-    const uint32_t n = *P.step_log_n;
-    if (n < P.step_log_cap) {
-      StepLog sl; sl.dir = st.dir; sl.i = si; sl.j = sj; sl.block_size = (uint32_t)B; sl.off = off;
-      sl.max = (int16_t)mxv; sl.right_max = (int16_t)right_max; sl.down_max = (int16_t)down_max;
-      P.step_log[n] = sl;
-    }
-    *P.step_log_n = n + 1;
-  }
-
-  // ---- post-step decisions (scan_block.rs:332-558 restricted to B == min_size, shift steps) ----
-  // No warp collectives below: groups diverge freely.
-  if (active) {
-    st.off = off;
-    st.steps++;
-    add_cells(st, (uint32_t)(kStep * B));
-    st.prev_dir = st.dir;
-    st.D_corner = d_corner;
-    st.off_max = off + mxv - kZero;
-    st.y_drop_iter++;
-    if (st.off_max > st.best_max) {
-      if (XDROP) {
-        const unsigned cp1 = (key >> 13) & 0x3fffu;
-        uint32_t v = key & 0x1fffu, c = 0;
-        if (cp1 == 0) v = 0; else c = cp1 - 1;
-        if (right) { st.best_i = si + v; st.best_j = sj + (B - kStep) + c; }
-        else { st.best_i = si + (B - kStep) + c; st.best_j = sj + v; }
-      }
-      if (B < (int)P.max_size) {
-        st.i_ckpt = si; st.j_ckpt = sj; st.off_ckpt = off;
-        if (TRACE) { st.ck_widx = st.widx; st.ck_ridx = st.ridx; }
-        // checkpoint copy of all four borders (scan_block.rs:413-420), FR entries per lane and array
-        int16_t *ka = right ? sm.kDc : sm.kDr, *kc = right ? sm.kCc : sm.kRr;
-        int16_t *ko = right ? sm.kDr : sm.kDc, *kr = right ? sm.kRr : sm.kCc;
-#pragma unroll
-        for (int t = 0; t < FR / 4; t++) {
-          uint2 v;
-          v.x = (uint32_t)pack16(f.aD[4 * t], f.aD[4 * t + 1]); v.y = (uint32_t)pack16(f.aD[4 * t + 2], f.aD[4 * t + 3]); *(uint2*)(ka + lg * FR + 4 * t) = v;
-          v.x = (uint32_t)pack16(f.aC[4 * t], f.aC[4 * t + 1]); v.y = (uint32_t)pack16(f.aC[4 * t + 2], f.aC[4 * t + 3]); *(uint2*)(kc + lg * FR + 4 * t) = v;
-          v.x = (uint32_t)pack16(f.oD[4 * t], f.oD[4 * t + 1]); v.y = (uint32_t)pack16(f.oD[4 * t + 2], f.oD[4 * t + 3]); *(uint2*)(ko + lg * FR + 4 * t) = v;
-          v.x = (uint32_t)pack16(f.oR[4 * t], f.oR[4 * t + 1]); v.y = (uint32_t)pack16(f.oR[4 * t + 2], f.oR[4 * t + 3]); *(uint2*)(kr + lg * FR + 4 * t) = v;
-        }
-      }
-      st.best_max = st.off_max;
-      st.y_drop_iter = 0;
-    }
-    int nstatus = kStFast;
-    if (XDROP) {
-      if (st.off_max < st.best_max - P.x_drop) {
-        if (st.x_drop_iter < kXDropIter - 1) st.x_drop_iter++;
-        else nstatus = kStDone;
-      } else {
-        st.x_drop_iter = 0;
-      }
-    }
-    if (TRACE && st.overflow) nstatus = kStDone;
-    if (nstatus == kStFast) {
-      if (si + B > st.qlen && sj + B > st.rlen) nstatus = kStDone;
-      else if (sj + B > st.rlen) { st.si = si + kStep; st.dir = kDown; }
-      else if (si + B > st.qlen) { st.sj = sj + kStep; st.dir = kRight; }
-      else if (2 * B <= (int)P.max_size && st.y_drop_iter > (B / kStep) - 1) nstatus = kStNeedGrow;   // state left untouched
-      else if (down_max > right_max) { st.si = si + kStep; st.dir = kDown; }
-      else { st.sj = sj + kStep; st.dir = kRight; }
-      if (nstatus == kStFast && !fast_eligible<SCORING, XDROP>(P, st)) nstatus = kStNeedGeneric;
-    }
-    status = nstatus;
-    // the registers are laid out for the executed direction; if the next fast step goes the other way the
-    // borders swap roles
-    if (nstatus == kStFast && st.dir != st.prev_dir) {
-#pragma unroll
-      for (int k = 0; k < FR; k++) {
-        int t = f.aD[k]; f.aD[k] = f.oD[k]; f.oD[k] = t;
-        t = f.aC[k]; f.aC[k] = f.oR[k]; f.oR[k] = t;
-      }
-    }
-  }
-}
-
 
 // ---------------------------------------------------------------------------------------------
 // Packed fast phase: 32 >> LGT alignments per warp, G = 1 << LGT lanes each (block size 8 * G == min_size),
 // borders in registers in the packed layout of ba_packed.cuh (entry e of a border: lane (e mod 4G) / 4,
-// register e mod 4, halfword e / 4G). Same step and the same decisions as fast_step, computed with
+// register e mod 4, halfword e / 4G). The rectangle of a step is computed with
 // pk_cols8; a group whose values leave the packed path's exact range is parked for the generic phase.
 // ---------------------------------------------------------------------------------------------
 struct PkFast { uint32_t aD[4], aC[4], oD[4], oR[4]; };
@@ -1468,15 +1133,14 @@ BA_DEV void bind_slot(const Params& P, uint32_t slot, WarpMem& w, SlotMem& sm, b
   }
 }
 
-// FM selects the fast phase: 0 = none (every step in the generic phase), 4 / 8 = s32 fast phase with that many
-// rows per lane (fast_step; the TRACE kernels), 16 + LGT = packed fast phase with 1 << LGT lanes per alignment.
+// FM selects the fast phase: 0 = none (every step in the generic phase), 16 + LGT = packed fast phase with
+// 1 << LGT lanes per alignment (min block size 8 << LGT).
 template <int SCORING, int FLAGS, int FM>
 BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, uint32_t warp_global) {
   constexpr bool TRACE = (FLAGS & kTrace) != 0;
   constexpr bool PKF = FM >= 16;
-  constexpr int LGT = PKF ? FM - 16 : 3;       // log2(lanes per alignment group)
+  constexpr int LGT = PKF ? FM - 16 : 5;       // log2(lanes per alignment group)
   constexpr int GW = 1 << LGT;
-  constexpr int FR = PKF ? 0 : FM;
   const int lane = wp::lane_id();
   const size_t ms = P.max_size < 32 ? 32 : P.max_size;
   WarpMem w;
@@ -1502,11 +1166,7 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
   st.off = 0; st.off_max = 0; st.best_max = 0; st.best_i = 0; st.best_j = 0; st.i_ckpt = 0; st.j_ckpt = 0; st.off_ckpt = 0;
   st.y_drop_iter = 0; st.x_drop_iter = 0; st.D_corner = 0; st.cells_lo = 0; st.cells_hi = 0; st.steps = 0;
   st.widx = 0; st.ridx = 0; st.ck_widx = 0; st.ck_ridx = 0; st.overflow = 0; st.ck_pk = 0;
-  constexpr int FRR = FR ? FR : 4;   // FR == 0: no s32 fast phase (that code is never reached)
-  FastRegs<FRR> f;
   PkFast pf;
-#pragma unroll
-  for (int k = 0; k < FRR; k++) { f.aD[k] = 0; f.aC[k] = 0; f.oD[k] = 0; f.oR[k] = 0; }
 #pragma unroll
   for (int k = 0; k < 4; k++) { pf.aD[k] = 0; pf.aC[k] = 0; pf.oD[k] = 0; pf.oR[k] = 0; }
   int status = kStEmpty;
@@ -1515,8 +1175,6 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
   SlotMem my_sm;
   { WarpMem tmpw = w; bind_slot(P, warp_global * spw + ((uint32_t)my_g < spw ? my_g : 0), tmpw, my_sm, TRACE); }
   bool tickets_left = true;
-  FastConst<FRR> fc;
-  fast_consts(fc, P.gap_extend);
 
   for (;;) {
     // ---- service: refill empty groups, run the generic phase for parked ones ----
@@ -1541,8 +1199,6 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
         if (PKF) {
           pk_fast_spill<LGT>(pf, w, gs.prev_dir, mine);
           if (gs.ck_pk) { pk_ckpt_flush<LGT>(w, sm, g, mine); gs.ck_pk = 0u; }
-        } else {
-          fast_spill(f, w, gs.prev_dir, mine);
         }
         if (sg == kStNeedGrow) apply_grow(gs, w, TRACE);
       }
@@ -1556,7 +1212,6 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
       }
       wp::syncwarp();
       if (PKF) pk_fast_load<LGT>(pf, w, gs.dir, mine);
-      else fast_load(f, w, gs.dir, mine);
       if (mine) {
         st = gs; status = kStFast;
         qp = P.seq + P.q_off[gs.pair];
@@ -1568,7 +1223,6 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
     // ---- fast phase: run until some group needs the generic phase ----
     for (;;) {
       if (PKF) pk_fast_step<SCORING, FLAGS, LGT>(P, w, st, pf, status, qp, rp, my_sm);
-      else if (FR) fast_step<SCORING, FLAGS, FRR>(P, w.mat, fc, st, f, status, qp, rp, my_sm);
       else break;
       if (wp::ballot(status != kStFast && status != kStEmpty) != 0u) break;
       if (wp::ballot(status == kStFast) == 0u) break;
