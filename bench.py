@@ -32,6 +32,16 @@ os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import numpy as np  # noqa: E402
 
+# Native libraries (the NCCL version banner, for one) write to file descriptor 1. The contract is ONE JSON line on
+# stdout, so fd 1 is pointed at stderr for the whole run and the line goes to a private copy of the real stdout.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
 OPS_PER_CELL = {0: 10, 2: 13, 1: 16, 3: 19}   # flags -> algorithmic i16 ops per cell
 
 
@@ -159,7 +169,7 @@ def main():
                 "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": cb["cores"], "kind": "port", "sample": cb["sample"]},
                 "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "alignments_per_s": sum(v["pairs"] for v in vals) / tot_s}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -294,7 +304,7 @@ def main():
         if not args.no_cpu_baseline and world == 1 and profiles is None:
             cb = cpu_sample(w, lib, n, args.cpu_seconds)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "alignments_per_s")}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
