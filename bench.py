@@ -186,7 +186,8 @@ def main():
     cfg = al.config(w["scoring"], matrix, w["gaps"], w["size"], w["x_drop"], w["flags"], bool(w.get("cigar_eq")))
     profiles = None
     if w["scoring"] == api.SCORING_PROFILE:
-        profiles = workloads.make_lib_profiles(lib, ra, ro, w["size"][1], seed=1234 + rank)
+        # raw PSSM rows in pinned host memory; the padded profiles are built on the device (ba_batch_upload_pssm)
+        profiles = workloads.make_pssm_batch(lib, ra, ro, seed=1234 + rank, pinned=True)
 
     def barrier():
         if world > 1:
@@ -220,12 +221,10 @@ def main():
     import ctypes as C
     st = api.BaStats()
 
-    parr = (C.c_void_p * n)(*[p.h for p in profiles]) if profiles is not None else None
-
     def e2e_once():
         if profiles is not None:
-            lib.check(lib.L.ba_align_batch_profiles(al.h, C.byref(cfg), n, qa.ctypes.data, qo.ctypes.data, parr,
-                                                    out.ctypes.data, C.byref(st)))
+            lib.check(lib.L.ba_align_batch_pssm(al.h, C.byref(cfg), n, qa.ctypes.data, qo.ctypes.data, C.byref(profiles.c),
+                                                out.ctypes.data, C.byref(st)))
         else:
             lib.check(lib.L.ba_align_batch(al.h, C.byref(cfg), n, qa.ctypes.data, qo.ctypes.data, ra.ctypes.data, ro.ctypes.data,
                                            out.ctypes.data, C.byref(st)))
@@ -242,7 +241,7 @@ def main():
         e2e_error = str(e)
         barrier()
         e2e_s = float("inf")
-    h2d = int(qa.nbytes + ra.nbytes + 2 * qo.nbytes + n * (8 + 8 + 4 + 4 + 4))
+    h2d = int(qa.nbytes + 2 * qo.nbytes + n * (8 + 8 + 4 + 4 + 4) + (profiles.nbytes() if profiles is not None else ra.nbytes))
     d2h = int(n * 56)
 
     # ---- max over ranks ----
@@ -257,8 +256,8 @@ def main():
     e2e_gcups = cells_all * args.steps / e2e_s / 1e9
 
     if rank == 0:
-        # the packed 2 x i16 path serves sequence-sequence batches without TRACE; its ceiling is the 16x2 issue rate
-        packed = profiles is None and not (w["flags"] & (api.TRACE | api.LOCAL_START | api.FREE_QUERY_START_GAPS)) \
+        # the packed 2 x i16 path serves sequence-sequence batches (not profiles, not the extended modes); its ceiling is the 16x2 issue rate
+        packed = profiles is None and not (w["flags"] & (api.LOCAL_START | api.FREE_QUERY_START_GAPS | api.FREE_QUERY_END_GAPS)) \
             and not os.environ.get("BA_NO_PACKED")
         peak_s32, peak_s16x2 = al.int_peak_gops(False), al.int_peak_gops(True)
         peak_gops = peak_s16x2 if packed else peak_s32
@@ -270,12 +269,14 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        alg_bytes = float(qa.nbytes + ra.nbytes + n * 56)
+        alg_bytes = float(qa.nbytes + (profiles.nbytes() if profiles is not None else ra.nbytes) + n * 56)
         traffic = None   # DRAM bytes per launch from the committed `ncu --set full` capture (per pair x pairs)
         try:
             caps = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_align_kernel_summary.json")))["captures"]
-            if args.workload.startswith("C2"):
-                traffic = caps[-1]["dram_bytes_per_pair"] * n
+            tag = args.workload.split("_")[0]
+            cap = [c for c in caps if tag in c["capture"].split()]
+            if cap:
+                traffic = cap[-1]["dram_bytes_per_pair"] * n
         except Exception:
             pass
         line = {
@@ -288,7 +289,7 @@ def main():
             "gpu_launches": args.steps * 1 + args.steps * 2,
             "roofline": {"bound": "int_alu", "achieved": achieved / 1e3, "peak": peak_gops / 1e3, "unit": "Tiop/s",
                          "frac": achieved / peak_gops if peak_gops else None, "traffic": traffic,
-                         "traffic_source": "profiles/r01_ncu_align_kernel_summary.json (dram bytes per pair of the 16000-pair capture x pairs)",
+                         "traffic_source": "profiles/r01_ncu_align_kernel_summary.json (dram bytes per pair of the newest capture of this workload x pairs)",
                          "ops_per_cell": ops, "arith": "s16x2 (two cells per DPX instruction)" if packed else "s32 (one cell per DPX instruction)",
                          "peak_s32": peak_s32 / 1e3, "peak_s16x2": peak_s16x2 / 1e3,
                          "peak_source": "ba_measure_int_peak[_packed] (DPX add-max / max3 issue rate measured on this GPU, "

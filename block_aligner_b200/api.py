@@ -52,6 +52,14 @@ class BaStats(C.Structure):
                 ("kernel_launches", C.c_uint32), ("n_failed", C.c_uint32)]
 
 
+class BaPssmBatch(C.Structure):
+    _fields_ = [("order", C.c_void_p), ("order_len", C.c_size_t), ("scores", C.c_void_p), ("score_off", C.c_void_p),
+                ("left_shift", C.c_size_t), ("right_shift", C.c_size_t), ("rev", C.c_int32),
+                ("gap_open_C", C.c_void_p), ("gap_close_C", C.c_void_p), ("gap_open_R", C.c_void_p), ("gap_off", C.c_void_p),
+                ("all_gap_open_C", C.c_int8), ("all_gap_close_C", C.c_int8), ("all_gap_open_R", C.c_int8),
+                ("gap_extend", C.c_int8)]
+
+
 class StepLog(C.Structure):
     _fields_ = [("dir", C.c_int32), ("i", C.c_uint32), ("j", C.c_uint32), ("block_size", C.c_uint32),
                 ("off", C.c_int32), ("max", C.c_int16), ("right_max", C.c_int16), ("down_max", C.c_int16)]
@@ -81,7 +89,7 @@ PART1_FUNCTIONS = (
 PART1_DATA = ["NW1", "BLOSUM45", "BLOSUM50", "BLOSUM62", "BLOSUM80", "BLOSUM90", "PAM100", "PAM120", "PAM160",
               "PAM200", "PAM250", "BYTES1"]
 PART2_FUNCTIONS = ["ba_error_string", "ba_last_error_message", "ba_create", "ba_destroy", "ba_batch_upload",
-                   "ba_batch_upload_profiles", "ba_batch_run", "ba_batch_download", "ba_batch_cigar",
+                   "ba_batch_upload_profiles", "ba_batch_upload_pssm", "ba_align_batch_pssm", "ba_batch_run", "ba_batch_download", "ba_batch_cigar",
                    "ba_batch_traceback", "ba_batch_total_stats", "ba_batch_pair_stats", "ba_batch_free",
                    "ba_align_batch", "ba_align_batch_exp", "ba_align_batch_profiles", "ba_new_simple_nucmatrix", "ba_set_nucmatrix", "ba_free_nucmatrix",
                    "ba_percent_len", "ba_cigar_format", "ba_measure_int_peak", "ba_measure_int_peak_packed"]
@@ -116,6 +124,8 @@ class Library:
         L.ba_align_batch.argtypes = [vp, C.POINTER(BaConfig), sz, vp, vp, vp, vp, vp, C.POINTER(BaStats)]
         L.ba_align_batch_exp.argtypes = [vp, C.POINTER(BaConfig), sz, vp, vp, vp, vp, vp, vp, vp, C.POINTER(BaStats)]
         L.ba_align_batch_profiles.argtypes = [vp, C.POINTER(BaConfig), sz, vp, vp, vp, vp, C.POINTER(BaStats)]
+        L.ba_batch_upload_pssm.argtypes = [vp, C.POINTER(BaConfig), sz, vp, vp, C.POINTER(BaPssmBatch), C.POINTER(vp)]
+        L.ba_align_batch_pssm.argtypes = [vp, C.POINTER(BaConfig), sz, vp, vp, C.POINTER(BaPssmBatch), vp, C.POINTER(BaStats)]
         L.ba_new_simple_nucmatrix.restype = vp
         L.ba_new_simple_nucmatrix.argtypes = [i8, i8]
         L.ba_set_nucmatrix.argtypes = [vp, u8, u8, i8]
@@ -294,6 +304,42 @@ def align_batch_exp(al, queries, references, scoring, matrix, gaps, size, target
     return res, [int(u) if u else None for u in used]
 
 
+class PssmBatch:
+    """Raw PSSM rows for profiles built on the device (BaPssmBatch in include/block_aligner_b200.h): the batch form of
+    AAProfile::new + set_all / set_all_rev + the gap setters (src/scores.rs:473-486, 532-538, 548-580).
+
+    scores: int8 array, all profiles concatenated, position-major rows of len(order) entries; score_off: uint64[n + 1].
+    gaps: None -> the three `all_gaps` values (open_C, close_C, open_R) apply to positions 0..=len; otherwise a tuple of
+    three int8 arrays (open_C, close_C, open_R) with len + 1 entries per profile, concatenated."""
+
+    def __init__(self, order, scores, score_off, gap_extend, all_gaps=(-10, 0, -10), gaps=None, left_shift=0, right_shift=0,
+                 rev=False):
+        self.order = np.frombuffer(bytes(order), dtype=np.uint8).copy()
+        self.scores = scores if (isinstance(scores, np.ndarray) and scores.dtype == np.int8 and scores.flags.c_contiguous) \
+            else np.ascontiguousarray(scores, dtype=np.int8)
+        self.score_off = np.ascontiguousarray(score_off, dtype=np.uint64)
+        self.n = len(self.score_off) - 1
+        self.gaps = None
+        self.gap_off = None
+        c = BaPssmBatch()
+        c.order, c.order_len = self.order.ctypes.data, len(self.order)
+        c.scores, c.score_off = self.scores.ctypes.data, self.score_off.ctypes.data
+        c.left_shift, c.right_shift, c.rev = left_shift, right_shift, int(bool(rev))
+        if gaps is not None:
+            self.gaps = tuple(np.ascontiguousarray(g, dtype=np.int8) for g in gaps)
+            lens = (self.score_off[1:] - self.score_off[:-1]) // np.uint64(len(self.order))
+            self.gap_off = np.zeros(self.n + 1, dtype=np.uint64)
+            np.cumsum(lens + np.uint64(1), out=self.gap_off[1:])
+            c.gap_open_C, c.gap_close_C, c.gap_open_R = (g.ctypes.data for g in self.gaps)
+            c.gap_off = self.gap_off.ctypes.data
+        c.all_gap_open_C, c.all_gap_close_C, c.all_gap_open_R = all_gaps
+        c.gap_extend = gap_extend
+        self.c = c
+
+    def nbytes(self):
+        return int(self.scores.nbytes + self.score_off.nbytes + (sum(g.nbytes for g in self.gaps) + self.gap_off.nbytes if self.gaps else 0))
+
+
 class Batch:
     def __init__(self, al, cfg, q_arena, q_off, r_arena, r_off, profiles):
         self.al, self.cfg = al, cfg
@@ -303,7 +349,10 @@ class Batch:
         L = al.lib.L
         qa = np.ascontiguousarray(q_arena, dtype=np.uint8)
         qo = np.ascontiguousarray(q_off, dtype=np.uint64)
-        if profiles is not None:
+        if isinstance(profiles, PssmBatch):
+            al.lib.check(L.ba_batch_upload_pssm(al.h, C.byref(cfg), self.n, qa.ctypes.data, qo.ctypes.data, C.byref(profiles.c),
+                                                C.byref(h)))
+        elif profiles is not None:
             arr = (C.c_void_p * self.n)(*[p.h for p in profiles])
             al.lib.check(L.ba_batch_upload_profiles(al.h, C.byref(cfg), self.n, qa.ctypes.data, qo.ctypes.data, arr, C.byref(h)))
         else:

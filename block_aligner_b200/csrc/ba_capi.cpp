@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <mutex>
 #include <string>
 
@@ -54,11 +55,12 @@ namespace ba { namespace host {
 size_t profile_len(const AAProfile* p) { return p->str_len; }
 size_t profile_curr_len(const AAProfile* p) { return p->curr_len; }
 int profile_gap_extend(const AAProfile* p) { return p->gap_extend; }
-void profile_export(const AAProfile* p, int8_t* pos_aa, int16_t* oc, int16_t* cc, int16_t* orr) {
-  memcpy(pos_aa, p->pos_aa.data(), p->curr_len * 32);
-  memcpy(oc, p->gap_open_C.data(), p->curr_len * 2);
-  memcpy(cc, p->gap_close_C.data(), p->curr_len * 2);
-  memcpy(orr, p->gap_open_R.data(), p->curr_len * 2);
+size_t profile_used_len(const AAProfile* p) { return std::min(p->hi_pos + 1, p->curr_len); }
+void profile_export(const AAProfile* p, size_t np, int8_t* pos_aa, int16_t* oc, int16_t* cc, int16_t* orr) {
+  memcpy(pos_aa, p->pos_aa.data(), np * 32);
+  memcpy(oc, p->gap_open_C.data(), np * 2);
+  memcpy(cc, p->gap_close_C.data(), np * 2);
+  memcpy(orr, p->gap_open_R.data(), np * 2);
 }
 }}
 
@@ -105,6 +107,7 @@ AAProfile* block_new_aaprofile(uintptr_t str_len, uintptr_t block_size, int8_t g
   p->gap_extend = gap_extend;
   p->curr_len = p->max_len;
   p->str_len = str_len;
+  p->hi_pos = 0;
   return p;
 }
 uintptr_t block_len_aaprofile(const AAProfile* p) { return p->str_len; }
@@ -117,12 +120,14 @@ void block_clear_aaprofile(AAProfile* p, uintptr_t str_len, uintptr_t block_size
   std::fill(p->gap_open_R.begin(), p->gap_open_R.begin() + cl, (int16_t)INT8_MIN);
   p->str_len = str_len;
   p->curr_len = cl;
+  p->hi_pos = 0;
 }
 void block_set_aaprofile(AAProfile* p, uintptr_t i, uint8_t b, int8_t score) {
   b = host::upper(b);
   REQUIRE(b >= 'A' && b <= 'Z' + 1, "AAProfile::set: byte out of range");
   REQUIRE(i < p->curr_len, "AAProfile::set: position out of range");
   p->pos_aa[i * 32 + (b - 'A')] = score;
+  p->hi_pos = std::max(p->hi_pos, (size_t)i);
 }
 static void set_all_core(AAProfile* p, const uint8_t* order, size_t order_len, const int8_t* scores, size_t scores_len,
                          size_t ls, size_t rs, bool rev) {   // scores.rs:677-714
@@ -141,6 +146,7 @@ static void set_all_core(AAProfile* p, const uint8_t* order, size_t order_len, c
     for (size_t j = 0; j < order_len; j++, si++)
       p->pos_aa[i * 32 + o[j]] = (int8_t)((int8_t)(scores[si] << ls) >> rs);
   }
+  p->hi_pos = std::max(p->hi_pos, p->str_len);
 }
 void block_set_all_aaprofile(AAProfile* p, const uint8_t* order, uintptr_t order_len, const int8_t* scores,
                              uintptr_t scores_len, uintptr_t left_shift, uintptr_t right_shift) {
@@ -154,26 +160,32 @@ void block_set_gap_open_C_aaprofile(AAProfile* p, uintptr_t i, int8_t gap) {
   REQUIRE(gap < 0, "Gap open cost must be negative!");
   REQUIRE(i < p->curr_len, "AAProfile: position out of range");
   p->gap_open_C[i] = gap;
+  p->hi_pos = std::max(p->hi_pos, (size_t)i);
 }
 void block_set_gap_close_C_aaprofile(AAProfile* p, uintptr_t i, int8_t gap) {
   REQUIRE(i < p->curr_len, "AAProfile: position out of range");
   p->gap_close_C[i] = gap;
+  p->hi_pos = std::max(p->hi_pos, (size_t)i);
 }
 void block_set_gap_open_R_aaprofile(AAProfile* p, uintptr_t i, int8_t gap) {
   REQUIRE(gap < 0, "Gap open cost must be negative!");
   REQUIRE(i < p->curr_len, "AAProfile: position out of range");
   p->gap_open_R[i] = gap;
+  p->hi_pos = std::max(p->hi_pos, (size_t)i);
 }
 void block_set_all_gap_open_C_aaprofile(AAProfile* p, int8_t gap) {
   REQUIRE(gap < 0, "Gap open cost must be negative!");
   std::fill(p->gap_open_C.begin(), p->gap_open_C.begin() + p->str_len + 1, (int16_t)gap);
+  p->hi_pos = std::max(p->hi_pos, p->str_len);
 }
 void block_set_all_gap_close_C_aaprofile(AAProfile* p, int8_t gap) {
   std::fill(p->gap_close_C.begin(), p->gap_close_C.begin() + p->str_len + 1, (int16_t)gap);
+  p->hi_pos = std::max(p->hi_pos, p->str_len);
 }
 void block_set_all_gap_open_R_aaprofile(AAProfile* p, int8_t gap) {
   REQUIRE(gap < 0, "Gap open cost must be negative!");
   std::fill(p->gap_open_R.begin(), p->gap_open_R.begin() + p->str_len + 1, (int16_t)gap);
+  p->hi_pos = std::max(p->hi_pos, p->str_len);
 }
 int8_t block_get_aaprofile(const AAProfile* p, uintptr_t i, uint8_t b) {
   b = host::upper(b);

@@ -21,6 +21,7 @@ struct AAProfile {
   std::vector<int16_t> gap_open_C, gap_close_C, gap_open_R;  // [max_len]
   int8_t gap_extend;
   size_t max_len, curr_len, str_len;
+  size_t hi_pos = 0;   // highest position written since new / clear: positions above it still hold the -128 defaults
 };
 
 // scan_block.rs:1790-1793
@@ -54,6 +55,9 @@ inline uint8_t convert_char(int scoring, uint8_t c, bool* ok) {
 size_t profile_len(const AAProfile* p);
 size_t profile_curr_len(const AAProfile* p);
 int profile_gap_extend(const AAProfile* p);
-void profile_export(const AAProfile* p, int8_t* pos_aa, int16_t* open_C, int16_t* close_C, int16_t* open_R);
+// number of leading positions that may differ from the defaults (the rest of the padded profile is -128 everywhere)
+size_t profile_used_len(const AAProfile* p);
+// first `np` positions of every array
+void profile_export(const AAProfile* p, size_t np, int8_t* pos_aa, int16_t* open_C, int16_t* close_C, int16_t* open_R);
 
 }}  // namespace ba::host

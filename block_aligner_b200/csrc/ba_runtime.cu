@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/block_aligner_b200.h"
@@ -63,7 +64,65 @@ struct PackArgs {
   uint32_t n; uint32_t pad; int32_t scoring; uint32_t* err;
 };
 
+// One padded device profile (ProfBuild, ba_types.h). `tid` / `nthreads`: the calling thread's share of the profile.
+// Layout written: pos_aa [curr_len][32] i8, then gap_open_C, gap_close_C, gap_open_R [curr_len] i16.
+BA_HD void prof_build_one(const ProfBuildArgs& a, uint32_t k, uint32_t tid, uint32_t nthreads, bool& bad) {
+  const ProfBuild d = a.desc[k];
+  uint8_t* base = a.arena + d.dst_off;
+  const uint32_t cl = d.curr_len;
+  uint32_t* w = (uint32_t*)base;
+  int16_t* oc = (int16_t*)(base + (uint64_t)cl * 32);
+  int16_t* cc = oc + cl;
+  int16_t* orr = cc + cl;
+  if (a.kind == 0) {
+    const uint32_t* src = (const uint32_t*)(a.stage + d.src_off);
+    const uint32_t nw = d.np * 8;
+    for (uint32_t t = tid; t < cl * 8; t += nthreads) w[t] = t < nw ? src[t] : 0x80808080u;
+    const int16_t* g = (const int16_t*)(a.stage + d.src_off + (uint64_t)d.np * 32);
+    for (uint32_t t = tid; t < cl; t += nthreads) {
+      const bool in = t < d.np;
+      oc[t] = in ? g[t] : (int16_t)-128;
+      cc[t] = in ? g[d.np + t] : (int16_t)-128;
+      orr[t] = in ? g[2 * d.np + t] : (int16_t)-128;
+    }
+  } else {
+    const uint32_t len = d.np;
+    const int8_t* sc = a.scores + d.src_off;
+    for (uint32_t t = tid; t < cl * 8; t += nthreads) {
+      const uint32_t pos = t >> 3, b0 = (t & 7u) * 4;
+      uint32_t word = 0x80808080u;
+      if (pos >= 1 && pos <= len) {
+        // set_all walks positions 1..=len, set_all_rev len..=1, consuming one score row each (scores.rs:686-712)
+        const uint32_t n = a.rev ? len - pos : pos - 1;
+        const int8_t* row = sc + (uint64_t)n * a.order_len;
+        word = 0;
+        for (int e = 0; e < 4; e++) {
+          const int j = a.inv[b0 + e];
+          const int8_t v = j >= 0 ? (int8_t)((int8_t)(row[j] << a.left_shift) >> a.right_shift) : (int8_t)-128;
+          word |= (uint32_t)(uint8_t)v << (8 * e);
+        }
+      }
+      w[t] = word;
+    }
+    for (uint32_t t = tid; t < cl; t += nthreads) {
+      int g0 = -128, g1 = -128, g2 = -128;
+      if (t <= len) {
+        g0 = a.gap_open_C ? (int)a.gap_open_C[d.gap_src_off + t] : a.all_open_C;
+        g1 = a.gap_close_C ? (int)a.gap_close_C[d.gap_src_off + t] : a.all_close_C;
+        g2 = a.gap_open_R ? (int)a.gap_open_R[d.gap_src_off + t] : a.all_open_R;
+        if (g0 >= 0 || g2 >= 0) bad = true;     // "Gap open cost must be negative!" (scores.rs:549, 560)
+      }
+      oc[t] = (int16_t)g0; cc[t] = (int16_t)g1; orr[t] = (int16_t)g2;
+    }
+  }
+}
+
 #ifdef BA_EMU
+static void prof_build_all(const ProfBuildArgs& a) {
+  bool bad = false;
+  for (uint32_t k = 0; k < a.n; k++) prof_build_one(a, k, 0, 1, bad);
+  if (bad) *a.err = 1;
+}
 static void pack_all(const PackArgs& a) {
   const int nseq = a.raw_r ? 2 : 1;
   for (uint32_t k = 0; k < a.n; k++)
@@ -132,6 +191,13 @@ __global__ void ba_pack_kernel(PackArgs a) {
     }
     for (uint32_t t = lane; t < a.pad; t += 32) dst[1 + len + t] = nul;
   }
+  if (bad) atomicOr(a.err, 1u);
+}
+
+// one CTA per profile (grid-stride): coalesced 32-bit stores over the whole padded profile
+__global__ void ba_profile_build_kernel(ProfBuildArgs a) {
+  bool bad = false;
+  for (uint32_t k = blockIdx.x; k < a.n; k += gridDim.x) prof_build_one(a, k, threadIdx.x, blockDim.x, bad);
   if (bad) atomicOr(a.err, 1u);
 }
 
@@ -234,7 +300,24 @@ struct BaAligner {
   std::vector<std::pair<void*, size_t>> pool_free;
   std::vector<std::pair<void*, size_t>> pool_live;
   size_t pool_cached = 0;
+  // pinned host staging for data the library has to re-pack before the upload (host AAProfile objects); grow-only
+  uint8_t* h_stage = nullptr; size_t h_stage_cap = 0;
 };
+
+static int stage_reserve(BaAligner* al, size_t n) {
+  if (n <= al->h_stage_cap) return 0;
+#ifdef BA_EMU
+  free(al->h_stage);
+  al->h_stage = (uint8_t*)malloc(n);
+  if (!al->h_stage) { al->h_stage_cap = 0; return 1; }
+#else
+  if (al->h_stage) cudaFreeHost(al->h_stage);
+  al->h_stage = nullptr; al->h_stage_cap = 0;
+  CK(cudaHostAlloc((void**)&al->h_stage, n, cudaHostAllocDefault));
+#endif
+  al->h_stage_cap = n;
+  return 0;
+}
 
 static int streams_acquire(BaAligner* al, StreamSet* ss) {
   if (!al->streams_free.empty()) { *ss = al->streams_free.back(); al->streams_free.pop_back(); return 0; }
@@ -376,6 +459,11 @@ extern "C" void ba_destroy(BaAligner* a) {
   }
 #endif
   a->streams_free.clear();
+#ifdef BA_EMU
+  free(a->h_stage);
+#else
+  if (a->h_stage) cudaFreeHost(a->h_stage);
+#endif
   for (auto& e : a->pool_free) dfree(e.first);
   for (auto& e : a->pool_live) dfree(e.first);   // batches must be freed before the aligner; be forgiving
   a->pool_free.clear(); a->pool_live.clear();
@@ -431,14 +519,24 @@ static int check_config(const BaConfig* cfg, uint32_t* mn, uint32_t* mx) {
 #define TRY(x) do { int _r = (x); if (_r) { ba_batch_free(b); return _r == 1 ? BA_ERR_CUDA : _r; } } while (0)
 
 static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uint8_t* q_bytes, const uint64_t* q_off,
-                         const uint8_t* r_bytes, const uint64_t* r_off, const AAProfile* const* profiles, BaBatch** out) {
+                         const uint8_t* r_bytes, const uint64_t* r_off, const AAProfile* const* profiles, const BaPssmBatch* pssm,
+                         BaBatch** out) {
   if (!al || !out) return fail(BA_ERR_ARG, "null aligner/out");
   uint32_t mn = 0, mx = 0;
   int rc = check_config(cfg, &mn, &mx);
   if (rc) return rc;
   if (mn > mx && false) return fail(BA_ERR_SIZE, "min > max");
   const bool prof = cfg->scoring == BA_SCORING_PROFILE;
-  if (prof != (profiles != nullptr)) return fail(BA_ERR_ARG, "profiles must be given exactly for BA_SCORING_PROFILE");
+  if (prof != (profiles != nullptr || pssm != nullptr)) return fail(BA_ERR_ARG, "profiles must be given exactly for BA_SCORING_PROFILE");
+  if (pssm) {
+    if (!pssm->order || pssm->order_len == 0 || pssm->order_len > 32) return fail(BA_ERR_ARG, "BaPssmBatch: order must hold 1..32 residues");
+    if (n && (!pssm->scores || !pssm->score_off)) return fail(BA_ERR_ARG, "BaPssmBatch: null scores");
+    if (pssm->gap_extend >= 0) return fail(BA_ERR_GAPS, "Gap extend cost must be negative!");
+    const bool per_pos = pssm->gap_open_C || pssm->gap_close_C || pssm->gap_open_R;
+    if (per_pos && !(pssm->gap_open_C && pssm->gap_close_C && pssm->gap_open_R && pssm->gap_off))
+      return fail(BA_ERR_ARG, "BaPssmBatch: give all three per-position gap arrays and gap_off, or none");
+    if (!per_pos && (pssm->all_gap_open_C >= 0 || pssm->all_gap_open_R >= 0)) return fail(BA_ERR_GAPS, "Gap open cost must be negative!");
+  }
   if (n >= ((size_t)1 << 31)) return fail(BA_ERR_ARG, "too many pairs");
   if (n && (!q_off || (!prof && !r_off))) return fail(BA_ERR_ARG, "null offsets");
 #ifndef BA_EMU
@@ -460,7 +558,11 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
   for (size_t k = 0; k < n; k++) {
     const uint64_t a = q_off[k + 1] - q_off[k];
     uint64_t c;
-    if (prof) {
+    if (pssm) {
+      const uint64_t ns = pssm->score_off[k + 1] - pssm->score_off[k];
+      if (ns % pssm->order_len) { ba_batch_free(b); return fail(BA_ERR_ARG, "BaPssmBatch: scores of a profile are not a multiple of order_len"); }
+      c = ns / pssm->order_len;
+    } else if (prof) {
       if (!profiles[k]) { ba_batch_free(b); return fail(BA_ERR_ARG, "null profile"); }
       c = host::profile_len(profiles[k]);
       if (host::profile_gap_extend(profiles[k]) >= 0) { ba_batch_free(b); return fail(BA_ERR_GAPS, "Gap extend cost must be negative!"); }
@@ -527,32 +629,114 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
     TRY2(pool_alloc(al, (void**)&b->d_matrix, mb));
     TRY2(h2d(b->d_matrix, cfg->matrix, mb, st));
   } else {
-    // one arena: per profile pos_aa [curr_len*32] then three i16 arrays [curr_len]
+    // One device arena: per profile pos_aa [curr_len][32] then three i16 arrays [curr_len]. Only the positions that
+    // can differ from AAProfile::new's defaults cross the bus (a host AAProfile's leading positions, or the raw
+    // PSSM rows of a BaPssmBatch); ba_profile_build_kernel expands them and writes the -128 padding on the device.
     std::vector<ProfileDev> pd(n);
-    std::vector<uint64_t> poff(n);
-    uint64_t ppos = 0;
+    std::vector<ProfBuild> bd(n);
+    uint64_t ppos = 0, spos = 0;
     for (size_t k = 0; k < n; k++) {
-      const uint64_t cl = host::profile_curr_len(profiles[k]);
-      poff[k] = ppos; ppos += ((cl * 32 + cl * 6) + 63) & ~(uint64_t)63;
+      const uint64_t cl = pssm ? (uint64_t)rl[k] + mx + 1 : host::profile_curr_len(profiles[k]);
+      bd[k].dst_off = ppos; bd[k].curr_len = (uint32_t)cl;
+      ppos += ((cl * 32 + cl * 6) + 63) & ~(uint64_t)63;
+      if (pssm) {
+        bd[k].np = rl[k];
+        bd[k].src_off = pssm->score_off[k] - pssm->score_off[0];
+        bd[k].gap_src_off = pssm->gap_off ? pssm->gap_off[k] - pssm->gap_off[0] : 0;
+        if (pssm->gap_off && pssm->gap_off[k + 1] - pssm->gap_off[k] != (uint64_t)rl[k] + 1) {
+          free_tmp(); ba_batch_free(b); return fail(BA_ERR_ARG, "BaPssmBatch: gap arrays need len + 1 entries per profile");
+        }
+      } else {
+        const uint64_t np = host::profile_used_len(profiles[k]);
+        bd[k].np = (uint32_t)np; bd[k].src_off = spos; bd[k].gap_src_off = 0;
+        spos += (np * 38 + 63) & ~(uint64_t)63;
+      }
     }
     TRY2(pool_alloc(al, (void**)&b->d_prof_arena, ppos + 64));
-    std::vector<uint8_t> stage(ppos + 64, 0);
     for (size_t k = 0; k < n; k++) {
-      const uint64_t cl = host::profile_curr_len(profiles[k]);
-      uint8_t* base = stage.data() + poff[k];
-      host::profile_export(profiles[k], (int8_t*)base, (int16_t*)(base + cl * 32), (int16_t*)(base + cl * 34), (int16_t*)(base + cl * 36));
-      uint8_t* dbase = b->d_prof_arena + poff[k];
+      const uint64_t cl = bd[k].curr_len;
+      uint8_t* dbase = b->d_prof_arena + bd[k].dst_off;
       pd[k].pos_aa = (const int8_t*)dbase;
       pd[k].gap_open_C = (const int16_t*)(dbase + cl * 32);
       pd[k].gap_close_C = (const int16_t*)(dbase + cl * 34);
       pd[k].gap_open_R = (const int16_t*)(dbase + cl * 36);
-      pd[k].len = (uint32_t)host::profile_len(profiles[k]);
-      pd[k].gap_extend = host::profile_gap_extend(profiles[k]);
+      pd[k].len = rl[k];
+      pd[k].gap_extend = pssm ? (int32_t)pssm->gap_extend : host::profile_gap_extend(profiles[k]);
     }
-    TRY2(h2d(b->d_prof_arena, stage.data(), ppos, st));
-    TRY2(pool_alloc(al, (void**)&b->d_profiles, n * sizeof(ProfileDev)));
-    TRY2(h2d(b->d_profiles, pd.data(), n * sizeof(ProfileDev), st));
+    ProfBuildArgs ba;
+    memset(&ba, 0, sizeof(ba));
+    ba.n = (uint32_t)n; ba.arena = b->d_prof_arena; ba.err = d_err;
+    ProfBuild* d_bd = nullptr; uint8_t* d_src = nullptr; int8_t* d_gaps = nullptr;
+    auto free_prof_tmp = [&]() { pool_release(al, d_bd); pool_release(al, d_src); pool_release(al, d_gaps); };
+#define TRY3(x) do { int _r = (x); if (_r) { free_prof_tmp(); free_tmp(); ba_batch_free(b); return _r == 1 ? BA_ERR_CUDA : _r; } } while (0)
+    TRY3(pool_alloc(al, (void**)&d_bd, std::max<size_t>(n, 1) * sizeof(ProfBuild)));
+    TRY3(h2d(d_bd, bd.data(), n * sizeof(ProfBuild), st));
+    ba.desc = d_bd;
+    if (pssm) {
+      ba.kind = 1;
+      const uint64_t sbytes = n ? pssm->score_off[n] - pssm->score_off[0] : 0;
+      TRY3(pool_alloc(al, (void**)&d_src, sbytes));
+      if (n) TRY3(h2d(d_src, pssm->scores + pssm->score_off[0], sbytes, st));
+      ba.scores = (const int8_t*)d_src;
+      if (pssm->gap_off) {
+        const uint64_t gb = n ? pssm->gap_off[n] - pssm->gap_off[0] : 0;
+        TRY3(pool_alloc(al, (void**)&d_gaps, 3 * gb));
+        if (n) {
+          TRY3(h2d(d_gaps, pssm->gap_open_C + pssm->gap_off[0], gb, st));
+          TRY3(h2d(d_gaps + gb, pssm->gap_close_C + pssm->gap_off[0], gb, st));
+          TRY3(h2d(d_gaps + 2 * gb, pssm->gap_open_R + pssm->gap_off[0], gb, st));
+        }
+        ba.gap_open_C = d_gaps; ba.gap_close_C = d_gaps + gb; ba.gap_open_R = d_gaps + 2 * gb;
+      }
+      ba.all_open_C = pssm->all_gap_open_C; ba.all_close_C = pssm->all_gap_close_C; ba.all_open_R = pssm->all_gap_open_R;
+      ba.order_len = (uint32_t)pssm->order_len;
+      ba.left_shift = (uint32_t)pssm->left_shift & 7u; ba.right_shift = (uint32_t)pssm->right_shift & 7u;
+      ba.rev = pssm->rev ? 1u : 0u;
+      for (int e = 0; e < 32; e++) ba.inv[e] = -1;
+      for (size_t j = 0; j < pssm->order_len; j++) {
+        const uint8_t c = host::upper(pssm->order[j]);
+        if (!(c >= 'A' && c <= 'Z' + 1)) { free_prof_tmp(); free_tmp(); ba_batch_free(b); return fail(BA_ERR_CHAR, "BaPssmBatch: order byte out of range"); }
+        ba.inv[c - 'A'] = (int8_t)j;
+      }
+    } else {
+      ba.kind = 0;
+      if (stage_reserve(al, spos + 64)) { free_prof_tmp(); free_tmp(); ba_batch_free(b); return fail(BA_ERR_NOMEM, "pinned staging allocation failed"); }
+      uint8_t* stage = al->h_stage;
+      auto export_range = [&](size_t lo, size_t hi) {
+        for (size_t k = lo; k < hi; k++) {
+          const size_t np = bd[k].np;
+          uint8_t* sb = stage + bd[k].src_off;
+          host::profile_export(profiles[k], np, (int8_t*)sb, (int16_t*)(sb + np * 32), (int16_t*)(sb + np * 34), (int16_t*)(sb + np * 36));
+        }
+      };
+      const size_t nthr = spos >= ((size_t)8 << 20) ? std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+      if (nthr <= 1) export_range(0, n);
+      else {
+        std::vector<std::thread> th;
+        for (size_t t = 0; t < nthr; t++) th.emplace_back(export_range, n * t / nthr, n * (t + 1) / nthr);
+        for (auto& t : th) t.join();
+      }
+      TRY3(pool_alloc(al, (void**)&d_src, spos + 64));
+      TRY3(h2d(d_src, stage, spos, st));
+      ba.stage = d_src;
+    }
+    if (n) {
+#ifdef BA_EMU
+      prof_build_all(ba);
+#else
+      const int pblocks = (int)std::min<uint64_t>(n, (uint64_t)al->sm_count * 16);
+      ba_profile_build_kernel<<<pblocks, 128, 0, st>>>(ba);
+      if (cudaGetLastError() != cudaSuccess) { free_prof_tmp(); free_tmp(); ba_batch_free(b); return fail(BA_ERR_CUDA, "profile build kernel launch failed"); }
+#endif
+    }
+    TRY3(pool_alloc(al, (void**)&b->d_profiles, n * sizeof(ProfileDev)));
+    TRY3(h2d(b->d_profiles, pd.data(), n * sizeof(ProfileDev), st));
+    TRY3(dsync(st));     // the staging buffers (host and device) are reused by the next upload
+    free_prof_tmp();
+    uint32_t perr = 0;
+    TRY2(d2h(&perr, d_err, 4, st));
     TRY2(dsync(st));
+    if (perr) { free_tmp(); ba_batch_free(b); return fail(BA_ERR_GAPS, "Gap open cost must be negative!"); }
   }
   // convert + pad on the device
   PackArgs pa;
@@ -670,13 +854,19 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
 extern "C" int ba_batch_upload(BaAligner* a, const BaConfig* cfg, size_t n, const uint8_t* q_bytes, const uint64_t* q_off,
                                const uint8_t* r_bytes, const uint64_t* r_off, BaBatch** out) {
   if (cfg && cfg->scoring == BA_SCORING_PROFILE) return fail(BA_ERR_ARG, "use ba_batch_upload_profiles");
-  return upload_common(a, cfg, n, q_bytes, q_off, r_bytes, r_off, nullptr, out);
+  return upload_common(a, cfg, n, q_bytes, q_off, r_bytes, r_off, nullptr, nullptr, out);
 }
 extern "C" int ba_batch_upload_profiles(BaAligner* a, const BaConfig* cfg, size_t n, const uint8_t* q_bytes, const uint64_t* q_off,
                                         const AAProfile* const* profiles, BaBatch** out) {
   if (cfg && cfg->scoring != BA_SCORING_PROFILE) return fail(BA_ERR_ARG, "scoring must be BA_SCORING_PROFILE");
   if (!profiles) return fail(BA_ERR_ARG, "profiles is null");
-  return upload_common(a, cfg, n, q_bytes, q_off, nullptr, nullptr, profiles, out);
+  return upload_common(a, cfg, n, q_bytes, q_off, nullptr, nullptr, profiles, nullptr, out);
+}
+extern "C" int ba_batch_upload_pssm(BaAligner* a, const BaConfig* cfg, size_t n, const uint8_t* q_bytes, const uint64_t* q_off,
+                                    const BaPssmBatch* pssm, BaBatch** out) {
+  if (cfg && cfg->scoring != BA_SCORING_PROFILE) return fail(BA_ERR_ARG, "scoring must be BA_SCORING_PROFILE");
+  if (!pssm) return fail(BA_ERR_ARG, "pssm is null");
+  return upload_common(a, cfg, n, q_bytes, q_off, nullptr, nullptr, nullptr, pssm, out);
 }
 
 static Params make_params(const BaBatch* b) {
@@ -971,12 +1161,24 @@ extern "C" int ba_align_batch_exp(BaAligner* a, const BaConfig* cfg, size_t n, c
 }
 
 // sequence-to-profile counterpart of ba_align_batch (no chunking: profiles are uploaded as one arena)
+static int align_uploaded_profiles(BaBatch* b, size_t n, AlignResult* out, BaStats* stats);
 extern "C" int ba_align_batch_profiles(BaAligner* a, const BaConfig* cfg, size_t n, const uint8_t* q_bytes, const uint64_t* q_off,
                                        const AAProfile* const* profiles, AlignResult* out, BaStats* stats) {
   BaBatch* b = nullptr;
   int rc = ba_batch_upload_profiles(a, cfg, n, q_bytes, q_off, profiles, &b);
   if (rc) return rc;
-  rc = ba_batch_run(b, stats);
+  return align_uploaded_profiles(b, n, out, stats);
+}
+// the same for profiles built on the device from raw PSSM rows (BaPssmBatch)
+extern "C" int ba_align_batch_pssm(BaAligner* a, const BaConfig* cfg, size_t n, const uint8_t* q_bytes, const uint64_t* q_off,
+                                   const BaPssmBatch* pssm, AlignResult* out, BaStats* stats) {
+  BaBatch* b = nullptr;
+  int rc = ba_batch_upload_pssm(a, cfg, n, q_bytes, q_off, pssm, &b);
+  if (rc) return rc;
+  return align_uploaded_profiles(b, n, out, stats);
+}
+static int align_uploaded_profiles(BaBatch* b, size_t n, AlignResult* out, BaStats* stats) {
+  int rc = ba_batch_run(b, stats);
   if (!rc) rc = ba_batch_download(b, out);
   if (!rc && stats) {
     for (size_t k = 0; k < n; k++) { stats->cells += b->h_out[k].cells; stats->steps += b->h_out[k].steps; if (b->h_out[k].status) stats->n_failed++; }

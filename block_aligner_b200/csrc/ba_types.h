@@ -36,6 +36,28 @@ struct ProfileDev {
   int32_t gap_extend;
 };
 
+// Construction of one padded device profile (ba_profile_build_kernel): AAProfile::new's -128 defaults
+// (src/scores.rs:473-486) everywhere, then either the leading `np` positions of a host AAProfile (kind 0) or
+// AAProfile::set_all / set_all_rev + the gap setters (src/scores.rs:532-538, 548-580, 676-715) applied to a raw
+// position-major score table (kind 1).
+struct ProfBuild {
+  uint64_t src_off;      // kind 0: byte offset of the staged compact profile; kind 1: offset of its scores [len][order_len]
+  uint64_t gap_src_off;  // kind 1: offset into the per-position gap arrays (len + 1 entries per profile)
+  uint64_t dst_off;      // byte offset inside the profile arena (64-byte aligned)
+  uint32_t np;           // kind 0: staged positions; kind 1: len
+  uint32_t curr_len;     // positions of the padded device profile
+};
+struct ProfBuildArgs {
+  const ProfBuild* desc; uint32_t n; int32_t kind;
+  const uint8_t* stage;  // kind 0
+  uint8_t* arena;
+  const int8_t* scores; const int8_t *gap_open_C, *gap_close_C, *gap_open_R;   // kind 1; gap arrays may be null
+  int32_t all_open_C, all_close_C, all_open_R;
+  uint32_t order_len, left_shift, right_shift, rev;
+  int8_t inv[32];        // residue code -> index in `order` (last occurrence wins like the reference's loop), -1 = absent
+  uint32_t* err;         // set when a gap open cost is not negative
+};
+
 // one computed rectangle (reference: Trace::add_block, src/scan_block.rs:1428-1443)
 struct Rect {
   uint32_t row, col;             // top-left cell in DP-matrix coordinates

@@ -142,3 +142,38 @@ def make_lib_profiles(lib, ra, ro, block_size, gap_open=-10, gap_extend=-1, seed
         p.set_gap_open_R(0, -128)
         out.append(p)
     return out
+
+
+def make_pssm_batch(lib, ra, ro, gap_open=-10, gap_extend=-1, seed=1234, pinned=False):
+    """The C4 profiles of make_lib_profiles as one api.PssmBatch (built on the device): same numbers, same rng order.
+    Per-position gap arrays with -128 at position 0 (the reference loader skips i == 0, examples/pssm_bench.rs:67-83)."""
+    b62 = lib.builtin_matrix("BLOSUM62")[1]
+    rng = np.random.default_rng(seed)
+    n = len(ro) - 1
+    lens = (ro[1:] - ro[:-1]).astype(np.uint64)
+    soff = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(lens * np.uint64(20), out=soff[1:])
+    goff = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(lens + np.uint64(1), out=goff[1:])
+
+    def buf(nbytes):
+        if pinned:
+            import torch
+            t = torch.empty(max(int(nbytes), 1), dtype=torch.int8).pin_memory()
+            a = t.numpy()[:int(nbytes)]
+            a._keep = None
+            return a, t
+        return np.zeros(int(nbytes), dtype=np.int8), None
+
+    scores, k0 = buf(soff[-1])
+    go, k1 = buf(goff[-1]); gc, k2 = buf(goff[-1]); gr, k3 = buf(goff[-1])
+    for k in range(n):
+        cons = ra[int(ro[k]):int(ro[k + 1])].tobytes()
+        if len(cons):
+            scores[int(soff[k]):int(soff[k + 1])] = pssm_scores(b62, cons, rng).reshape(-1)
+        a, e = int(goff[k]), int(goff[k + 1])
+        go[a:e] = gap_open; gc[a:e] = 0; gr[a:e] = gap_open
+        go[a] = gc[a] = gr[a] = -128
+    pb = api.PssmBatch(MAP20, scores, soff, gap_extend, gaps=(go, gc, gr))
+    pb._pinned = (k0, k1, k2, k3)
+    return pb

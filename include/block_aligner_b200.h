@@ -164,6 +164,25 @@ int ba_batch_upload(BaAligner* a, const BaConfig* cfg, size_t n,
 int ba_batch_upload_profiles(BaAligner* a, const BaConfig* cfg, size_t n,
                              const uint8_t* q_bytes, const uint64_t* q_off,
                              const struct AAProfile* const* profiles, BaBatch** out);
+/* Raw position-specific score tables for a batch of profiles that the library builds on the device
+ * (AAProfile::new + set_all / set_all_rev + the gap setters, src/scores.rs:473-486, 532-538, 548-580, 676-715;
+ * SURVEY 8(f) rank 3). Profile k has len_k = (score_off[k+1] - score_off[k]) / order_len positions; its scores
+ * are position-major, scores[score_off[k] + p * order_len + j] = score of residue order[j] at profile position
+ * p + 1 (rev != 0: position len_k - p, as set_all_rev). Stored value = (score << left_shift) >> right_shift as i8.
+ * Residues absent from `order` and the padding positions keep the -128 default. Gaps: either three per-position
+ * arrays with len_k + 1 entries per profile (positions 0..=len_k, profile k at gap_off[k]; gap_off has n + 1
+ * entries), or all three NULL and the all_gap_* values are applied to positions 0..=len_k like set_all_gap_*. */
+typedef struct BaPssmBatch {
+  const uint8_t* order; uintptr_t order_len;
+  const int8_t* scores; const uint64_t* score_off;          /* n + 1 offsets */
+  uintptr_t left_shift, right_shift; int32_t rev;
+  const int8_t* gap_open_C; const int8_t* gap_close_C; const int8_t* gap_open_R; const uint64_t* gap_off;
+  int8_t all_gap_open_C, all_gap_close_C, all_gap_open_R;
+  int8_t gap_extend;
+} BaPssmBatch;
+/* like ba_batch_upload_profiles, with the profiles constructed on the device from `pssm` */
+int ba_batch_upload_pssm(BaAligner* a, const BaConfig* cfg, size_t n,
+                         const uint8_t* q_bytes, const uint64_t* q_off, const BaPssmBatch* pssm, BaBatch** out);
 /* Run the alignment kernel on a resident batch (may be repeated; outputs are overwritten). */
 int ba_batch_run(BaBatch* b, BaStats* stats);
 /* Copy results back. `out` has n entries. */
@@ -194,6 +213,10 @@ int ba_align_batch_exp(BaAligner* a, const BaConfig* cfg, size_t n,
 int ba_align_batch_profiles(BaAligner* a, const BaConfig* cfg, size_t n,
                             const uint8_t* q_bytes, const uint64_t* q_off,
                             const struct AAProfile* const* profiles, AlignResult* out, BaStats* stats);
+
+int ba_align_batch_pssm(BaAligner* a, const BaConfig* cfg, size_t n,
+                        const uint8_t* q_bytes, const uint64_t* q_off,
+                        const BaPssmBatch* pssm, AlignResult* out, BaStats* stats);
 
 /* Measured integer-ALU roofline denominators for this device (giga add/max operations per second); see DESIGN.md.
  * ba_measure_int_peak: DPX add-max / max3 on one 32-bit value per lane (the exact path);

@@ -164,3 +164,39 @@ def check_workload(lib, al, w, n, first=0, seed=1234, with_trace=None, size=None
     got = run_lib(lib, al, scoring, matrix, w["gaps"], size, w["x_drop"], flags, cigar_eq, qa, qo, ra, ro, lp)
     exp = oracle_batch(scoring, matrix, w["gaps"], size, w["x_drop"], flags, cigar_eq, qa, qo, ra, ro, op)
     return compare(f"{scoring}/{flags}/{size}", got, exp, verbose)
+
+
+def check_pssm(lib, al, n, seed, rev, shifts, uniform_gaps, size=(32, 128), flags=api.XDROP):
+    """The same numbers go to the oracle through Profile::new + set_all[_rev] + gap setters (scores.rs:532-580)."""
+    w = workloads.WORKLOADS["C4_seq_to_profile_xdrop"]
+    qa, qo, ra, ro = workloads.generate(w["gen"], n, seed=seed, stream=4)
+    b62 = lib.builtin_matrix("BLOSUM62")[1]
+    rng = np.random.default_rng(seed)
+    ls, rs = shifts
+    scores, soff, ops = [], [0], []
+    go, gc, gr = [], [], []
+    for k in range(n):
+        cons = ra[int(ro[k]):int(ro[k + 1])].tobytes()
+        sc = workloads.pssm_scores(b62, cons, rng)
+        scores.append(sc.reshape(-1))
+        soff.append(soff[-1] + sc.size)
+        o = ora.Profile.new(len(cons), size[1], -1)
+        if len(cons):
+            assert ora.lib().ora_profile_set_all(o.h, workloads.MAP20, 20, sc.ctypes.data, sc.size, ls, rs, int(rev)) == 0
+        g = rng.integers(-12, -5, size=(3, len(cons) + 1)).astype(np.int8)
+        g[1] = rng.integers(-2, 1, size=len(cons) + 1)
+        if uniform_gaps:
+            g[0, :] = -9; g[1, :] = -1; g[2, :] = -7
+        for i in range(len(cons) + 1):
+            o.set_gap_open_C(i, int(g[0, i])); o.set_gap_close_C(i, int(g[1, i])); o.set_gap_open_R(i, int(g[2, i]))
+        go.append(g[0]); gc.append(g[1]); gr.append(g[2])
+        ops.append(o)
+    scores = np.concatenate(scores) if scores else np.zeros(0, dtype=np.int8)
+    if uniform_gaps:
+        pb = api.PssmBatch(workloads.MAP20, scores, soff, -1, all_gaps=(-9, -1, -7), left_shift=ls, right_shift=rs, rev=rev)
+    else:
+        pb = api.PssmBatch(workloads.MAP20, scores, soff, -1, gaps=(np.concatenate(go), np.concatenate(gc), np.concatenate(gr)),
+                           left_shift=ls, right_shift=rs, rev=rev)
+    got = run_lib(lib, al, api.SCORING_PROFILE, None, None, size, w["x_drop"], flags, False, qa, qo, ra, ro, pb)
+    exp = oracle_batch(api.SCORING_PROFILE, None, None, size, w["x_drop"], flags, False, qa, qo, ra, ro, ops)
+    return compare("pssm", got, exp)

@@ -186,3 +186,30 @@ def test_extended_modes_protein_and_profile(env, mode):
     w = dict(workloads.WORKLOADS["C4_seq_to_profile_xdrop"])
     w["flags"] = api.TRACE | mode
     assert parity.check_workload(*env, w, 6, size=(32, 128), seed=29) == 0
+
+
+# ---- profiles built on the device from raw PSSM rows (ba_batch_upload_pssm) ----
+@pytest.mark.parametrize("rev,shifts,uniform", [(False, (0, 0), False), (True, (0, 0), False), (False, (1, 0), True),
+                                                (True, (0, 1), True)])
+def test_pssm_batch_device_profiles(env, rev, shifts, uniform):
+    assert parity.check_pssm(*env, 24, 77, rev, shifts, uniform) == 0
+
+
+def test_pssm_batch_trace(env):
+    assert parity.check_pssm(*env, 12, 78, False, (0, 0), False, flags=api.XDROP | api.TRACE) == 0
+
+
+def test_pssm_batch_rejects_bad_input(env):
+    lib, al = env
+    qa, qo = api.concat([b"ACD", b"ACDE"])
+    sc = np.zeros(7 * 20, dtype=np.int8)
+    cfg = al.config(api.SCORING_PROFILE, None, None, (32, 32), 10, api.XDROP, False)
+    with pytest.raises(api.BlockAlignerError):     # gap open must be negative (scores.rs:549)
+        al.upload(cfg, qa, qo, None, None, api.PssmBatch(workloads.MAP20, sc, [0, 60, 140], -1, all_gaps=(0, 0, -1)))
+    with pytest.raises(api.BlockAlignerError):     # per-position gap open >= 0 is caught by the build kernel
+        g = np.full(9, -3, dtype=np.int8); g2 = g.copy(); g2[4] = 1
+        al.upload(cfg, qa, qo, None, None, api.PssmBatch(workloads.MAP20, sc, [0, 60, 140], -1, gaps=(g2, g, g)))
+    with pytest.raises(api.BlockAlignerError):     # scores not a multiple of order_len
+        al.upload(cfg, qa, qo, None, None, api.PssmBatch(workloads.MAP20, sc, [0, 61, 140], -1))
+    with pytest.raises(api.BlockAlignerError):     # gap extend must be negative
+        al.upload(cfg, qa, qo, None, None, api.PssmBatch(workloads.MAP20, sc, [0, 60, 140], 0))

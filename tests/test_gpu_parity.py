@@ -191,3 +191,35 @@ def test_free_query_end_gaps(env, flags, size):
     got = parity.run_lib(lib, al, api.SCORING_NUC, m, (-2, -1), size, 0, fl, bool(fl & api.TRACE), qa, qo, ra, ro)
     exp = parity.oracle_batch(api.SCORING_NUC, m, (-2, -1), size, 0, fl, bool(fl & api.TRACE), qa, qo, ra, ro)
     assert parity.compare(f"fqe/{flags}/{size}", got, exp) == 0
+
+
+# ---- profiles built on the device from raw PSSM rows (ba_batch_upload_pssm) ----
+@pytest.mark.gpu
+@pytest.mark.parametrize("rev,shifts,uniform", [(False, (0, 0), False), (True, (0, 0), False), (False, (1, 0), True),
+                                                (True, (0, 1), True)])
+def test_pssm_batch_device_profiles(env, rev, shifts, uniform):
+    assert parity.check_pssm(*env, 300, 77, rev, shifts, uniform, size=(32, 256)) == 0
+
+
+@pytest.mark.gpu
+def test_pssm_batch_trace(env):
+    assert parity.check_pssm(*env, 200, 78, False, (0, 0), False, flags=api.XDROP | api.TRACE) == 0
+
+
+@pytest.mark.gpu
+def test_pssm_batch_matches_host_profiles_c4(env):
+    """C4 through both profile entry points: host AAProfile objects (compact upload) and device-built PSSM batch"""
+    lib, al = env
+    w = workloads.WORKLOADS["C4_seq_to_profile_xdrop"]
+    n = 2000
+    qa, qo, ra, ro = workloads.generate(w["gen"], n, stream=w["stream"])
+    cfg = al.config(api.SCORING_PROFILE, None, None, w["size"], w["x_drop"], w["flags"], False)
+    profs = workloads.make_lib_profiles(lib, ra, ro, w["size"][1], seed=99)
+    pb = workloads.make_pssm_batch(lib, ra, ro, seed=99)
+    outs = []
+    for p in (profs, pb):
+        b = al.upload(cfg, qa, qo, None, None, p)
+        b.run()
+        outs.append(b.download().copy())
+        b.free()
+    assert (outs[0] == outs[1]).all()
