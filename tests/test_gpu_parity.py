@@ -223,3 +223,13 @@ def test_pssm_batch_matches_host_profiles_c4(env):
         outs.append(b.download().copy())
         b.free()
     assert (outs[0] == outs[1]).all()
+
+
+# ---- size-independent properties at the BASELINE lengths (tests/test_properties.py) ----
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,n,scorer", [("C2_nanopore_xdrop_10k", 24, (1, -1)), ("C5_longread_trace_50k", 6, (2, -4))])
+def test_cigar_consumes_end_position_and_rescores_full_length(env, name, n, scorer):
+    import test_properties as tp
+    w = workloads.WORKLOADS[name]
+    flags = w["flags"] | api.TRACE
+    assert tp.check_cigars(*env, w, n, 1234, w["size"], flags, w["x_drop"], tp.nuc_scorer(*scorer)) == [0, 0]
