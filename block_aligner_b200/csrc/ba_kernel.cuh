@@ -481,78 +481,103 @@ BA_DEV uint32_t* trace_push(AlnState& st, const SlotMem& sm, uint32_t row, uint3
 // Traceback (Trace::cigar_core, scan_block.rs:1482-1672). Lane 0 walks from (i, j) back to the
 // origin through the stack of rectangles; runs are produced reversed and run-length merged
 // exactly like Cigar::add (cigar.rs:71-79), then written forward into the output stream.
+// The walk is one dependent chain (trace word -> step -> next cell), so its speed is the latency of
+// that chain: the other lanes keep the trace words of the rectangles the walk reaches next in L1
+// (the words were written tens of thousands of steps ago and live in DRAM by now), and the
+// per-cell decision is one lookup in a 128-entry table instead of a branch tree.
 // ---------------------------------------------------------------------------------------------
-BA_DEV void traceback_walk(const uint32_t* words, const uint32_t* zwords, bool fqs, const Rect* rects, uint32_t ridx,
-                           uint32_t i, uint32_t j, const uint8_t* q, const uint8_t* r, bool eq, uint32_t* runs,
-                           uint32_t cap, uint32_t& nruns, uint32_t& bad) {
-  int table = 0;  // 0 = D, 1 = C, 2 = R
-  uint32_t cur_op = 0, cur_len = 0;
-  nruns = 0; bad = 0;
-  bool stop = false;
-  while ((i > 0 || j > 0) && !bad && !stop) {
-    Rect rc;
-    for (;;) {   // find the newest rectangle containing (i, j) (scan_block.rs:1578-1590)
-      if (ridx == 0) { bad = 1; break; }
-      ridx--;
-      rc = rects[ridx];
-      if (i >= rc.row && j >= rc.col) break;
-    }
-    if (bad) break;
-    const int H = rc.h, W = rc.w;
-    const bool rc_right = (rc.right & 1u) != 0;
-    const uint32_t layout = (rc.right >> 1) & 3u;
-    const int R = layout == 1u ? 8 : rect_rows_per_lane(H);
-    const int CH = 32 * R;
-    const int ngroups = W >> 3;
-    const uint32_t* tw = words + rc.word_off;
-    // The 64-entry OP_LUT (scan_block.rs:1508-1572) folded into branches. Bit 0 of trace/trace2
-    // talks about the gap table that runs along the rectangle's sequential columns (C for a right
-    // rectangle, R for a down rectangle), bit 1 about the table along its vectors.
-    const int tabA = rc_right ? 1 : 2, tabB = rc_right ? 2 : 1;
-    const uint32_t opA = rc_right ? 5u : 4u, opB = rc_right ? 4u : 5u;   // D : I
-    while (i >= rc.row && j >= rc.col && (i > 0 || j > 0)) {
-      // FREE_QUERY_START_GAPS: stop on row 0, which always lies in right rectangles (scan_block.rs:1597-1600)
-      if (fqs && rc_right && i == 0) { stop = true; break; }
-      const uint32_t v = rc_right ? i - rc.row : j - rc.col;
-      const uint32_t c = rc_right ? j - rc.col : i - rc.row;
+struct WalkState {
+  uint32_t i, j, ridx, table, cur_op, cur_len, nruns, bad, stop;
+};
+
+// lane 0: walk inside rectangle rc until the path leaves it
+BA_DEV void traceback_rect(const uint8_t* lut, const uint32_t* words, const uint32_t* zwords, bool fqs, const Rect& rc,
+                           const uint8_t* q, const uint8_t* r, bool eq, uint32_t* runs, uint32_t cap, WalkState& s) {
+  const int H = rc.h, W = rc.w;
+  const bool rc_right = (rc.right & 1u) != 0;
+  const uint32_t layout = (rc.right >> 1) & 3u;
+  const int R = layout == 1u ? 8 : rect_rows_per_lane(H);
+  const int CH = 32 * R;
+  const int ngroups = W >> 3;
+  const uint32_t* tw = words + rc.word_off;
+  const uint32_t lbase = rc_right ? 64u : 0u;
+  const uint32_t hh = (uint32_t)(H >> 1), G = (uint32_t)(H >> 3);
+  uint32_t i = s.i, j = s.j, table = s.table;
+  while (i >= rc.row && j >= rc.col && (i > 0 || j > 0)) {
+    // FREE_QUERY_START_GAPS: stop on row 0, which always lies in right rectangles (scan_block.rs:1597-1600)
+    if (fqs && rc_right && i == 0) { s.stop = 1u; break; }
+    const uint32_t v = rc_right ? i - rc.row : j - rc.col;
+    const uint32_t c = rc_right ? j - rc.col : i - rc.row;
+    uint32_t nib;
+    if (layout == 3u) {     // packed path: word (column, lane in group), nibble (row mod 4) of the half-block's 16 bits
+      const uint32_t half = v >= hh ? 1u : 0u, vv = v - half * hh;
+      nib = (tw[(size_t)c * G + (vv >> 2)] >> (16u * half + 4u * (vv & 3u))) & 15u;
+    } else {
       const uint32_t ch = v / CH, ln = (v % CH) / R, k = v % R;
-      uint32_t nib;
-      if (layout == 3u) {     // packed path: word (column, lane in group), nibble (row mod 4) of the half-block's 16 bits
-        const uint32_t half = v >= (uint32_t)(H >> 1) ? 1u : 0u, vv = v - half * (uint32_t)(H >> 1);
-        nib = (tw[(size_t)c * (H >> 3) + (vv >> 2)] >> (16u * half + 4u * (vv & 3u))) & 15u;
-      } else {
-        const size_t widx = (((size_t)ch * ngroups + (c >> 3)) * R + k) * 32 + ln;
-        // LOCAL_START: the alignment starts at a cell equal to relative_zero (scan_block.rs:1606-1612)
-        if (zwords && table == 0 && ((zwords[rc.word_off + widx] >> (c & 7)) & 1u)) { stop = true; break; }
-        nib = (tw[widx] >> (4 * (c & 7))) & 15u;
-      }
-      const uint32_t t = nib & 3u, t2 = nib >> 2;
-      uint32_t op; int ntab;
-      if (table == tabA) { op = opA; ntab = (t2 & 1u) ? 0 : tabA; }
-      else if (table == tabB) { op = opB; ntab = (t2 & 2u) ? 0 : tabB; }
-      else if (t == 0) { op = 1u; ntab = 0; }
-      else if (t & 1u) { op = opA; ntab = (t2 & 1u) ? 0 : tabA; }
-      else { op = opB; ntab = (t2 & 2u) ? 0 : tabB; }
-      const uint32_t di = (op == 5u) ? 0u : 1u, dj = (op == 4u) ? 0u : 1u;
-      if (op == 1u && eq) op = (q[i] == r[j]) ? 2u : 3u;   // scan_block.rs:1620-1628
-      if ((di && i == 0) || (dj && j == 0)) { bad = 1; break; }
-      i -= di; j -= dj; table = ntab;
-      if (op == cur_op) cur_len++;
-      else {
-        if (cur_len) { if (nruns < cap) runs[nruns] = (cur_len << 4) | cur_op; nruns++; }
-        cur_op = op; cur_len = 1;
-      }
+      const size_t widx = (((size_t)ch * ngroups + (c >> 3)) * R + k) * 32 + ln;
+      // LOCAL_START: the alignment starts at a cell equal to relative_zero (scan_block.rs:1606-1612)
+      if (zwords && table == 0 && ((zwords[rc.word_off + widx] >> (c & 7)) & 1u)) { s.stop = 1u; break; }
+      nib = (tw[widx] >> (4 * (c & 7))) & 15u;
+    }
+    const uint32_t e = lut[lbase | (table << 4) | nib];
+    uint32_t op = e & 7u;
+    const uint32_t di = (e >> 3) & 1u, dj = (e >> 4) & 1u;
+    if (op == 1u && eq) op = (q[i] == r[j]) ? 2u : 3u;   // scan_block.rs:1620-1628
+    if ((di && i == 0) || (dj && j == 0)) { s.bad = 1u; break; }
+    i -= di; j -= dj; table = e >> 5;
+    if (op == s.cur_op) s.cur_len++;
+    else {
+      if (s.cur_len) { if (s.nruns < cap) runs[s.nruns] = (s.cur_len << 4) | s.cur_op; s.nruns++; }
+      s.cur_op = op; s.cur_len = 1;
     }
   }
-  if (cur_len) { if (nruns < cap) runs[nruns] = (cur_len << 4) | cur_op; nruns++; }
+  s.i = i; s.j = j; s.table = table;
 }
 
-BA_DEV void emit_cigar(const Params& P, const uint32_t* words, const uint32_t* zwords, bool fqs, const Rect* rects,
+// Whole warp. Lane 0 walks; the other lanes touch the trace words of the rectangle kTbAhead records further down
+// the stack (the next ones the walk will usually enter), so that they are in L1 when lane 0 gets there.
+constexpr uint32_t kTbAhead = 8;
+BA_DEV void traceback_walk(const uint8_t* lut, const uint32_t* words, const uint32_t* zwords, bool fqs, const Rect* rects,
+                           uint32_t ridx, uint32_t i, uint32_t j, const uint8_t* q, const uint8_t* r, bool eq, uint32_t* runs,
+                           uint32_t cap, uint32_t& nruns, uint32_t& bad) {
+  const int lane = wp::lane_id();
+  WalkState s;
+  s.i = i; s.j = j; s.ridx = ridx; s.table = 0; s.cur_op = 0; s.cur_len = 0; s.nruns = 0; s.bad = 0; s.stop = 0;
+  for (;;) {
+    uint32_t go = 0;
+    Rect rc;
+    rc.row = 0; rc.col = 0; rc.h = 0; rc.w = 0; rc.right = 0; rc.word_off = 0;
+    if (lane == 0 && (s.i > 0 || s.j > 0) && !s.bad && !s.stop) {
+      for (;;) {   // find the newest rectangle containing (i, j) (scan_block.rs:1578-1590)
+        if (s.ridx == 0) { s.bad = 1u; break; }
+        s.ridx--;
+        rc = rects[s.ridx];
+        if (s.i >= rc.row && s.j >= rc.col) break;
+      }
+      go = s.bad ? 0u : 1u;
+    }
+    go = (uint32_t)wp::shfl_idx((int)go, 0);
+    if (!go) break;
+    const uint32_t cur = (uint32_t)wp::shfl_idx((int)s.ridx, 0);
+    if (lane == 0) {
+      traceback_rect(lut, words, zwords, fqs, rc, q, r, eq, runs, cap, s);
+    } else if (lane <= 4 && cur >= kTbAhead) {
+      const Rect pr = rects[cur - kTbAhead];
+      const uint64_t nw = (uint64_t)(pr.h >> 3) * pr.w;     // layout 3 shift rectangles: h words, 32 per 128-byte line
+      if (((pr.right >> 1) & 3u) == 3u && nw <= 128u && (uint64_t)(lane - 1) * 32u < nw) wp::touch(words + pr.word_off + (lane - 1) * 32);
+    }
+    wp::syncwarp();
+  }
+  if (lane == 0 && s.cur_len) { if (s.nruns < cap) runs[s.nruns] = (s.cur_len << 4) | s.cur_op; s.nruns++; }
+  nruns = s.nruns; bad = s.bad;
+}
+
+BA_DEV void emit_cigar(const Params& P, const uint8_t* lut, const uint32_t* words, const uint32_t* zwords, bool fqs, const Rect* rects,
                        uint32_t ridx, uint32_t qi, uint32_t rj, const uint8_t* q, const uint8_t* r, bool eq, uint32_t* runs,
                        DevResult& res) {
   const int lane = wp::lane_id();
   uint32_t nruns = 0, bad = 0;
-  if (lane == 0) traceback_walk(words, zwords, fqs, rects, ridx, qi, rj, q, r, eq, runs, P.runs_per_warp, nruns, bad);
+  traceback_walk(lut, words, zwords, fqs, rects, ridx, qi, rj, q, r, eq, runs, P.runs_per_warp, nruns, bad);
   nruns = (uint32_t)wp::shfl_idx((int)nruns, 0);
   bad = (uint32_t)wp::shfl_idx((int)bad, 0);
   res.cigar_n = 0; res.cigar_off = 0;
@@ -874,7 +899,7 @@ BA_DEV void finish_alignment(const Params& P, const AlnState& st, const WarpMem&
     const uint8_t* q = P.seq + P.q_off[st.pair];
     const uint8_t* r = (SCORING == kProfile) ? nullptr : P.seq + P.r_off[st.pair];
     uint32_t* runs = P.run_scratch + (size_t)warp_global * P.runs_per_warp;
-    emit_cigar(P, sm.words, (P.ext_flags & kLocalStart) ? sm.zwords : nullptr, (P.ext_flags & kFreeQueryStartGaps) != 0,
+    emit_cigar(P, w.smem0 + kMatBytes + kPkTabBytes, sm.words, (P.ext_flags & kLocalStart) ? sm.zwords : nullptr, (P.ext_flags & kFreeQueryStartGaps) != 0,
                sm.rects, st.ridx, res.query_idx, res.reference_idx, q, r, P.cigar_eq != 0, runs, res);
   }
   if (lane == 0) {
@@ -1232,7 +1257,7 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
 
 // Traceback from an arbitrary end position of a pair that already ran (legacy block_cigar_* calls):
 // the trace of pair `pair` is still in the arena of the slot that aligned it.
-BA_DEV void warp_traceback(const Params& P, uint32_t pair, uint32_t qi, uint32_t rj, bool eq, DevResult* out1) {
+BA_DEV void warp_traceback(const Params& P, const uint8_t* lut, uint32_t pair, uint32_t qi, uint32_t rj, bool eq, DevResult* out1) {
   DevResult res = P.out[pair];
   const uint32_t slot = res.warp;
   const uint32_t* words = P.trace_words + (size_t)slot * P.trace_words_per_warp;
@@ -1242,7 +1267,7 @@ BA_DEV void warp_traceback(const Params& P, uint32_t pair, uint32_t qi, uint32_t
   const uint8_t* r = P.profiles ? nullptr : P.seq + P.r_off[pair];
   res.status = (uint32_t)kOk;
   const uint32_t* zwords = ((P.ext_flags & kLocalStart) && P.trace_zwords) ? P.trace_zwords + (size_t)slot * P.trace_words_per_warp : nullptr;
-  emit_cigar(P, words, zwords, (P.ext_flags & kFreeQueryStartGaps) != 0, rects, res.rect_n, qi, rj, q, r, eq, runs, res);
+  emit_cigar(P, lut, words, zwords, (P.ext_flags & kFreeQueryStartGaps) != 0, rects, res.rect_n, qi, rj, q, r, eq, runs, res);
   if (wp::lane_id() == 0) *out1 = res;
 }
 

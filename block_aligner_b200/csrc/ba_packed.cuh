@@ -31,7 +31,26 @@ constexpr int kPkUnroll = BA_PK_UNROLL;    // 1, 2 or 4
 // shared-memory scoring tables of the packed path (one copy per CTA, built by stage_tables)
 constexpr int kMatBytes = 1024;            // raw matrix (exact path)
 constexpr int kPkTabBytes = 8192;          // kNuc: [8 classes][16][16] packed score pairs; kAA: [27][32] i16
-constexpr int kSmemHeader = kMatBytes + kPkTabBytes;
+constexpr int kTbLutBytes = 128;           // traceback step table (tb_entry, ba_kernel.cuh)
+constexpr int kSmemHeader = kMatBytes + kPkTabBytes + kTbLutBytes;
+
+// Step table: the reference's 64-entry OP_LUT (scan_block.rs:1508-1572) folded per rectangle orientation.
+// index = nibble (bit 0 D == A, bit 1 D == B, bit 2 A opened here, bit 3 B opened at the row above; A = the gap
+// table along the rectangle's sequential columns, B = the one along its vectors) | table << 4 | right << 6;
+// value = op | di << 3 | dj << 4 | next table << 5   (tables: 0 = D, 1 = C, 2 = R; ops: 1 M, 4 I, 5 D)
+BA_HD uint8_t tb_entry(uint32_t idx) {
+  const uint32_t nib = idx & 15u, table = (idx >> 4) & 3u, right = (idx >> 6) & 1u;
+  const uint32_t t = nib & 3u, t2 = nib >> 2;
+  const uint32_t tabA = right ? 1u : 2u, tabB = right ? 2u : 1u, opA = right ? 5u : 4u, opB = right ? 4u : 5u;
+  uint32_t op, ntab;
+  if (table == tabA) { op = opA; ntab = (t2 & 1u) ? 0u : tabA; }
+  else if (table == tabB) { op = opB; ntab = (t2 & 2u) ? 0u : tabB; }
+  else if (t == 0) { op = 1u; ntab = 0u; }
+  else if (t & 1u) { op = opA; ntab = (t2 & 1u) ? 0u : tabA; }      // C wins over R when both equal D (scan_block.rs:1539-1542)
+  else { op = opB; ntab = (t2 & 2u) ? 0u : tabB; }
+  const uint32_t di = (op == 5u) ? 0u : 1u, dj = (op == 4u) ? 0u : 1u;
+  return (uint8_t)(op | (di << 3) | (dj << 4) | (ntab << 5));
+}
 
 template <int KIND> struct PkScorer;
 // NucMatrix (scores.rs:195-209): row (c & 7) * 16, column b & 15
@@ -81,6 +100,7 @@ template <> struct PkScorer<kByte> {
 template <int SCORING>
 BA_DEV void stage_tables(unsigned char* smem, int tid, int nthreads) {
   const int8_t* mat = (const int8_t*)smem;
+  for (int i = tid; i < kTbLutBytes; i += nthreads) smem[kMatBytes + kPkTabBytes + i] = tb_entry((uint32_t)i);
   if (SCORING == kNuc) {
     uint32_t* t = (uint32_t*)(smem + kMatBytes);
     for (int i = tid; i < 2048; i += nthreads) {

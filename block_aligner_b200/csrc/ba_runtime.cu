@@ -143,7 +143,12 @@ static void emu_warp_entry(void* arg) {
   warp_main<SCORING, FLAGS, FR>(*l->P, l->smem, 0, l->wg);
 }
 struct EmuTb { const Params* P; uint32_t pair, qi, rj; int eq; DevResult* out1; };
-static void emu_tb_entry(void* arg) { auto* t = (EmuTb*)arg; warp_traceback(*t->P, t->pair, t->qi, t->rj, t->eq != 0, t->out1); }
+static void emu_tb_entry(void* arg) {
+  auto* t = (EmuTb*)arg;
+  static uint8_t lut[128];
+  for (uint32_t i = 0; i < 128; i++) lut[i] = tb_entry(i);
+  warp_traceback(*t->P, lut, t->pair, t->qi, t->rj, t->eq != 0, t->out1);
+}
 static int launch_traceback(const Params& P, uint32_t pair, uint32_t qi, uint32_t rj, int eq, DevResult* out1, dev_stream_t) {
   EmuTb t{&P, pair, qi, rj, eq, out1};
   emu::run_warp(&emu_tb_entry, &t);
@@ -219,7 +224,10 @@ __global__ void __launch_bounds__(128, BA_LB_BLOCKS) ba_align_kernel(const __gri
 }
 
 __global__ void ba_traceback_kernel(const __grid_constant__ Params P, uint32_t pair, uint32_t qi, uint32_t rj, int eq, DevResult* out1) {
-  warp_traceback(P, pair, qi, rj, eq != 0, out1);
+  __shared__ uint8_t lut[128];
+  for (uint32_t i = threadIdx.x; i < 128; i += blockDim.x) lut[i] = tb_entry(i);
+  __syncthreads();
+  warp_traceback(P, lut, pair, qi, rj, eq != 0, out1);
 }
 static int launch_traceback(const Params& P, uint32_t pair, uint32_t qi, uint32_t rj, int eq, DevResult* out1, dev_stream_t st) {
   ba_traceback_kernel<<<1, 32, 0, st>>>(P, pair, qi, rj, eq, out1);
@@ -387,6 +395,11 @@ struct BaBatch {
   StepLog* d_steplog = nullptr; uint32_t* d_steplog_n = nullptr;
   uint32_t* d_overflow_list = nullptr; uint32_t* d_overflow_n = nullptr;
   uint32_t* d_zwords = nullptr;     // zero masks (TRACE && LOCAL_START)
+  // scratch of the overflow retry (worst-case trace arenas for the few alignments that did not fit the first-pass
+  // arenas); kept until the next launch / free so that the trace of a retried pair can still be walked
+  uint32_t* r_trace = nullptr; uint32_t* r_zwords = nullptr; Rect* r_rects = nullptr; int16_t* r_ckpt = nullptr; uint32_t* r_runs = nullptr;
+  bool retried = false;
+  uint32_t rects_bound = 0;         // worst-case rectangle records per alignment
   int kflags = 0;                   // template FLAGS of the kernel: (flags & 3) | kExt
   int pk_smax = 0; uint32_t pk_enable = 0;   // packed 2 x i16 path (ba_packed.cuh): largest matrix entry, on/off
   uint64_t trace_words_bound = 0;   // worst case per alignment (the reference's Trace::new size)
@@ -484,7 +497,8 @@ extern "C" void ba_batch_free(BaBatch* b) {
   BaAligner* al = b->al;
   void* bufs[] = {b->d_seq, b->d_qoff, b->d_roff, b->d_qlen, b->d_rlen, b->d_order, b->d_matrix, b->d_profiles, b->d_prof_arena,
                   b->d_out, b->d_ticket, b->d_ckpt, b->d_trace, b->d_rects, b->d_runs, b->d_cigar, b->d_cigar_used,
-                  b->d_steplog, b->d_steplog_n, b->d_tb_res, b->d_overflow_list, b->d_overflow_n, b->d_zwords};
+                  b->d_steplog, b->d_steplog_n, b->d_tb_res, b->d_overflow_list, b->d_overflow_n, b->d_zwords,
+                  b->r_trace, b->r_zwords, b->r_rects, b->r_ckpt, b->r_runs};
   for (void* q : bufs) pool_release(al, q);
   if (b->has_ss) { dsync(b->ss.stream); streams_release(al, b->ss); }
   delete b;
@@ -803,7 +817,7 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
   if (trace) {
     // Worst case per alignment = the reference's Trace::new (scan_block.rs:1364-1369): the block sits at its
     // maximum size all the time. Real alignments spend most steps at the minimum size, so the first pass runs
-    // with arenas sized for 4x the all-minimum-size path plus one maximum-size grow; alignments that overflow
+    // with arenas sized for 2x the all-minimum-size path plus one maximum-size grow; alignments that overflow
     // are re-run with worst-case arenas (ba_batch_run).
     const uint64_t len = (uint64_t)b->max_pair_len + 2;
     uint64_t words = 2 * (uint64_t)(mx / 16) * (len + 2 * (uint64_t)mx);
@@ -812,10 +826,12 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
     if (cfg->flags & BA_FREE_QUERY_END_GAPS) words = std::max<uint64_t>(words, 32 * (len + 2 * (uint64_t)mx));
     if (words + 64 >= ((uint64_t)1 << 32)) { ba_batch_free(b); return fail(BA_ERR_SIZE, "trace arena of one alignment exceeds 2^32 words"); }
     b->trace_words_bound = words + 64;
-    uint64_t first = 4 * len * (uint64_t)std::max<uint32_t>(mn, 32) / 8 + (uint64_t)mx * mx / 4 + 4096;
+    uint64_t first = 2 * len * (uint64_t)std::max<uint32_t>(mn, 32) / 8 + (uint64_t)mx * mx / 4 + 4096;
     if (getenv("BA_TRACE_WORST_CASE") || (cfg->flags & BA_FREE_QUERY_END_GAPS)) first = b->trace_words_bound;
     b->trace_words_per_warp = std::min<uint64_t>(b->trace_words_bound, first);
-    b->rects_per_warp = (uint32_t)std::min<uint64_t>(len * 2 + 8, 0x7fffffffu);
+    // one record per step (len / 8 shift steps; grow retries pop theirs again): the first pass gets twice that
+    b->rects_bound = (uint32_t)std::min<uint64_t>(len * 2 + 8, 0x7fffffffu);
+    b->rects_per_warp = b->trace_words_per_warp < b->trace_words_bound ? (uint32_t)std::min<uint64_t>(len / 4 + 1024, b->rects_bound) : b->rects_bound;
     b->runs_per_warp = (uint32_t)std::min<uint64_t>(len + 8, 0x7fffffffu);
     const uint64_t zmul = (cfg->flags & BA_LOCAL_START) ? 2 : 1;
     const uint64_t per_warp = spw * (zmul * b->trace_words_per_warp * 4 + (uint64_t)b->rects_per_warp * sizeof(Rect)) + (uint64_t)b->runs_per_warp * 4;
@@ -828,6 +844,19 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
   b->blocks = (int)std::min<uint64_t>(want, max_blocks);
   const uint64_t nwarps = (uint64_t)b->blocks * wpb;
   const uint64_t nslots = nwarps * spw;
+  if (trace && b->trace_words_per_warp < b->trace_words_bound) {
+    // The retry pass of an overflowed alignment runs almost alone on the GPU (measured on C5: one retried 50 kbp pair
+    // costs 90 ms), so once the number of slots is fixed the first-pass arenas take what is left of the budget, up to
+    // twice the initial estimate (4x the all-minimum-size path).
+    const uint64_t zmul = (cfg->flags & BA_LOCAL_START) ? 2 : 1;
+    const uint64_t fixed = nslots * (uint64_t)b->rects_per_warp * sizeof(Rect) + nwarps * (uint64_t)b->runs_per_warp * 4;
+    const uint64_t len = (uint64_t)b->max_pair_len + 2;
+    const uint64_t cap = std::min<uint64_t>(b->trace_words_bound, 4 * len * (uint64_t)std::max<uint32_t>(mn, 32) / 8 + (uint64_t)mx * mx / 4 + 4096);
+    if (b->mem_budget > fixed) {
+      const uint64_t fit = (b->mem_budget - fixed) / (nslots * zmul * 4);
+      b->trace_words_per_warp = std::max<uint64_t>(b->trace_words_per_warp, std::min<uint64_t>(cap, fit));
+    }
+  }
   TRY(pool_alloc(al, (void**)&b->d_ckpt, nslots * 4 * ms * sizeof(int16_t)));
   if (trace) {
     TRY(pool_alloc(al, (void**)&b->d_trace, nslots * b->trace_words_per_warp * 4));
@@ -869,7 +898,7 @@ extern "C" int ba_batch_upload_pssm(BaAligner* a, const BaConfig* cfg, size_t n,
   return upload_common(a, cfg, n, q_bytes, q_off, nullptr, nullptr, nullptr, pssm, out);
 }
 
-static Params make_params(const BaBatch* b) {
+static Params make_params(const BaBatch* b, bool retry = false) {
   Params P;
   memset(&P, 0, sizeof(P));
   const bool prof = b->cfg.scoring == BA_SCORING_PROFILE;
@@ -900,6 +929,10 @@ static Params make_params(const BaBatch* b) {
   P.cigar_eq = b->cfg.cigar_eq ? 1u : 0u;
   P.overflow_list = b->d_overflow_list; P.overflow_n = b->d_overflow_n;
   P.step_log = b->d_steplog; P.step_log_cap = b->d_steplog ? (1u << 20) : 0u; P.step_log_n = b->d_steplog_n;
+  if (retry) {
+    P.ckpt = b->r_ckpt; P.trace_words = b->r_trace; P.trace_words_per_warp = b->trace_words_bound; P.trace_zwords = b->r_zwords;
+    P.rects = b->r_rects; P.rects_per_warp = b->rects_bound; P.run_scratch = b->r_runs;
+  }
   return P;
 }
 
@@ -918,6 +951,7 @@ static int batch_launch(BaBatch* b) {
   if (b->d_steplog_n && dzero(b->d_steplog_n, 4, st)) return BA_ERR_CUDA;
   b->downloaded = false;
   b->launches = 0;
+  b->retried = false;
   if (b->n) {
 #ifndef BA_EMU
     cudaEventRecord(b->ss.ev0, st);
@@ -942,30 +976,29 @@ static int batch_wait(BaBatch* b, BaStats* stats) {
     if (b->d_overflow_n && b->trace_words_per_warp < b->trace_words_bound) {
       uint32_t n_over = 0;
       if (d2h(&n_over, b->d_overflow_n, 4, st) || dsync(st)) return BA_ERR_CUDA;
+      if (getenv("BA_TIMING")) fprintf(stderr, "batch_wait: %zu pairs, %d blocks x %d warps, %u slots/warp, trace words/slot %llu (bound %llu), %u overflowed\n",
+                                       b->n, b->blocks, b->wpb, b->slots_per_warp, (unsigned long long)b->trace_words_per_warp,
+                                       (unsigned long long)b->trace_words_bound, n_over);
       if (n_over) {
+        // second pass over the overflowed pairs only, with worst-case arenas in separate scratch (the first-pass
+        // arenas stay as they are, so the batch can be run again)
         const uint64_t spw = b->slots_per_warp;
-        const uint64_t per_warp = spw * (b->trace_words_bound * 4 + (uint64_t)b->rects_per_warp * sizeof(Rect)) + (uint64_t)b->runs_per_warp * 4;
-        const uint64_t fit_warps = std::max<uint64_t>(1, b->mem_budget / std::max<uint64_t>(per_warp, 1));
+        const uint64_t zmul = b->d_zwords ? 2 : 1;
+        const uint64_t per_warp = spw * (zmul * b->trace_words_bound * 4 + (uint64_t)b->rects_bound * sizeof(Rect)) + (uint64_t)b->runs_per_warp * 4;
+        const uint64_t fit_warps = std::max<uint64_t>(1, (uint64_t)(b->mem_budget * 0.6) / std::max<uint64_t>(per_warp, 1));
         uint64_t blocks2 = std::max<uint64_t>(1, std::min<uint64_t>(b->max_blocks_hw, fit_warps / b->wpb));
         blocks2 = std::min<uint64_t>(blocks2, (n_over + b->wpb * spw - 1) / (b->wpb * spw));
         const uint64_t nslots2 = blocks2 * b->wpb * spw;
-        pool_release(al, b->d_trace); b->d_trace = nullptr;
-        pool_release(al, b->d_rects); b->d_rects = nullptr;
-        if (pool_alloc(al, (void**)&b->d_trace, nslots2 * b->trace_words_bound * 4)) return BA_ERR_NOMEM;
-        if (b->d_zwords) {
-          pool_release(al, b->d_zwords); b->d_zwords = nullptr;
-          if (pool_alloc(al, (void**)&b->d_zwords, nslots2 * b->trace_words_bound * 4)) return BA_ERR_NOMEM;
-        }
-        if (pool_alloc(al, (void**)&b->d_rects, nslots2 * (uint64_t)b->rects_per_warp * sizeof(Rect))) return BA_ERR_NOMEM;
-        if ((uint64_t)b->blocks < blocks2) {   // per-slot / per-warp scratch of the first pass is too small: regrow
-          const size_t msz = b->max_size < 32 ? 32 : b->max_size;
-          pool_release(al, b->d_ckpt); pool_release(al, b->d_runs); b->d_ckpt = nullptr; b->d_runs = nullptr;
-          if (pool_alloc(al, (void**)&b->d_ckpt, nslots2 * 4 * msz * sizeof(int16_t))) return BA_ERR_NOMEM;
-          if (pool_alloc(al, (void**)&b->d_runs, blocks2 * b->wpb * (uint64_t)b->runs_per_warp * 4)) return BA_ERR_NOMEM;
-        }
-        b->trace_words_per_warp = b->trace_words_bound;
-        b->blocks = (int)std::max<uint64_t>((uint64_t)b->blocks, blocks2);
-        Params P2 = make_params(b);
+        const size_t msz = b->max_size < 32 ? 32 : b->max_size;
+        void** rb[] = {(void**)&b->r_trace, (void**)&b->r_zwords, (void**)&b->r_rects, (void**)&b->r_ckpt, (void**)&b->r_runs};
+        for (void** q : rb) { pool_release(al, *q); *q = nullptr; }
+        if (pool_alloc(al, (void**)&b->r_trace, nslots2 * b->trace_words_bound * 4)) return BA_ERR_NOMEM;
+        if (b->d_zwords && pool_alloc(al, (void**)&b->r_zwords, nslots2 * b->trace_words_bound * 4)) return BA_ERR_NOMEM;
+        if (pool_alloc(al, (void**)&b->r_rects, nslots2 * (uint64_t)b->rects_bound * sizeof(Rect))) return BA_ERR_NOMEM;
+        if (pool_alloc(al, (void**)&b->r_ckpt, nslots2 * 4 * msz * sizeof(int16_t))) return BA_ERR_NOMEM;
+        if (pool_alloc(al, (void**)&b->r_runs, blocks2 * b->wpb * (uint64_t)b->runs_per_warp * 4)) return BA_ERR_NOMEM;
+        b->retried = true;
+        Params P2 = make_params(b, true);
         P2.order = b->d_overflow_list;     // the kernel appends to this list only on overflow, which cannot
         P2.n_pairs = n_over;               // happen with worst-case arenas, so reading it as the work list is safe
         P2.overflow_list = nullptr; P2.overflow_n = nullptr;
@@ -1071,8 +1104,18 @@ extern "C" int ba_align_batch(BaAligner* a, const BaConfig* cfg, size_t n, const
   const uint64_t bytes = n ? (q_off[n] - q_off[0]) + (r_off[n] - r_off[0]) : 0;
   if (n >= 8192 && bytes >= ((uint64_t)32 << 20)) K = 4;
   if (const char* e = getenv("BA_PIPELINE_CHUNKS")) K = std::max<size_t>(1, std::min<size_t>((size_t)atoi(e), 64));
-  // TRACE: every chunk in flight owns trace arenas, so fewer chunks and a split memory budget
+  // TRACE: every chunk in flight owns trace arenas and the memory budget is split between them. Their kernels cannot
+  // overlap anyway (one chunk fills the GPU), so pipelining only hides the H2D copy; it is given up when halving the
+  // budget would shrink the first-pass arenas (an overflow retry costs far more than the copy).
   if (cfg && (cfg->flags & BA_TRACE) && K > 2) K = 2;
+  if (cfg && (cfg->flags & BA_TRACE) && K == 2 && n) {
+    uint64_t max_len = 0;
+    for (size_t k = 0; k < n; k++) max_len = std::max<uint64_t>(max_len, (q_off[k + 1] - q_off[k]) + (r_off[k + 1] - r_off[k]));
+    const uint64_t mnb = std::max<uint64_t>(cfg->size.min, 32), mxb = cfg->size.max;
+    const uint64_t want_words = 4 * (max_len + 2) * mnb / 8 + mxb * mxb / 4 + 4096;
+    const uint64_t slots = (uint64_t)a->sm_count * 16 * 8;       // upper bound of the alignments in flight
+    if (want_words * 4 * slots > (uint64_t)(a->mem_total * a->budget_frac / 2)) K = 1;
+  }
   if (K > n) K = n ? n : 1;
   const double budget_saved = a->budget_frac;
   a->budget_frac = budget_saved / (double)K;
@@ -1199,7 +1242,7 @@ extern "C" int ba_batch_traceback(BaBatch* b, size_t k, size_t query_idx, size_t
 #ifndef BA_EMU
   if (cudaSetDevice(al->device) != cudaSuccess) return fail(BA_ERR_CUDA, "cudaSetDevice failed");
 #endif
-  Params P = make_params(b);
+  Params P = make_params(b, b->retried && b->n == 1);
   if (!b->d_tb_res && pool_alloc(al, (void**)&b->d_tb_res, sizeof(DevResult))) return BA_ERR_CUDA;
   if (dzero(b->d_cigar_used, 8, st)) return BA_ERR_CUDA;
   if (launch_traceback(P, (uint32_t)k, (uint32_t)query_idx, (uint32_t)reference_idx, eq, b->d_tb_res, st)) return BA_ERR_CUDA;

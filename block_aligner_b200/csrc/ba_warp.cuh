@@ -57,6 +57,7 @@ inline int vimax3(int a, int b, int c) { int m = a > b ? a : b; return m > c ? m
 inline int imax(int a, int b) { return a > b ? a : b; }
 inline int imin(int a, int b) { return a < b ? a : b; }
 template <class T> inline T ldg(const T* p) { return *p; }
+inline void touch(const void*) {}
 }}  // namespace ba::wp
 #else
 #define BA_DEV __device__ __forceinline__
@@ -102,5 +103,7 @@ BA_DEV int vimax3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
 BA_DEV int imax(int a, int b) { return max(a, b); }
 BA_DEV int imin(int a, int b) { return min(a, b); }
 template <class T> BA_DEV T ldg(const T* p) { return __ldg(p); }
+// bring the 128-byte line of p into L1 / L2 without waiting for it (a load whose result is never used)
+BA_DEV void touch(const void* p) { unsigned d; asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(d) : "l"(p)); (void)d; }
 }}  // namespace ba::wp
 #endif

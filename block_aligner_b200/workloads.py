@@ -160,9 +160,7 @@ def make_pssm_batch(lib, ra, ro, gap_open=-10, gap_extend=-1, seed=1234, pinned=
         if pinned:
             import torch
             t = torch.empty(max(int(nbytes), 1), dtype=torch.int8).pin_memory()
-            a = t.numpy()[:int(nbytes)]
-            a._keep = None
-            return a, t
+            return t.numpy()[:int(nbytes)], t
         return np.zeros(int(nbytes), dtype=np.int8), None
 
     scores, k0 = buf(soff[-1])

@@ -213,3 +213,22 @@ def test_pssm_batch_rejects_bad_input(env):
         al.upload(cfg, qa, qo, None, None, api.PssmBatch(workloads.MAP20, sc, [0, 61, 140], -1))
     with pytest.raises(api.BlockAlignerError):     # gap extend must be negative
         al.upload(cfg, qa, qo, None, None, api.PssmBatch(workloads.MAP20, sc, [0, 60, 140], 0))
+
+
+def test_batch_with_overflow_retry_can_run_again(env):
+    """ba_batch_run twice on a resident batch whose first run needed the retry pass: the retry scratch must not
+    replace the first-pass arenas (found on the GPU with C5: illegal address on the second run)."""
+    lib, al = env
+    w = dict(scoring=api.SCORING_NUC, matrix="NW1", gaps=(-2, -1), size=(32, 512), x_drop=0, flags=api.TRACE, stream=31,
+             gen=P(alphabet=0, len_dist=0, len_min=1500, len_max=2500, sub_rate=0.75, ins_rate=0.0, del_rate=0.0))
+    qa, qo, ra, ro = workloads.generate(w["gen"], 6, stream=31)
+    cfg = al.config(w["scoring"], workloads.matrix_of(lib, w), w["gaps"], w["size"], 0, api.TRACE, True)
+    b = al.upload(cfg, qa, qo, ra, ro)
+    outs = []
+    for _ in range(3):
+        st = b.run()
+        assert st.kernel_launches == 2
+        r = b.download()
+        outs.append((r.copy(), [b.cigar_string(k) for k in range(len(qo) - 1)]))
+    b.free()
+    assert all((o[0] == outs[0][0]).all() and o[1] == outs[0][1] for o in outs[1:])
