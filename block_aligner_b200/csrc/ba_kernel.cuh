@@ -982,9 +982,9 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast
   sc.rows(*(const uint32_t*)(vec + vec_base + 4 * lg), *(const uint32_t*)(vec + vec_base + 4 * G + 4 * lg));
   const uint2 cw = *(const uint2*)(col + col_base);
 
-  uint32_t D[4], C[4], m[4], mc[4];
+  uint32_t D[4], C[4], m[4], mc[kMcN] = {};
 #pragma unroll
-  for (int k = 0; k < 4; k++) { D[k] = wp::vadd2(f.aD[k], oa2); C[k] = wp::vadd2(f.aC[k], oa2); m[k] = 0u; mc[k] = 0u; }
+  for (int k = 0; k < 4; k++) { D[k] = wp::vadd2(f.aD[k], oa2); C[k] = wp::vadd2(f.aC[k], oa2); m[k] = 0u; }
   uint32_t* fr = w.fr + grp * 8;
   uint32_t* tw = nullptr;
   if (TRACE && active) tw = trace_push(st, sm, right ? si : si + (B - kStep), right ? sj + (B - kStep) : sj, kStep, B, right, lg == 0, 3);

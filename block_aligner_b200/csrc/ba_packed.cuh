@@ -26,6 +26,20 @@ BA_DEV uint32_t pk2(int v) { return wp::h_pack(v, v); }
 #ifndef BA_PK_UNROLL
 #define BA_PK_UNROLL 1
 #endif
+// Tuning switches kept for the record (tools/build_variant.sh), both off: measured on B200 / C2 they change nothing
+// (1077-1087 GCUPS in every variant at 50 k pairs), i.e. the column loop is not limited by the ALU pipe alone.
+// BA_PK_IMAD = 1: the plain adds of the column loop are issued as IMAD (x * 1 + y, the 1 opaque to the compiler) and
+// run on the FMA pipe instead of the ALU pipe.
+#ifndef BA_PK_IMAD
+#define BA_PK_IMAD 0
+#endif
+#define BA_PK_ONE 1u
+// BA_PK_SPLIT_MC = 1: the X-drop column trackers of the two half-blocks live in separate registers (mc[k], mc[4 + k])
+// and are updated with predicated moves (ptxas emits SEL, the same pipe as PRMT); 0: both in one register, PRMT
+#ifndef BA_PK_SPLIT_MC
+#define BA_PK_SPLIT_MC 0
+#endif
+constexpr int kMcN = BA_PK_SPLIT_MC ? 8 : 4;
 constexpr int kPkUnroll = BA_PK_UNROLL;    // 1, 2 or 4
 
 // shared-memory scoring tables of the packed path (one copy per CTA, built by stage_tables)
@@ -55,15 +69,17 @@ BA_HD uint8_t tb_entry(uint32_t idx) {
 template <int KIND> struct PkScorer;
 // NucMatrix (scores.rs:195-209): row (c & 7) * 16, column b & 15
 template <> struct PkScorer<kNuc> {
-  const unsigned char* tab; uint32_t rt[4];
-  BA_DEV void init(const unsigned char* smem, const Params&) { tab = smem + kMatBytes; }
+  const unsigned char* tab; uint32_t rt[4]; uint32_t one;
+  BA_DEV void init(const unsigned char* smem, const Params&) { tab = smem + kMatBytes; one = wp::opaque_zero() + BA_PK_ONE; }
   BA_DEV void rows(uint32_t wlo, uint32_t whi) {
     const uint32_t t = ((wlo & 0x0f0f0f0fu) << 4) | (whi & 0x0f0f0f0fu);
 #pragma unroll
     for (int k = 0; k < 4; k++) rt[k] = ((t >> (8 * k)) & 0xffu) << 2;
   }
   BA_DEV uint32_t colh(uint32_t cb) const { return (cb & 7u) << 10; }
-  BA_DEV uint32_t score(uint32_t ch, int k) const { return *(const uint32_t*)(tab + (ch | rt[k])); }
+  // ch and rt[k] have no bits in common; with BA_PK_IMAD the OR is issued as an IMAD (ch * 1 + rt) on the FMA pipe: the
+  // ALU pipe is the kernel's bottleneck (ncu: pipe_alu 71 %, math_pipe_throttle), the FMA pipe is nearly idle
+  BA_DEV uint32_t score(uint32_t ch, int k) const { return *(const uint32_t*)(tab + (BA_PK_IMAD ? ch * one + rt[k] : (ch | rt[k]))); }
 };
 // AAMatrix (scores.rs:110-127): row c * 32, column b & 31
 template <> struct PkScorer<kAA> {
@@ -134,7 +150,7 @@ BA_DEV uint32_t pk_eqmask(uint32_t y, uint32_t x) { return wp::viaddmin2(y, ~x, 
 
 template <int KIND, bool XDROP, int LGT, bool TRACE = false>
 BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int LGr, int lg, uint32_t cw0, uint32_t cw1,
-                     uint32_t (&D)[4], uint32_t (&C)[4], uint32_t corner_lo, int cbase, uint32_t (&m)[4], uint32_t (&mc)[4],
+                     uint32_t (&D)[4], uint32_t (&C)[4], uint32_t corner_lo, int cbase, uint32_t (&m)[4], uint32_t (&mc)[kMcN],
                      uint32_t* fr, bool writer, uint32_t* tw = nullptr, bool tstore = false) {
   const int LG = LGT ? LGT : LGr;
   const int G = 1 << LG;
@@ -144,6 +160,7 @@ BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int LGr, int l
   const uint32_t ge2 = kc.ge2 + z, or2 = kc.or2 + z;
   const uint32_t kge1 = kc.kge[1] + z, kge2 = kc.kge[2] + z, kge3 = kc.kge[3] + z;
   const uint32_t lanedec = (uint32_t)lg * kc.lane1 + (lg ? 0x10000u : 0u);   // packed 4 * lg * gap_extend
+  const uint32_t one = z + BA_PK_ONE;
   // kPkUnroll columns per iteration of the rolled loop: the kernel's hot code has to stay inside the SM's
   // instruction cache (ncu: sm__icc_request_hit_rate), which a fully unrolled 8-column body does not
   uint64_t cwq = ((uint64_t)cw1 << 32) | cw0;
@@ -166,7 +183,8 @@ BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int LGr, int l
       for (int k = 0; k < 4; k++) {
         const uint32_t s2 = sc.score(ch, k);
         const uint32_t d00 = k ? D[k - 1] : up;
-        const uint32_t c11o = D[k] + kc.go1;      // packed add as one 32-bit add: no borrow, both halves >= |open| (guard)
+        // packed add as one 32-bit add: no borrow, both halves >= |open| (guard)
+        const uint32_t c11o = BA_PK_IMAD ? D[k] * one + kc.go1 : D[k] + kc.go1;
         c11[k] = wp::viaddmax2(C[k], ge2, c11o);
         if (TRACE) acc[k] = pk_eqmask(c11[k], c11o) & 0x00040004u;       // C opened here <=> C == D10 + open
         dd[k] = wp::viaddmax2(d00, s2, c11[k]);
@@ -213,8 +231,14 @@ BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int LGr, int l
           m[k] = wp::vibmax2(Dn, m[k], ph, pl);
           // kept in a vector register (opaque_zero) so that PRMT can take its selector as an immediate
           const uint32_t c1 = (uint32_t)(cbase + cidx + 1) + wp::opaque_zero();
+#if BA_PK_SPLIT_MC
+          // column trackers of the two halves in separate registers: a predicated move (FMA pipe) instead of PRMT (ALU)
+          if (pl) mc[k] = c1;
+          if (ph) mc[4 + k] = c1;
+#else
           if (pl) mc[k] = wp::prmt(mc[k], c1, 0x3254u);
           if (ph) mc[k] = wp::prmt(mc[k], c1, 0x5410u);
+#endif
         } else {
           m[0] = wp::vmax2(m[0], Dn);
         }
@@ -238,7 +262,7 @@ BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int LGr, int l
 // (scan_block.rs:1194-1201, avx2.rs:271-274). pk_lane_key: key of the lane's best cell among those equal to M
 // (0 if none); key format as in place_rect_r: (15 - class) << 27 | (column + 1) << 13 | row. Every row has seen
 // a cell >= 0 (guard), so there is no "no cell" case.
-BA_DEV unsigned pk_lane_key(const uint32_t (&m)[4], const uint32_t (&mc)[4], int lg, int G, int M) {
+BA_DEV unsigned pk_lane_key(const uint32_t (&m)[4], const uint32_t (&mc)[kMcN], int lg, int G, int M) {
   const uint32_t M2 = pk2(M);
   const unsigned base0 = ((15u - (unsigned)((4 * lg) & 15)) << 27) | (unsigned)(4 * lg);
   unsigned key = 0;
@@ -247,8 +271,13 @@ BA_DEV unsigned pk_lane_key(const uint32_t (&m)[4], const uint32_t (&mc)[4], int
     bool ph, pl;
     wp::vibmax2(m[k], M2, ph, pl);            // m >= M, i.e. m == M for M = the maximum
     const unsigned base = base0 - ((unsigned)k << 27) + (unsigned)k;
+#if BA_PK_SPLIT_MC
+    const unsigned klo = base | (mc[k] << 13);
+    const unsigned khi = (base + (unsigned)(4 * G)) | (mc[4 + k] << 13);
+#else
     const unsigned klo = base | ((mc[k] & 0xffffu) << 13);
     const unsigned khi = (base + (unsigned)(4 * G)) | ((mc[k] >> 16) << 13);
+#endif
     if (pl && klo > key) key = klo;
     if (ph && khi > key) key = khi;
   }
@@ -343,7 +372,7 @@ BA_DEV void place_rect_pk(const unsigned char* smem, const Params& P, const PkCo
   PkScorer<KIND> sc;
   sc.init(smem, P);
   sc.rows(*(const uint32_t*)(vec + a.vec_base + 4 * lg), *(const uint32_t*)(vec + a.vec_base + 4 * G + 4 * lg));
-  uint32_t m[4] = {0u, 0u, 0u, 0u}, mc[4] = {0u, 0u, 0u, 0u};
+  uint32_t m[4] = {0u, 0u, 0u, 0u}, mc[kMcN] = {};
   const bool writer = lane == G - 1;
   for (int cb = 0; cb < W; cb += 8) {
     const uint2 cw = *(const uint2*)(col + a.col_base + cb);

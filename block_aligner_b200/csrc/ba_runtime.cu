@@ -1103,6 +1103,7 @@ extern "C" int ba_align_batch(BaAligner* a, const BaConfig* cfg, size_t n, const
   size_t K = 1;
   const uint64_t bytes = n ? (q_off[n] - q_off[0]) + (r_off[n] - r_off[0]) : 0;
   if (n >= 8192 && bytes >= ((uint64_t)32 << 20)) K = 4;
+  if (n >= 65536 && bytes >= ((uint64_t)512 << 20)) K = 8;   // measured on C2 (2.1 GB): 4 chunks 105.9 ms, 6-16 chunks 99-100 ms
   if (const char* e = getenv("BA_PIPELINE_CHUNKS")) K = std::max<size_t>(1, std::min<size_t>((size_t)atoi(e), 64));
   // TRACE: every chunk in flight owns trace arenas and the memory budget is split between them. Their kernels cannot
   // overlap anyway (one chunk fills the GPU), so pipelining only hides the H2D copy; it is given up when halving the
