@@ -92,8 +92,9 @@ def test_align_batch_pipelined_chunks(env, monkeypatch):
     m = workloads.matrix_of(lib, w)
     ref = parity.run_lib(lib, al, w["scoring"], m, w["gaps"], w["size"], w["x_drop"], w["flags"], False, qa, qo, ra, ro)
     cfg = al.config(w["scoring"], m, w["gaps"], w["size"], w["x_drop"], w["flags"], False)
-    for chunks in ("1", "3", "64"):
+    for chunks, geom in (("1", "0"), ("3", "0"), ("64", "0"), ("5", "1"), ("12", "1")):
         monkeypatch.setenv("BA_PIPELINE_CHUNKS", chunks)
+        monkeypatch.setenv("BA_PIPELINE_GEOM", geom)     # geometric chunk sizes (the default for large batches)
         out = np.zeros(37, dtype=np.dtype([("score", np.int32), ("q", np.uint64), ("r", np.uint64)], align=True))
         st = api.BaStats()
         lib.check(lib.L.ba_align_batch(al.h, C.byref(cfg), 37, qa.ctypes.data, qo.ctypes.data, ra.ctypes.data, ro.ctypes.data,
