@@ -221,8 +221,20 @@ def main():
     import ctypes as C
     st = api.BaStats()
 
+    # TRACE workloads: the CIGARs come back too, straight into a pinned caller buffer (ba_align_batch_cigar)
+    trace = bool(w["flags"] & api.TRACE)
+    cig = None
+    if trace:
+        cap = int(0.3 * (qa.nbytes + ra.nbytes)) + 16 * n
+        cig = dict(cap=cap, runs=torch.empty(cap, dtype=torch.int32).pin_memory(), off=np.zeros(n, dtype=np.uint64),
+                   len=np.zeros(n, dtype=np.uint32), used=C.c_size_t())
+
     def e2e_once():
-        if profiles is not None:
+        if trace:
+            lib.check(lib.L.ba_align_batch_cigar(al.h, C.byref(cfg), n, qa.ctypes.data, qo.ctypes.data, ra.ctypes.data, ro.ctypes.data,
+                                                 out.ctypes.data, cig["runs"].data_ptr(), cig["cap"], cig["off"].ctypes.data,
+                                                 cig["len"].ctypes.data, C.byref(cig["used"]), C.byref(st)))
+        elif profiles is not None:
             lib.check(lib.L.ba_align_batch_pssm(al.h, C.byref(cfg), n, qa.ctypes.data, qo.ctypes.data, C.byref(profiles.c),
                                                 out.ctypes.data, C.byref(st)))
         else:
@@ -242,7 +254,7 @@ def main():
         barrier()
         e2e_s = float("inf")
     h2d = int(qa.nbytes + 2 * qo.nbytes + n * (8 + 8 + 4 + 4 + 4) + (profiles.nbytes() if profiles is not None else ra.nbytes))
-    d2h = int(n * 56)
+    d2h = int(n * 56) + (int(cig["used"].value) * 4 if trace else 0)
 
     # ---- max over ranks ----
     vals = torch.tensor([dev_s, e2e_s, wall], dtype=torch.float64, device="cuda")

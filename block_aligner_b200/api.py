@@ -91,7 +91,7 @@ PART1_DATA = ["NW1", "BLOSUM45", "BLOSUM50", "BLOSUM62", "BLOSUM80", "BLOSUM90",
 PART2_FUNCTIONS = ["ba_error_string", "ba_last_error_message", "ba_create", "ba_destroy", "ba_batch_upload",
                    "ba_batch_upload_profiles", "ba_batch_upload_pssm", "ba_align_batch_pssm", "ba_batch_run", "ba_batch_download", "ba_batch_cigar",
                    "ba_batch_traceback", "ba_batch_total_stats", "ba_batch_pair_stats", "ba_batch_free",
-                   "ba_align_batch", "ba_align_batch_exp", "ba_align_batch_profiles", "ba_new_simple_nucmatrix", "ba_set_nucmatrix", "ba_free_nucmatrix",
+                   "ba_align_batch", "ba_align_batch_cigar", "ba_align_batch_exp", "ba_align_batch_profiles", "ba_new_simple_nucmatrix", "ba_set_nucmatrix", "ba_free_nucmatrix",
                    "ba_percent_len", "ba_cigar_format", "ba_measure_int_peak", "ba_measure_int_peak_packed"]
 
 
@@ -124,6 +124,8 @@ class Library:
         L.ba_align_batch.argtypes = [vp, C.POINTER(BaConfig), sz, vp, vp, vp, vp, vp, C.POINTER(BaStats)]
         L.ba_align_batch_exp.argtypes = [vp, C.POINTER(BaConfig), sz, vp, vp, vp, vp, vp, vp, vp, C.POINTER(BaStats)]
         L.ba_align_batch_profiles.argtypes = [vp, C.POINTER(BaConfig), sz, vp, vp, vp, vp, C.POINTER(BaStats)]
+        L.ba_align_batch_cigar.argtypes = [vp, C.POINTER(BaConfig), sz, vp, vp, vp, vp, vp, vp, sz, vp, vp, C.POINTER(sz),
+                                           C.POINTER(BaStats)]
         L.ba_batch_upload_pssm.argtypes = [vp, C.POINTER(BaConfig), sz, vp, vp, C.POINTER(BaPssmBatch), C.POINTER(vp)]
         L.ba_align_batch_pssm.argtypes = [vp, C.POINTER(BaConfig), sz, vp, vp, C.POINTER(BaPssmBatch), vp, C.POINTER(BaStats)]
         L.ba_new_simple_nucmatrix.restype = vp

@@ -457,24 +457,41 @@ BA_HD uint64_t rect_words(int H, int W, int layout = 0) {
   const int nch = (H + CH - 1) / CH;
   return (uint64_t)nch * (uint64_t)(W >> 3) * R * 32;
 }
-// Trace::add_block (scan_block.rs:1428-1443); returns where this rectangle's words go
+// Trace::add_block (scan_block.rs:1428-1443); returns where this rectangle's words go.
 // The word layout of the rectangle is recorded in bits 1-2 of Rect::right so that the walk-back indexes the words
-// the same way
-BA_DEV uint32_t* trace_push(AlnState& st, const SlotMem& sm, uint32_t row, uint32_t col, int W, int H, bool right, bool writer,
-                            int layout = 0) {
+// the same way. A rectangle that does not fit the slot's own arena is placed in the batch-wide overflow pool
+// (bit 3 of Rect::right, word_off in units of 16 words): slot arenas are sized for the common path, and the few
+// alignments that sit at large block sizes for long borrow from the pool instead of being re-run.
+// Called by all 32 lanes; `want`: this lane's alignment really pushes (fast phase: groups of GW lanes decide
+// independently), `writer`: the lane that stores the record.
+constexpr uint32_t kRectPool = 8u;
+BA_DEV uint32_t* trace_push(const Params& P, AlnState& st, const SlotMem& sm, uint32_t row, uint32_t col, int W, int H, bool right,
+                            bool writer, int layout = 0, bool want = true, int GW = 32) {
   const uint64_t need = rect_words(H, W, layout);
-  if (st.ridx >= sm.rects_cap || (uint64_t)st.widx + need > sm.words_cap || ((uint64_t)st.widx + need) >> 32) {
-    st.overflow = 1u;
-    return sm.words;
+  bool over = false, pool = false;
+  if (want) {
+    if (st.ridx >= sm.rects_cap) over = true;
+    else if ((uint64_t)st.widx + need > sm.words_cap || ((uint64_t)st.widx + need) >> 32) pool = true;
   }
-  if (writer) {
-    Rect r; r.row = row; r.col = col; r.h = (uint16_t)H; r.w = (uint16_t)W; r.right = (right ? 1u : 0u) | ((uint32_t)layout << 1); r.word_off = st.widx;
-    sm.rects[st.ridx] = r;
+  uint32_t pbase = 0;
+  if (wp::ballot(pool) != 0u) {
+    const uint32_t units = (uint32_t)((need + 15) >> 4);
+    if (pool && writer && P.trace_pool) pbase = wp::atomic_add(P.trace_pool_cursor, units);
+    pbase = (uint32_t)wp::shfl_idx_w((int)pbase, 0, GW);
+    if (pool && (!P.trace_pool || (uint64_t)pbase + units > P.trace_pool_units)) { over = true; pool = false; }
   }
-  uint32_t* p = sm.words + st.widx;
-  st.widx += (uint32_t)need;
+  if (!want) return sm.words;
+  if (over) { st.overflow = 1u; return sm.words; }
+  Rect r; r.row = row; r.col = col; r.h = (uint16_t)H; r.w = (uint16_t)W; r.right = (right ? 1u : 0u) | ((uint32_t)layout << 1);
+  uint32_t* p;
+  if (pool) { r.right |= kRectPool; r.word_off = pbase; p = P.trace_pool + (size_t)pbase * 16; }
+  else { r.word_off = st.widx; p = sm.words + st.widx; st.widx += (uint32_t)need; }
+  if (writer) sm.rects[st.ridx] = r;
   st.ridx += 1;
   return p;
+}
+BA_DEV const uint32_t* rect_words_ptr(const uint32_t* words, const uint32_t* pool, const Rect& rc) {
+  return (rc.right & kRectPool) ? pool + (size_t)rc.word_off * 16 : words + rc.word_off;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -491,7 +508,7 @@ struct WalkState {
 };
 
 // lane 0: walk inside rectangle rc until the path leaves it
-BA_DEV void traceback_rect(const uint8_t* lut, const uint32_t* words, const uint32_t* zwords, bool fqs, const Rect& rc,
+BA_DEV void traceback_rect(const uint8_t* lut, const uint32_t* words, const uint32_t* pool, const uint32_t* zwords, bool fqs, const Rect& rc,
                            const uint8_t* q, const uint8_t* r, bool eq, uint32_t* runs, uint32_t cap, WalkState& s) {
   const int H = rc.h, W = rc.w;
   const bool rc_right = (rc.right & 1u) != 0;
@@ -499,7 +516,7 @@ BA_DEV void traceback_rect(const uint8_t* lut, const uint32_t* words, const uint
   const int R = layout == 1u ? 8 : rect_rows_per_lane(H);
   const int CH = 32 * R;
   const int ngroups = W >> 3;
-  const uint32_t* tw = words + rc.word_off;
+  const uint32_t* tw = rect_words_ptr(words, pool, rc);
   const uint32_t lbase = rc_right ? 64u : 0u;
   const uint32_t hh = (uint32_t)(H >> 1), G = (uint32_t)(H >> 3);
   uint32_t i = s.i, j = s.j, table = s.table;
@@ -537,7 +554,7 @@ BA_DEV void traceback_rect(const uint8_t* lut, const uint32_t* words, const uint
 // Whole warp. Lane 0 walks; the other lanes touch the trace words of the rectangle kTbAhead records further down
 // the stack (the next ones the walk will usually enter), so that they are in L1 when lane 0 gets there.
 constexpr uint32_t kTbAhead = 8;
-BA_DEV void traceback_walk(const uint8_t* lut, const uint32_t* words, const uint32_t* zwords, bool fqs, const Rect* rects,
+BA_DEV void traceback_walk(const uint8_t* lut, const uint32_t* words, const uint32_t* pool, const uint32_t* zwords, bool fqs, const Rect* rects,
                            uint32_t ridx, uint32_t i, uint32_t j, const uint8_t* q, const uint8_t* r, bool eq, uint32_t* runs,
                            uint32_t cap, uint32_t& nruns, uint32_t& bad) {
   const int lane = wp::lane_id();
@@ -560,11 +577,11 @@ BA_DEV void traceback_walk(const uint8_t* lut, const uint32_t* words, const uint
     if (!go) break;
     const uint32_t cur = (uint32_t)wp::shfl_idx((int)s.ridx, 0);
     if (lane == 0) {
-      traceback_rect(lut, words, zwords, fqs, rc, q, r, eq, runs, cap, s);
+      traceback_rect(lut, words, pool, zwords, fqs, rc, q, r, eq, runs, cap, s);
     } else if (lane <= 4 && cur >= kTbAhead) {
       const Rect pr = rects[cur - kTbAhead];
       const uint64_t nw = (uint64_t)(pr.h >> 3) * pr.w;     // layout 3 shift rectangles: h words, 32 per 128-byte line
-      if (((pr.right >> 1) & 3u) == 3u && nw <= 128u && (uint64_t)(lane - 1) * 32u < nw) wp::touch(words + pr.word_off + (lane - 1) * 32);
+      if (((pr.right >> 1) & 3u) == 3u && nw <= 128u && (uint64_t)(lane - 1) * 32u < nw) wp::touch(rect_words_ptr(words, pool, pr) + (lane - 1) * 32);
     }
     wp::syncwarp();
   }
@@ -577,7 +594,7 @@ BA_DEV void emit_cigar(const Params& P, const uint8_t* lut, const uint32_t* word
                        DevResult& res) {
   const int lane = wp::lane_id();
   uint32_t nruns = 0, bad = 0;
-  traceback_walk(lut, words, zwords, fqs, rects, ridx, qi, rj, q, r, eq, runs, P.runs_per_warp, nruns, bad);
+  traceback_walk(lut, words, P.trace_pool, zwords, fqs, rects, ridx, qi, rj, q, r, eq, runs, P.runs_per_warp, nruns, bad);
   nruns = (uint32_t)wp::shfl_idx((int)nruns, 0);
   bad = (uint32_t)wp::shfl_idx((int)bad, 0);
   res.cigar_n = 0; res.cigar_off = 0;
@@ -755,7 +772,7 @@ BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const Sl
       if (TRACE && a.W > 0 && a.H >= 0) {
         const uint32_t woff = st.widx;
         if (m_local && sm.zwords) a.tz = sm.zwords + woff;
-        a.tw = trace_push(st, sm, rect_right ? a.vec_base : a.col_base, rect_right ? a.col_base : a.vec_base, a.W, a.H, rect_right, lane == 0, pk_ok ? 3 : (m_fqe ? 1 : 0));
+        a.tw = trace_push(P, st, sm, rect_right ? a.vec_base : a.col_base, rect_right ? a.col_base : a.vec_base, a.W, a.H, rect_right, lane == 0, pk_ok ? 3 : (m_fqe ? 1 : 0));
       }
       add_cells(st, (uint32_t)(a.W * a.H));
       sc.vec = rect_right ? q : r; sc.col = rect_right ? r : q;
@@ -987,7 +1004,7 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast
   for (int k = 0; k < 4; k++) { D[k] = wp::vadd2(f.aD[k], oa2); C[k] = wp::vadd2(f.aC[k], oa2); m[k] = 0u; }
   uint32_t* fr = w.fr + grp * 8;
   uint32_t* tw = nullptr;
-  if (TRACE && active) tw = trace_push(st, sm, right ? si : si + (B - kStep), right ? sj + (B - kStep) : sj, kStep, B, right, lg == 0, 3);
+  if (TRACE) tw = trace_push(P, st, sm, right ? si : si + (B - kStep), right ? sj + (B - kStep) : sj, kStep, B, right, lg == 0, 3, active, G);
   pk_cols8<KIND, XDROP, LGT, TRACE>(sc, P.kc, LGT, lg, cw.x, cw.y, D, C, (uint32_t)corner & 0xffffu, 0, m, mc, fr, lg == G - 1, tw, TRACE && active);
   wp::syncwarp();
 
@@ -1136,9 +1153,12 @@ BA_DEV void bcast_state(AlnState& d, const AlnState& s, int src) {
 // Warp main: carve shared memory, then keep up to four alignments in flight until the ticket
 // counter runs dry.
 // ---------------------------------------------------------------------------------------------
-BA_HD size_t warp_smem_bytes(uint32_t max_size) {
+// gb: the four live borders of the generic phase are in global memory (P.gborders) instead of shared memory. At
+// max block sizes >= 1024 they are 8-32 KB per warp and would cap the SM at 8 warps or fewer; the generic phase
+// touches only the first B entries, and the fast phase keeps its borders in registers anyway.
+BA_HD size_t warp_smem_bytes(uint32_t max_size, bool gb = false) {
   const size_t ms = max_size < 32 ? 32 : max_size;
-  size_t b = 4 * ms * sizeof(int16_t) + 2 * 16 * sizeof(int16_t) + 4 * sizeof(int32_t) + 64 * sizeof(uint32_t) + 512 * sizeof(uint32_t);
+  size_t b = (gb ? 0 : 4 * ms * sizeof(int16_t)) + 2 * 16 * sizeof(int16_t) + 4 * sizeof(int32_t) + 64 * sizeof(uint32_t) + 512 * sizeof(uint32_t);
   if (max_size > 32) b += ms;   // ecarry (rectangles swept in several chunks, TRACE)
   return (b + 15) & ~(size_t)15;
 }
@@ -1159,21 +1179,27 @@ BA_DEV void bind_slot(const Params& P, uint32_t slot, WarpMem& w, SlotMem& sm, b
 }
 
 // FM selects the fast phase: 0 = none (every step in the generic phase), 16 + LGT = packed fast phase with
-// 1 << LGT lanes per alignment (min block size 8 << LGT).
+// 1 << LGT lanes per alignment (min block size 8 << LGT); + 16 (FM >= 32): live borders in global memory.
 template <int SCORING, int FLAGS, int FM>
 BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, uint32_t warp_global) {
   constexpr bool TRACE = (FLAGS & kTrace) != 0;
+  constexpr bool GB = FM >= 32;
   constexpr bool PKF = FM >= 16;
-  constexpr int LGT = PKF ? FM - 16 : 5;       // log2(lanes per alignment group)
+  constexpr int LGT = PKF ? (FM & 15) : 5;     // log2(lanes per alignment group)
   constexpr int GW = 1 << LGT;
   const int lane = wp::lane_id();
   const size_t ms = P.max_size < 32 ? 32 : P.max_size;
   WarpMem w;
   w.mat = (const int8_t*)smem;                     // header: matrix, then the packed-path tables
   w.smem0 = smem;
-  unsigned char* base = smem + kSmemHeader + (size_t)warp_in_block * warp_smem_bytes(P.max_size);
+  unsigned char* base = smem + kSmemHeader + (size_t)warp_in_block * warp_smem_bytes(P.max_size, GB);
   int16_t* p16 = (int16_t*)base;
-  w.Dc = p16; p16 += ms; w.Cc = p16; p16 += ms; w.Dr = p16; p16 += ms; w.Rr = p16; p16 += ms;
+  if (GB) {
+    int16_t* g16 = P.gborders + (size_t)warp_global * 4 * ms;
+    w.Dc = g16; w.Cc = g16 + ms; w.Dr = g16 + 2 * ms; w.Rr = g16 + 3 * ms;
+  } else {
+    w.Dc = p16; p16 += ms; w.Cc = p16; p16 += ms; w.Dr = p16; p16 += ms; w.Rr = p16; p16 += ms;
+  }
   w.t1 = p16; p16 += 16; w.t2 = p16; p16 += 16;
   w.misc = (int32_t*)p16; p16 += 8;
   w.fr = (uint32_t*)p16; p16 += 128;

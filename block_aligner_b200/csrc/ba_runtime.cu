@@ -252,10 +252,12 @@ static int occupancy(int wpb, size_t smem_bytes, int* blocks_per_sm) {
 
 // kernel instantiations: scoring x flags x rows-per-lane of the fast phase (0 = generic phase only)
 // flags 4..7 = kExt | {TRACE, X_DROP}: LOCAL_START / FREE_QUERY_START_GAPS selected at run time, generic phase only
+// fast-phase modes 34 / 35 = 18 / 19 with the live borders in global memory (max block size >= 1024)
 #define BA_FOR_SEQ(X, S) X(S, 0, 0) X(S, 1, 0) X(S, 2, 0) X(S, 3, 0) X(S, 4, 0) X(S, 5, 0) X(S, 6, 0) X(S, 7, 0) \
-                         X(S, 0, 18) X(S, 1, 18) X(S, 2, 18) X(S, 3, 18) X(S, 0, 19) X(S, 1, 19) X(S, 2, 19) X(S, 3, 19)
+                         X(S, 0, 18) X(S, 1, 18) X(S, 2, 18) X(S, 3, 18) X(S, 0, 19) X(S, 1, 19) X(S, 2, 19) X(S, 3, 19) \
+                         X(S, 0, 34) X(S, 1, 34) X(S, 2, 34) X(S, 3, 34) X(S, 0, 35) X(S, 1, 35) X(S, 2, 35) X(S, 3, 35)
 #ifdef BA_MINIMAL   // tuning builds (tools/build_variant.sh): only the kernels of the C2 workload
-#define BA_FOR_KERNELS(X) X(kNuc, 2, 0) X(kNuc, 2, 18) X(kNuc, 3, 19)
+#define BA_FOR_KERNELS(X) X(kNuc, 2, 0) X(kNuc, 2, 18) X(kNuc, 3, 19) X(kNuc, 3, 35)
 #else
 #define BA_FOR_KERNELS(X) BA_FOR_SEQ(X, kNuc) BA_FOR_SEQ(X, kAA) BA_FOR_SEQ(X, kByte) \
   X(kProfile, 0, 0) X(kProfile, 1, 0) X(kProfile, 2, 0) X(kProfile, 3, 0) \
@@ -370,8 +372,10 @@ static void pool_release(BaAligner* al, void* p) {
     if (al->pool_live[i].first == p) {
       const size_t sz = al->pool_live[i].second;
       al->pool_live.erase(al->pool_live.begin() + i);
-      // keep at most half of the device memory cached
-      if (al->pool_cached + sz <= al->mem_total / 2) { al->pool_free.push_back({p, sz}); al->pool_cached += sz; }
+      // Keep up to 90 % of the device memory cached: the trace arenas of one TRACE batch alone are 55 % (measured on
+      // C5: with a 50 % cap some of them were cudaFree'd and cudaMalloc'ed again on every call, 400 ms each time).
+      // pool_alloc drops the cache and retries when a fresh allocation fails.
+      if (al->pool_cached + sz <= al->mem_total / 10 * 9) { al->pool_free.push_back({p, sz}); al->pool_cached += sz; }
       else dfree(p);
       return;
     }
@@ -405,11 +409,15 @@ struct BaBatch {
   uint64_t trace_words_bound = 0;   // worst case per alignment (the reference's Trace::new size)
   uint64_t mem_budget = 0; uint64_t max_blocks_hw = 1;
   // launch geometry
-  int blocks = 0, wpb = 0; size_t smem_bytes = 0; uint32_t slots_per_warp = 1; int fast_rows = 0;
+  int blocks = 0, wpb = 0; size_t smem_bytes = 0; uint32_t slots_per_warp = 1; int fast_rows = 0; bool gb = false;
+  int16_t* d_gborders = nullptr;
+  uint32_t* d_trace_pool = nullptr; uint32_t* d_trace_pool_cursor = nullptr; uint64_t trace_pool_units = 0;
   uint64_t trace_words_per_warp = 0; uint32_t rects_per_warp = 0, runs_per_warp = 0;
   // host results
   std::vector<DevResult> h_out;
   std::vector<uint32_t> h_cigar;
+  uint32_t* cigar_dst = nullptr; uint64_t cigar_dst_cap = 0; uint64_t cigar_dst_used = 0;   // ba_align_batch_cigar: caller's buffer
+  bool cigar_skip = false;   // ba_align_batch (no CIGAR output): do not copy the stream back at all
   std::vector<uint32_t> h_tb;      // runs of the last ba_batch_traceback
   DevResult* d_tb_res = nullptr;
   float pack_ms = 0;
@@ -498,7 +506,7 @@ extern "C" void ba_batch_free(BaBatch* b) {
   void* bufs[] = {b->d_seq, b->d_qoff, b->d_roff, b->d_qlen, b->d_rlen, b->d_order, b->d_matrix, b->d_profiles, b->d_prof_arena,
                   b->d_out, b->d_ticket, b->d_ckpt, b->d_trace, b->d_rects, b->d_runs, b->d_cigar, b->d_cigar_used,
                   b->d_steplog, b->d_steplog_n, b->d_tb_res, b->d_overflow_list, b->d_overflow_n, b->d_zwords,
-                  b->r_trace, b->r_zwords, b->r_rects, b->r_ckpt, b->r_runs};
+                  b->r_trace, b->r_zwords, b->r_rects, b->r_ckpt, b->r_runs, b->d_gborders, b->d_trace_pool, b->d_trace_pool_cursor};
   for (void* q : bufs) pool_release(al, q);
   if (b->has_ss) { dsync(b->ss.stream); streams_release(al, b->ss); }
   delete b;
@@ -798,7 +806,12 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
     b->fast_rows = 16 + lgt;
     b->slots_per_warp = 32u >> lgt;
   }
-  const size_t wbytes = warp_smem_bytes(mx);
+  // max block >= 1024: the four live borders (8-32 KB per warp) move to global memory so that shared memory does not
+  // cap the SM at 8 warps or fewer (C5: 64..=2048)
+  const bool gb = b->fast_rows >= 16 && mx >= 1024 && !getenv("BA_NO_GLOBAL_BORDERS");
+  if (gb) b->fast_rows += 16;
+  b->gb = gb;
+  const size_t wbytes = warp_smem_bytes(mx, gb);
   int wpb = 4;
   while (wpb > 1 && kSmemHeader + wpb * wbytes > al->smem_optin - 1024) wpb >>= 1;
   if (kSmemHeader + wpb * wbytes > al->smem_optin) { ba_batch_free(b); return fail(BA_ERR_SIZE, "max block size does not fit in shared memory"); }
@@ -836,6 +849,18 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
     const uint64_t zmul = (cfg->flags & BA_LOCAL_START) ? 2 : 1;
     const uint64_t per_warp = spw * (zmul * b->trace_words_per_warp * 4 + (uint64_t)b->rects_per_warp * sizeof(Rect)) + (uint64_t)b->runs_per_warp * 4;
     b->mem_budget = (uint64_t)(al->mem_total * al->budget_frac);
+    // A tenth of the budget is a batch-wide overflow pool (trace_push): rectangles that do not fit a slot's own arena
+    // are bump-allocated there, so the rare alignment that sits at a large block size for long does not need the
+    // retry pass. Not with LOCAL_START (the zero masks mirror the per-slot layout).
+    if (!(cfg->flags & BA_LOCAL_START) && b->trace_words_per_warp < b->trace_words_bound && !getenv("BA_NO_TRACE_POOL")) {
+      uint64_t pool_bytes = b->mem_budget / 10;
+#ifdef BA_EMU
+      pool_bytes = std::min<uint64_t>(pool_bytes, (uint64_t)8 << 20);
+#endif
+      if (const char* e = getenv("BA_TRACE_POOL_BYTES")) pool_bytes = (uint64_t)atoll(e);   // tests: force exhaustion
+      b->trace_pool_units = pool_bytes / 64;
+      b->mem_budget -= b->trace_pool_units * 64;
+    }
     const uint64_t fit_warps = std::max<uint64_t>(1, b->mem_budget / std::max<uint64_t>(per_warp, 1));
     max_blocks = std::max<uint64_t>(1, std::min<uint64_t>(max_blocks, fit_warps / wpb));
   }
@@ -858,7 +883,12 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
     }
   }
   TRY(pool_alloc(al, (void**)&b->d_ckpt, nslots * 4 * ms * sizeof(int16_t)));
+  if (b->gb) TRY(pool_alloc(al, (void**)&b->d_gborders, nwarps * 4 * ms * sizeof(int16_t)));
   if (trace) {
+    if (b->trace_pool_units) {
+      TRY(pool_alloc(al, (void**)&b->d_trace_pool, b->trace_pool_units * 64));
+      TRY(pool_alloc(al, (void**)&b->d_trace_pool_cursor, 4));
+    }
     TRY(pool_alloc(al, (void**)&b->d_trace, nslots * b->trace_words_per_warp * 4));
     if (cfg->flags & BA_LOCAL_START) TRY(pool_alloc(al, (void**)&b->d_zwords, nslots * b->trace_words_per_warp * 4));
     TRY(pool_alloc(al, (void**)&b->d_rects, nslots * (uint64_t)b->rects_per_warp * sizeof(Rect)));
@@ -919,10 +949,11 @@ static Params make_params(const BaBatch* b, bool retry = false) {
   }
   P.ext_flags = (uint32_t)(b->cfg.flags & (BA_LOCAL_START | BA_FREE_QUERY_START_GAPS | BA_FREE_QUERY_END_GAPS)); P.trace_zwords = b->d_zwords;
   P.out = b->d_out; P.ticket = b->d_ticket;
-  P.ckpt = b->d_ckpt; P.slots_per_warp = b->slots_per_warp;
-  P.fast_block = b->fast_rows >= 16 ? (8u << (b->fast_rows - 16)) : (uint32_t)(8 * b->fast_rows);
+  P.ckpt = b->d_ckpt; P.slots_per_warp = b->slots_per_warp; P.gborders = b->d_gborders;
+  P.fast_block = b->fast_rows >= 16 ? (8u << (b->fast_rows & 15)) : (uint32_t)(8 * b->fast_rows);
   P.pk_fast = b->fast_rows >= 16 ? 1u : 0u;
   P.trace_words = b->d_trace; P.trace_words_per_warp = b->trace_words_per_warp;
+  P.trace_pool = b->d_trace_pool; P.trace_pool_cursor = b->d_trace_pool_cursor; P.trace_pool_units = b->trace_pool_units;
   P.rects = b->d_rects; P.rects_per_warp = b->rects_per_warp;
   P.run_scratch = b->d_runs; P.runs_per_warp = b->runs_per_warp;
   P.cigar_stream = b->d_cigar; P.cigar_cap = b->cigar_cap; P.cigar_used = b->d_cigar_used;
@@ -948,6 +979,7 @@ static int batch_launch(BaBatch* b) {
   if (dzero(b->d_ticket, 4, st)) return BA_ERR_CUDA;
   if (b->d_cigar_used && dzero(b->d_cigar_used, 8, st)) return BA_ERR_CUDA;
   if (b->d_overflow_n && dzero(b->d_overflow_n, 4, st)) return BA_ERR_CUDA;
+  if (b->d_trace_pool_cursor && dzero(b->d_trace_pool_cursor, 4, st)) return BA_ERR_CUDA;
   if (b->d_steplog_n && dzero(b->d_steplog_n, 4, st)) return BA_ERR_CUDA;
   b->downloaded = false;
   b->launches = 0;
@@ -988,6 +1020,7 @@ static int batch_wait(BaBatch* b, BaStats* stats) {
         const uint64_t fit_warps = std::max<uint64_t>(1, (uint64_t)(b->mem_budget * 0.6) / std::max<uint64_t>(per_warp, 1));
         uint64_t blocks2 = std::max<uint64_t>(1, std::min<uint64_t>(b->max_blocks_hw, fit_warps / b->wpb));
         blocks2 = std::min<uint64_t>(blocks2, (n_over + b->wpb * spw - 1) / (b->wpb * spw));
+        if (b->gb) blocks2 = std::min<uint64_t>(blocks2, (uint64_t)b->blocks);   // d_gborders is sized for the first pass
         const uint64_t nslots2 = blocks2 * b->wpb * spw;
         const size_t msz = b->max_size < 32 ? 32 : b->max_size;
         void** rb[] = {(void**)&b->r_trace, (void**)&b->r_zwords, (void**)&b->r_rects, (void**)&b->r_ckpt, (void**)&b->r_runs};
@@ -1041,10 +1074,16 @@ extern "C" int ba_batch_download(BaBatch* b, AlignResult* out) {
   unsigned long long used = 0;
   if (b->d_cigar_used && d2h(&used, b->d_cigar_used, 8, st)) return BA_ERR_CUDA;
   if (dsync(st)) return BA_ERR_CUDA;
-  if (b->d_cigar) {
+  if (b->d_cigar && !b->cigar_skip) {
     used = std::min<unsigned long long>(used, b->cigar_cap);
-    b->h_cigar.resize(used);
-    if (d2h(b->h_cigar.data(), b->d_cigar, used * 4, st)) return BA_ERR_CUDA;
+    if (b->cigar_dst) {     // straight into the caller's buffer (no host copy of the stream is kept)
+      if (used > b->cigar_dst_cap) return fail(BA_ERR_OVERFLOW, "caller's CIGAR buffer is too small");
+      if (d2h(b->cigar_dst, b->d_cigar, used * 4, st)) return BA_ERR_CUDA;
+      b->cigar_dst_used = used;
+    } else {
+      b->h_cigar.resize(used);
+      if (d2h(b->h_cigar.data(), b->d_cigar, used * 4, st)) return BA_ERR_CUDA;
+    }
     if (dsync(st)) return BA_ERR_CUDA;
   }
   int bad = 0;
@@ -1059,7 +1098,7 @@ extern "C" int ba_batch_download(BaBatch* b, AlignResult* out) {
 }
 
 extern "C" int ba_batch_cigar(const BaBatch* b, size_t k, const uint32_t** runs, size_t* n_runs) {
-  if (!b || !b->downloaded || k >= b->n || !(b->cfg.flags & BA_TRACE)) return fail(BA_ERR_ARG, "no CIGAR available");
+  if (!b || !b->downloaded || k >= b->n || !(b->cfg.flags & BA_TRACE) || b->cigar_dst) return fail(BA_ERR_ARG, "no CIGAR available");
   const DevResult& r = b->h_out[k];
   if (r.cigar_off + r.cigar_n > b->h_cigar.size()) return fail(BA_ERR_OVERFLOW, "cigar stream overflow");
   *runs = b->h_cigar.data() + r.cigar_off; *n_runs = r.cigar_n;
@@ -1094,8 +1133,28 @@ extern "C" size_t ba_debug_step_log(BaBatch* b, StepLog* out, size_t cap) {
 // upload + run + download. Large batches are cut into chunks that are pipelined: every chunk has its own
 // stream, so the H2D copy (and convert/pad) of chunk k+1 overlaps the alignment kernel of chunk k, and the
 // tail of kernel k overlaps the head of kernel k+1.
+struct CigarOut { uint32_t* runs; size_t cap; uint64_t* off; uint32_t* len; size_t used; };
+static int align_batch_impl(BaAligner* a, const BaConfig* cfg, size_t n, const uint8_t* q_bytes, const uint64_t* q_off,
+                            const uint8_t* r_bytes, const uint64_t* r_off, AlignResult* out, BaStats* stats, CigarOut* cg);
 extern "C" int ba_align_batch(BaAligner* a, const BaConfig* cfg, size_t n, const uint8_t* q_bytes, const uint64_t* q_off,
                               const uint8_t* r_bytes, const uint64_t* r_off, AlignResult* out, BaStats* stats) {
+  return align_batch_impl(a, cfg, n, q_bytes, q_off, r_bytes, r_off, out, stats, nullptr);
+}
+// ba_align_batch for BA_TRACE batches with the CIGARs delivered into the caller's buffer: pair k's runs are
+// runs[run_off[k] .. run_off[k] + run_len[k]), packed (len << 4) | Operation, forward order.
+extern "C" int ba_align_batch_cigar(BaAligner* a, const BaConfig* cfg, size_t n, const uint8_t* q_bytes, const uint64_t* q_off,
+                                    const uint8_t* r_bytes, const uint64_t* r_off, AlignResult* out,
+                                    uint32_t* runs, size_t runs_cap, uint64_t* run_off, uint32_t* run_len, size_t* runs_used,
+                                    BaStats* stats) {
+  if (!cfg || !(cfg->flags & BA_TRACE)) return fail(BA_ERR_ARG, "ba_align_batch_cigar needs BA_TRACE");
+  if (n && (!runs || !run_off || !run_len)) return fail(BA_ERR_ARG, "null CIGAR output");
+  CigarOut cg{runs, runs_cap, run_off, run_len, 0};
+  const int rc = align_batch_impl(a, cfg, n, q_bytes, q_off, r_bytes, r_off, out, stats, &cg);
+  if (runs_used) *runs_used = cg.used;
+  return rc;
+}
+static int align_batch_impl(BaAligner* a, const BaConfig* cfg, size_t n, const uint8_t* q_bytes, const uint64_t* q_off,
+                            const uint8_t* r_bytes, const uint64_t* r_off, AlignResult* out, BaStats* stats, CigarOut* cg) {
   if (!a) return fail(BA_ERR_ARG, "aligner is null");
   if (n && (!q_off || !r_off)) return fail(BA_ERR_ARG, "null offsets");
   const bool timing = getenv("BA_TIMING") != nullptr;
@@ -1147,7 +1206,16 @@ extern "C" int ba_align_batch(BaAligner* a, const BaConfig* cfg, size_t n, const
     if (!bs[c]) continue;
     BaStats st1;
     if (!rc) rc = batch_wait(bs[c], &st1);
+    if (!rc && cg) { bs[c]->cigar_dst = cg->runs + cg->used; bs[c]->cigar_dst_cap = cg->cap - cg->used; }
+    if (!rc && !cg) bs[c]->cigar_skip = true;
     if (!rc) rc = ba_batch_download(bs[c], out ? out + cut[c] : nullptr);
+    if (!rc && cg) {
+      for (size_t k = 0; k < bs[c]->n; k++) {
+        cg->off[cut[c] + k] = cg->used + bs[c]->h_out[k].cigar_off;
+        cg->len[cut[c] + k] = bs[c]->h_out[k].cigar_n;
+      }
+      cg->used += bs[c]->cigar_dst_used;
+    }
     if (!rc) {
       tot.kernel_ms += st1.kernel_ms; tot.pack_ms += st1.pack_ms; tot.kernel_launches += st1.kernel_launches + (bs[c]->n ? 1 : 0);
       for (size_t k = 0; k < bs[c]->n; k++) {

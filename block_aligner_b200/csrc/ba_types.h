@@ -115,7 +115,10 @@ struct Params {
   uint32_t slots_per_warp;
   uint32_t fast_block;           // 0: fast phase off; 32 / 64: block size served by the fast phase (== min_size)
   int16_t* ckpt;                 // 4 * max(max_size, 32) int16 per slot: checkpoint borders
+  int16_t* gborders;             // kernels with global live borders (FM >= 32): 4 * max(max_size, 32) int16 per warp
   uint32_t* trace_words; uint64_t trace_words_per_warp;   // per slot (name kept: per-"warp" arena of v0)
+  // shared overflow pool for rectangles that do not fit a slot's own arena: bump-allocated in units of 16 words
+  uint32_t* trace_pool; uint32_t* trace_pool_cursor; uint64_t trace_pool_units;
   Rect* rects; uint32_t rects_per_warp;                   // per slot
   uint32_t* run_scratch; uint32_t runs_per_warp;  // reversed CIGAR runs while walking back
   // cigar output stream: runs packed as (len << 4) | op, allocated with atomicAdd on *cigar_used

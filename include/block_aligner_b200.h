@@ -205,6 +205,16 @@ int ba_align_batch(BaAligner* a, const BaConfig* cfg, size_t n,
                    const uint8_t* r_bytes, const uint64_t* r_off,
                    AlignResult* out, BaStats* stats);
 
+/* ba_align_batch for BA_TRACE batches, CIGARs included: pair k's runs are runs[run_off[k] .. run_off[k] + run_len[k]),
+ * packed (len << 4) | Operation in forward order (what Trace::cigar / cigar_eq at the result's end position produce,
+ * src/scan_block.rs:1469-1480). `runs` holds runs_cap words (pinned memory makes the copy faster); BA_ERR_OVERFLOW
+ * if the batch produced more. *runs_used = words written. */
+int ba_align_batch_cigar(BaAligner* a, const BaConfig* cfg, size_t n,
+                         const uint8_t* q_bytes, const uint64_t* q_off,
+                         const uint8_t* r_bytes, const uint64_t* r_off,
+                         AlignResult* out, uint32_t* runs, size_t runs_cap, uint64_t* run_off, uint32_t* run_len,
+                         size_t* runs_used, BaStats* stats);
+
 /* Block::align_exp (src/scan_block.rs:884-902) for a batch: retry with doubled min block size until
  * score >= target_score[k]. min_size_used[k] = the min size that reached the target, 0 = None. */
 int ba_align_batch_exp(BaAligner* a, const BaConfig* cfg, size_t n,

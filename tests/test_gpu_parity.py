@@ -121,16 +121,20 @@ def test_results_independent_of_batch_order_and_reuse(env):
     assert (r1[0] == r2[0]).all() and (r1[1] == r2[1]).all()
 
 
-def test_trace_arena_overflow_is_retried(env):
-    """Unrelated sequences keep the block at its maximum size, which overflows the (deliberately small) first-pass
-    trace arenas; those pairs are re-run with worst-case arenas and must still be bit-exact."""
+@pytest.mark.parametrize("pool", [True, False])
+def test_trace_arena_overflow_is_retried(env, pool, monkeypatch):
+    """Unrelated sequences keep the block at its maximum size, which overflows the (deliberately small) per-slot
+    trace arenas. With the batch-wide overflow pool the rectangles spill there (one launch); without it those pairs
+    are re-run with worst-case arenas (second launch). Bit-exact either way."""
     lib, al = env
+    if not pool:
+        monkeypatch.setenv("BA_NO_TRACE_POOL", "1")
     w = dict(scoring=api.SCORING_NUC, matrix="NW1", gaps=(-2, -1), size=(32, 512), x_drop=0, flags=api.TRACE, stream=31,
              gen=P(alphabet=0, len_dist=0, len_min=1500, len_max=2500, sub_rate=0.75, ins_rate=0.0, del_rate=0.0))
     qa, qo, ra, ro = workloads.generate(w["gen"], 200, stream=31)
     m = workloads.matrix_of(lib, w)
     got = parity.run_lib(lib, al, w["scoring"], m, w["gaps"], w["size"], 0, api.TRACE, True, qa, qo, ra, ro)
-    assert got[3].kernel_launches == 2, "expected the overflow retry pass to run"
+    assert got[3].kernel_launches == (1 if pool else 2), "expected the overflow pool / the retry pass to be used"
     exp = parity.oracle_batch(w["scoring"], m, w["gaps"], w["size"], 0, api.TRACE, True, qa, qo, ra, ro)
     assert parity.compare("overflow-retry", got, exp) == 0
 
@@ -236,10 +240,11 @@ def test_cigar_consumes_end_position_and_rescores_full_length(env, name, n, scor
 
 
 @pytest.mark.gpu
-def test_batch_with_overflow_retry_can_run_again(env):
+def test_batch_with_overflow_retry_can_run_again(env, monkeypatch):
     """ba_batch_run twice on a resident batch whose first run needed the retry pass: the retry scratch must not
     replace the first-pass arenas (found on the GPU with C5: illegal address on the second run)."""
     lib, al = env
+    monkeypatch.setenv("BA_NO_TRACE_POOL", "1")
     w = dict(scoring=api.SCORING_NUC, matrix="NW1", gaps=(-2, -1), size=(32, 512), x_drop=0, flags=api.TRACE, stream=31,
              gen=P(alphabet=0, len_dist=0, len_min=1500, len_max=2500, sub_rate=0.75, ins_rate=0.0, del_rate=0.0))
     qa, qo, ra, ro = workloads.generate(w["gen"], 200, stream=31)
@@ -253,3 +258,18 @@ def test_batch_with_overflow_retry_can_run_again(env):
         outs.append((r.copy(), [b.cigar_string(k) for k in range(len(qo) - 1)]))
     b.free()
     assert all((o[0] == outs[0][0]).all() and o[1] == outs[0][1] for o in outs[1:])
+
+
+@pytest.mark.gpu
+def test_trace_pool_exhaustion_falls_back_to_retry(env, monkeypatch):
+    """A pool too small for the spill: the alignments that cannot get pool space are re-run by the retry pass."""
+    lib, al = env
+    monkeypatch.setenv("BA_TRACE_POOL_BYTES", "65536")
+    w = dict(scoring=api.SCORING_NUC, matrix="NW1", gaps=(-2, -1), size=(32, 512), x_drop=0, flags=api.TRACE, stream=31,
+             gen=P(alphabet=0, len_dist=0, len_min=1500, len_max=2500, sub_rate=0.75, ins_rate=0.0, del_rate=0.0))
+    qa, qo, ra, ro = workloads.generate(w["gen"], 200, stream=31)
+    m = workloads.matrix_of(lib, w)
+    got = parity.run_lib(lib, al, w["scoring"], m, w["gaps"], w["size"], 0, api.TRACE, True, qa, qo, ra, ro)
+    assert got[3].kernel_launches == 2
+    exp = parity.oracle_batch(w["scoring"], m, w["gaps"], w["size"], 0, api.TRACE, True, qa, qo, ra, ro)
+    assert parity.compare("pool-exhausted", got, exp) == 0

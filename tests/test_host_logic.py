@@ -130,3 +130,39 @@ def test_align_exp_matches_reference_loop(env):
             mn *= 2
         assert res[k] == exp_res and used[k] == exp_used, (k, res[k], exp_res, used[k], exp_used)
     assert any(u != 32 for u in used), "test inputs should need at least one retry"
+
+
+def test_align_batch_cigar_delivers_runs_into_caller_buffer(env, monkeypatch):
+    """ba_align_batch_cigar == upload/run/download + ba_batch_cigar for every pair, across pipelined chunks"""
+    import parity
+    from block_aligner_b200 import workloads
+    lib, al = env
+    gen = workloads.params(alphabet=0, len_dist=0, len_min=100, len_max=900, sub_rate=0.04, ins_rate=0.04, del_rate=0.04, suffix_len=60)
+    n = 41
+    qa, qo, ra, ro = workloads.generate(gen, n, stream=2)
+    m = lib.builtin_matrix("NW1")[1]
+    flags = api.TRACE | api.XDROP
+    ref = parity.run_lib(lib, al, api.SCORING_NUC, m, (-2, -1), (32, 256), 50, flags, True, qa, qo, ra, ro)
+    cfg = al.config(api.SCORING_NUC, m, (-2, -1), (32, 256), 50, flags, True)
+    for chunks in ("1", "4"):
+        monkeypatch.setenv("BA_PIPELINE_CHUNKS", chunks)
+        out = np.zeros(n, dtype=np.dtype([("score", np.int32), ("q", np.uint64), ("r", np.uint64)], align=True))
+        cap = int(qo[-1] + ro[-1]) + 5 * n
+        runs = np.zeros(cap, dtype=np.uint32)
+        off = np.zeros(n, dtype=np.uint64)
+        ln = np.zeros(n, dtype=np.uint32)
+        used = C.c_size_t()
+        st = api.BaStats()
+        lib.check(lib.L.ba_align_batch_cigar(al.h, C.byref(cfg), n, qa.ctypes.data, qo.ctypes.data, ra.ctypes.data, ro.ctypes.data,
+                                             out.ctypes.data, runs.ctypes.data, cap, off.ctypes.data, ln.ctypes.data,
+                                             C.byref(used), C.byref(st)))
+        assert (out["score"] == ref[0][:, 0]).all()
+        assert used.value == int(ln.sum())
+        for k in range(n):
+            got = runs[int(off[k]):int(off[k]) + int(ln[k])].astype(np.uint64)
+            assert len(got) == len(ref[2][k]) and (got == ref[2][k]).all()
+    # a buffer that is too small is an error, not a truncation
+    small = np.zeros(8, dtype=np.uint32)
+    rc = lib.L.ba_align_batch_cigar(al.h, C.byref(cfg), n, qa.ctypes.data, qo.ctypes.data, ra.ctypes.data, ro.ctypes.data,
+                                    out.ctypes.data, small.ctypes.data, 8, off.ctypes.data, ln.ctypes.data, C.byref(used), C.byref(st))
+    assert rc == api.ERR_OVERFLOW if hasattr(api, "ERR_OVERFLOW") else rc != 0
