@@ -16,6 +16,7 @@ DEFAULT_LIB = os.path.join(_HERE, "libblock_aligner_b200.so")
 
 SCORING_NUC, SCORING_AA, SCORING_BYTE, SCORING_PROFILE = 0, 1, 2, 3
 TRACE, XDROP, LOCAL_START, FREE_QUERY_START_GAPS, FREE_QUERY_END_GAPS = 1, 2, 4, 8, 16
+REV_QUERY, REV_REFERENCE = 32, 64      # PaddedBytes::set_bytes_rev for the whole batch (done on the device)
 OPS = {0: "?", 1: "M", 2: "=", 3: "X", 4: "I", 5: "D"}
 
 

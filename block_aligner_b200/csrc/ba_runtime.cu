@@ -62,6 +62,7 @@ struct PackArgs {
   const uint8_t* raw_r; const uint64_t* raw_r_off;   // raw_r may be null (profiles)
   uint8_t* seq; const uint64_t* pq_off; const uint64_t* pr_off;
   uint32_t n; uint32_t pad; int32_t scoring; uint32_t* err;
+  uint32_t rev_q, rev_r;      // PaddedBytes::set_bytes_rev (scan_block.rs:1815-1822)
 };
 
 // One padded device profile (ProfBuild, ba_types.h). `tid` / `nthreads`: the calling thread's share of the profile.
@@ -132,7 +133,8 @@ static void pack_all(const PackArgs& a) {
       uint8_t* dst = a.seq + (which ? a.pr_off[k] : a.pq_off[k]);
       const uint8_t nul = host::null_code(a.scoring);
       dst[0] = nul;
-      for (uint64_t t = 0; t < len; t++) { bool ok; dst[1 + t] = host::convert_char(a.scoring, src[t], &ok); if (!ok) *a.err = 1; }
+      const bool rev = which ? a.rev_r != 0 : a.rev_q != 0;
+      for (uint64_t t = 0; t < len; t++) { bool ok; dst[1 + t] = host::convert_char(a.scoring, src[rev ? len - 1 - t : t], &ok); if (!ok) *a.err = 1; }
       for (uint32_t t = 0; t < a.pad; t++) dst[1 + len + t] = nul;
     }
 }
@@ -185,8 +187,9 @@ __global__ void ba_pack_kernel(PackArgs a) {
     const uint64_t len = which ? a.raw_r_off[k + 1] - a.raw_r_off[k] : a.raw_q_off[k + 1] - a.raw_q_off[k];
     uint8_t* dst = a.seq + (which ? a.pr_off[k] : a.pq_off[k]);
     if (lane == 0) dst[0] = nul;
+    const bool rev = which ? a.rev_r != 0 : a.rev_q != 0;
     for (uint64_t t = lane; t < len; t += 32) {
-      uint8_t c = src[t];
+      uint8_t c = src[rev ? len - 1 - t : t];
       if (a.scoring != kByte) {
         if (c >= 'a' && c <= 'z') c -= 32;                      // to_ascii_uppercase
         if (a.scoring == kNuc) { if (!(c >= 'A' && c <= 'Z')) bad = true; }          // scores.rs:212-216
@@ -516,7 +519,8 @@ extern "C" void ba_batch_free(BaBatch* b) {
 static int check_config(const BaConfig* cfg, uint32_t* mn, uint32_t* mx) {
   if (!cfg) return fail(BA_ERR_ARG, "cfg is null");
   if (cfg->scoring < 0 || cfg->scoring > 3) return fail(BA_ERR_ARG, "bad scoring kind");
-  if (cfg->flags & ~(BA_TRACE | BA_XDROP | BA_LOCAL_START | BA_FREE_QUERY_START_GAPS | BA_FREE_QUERY_END_GAPS)) return fail(BA_ERR_ARG, "unsupported flags");
+  if (cfg->flags & ~(BA_TRACE | BA_XDROP | BA_LOCAL_START | BA_FREE_QUERY_START_GAPS | BA_FREE_QUERY_END_GAPS | BA_REV_QUERY | BA_REV_REFERENCE))
+    return fail(BA_ERR_ARG, "unsupported flags");
   if ((cfg->flags & BA_XDROP) && (cfg->flags & BA_FREE_QUERY_END_GAPS))
     return fail(BA_ERR_ARG, "Cannot set both X_DROP and FREE_QUERY_END_GAPS!");   // scan_block.rs:861
   if ((cfg->flags & BA_LOCAL_START) && (cfg->flags & BA_FREE_QUERY_START_GAPS))
@@ -765,6 +769,7 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
   pa.raw_q = d_rawq; pa.raw_q_off = d_rawqoff; pa.raw_r = d_rawr; pa.raw_r_off = d_rawroff;
   pa.seq = b->d_seq; pa.pq_off = b->d_qoff; pa.pr_off = b->d_roff; pa.n = (uint32_t)n; pa.pad = pad;
   pa.scoring = prof ? (int)kAA : cfg->scoring; pa.err = d_err;
+  pa.rev_q = (cfg->flags & BA_REV_QUERY) ? 1u : 0u; pa.rev_r = (cfg->flags & BA_REV_REFERENCE) ? 1u : 0u;
   if (n) {
 #ifdef BA_EMU
     pack_all(pa);

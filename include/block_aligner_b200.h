@@ -124,7 +124,11 @@ enum { BA_SCORING_NUC = 0, BA_SCORING_AA = 1, BA_SCORING_BYTE = 2, BA_SCORING_PR
 /* Block<TRACE, X_DROP, LOCAL_START, FREE_QUERY_START_GAPS, FREE_QUERY_END_GAPS> const generics
  * (src/scan_block.rs:89) as flags. BA_FREE_QUERY_END_GAPS: min block size <= 256 (and, as in the reference, larger
  * than every query and not combined with BA_XDROP). */
-enum { BA_TRACE = 1, BA_XDROP = 2, BA_LOCAL_START = 4, BA_FREE_QUERY_START_GAPS = 8, BA_FREE_QUERY_END_GAPS = 16 };
+enum { BA_TRACE = 1, BA_XDROP = 2, BA_LOCAL_START = 4, BA_FREE_QUERY_START_GAPS = 8, BA_FREE_QUERY_END_GAPS = 16,
+       /* PaddedBytes::set_bytes_rev (src/scan_block.rs:1815-1822) for the whole batch: the queries / references are
+        * reversed while they are converted and padded on the device (reverse-extension pipelines; with BaPssmBatch.rev
+        * for the profile side) */
+       BA_REV_QUERY = 32, BA_REV_REFERENCE = 64 };
 
 typedef struct BaAligner BaAligner; /* one per GPU: stream + reusable device scratch */
 typedef struct BaBatch BaBatch;     /* one uploaded batch: device-resident inputs and outputs */

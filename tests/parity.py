@@ -200,3 +200,24 @@ def check_pssm(lib, al, n, seed, rev, shifts, uniform_gaps, size=(32, 128), flag
     got = run_lib(lib, al, api.SCORING_PROFILE, None, None, size, w["x_drop"], flags, False, qa, qo, ra, ro, pb)
     exp = oracle_batch(api.SCORING_PROFILE, None, None, size, w["x_drop"], flags, False, qa, qo, ra, ro, ops)
     return compare("pssm", got, exp)
+
+
+def check_reversed(lib, al, n, rev, seed=5):
+    """Library with BA_REV_* flags on the original inputs vs the oracle on inputs reversed on the host."""
+    w = workloads.WORKLOADS["C2_nanopore_xdrop_10k"]
+    gen = workloads.params(alphabet=0, len_dist=0, len_min=200, len_max=1500, sub_rate=0.05, ins_rate=0.04, del_rate=0.04,
+                           long_indel_mean=1.0, long_indel_len=40.0, suffix_len=100)
+    qa, qo, ra, ro = workloads.generate(gen, n, seed=seed, stream=2)
+
+    def reversed_arena(a, off):
+        out = a.copy()
+        for k in range(len(off) - 1):
+            out[int(off[k]):int(off[k + 1])] = a[int(off[k]):int(off[k + 1])][::-1]
+        return out
+    qh = reversed_arena(qa, qo) if rev & api.REV_QUERY else qa
+    rh = reversed_arena(ra, ro) if rev & api.REV_REFERENCE else ra
+    m = workloads.matrix_of(lib, w)
+    flags = api.XDROP | api.TRACE
+    got = run_lib(lib, al, w["scoring"], m, w["gaps"], (32, 256), 50, flags | rev, True, qa, qo, ra, ro)
+    exp = oracle_batch(w["scoring"], m, w["gaps"], (32, 256), 50, flags, True, qh, qo, rh, ro)
+    return compare(f"rev{rev}", got, exp)

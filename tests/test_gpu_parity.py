@@ -273,3 +273,9 @@ def test_trace_pool_exhaustion_falls_back_to_retry(env, monkeypatch):
     assert got[3].kernel_launches == 2
     exp = parity.oracle_batch(w["scoring"], m, w["gaps"], w["size"], 0, api.TRACE, True, qa, qo, ra, ro)
     assert parity.compare("pool-exhausted", got, exp) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rev", [api.REV_QUERY, api.REV_REFERENCE, api.REV_QUERY | api.REV_REFERENCE])
+def test_reverse_on_device_matches_host_reversed_inputs(env, rev):
+    assert parity.check_reversed(*env, 300, rev) == 0
