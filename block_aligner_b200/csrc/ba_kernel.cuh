@@ -998,6 +998,13 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast
   sc.init(w.smem0, P);
   sc.rows(*(const uint32_t*)(vec + vec_base + 4 * lg), *(const uint32_t*)(vec + vec_base + 4 * G + 4 * lg));
   const uint2 cw = *(const uint2*)(col + col_base);
+  // (Tried: touching the next 128-byte line of both sequences every step so that the token loads never leave L1 --
+  // 89 % of the kernel's long-scoreboard samples sit at the first use of cw. Measured on B200 it costs 10 % on C2
+  // (1156 -> 1042 GCUPS) and 16 % on C3: the extra loads hurt more than the misses they hide. BA_SEQ_PREFETCH re-enables.)
+#ifdef BA_SEQ_PREFETCH
+  if (lg == 0) wp::touch(vec + vec_base + B + 128);
+  if (lg == 1) wp::touch(col + col_base + kStep + 128);
+#endif
 
   uint32_t D[4], C[4], m[4], mc[kMcN] = {};
 #pragma unroll

@@ -214,8 +214,13 @@ __global__ void ba_profile_build_kernel(ProfBuildArgs a) {
 #ifndef BA_LB_BLOCKS
 #define BA_LB_BLOCKS 4
 #endif
+// TRACE kernels carry the trace-word accumulators on top of everything else: at 128 registers ptxas spills 390 bytes
+// per thread (local-memory round trips inside the column loop); BA_LB_BLOCKS_TRACE = 3 gives them 168.
+#ifndef BA_LB_BLOCKS_TRACE
+#define BA_LB_BLOCKS_TRACE BA_LB_BLOCKS
+#endif
 template <int SCORING, int FLAGS, int FR>
-__global__ void __launch_bounds__(128, BA_LB_BLOCKS) ba_align_kernel(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(128, (FLAGS & kTrace) ? BA_LB_BLOCKS_TRACE : BA_LB_BLOCKS) ba_align_kernel(const __grid_constant__ Params P) {
   extern __shared__ __align__(16) unsigned char ba_smem[];
   const int nm = SCORING == kNuc ? 128 : (SCORING == kAA ? 864 : 0);
   for (int i = threadIdx.x; i < nm; i += blockDim.x) ba_smem[i] = (unsigned char)P.matrix[i];
@@ -615,7 +620,7 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
     for (size_t i = 0; i < nb; i++) { uint32_t c = cnt[i]; cnt[i] = run; run += c; }
     for (size_t k = 0; k < n; k++) order[cnt[nb - 1 - (((uint64_t)ql[k] + rl[k]) >> SH)]++] = (uint32_t)k;
   }
-  const uint64_t seq_bytes = pos + 64;
+  const uint64_t seq_bytes = pos + 512;   // slack: the fast phase touches up to B + 136 bytes past the position it reads (pk_fast_step)
   const auto tu1 = std::chrono::steady_clock::now();
 
   const uint64_t qraw = n ? q_off[n] - q_off[0] : 0;
