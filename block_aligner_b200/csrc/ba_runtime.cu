@@ -1307,6 +1307,7 @@ extern "C" int ba_align_batch_pssm(BaAligner* a, const BaConfig* cfg, size_t n, 
 }
 static int align_uploaded_profiles(BaBatch* b, size_t n, AlignResult* out, BaStats* stats) {
   int rc = ba_batch_run(b, stats);
+  if (!rc && stats && n) stats->kernel_launches += 2;   // convert/pad + profile build kernels of the upload
   if (!rc) rc = ba_batch_download(b, out);
   if (!rc && stats) {
     for (size_t k = 0; k < n; k++) { stats->cells += b->h_out[k].cells; stats->steps += b->h_out[k].steps; if (b->h_out[k].status) stats->n_failed++; }
