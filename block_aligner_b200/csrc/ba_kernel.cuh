@@ -462,8 +462,8 @@ BA_HD uint64_t rect_words(int H, int W, int layout = 0) {
 // the same way. A rectangle that does not fit the slot's own arena is placed in the batch-wide overflow pool
 // (bit 3 of Rect::right, word_off in units of 16 words): slot arenas are sized for the common path, and the few
 // alignments that sit at large block sizes for long borrow from the pool instead of being re-run.
-// Called by all 32 lanes; `want`: this lane's alignment really pushes (fast phase: groups of GW lanes decide
-// independently), `writer`: the lane that stores the record.
+// Called by all 32 lanes of a warp that services one alignment (generic phase); `writer`: the lane that stores the
+// record.
 constexpr uint32_t kRectPool = 8u;
 BA_DEV uint32_t* trace_push(const Params& P, AlnState& st, const SlotMem& sm, uint32_t row, uint32_t col, int W, int H, bool right,
                             bool writer, int layout = 0, bool want = true, int GW = 32) {
@@ -489,6 +489,28 @@ BA_DEV uint32_t* trace_push(const Params& P, AlnState& st, const SlotMem& sm, ui
   if (writer) sm.rects[st.ridx] = r;
   st.ridx += 1;
   return p;
+}
+// Fast-phase variant: the slot's own arena only, no pool (the atomic + shuffle of the pool path in the middle of the
+// step cost 1000 bytes of extra register spills per thread). A group whose arena cannot take another step is parked
+// first (trace_room) and finishes in the generic phase, which can use the pool.
+BA_DEV uint32_t* trace_push_local(AlnState& st, const SlotMem& sm, uint32_t row, uint32_t col, int W, int H, bool right, bool writer, int layout) {
+  const uint64_t need = rect_words(H, W, layout);
+  if (st.ridx >= sm.rects_cap || (uint64_t)st.widx + need > sm.words_cap || ((uint64_t)st.widx + need) >> 32) {
+    st.overflow = 1u;
+    return sm.words;
+  }
+  if (writer) {
+    Rect r; r.row = row; r.col = col; r.h = (uint16_t)H; r.w = (uint16_t)W; r.right = (right ? 1u : 0u) | ((uint32_t)layout << 1); r.word_off = st.widx;
+    sm.rects[st.ridx] = r;
+  }
+  uint32_t* p = sm.words + st.widx;
+  st.widx += (uint32_t)need;
+  st.ridx += 1;
+  return p;
+}
+// room for one more fast-phase step (B rows x 8 columns, layout 3: B words, one record) in the slot's own arena
+BA_DEV bool trace_room(const AlnState& st, uint64_t words_cap, uint32_t rects_cap, int B) {
+  return (uint64_t)st.widx + (uint64_t)B <= words_cap && st.ridx < rects_cap;
 }
 BA_DEV const uint32_t* rect_words_ptr(const uint32_t* words, const uint32_t* pool, const Rect& rc) {
   return (rc.right & kRectPool) ? pool + (size_t)rc.word_off * 16 : words + rc.word_off;
@@ -721,7 +743,8 @@ BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const Sl
   const int min_size = (int)P.min_size, max_size = (int)P.max_size;
 
   for (;;) {
-    if (fast_eligible<SCORING, XDROP>(P, st) && (!P.pk_fast || pk_borders_ok(P, st, w))) return kRunFast;
+    if (fast_eligible<SCORING, XDROP>(P, st) && (!TRACE || trace_room(st, sm.words_cap, sm.rects_cap, st.B)) &&
+        (!P.pk_fast || pk_borders_ok(P, st, w))) return kRunFast;
     const int prev_off = st.off;
     int bv = 0, gbv = 0; unsigned bkey = 15u << 27, gbkey = 15u << 27;
     int right_max, down_max;
@@ -974,7 +997,17 @@ BA_DEV void pk_fast_spill(const PkFast& f, const WarpMem& w, int dir, bool mine)
 
 template <int SCORING, int FLAGS, int LGT>
 BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast& f, int& status,
-                         const uint8_t* qp, const uint8_t* rp, const SlotMem& sm) {
+                         const uint8_t* qp, const uint8_t* rp, uint32_t my_slot) {
+  // The slot's trace arena and rectangle stack are recomputed from the slot index where they are needed: carried
+  // across the loop they are 11 more live registers in kernels that already spill (TRACE, 128-register cap).
+  SlotMem sm;
+  sm.kDc = sm.kCc = sm.kDr = sm.kRr = nullptr; sm.words = nullptr; sm.words_cap = 0; sm.zwords = nullptr; sm.rects = nullptr; sm.rects_cap = 0;
+  if ((FLAGS & kTrace) != 0) {
+    sm.words = P.trace_words + (size_t)my_slot * P.trace_words_per_warp;
+    sm.words_cap = P.trace_words_per_warp;
+    sm.rects = P.rects + (size_t)my_slot * P.rects_per_warp;
+    sm.rects_cap = P.rects_per_warp;
+  }
   constexpr bool XDROP = (FLAGS & kXDrop) != 0, TRACE = (FLAGS & kTrace) != 0;
   constexpr int KIND = (SCORING == kProfile) ? kAA : SCORING;
   constexpr int G = 1 << LGT;
@@ -1011,7 +1044,7 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast
   for (int k = 0; k < 4; k++) { D[k] = wp::vadd2(f.aD[k], oa2); C[k] = wp::vadd2(f.aC[k], oa2); m[k] = 0u; }
   uint32_t* fr = w.fr + grp * 8;
   uint32_t* tw = nullptr;
-  if (TRACE) tw = trace_push(P, st, sm, right ? si : si + (B - kStep), right ? sj + (B - kStep) : sj, kStep, B, right, lg == 0, 3, active, G);
+  if (TRACE && active) tw = trace_push_local(st, sm, right ? si : si + (B - kStep), right ? sj + (B - kStep) : sj, kStep, B, right, lg == 0, 3);
   pk_cols8<KIND, XDROP, LGT, TRACE>(sc, P.kc, LGT, lg, cw.x, cw.y, D, C, (uint32_t)corner & 0xffffu, 0, m, mc, fr, lg == G - 1, tw, TRACE && active);
   wp::syncwarp();
 
@@ -1114,6 +1147,7 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast
       else if (down_max > right_max) { st.si = si + kStep; st.dir = kDown; }
       else { st.sj = sj + kStep; st.dir = kRight; }
       if (nstatus == kStFast && !fast_eligible<SCORING, XDROP>(P, st)) nstatus = kStNeedGeneric;
+      if (TRACE && nstatus == kStFast && !trace_room(st, sm.words_cap, sm.rects_cap, B)) nstatus = kStNeedGeneric;
     }
     status = nstatus;
   }
@@ -1230,8 +1264,7 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
   int status = kStEmpty;
   const uint8_t* qp = P.seq;
   const uint8_t* rp = P.seq;
-  SlotMem my_sm;
-  { WarpMem tmpw = w; bind_slot(P, warp_global * spw + ((uint32_t)my_g < spw ? my_g : 0), tmpw, my_sm, TRACE); }
+  const uint32_t my_slot = warp_global * spw + ((uint32_t)my_g < spw ? (uint32_t)my_g : 0u);
   bool tickets_left = true;
 
   for (;;) {
@@ -1280,7 +1313,7 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
     if (wp::ballot(status == kStFast) == 0u) break;
     // ---- fast phase: run until some group needs the generic phase ----
     for (;;) {
-      if (PKF) pk_fast_step<SCORING, FLAGS, LGT>(P, w, st, pf, status, qp, rp, my_sm);
+      if (PKF) pk_fast_step<SCORING, FLAGS, LGT>(P, w, st, pf, status, qp, rp, my_slot);
       else break;
       if (wp::ballot(status != kStFast && status != kStEmpty) != 0u) break;
       if (wp::ballot(status == kStFast) == 0u) break;
