@@ -410,7 +410,7 @@ struct BaBatch {
   // scratch of the overflow retry (worst-case trace arenas for the few alignments that did not fit the first-pass
   // arenas); kept until the next launch / free so that the trace of a retried pair can still be walked
   uint32_t* r_trace = nullptr; uint32_t* r_zwords = nullptr; Rect* r_rects = nullptr; int16_t* r_ckpt = nullptr; uint32_t* r_runs = nullptr;
-  bool retried = false;
+  bool retried = false; bool arena_forced = false;
   uint32_t rects_bound = 0;         // worst-case rectangle records per alignment
   int kflags = 0;                   // template FLAGS of the kernel: (flags & 3) | kExt
   int pk_smax = 0; uint32_t pk_enable = 0;   // packed 2 x i16 path (ba_packed.cuh): largest matrix entry, on/off
@@ -852,6 +852,12 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
     uint64_t first = 2 * len * (uint64_t)std::max<uint32_t>(mn, 32) / 8 + (uint64_t)mx * mx / 4 + 4096;
     if (getenv("BA_TRACE_WORST_CASE") || (cfg->flags & BA_FREE_QUERY_END_GAPS)) first = b->trace_words_bound;
     b->trace_words_per_warp = std::min<uint64_t>(b->trace_words_bound, first);
+    bool arena_forced = false;
+    if (const char* e = getenv("BA_TRACE_ARENA_WORDS")) {   // tests: tiny slot arenas exercise the pool / parking paths
+      b->trace_words_per_warp = std::min<uint64_t>(b->trace_words_bound, std::max<uint64_t>(64, (uint64_t)atoll(e)));
+      arena_forced = true;
+    }
+    b->arena_forced = arena_forced;
     // one record per step (len / 8 shift steps; grow retries pop theirs again): the first pass gets twice that
     b->rects_bound = (uint32_t)std::min<uint64_t>(len * 2 + 8, 0x7fffffffu);
     b->rects_per_warp = b->trace_words_per_warp < b->trace_words_bound ? (uint32_t)std::min<uint64_t>(len / 4 + 1024, b->rects_bound) : b->rects_bound;
@@ -879,7 +885,7 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
   b->blocks = (int)std::min<uint64_t>(want, max_blocks);
   const uint64_t nwarps = (uint64_t)b->blocks * wpb;
   const uint64_t nslots = nwarps * spw;
-  if (trace && b->trace_words_per_warp < b->trace_words_bound) {
+  if (trace && b->trace_words_per_warp < b->trace_words_bound && !b->arena_forced) {
     // The retry pass of an overflowed alignment runs almost alone on the GPU (measured on C5: one retried 50 kbp pair
     // costs 90 ms), so once the number of slots is fixed the first-pass arenas take what is left of the budget, up to
     // twice the initial estimate (4x the all-minimum-size path).

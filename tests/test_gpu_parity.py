@@ -279,3 +279,20 @@ def test_trace_pool_exhaustion_falls_back_to_retry(env, monkeypatch):
 @pytest.mark.parametrize("rev", [api.REV_QUERY, api.REV_REFERENCE, api.REV_QUERY | api.REV_REFERENCE])
 def test_reverse_on_device_matches_host_reversed_inputs(env, rev):
     assert parity.check_reversed(*env, 300, rev) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size", [(32, 256), (64, 2048)])
+def test_full_slot_arena_parks_fast_phase_and_spills_to_pool(env, size, monkeypatch):
+    """Slot arenas far too small for the path: the fast phase parks the group when its arena cannot take another step
+    and the generic phase continues with rectangles from the overflow pool. Bit-exact, no retry launch."""
+    lib, al = env
+    monkeypatch.setenv("BA_TRACE_ARENA_WORDS", "4096")
+    w = dict(scoring=api.SCORING_NUC, matrix="NW1", gaps=(-2, -1), size=size, x_drop=80, flags=api.TRACE | api.XDROP, stream=51,
+             gen=P(alphabet=0, len_dist=0, len_min=300, len_max=3000, suffix_len=100, **NOISY))
+    qa, qo, ra, ro = workloads.generate(w["gen"], 300, stream=51)
+    m = workloads.matrix_of(lib, w)
+    got = parity.run_lib(lib, al, w["scoring"], m, w["gaps"], size, 80, w["flags"], True, qa, qo, ra, ro)
+    assert got[3].kernel_launches == 1
+    exp = parity.oracle_batch(w["scoring"], m, w["gaps"], size, 80, w["flags"], True, qa, qo, ra, ro)
+    assert parity.compare("tiny-arena", got, exp) == 0
