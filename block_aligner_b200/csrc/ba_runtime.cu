@@ -556,7 +556,9 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
   uint32_t mn = 0, mx = 0;
   int rc = check_config(cfg, &mn, &mx);
   if (rc) return rc;
-  if (mn > mx && false) return fail(BA_ERR_SIZE, "min > max");
+  // The reference does not check min <= max (its scratch is sized by max, so min > max walks off the end of it); here
+  // that is an argument error.
+  if (mn > mx) return fail(BA_ERR_SIZE, "min block size is larger than max block size");
   const bool prof = cfg->scoring == BA_SCORING_PROFILE;
   if (prof != (profiles != nullptr || pssm != nullptr)) return fail(BA_ERR_ARG, "profiles must be given exactly for BA_SCORING_PROFILE");
   if (pssm) {

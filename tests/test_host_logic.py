@@ -32,6 +32,8 @@ def test_argument_rules(env):
         _run(al, b"ACGT", b"ACGT", x_drop=-1, flags=api.XDROP)
     with pytest.raises(api.BlockAlignerError, match="8192"):
         _run(al, b"ACGT", b"ACGT", size=(32, 16384))
+    with pytest.raises(api.BlockAlignerError, match="larger than max"):      # our rule: the reference walks off its scratch here
+        _run(al, b"ACGT", b"ACGT", size=(64, 32))
     assert _run(al, b"ACGT", b"ACGT", size=(4, 8)) == (4, 4, 4)     # sizes below L are clamped up to 16
 
 
