@@ -32,6 +32,22 @@ def test_example_links_against_product_library():
     assert os.path.exists(EXE)
 
 
+def test_batch_example_on_emulated_library(tmp_path):
+    """examples/batch_example.c (Part 2: ba_align_batch_cigar) against the emulated library: the doc-test pair of the
+    reference (src/lib.rs:8-35) and a golden pair of src/scan_block.rs:2085-2094 come out right."""
+    import backend
+    backend.emu_lib()
+    exe = str(tmp_path / "batch_example")
+    emu = os.path.join(ROOT, "tests", "emu")
+    subprocess.check_call(["gcc", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "batch_example.c"),
+                           "-o", exe, "-L", emu, "-lba_emu", f"-Wl,-rpath,{emu}"])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().split("\n")
+    assert lines[0] == "pair 0: score=7 idx=(24,21) cigar=2=6I16=3D"
+    assert lines[1] == "pair 1: score=8 idx=(16,13) cigar=9=2I4=1I"
+
+
 def test_reference_example_links_unchanged(tmp_path):
     ref = "/root/reference/c"
     if not os.path.exists(os.path.join(ref, "example.c")):
