@@ -176,3 +176,32 @@ def test_argument_rules():
         Block(10, 10, 48, 0)                                       # scan_block.rs:799
     # sizes below L are clamped up to 16 (scan_block.rs:853-854)
     assert a.align(q, q, NUC, ora.nw1(), (-2, -1), (4, 8), 0) == (4, 4, 4)
+
+
+def test_golden_fixture_file_matches_and_oracle_reproduces_it():
+    """tests/golden/reference_unit_tests.json (made by tests/golden/make_golden.py) is in step with golden_cases.py,
+    and the oracle reproduces every vector in it when driven from the file alone."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_unit_tests.json")
+    doc = json.load(open(path))
+    import golden_cases as G
+    assert len(doc["cases"]) == len(G.SEQ_CASES)
+    kinds = {"AAMatrix": ora.AA, "NucMatrix": ora.NUC, "ByteMatrix": ora.BYTE}
+    for c in doc["cases"]:
+        kind = kinds[c["matrix_kind"]]
+        if c["matrix"] == "NW1":
+            m = ora.nw1()
+        elif c["matrix"] == "BYTES1":
+            m = np.array([1, -1], dtype=np.int8)
+        elif isinstance(c["matrix"], str):
+            m = ora.builtin(c["matrix"])
+        else:
+            m = ora.nuc_matrix(*c["matrix"])
+        pad = c["size"][1]
+        q, r = ora.Padded(kind, c["query"].encode(), pad), ora.Padded(kind, c["reference"].encode(), pad)
+        b = ora.Block(len(q), len(r), pad, (ora.TRACE if c["trace"] else 0) | (ora.XDROP if c["x_drop_mode"] else 0))
+        res = b.align(q, r, kind, m, tuple(c["gaps"]), tuple(c["size"]), c["x_drop"])
+        assert res == (c["score"], c["query_idx"], c["reference_idx"]), c
+        if c["cigar"] is not None:
+            assert b.cigar(res[1], res[2], c["cigar_eq"]) == c["cigar"], c
