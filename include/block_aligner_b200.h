@@ -130,7 +130,9 @@ enum { BA_TRACE = 1, BA_XDROP = 2, BA_LOCAL_START = 4, BA_FREE_QUERY_START_GAPS 
         * for the profile side) */
        BA_REV_QUERY = 32, BA_REV_REFERENCE = 64 };
 
-typedef struct BaAligner BaAligner; /* one per GPU: stream + reusable device scratch */
+typedef struct BaAligner BaAligner; /* one per GPU: streams + reusable device scratch. Not thread-safe: calls on one
+                                      * BaAligner (and its batches) must come from one host thread at a time, like a
+                                      * reference Block (src/scan_block.rs:1716: raw pointers, neither Send nor Sync) */
 typedef struct BaBatch BaBatch;     /* one uploaded batch: device-resident inputs and outputs */
 
 typedef struct BaConfig {
