@@ -179,7 +179,39 @@ static void test_doc_example_and_helpers() {     // lib.rs:8-35, lib.rs:109-111,
   CHECK(cigs[0] == "2=6I16=3D" && cigs[1] == "9=2I4=1I");
 }
 
+static void test_containers() {          // scan_block.rs:1807-1822, scores.rs:48-106, 150-183, 532-538
+  auto fwd = PaddedBytes::from_bytes<NucMatrix>("TTGCA", 16);
+  auto rev = PaddedBytes::new_<NucMatrix>(5, 16);
+  rev.set_bytes_rev<NucMatrix>("ACGTT", 16);
+  bool same = fwd.len() == rev.len();
+  for (size_t i = 0; i <= fwd.len() + 16 && same; i++) same = fwd.get(i) == rev.get(i);
+  CHECK(same);
+  CHECK(fwd.get(0) == 'Z' && fwd.get(6) == 'Z');
+  auto aa = PaddedBytes::from_bytes<AAMatrix>("arn", 16);          // lower case is upper-cased, stored as c - 'A'
+  CHECK(aa.get(0) == 26 && aa.get(1) == 0 && aa.get(2) == 17 && aa.get(3) == 13);
+  AAMatrix m = AAMatrix::new_simple(3, -2);
+  CHECK(m.get('A', 'A') == 3 && m.get('A', 'R') == -2);
+  m.set('A', 'R', 7);
+  CHECK(m.get('R', 'A') == 7 && m.get('a', 'r') == 7);
+  CHECK(BLOSUM62().get('A', 'A') == 4 && BLOSUM62().get('W', 'W') == 11 && BLOSUM62().get('A', 'R') == -1);
+  NucMatrix n = NucMatrix::new_simple(2, -3);
+  CHECK(n.get('A', 'A') == 2 && n.get('A', 'C') == -3 && NW1().get('G', 'G') == 1 && NW1().get('G', 'T') == -1);
+  AAProfile p(3, 16, -1);
+  p.set_all("AR", {1, 2, 3, 4, 5, 6});
+  CHECK(p.len() == 3 && p.get(1, 'A') == 1 && p.get(1, 'R') == 2 && p.get(3, 'R') == 6 && p.get(2, 'N') == -128);
+  p.set_all_rev("AR", {1, 2, 3, 4, 5, 6});
+  CHECK(p.get(3, 'A') == 1 && p.get(1, 'R') == 6 && p.get_gap_extend() == -1);
+  // a profile built from the same numbers as a sequence aligns like the sequence (scan_block.rs:2122-2127)
+  Block<false, false> a(100, 100, 16);
+  auto q = PaddedBytes::from_bytes<AAMatrix>("AAAA", 16);
+  auto prof = AAProfile::from_bytes("AAAA", 16, 1, -1, -1, 0, -1, -1);
+  a.align_profile(q, prof, {16, 16}, 0);
+  CHECK(a.res().score == 4);
+  CHECK(a.align_profile_exp(q, prof, {16, 16}, 0, 4).has_value());
+}
+
 int main() {
+  test_containers();
   test_no_x_drop();
   test_x_drop();
   test_trace();
