@@ -89,7 +89,7 @@ PART1_FUNCTIONS = (
     + list(_CIGAR_FN.values()) + list(_CIGAR_EQ_FN.values()))
 PART1_DATA = ["NW1", "BLOSUM45", "BLOSUM50", "BLOSUM62", "BLOSUM80", "BLOSUM90", "PAM100", "PAM120", "PAM160",
               "PAM200", "PAM250", "BYTES1"]
-PART2_FUNCTIONS = ["ba_error_string", "ba_last_error_message", "ba_create", "ba_destroy", "ba_batch_upload",
+PART2_FUNCTIONS = ["ba_error_string", "ba_last_error_message", "ba_create", "ba_destroy", "ba_trim", "ba_batch_upload",
                    "ba_batch_upload_profiles", "ba_batch_upload_pssm", "ba_align_batch_pssm", "ba_batch_run", "ba_batch_download", "ba_batch_cigar",
                    "ba_batch_traceback", "ba_batch_total_stats", "ba_batch_pair_stats", "ba_batch_free",
                    "ba_align_batch", "ba_align_batch_cigar", "ba_align_batch_exp", "ba_align_batch_profiles", "ba_new_simple_nucmatrix", "ba_set_nucmatrix", "ba_free_nucmatrix",
@@ -113,6 +113,7 @@ class Library:
         L.ba_last_error_message.restype = C.c_char_p
         L.ba_create.argtypes = [C.c_int, C.POINTER(vp)]
         L.ba_destroy.argtypes = [vp]
+        L.ba_trim.argtypes = [vp]
         L.ba_batch_upload.argtypes = [vp, C.POINTER(BaConfig), sz, vp, vp, vp, vp, C.POINTER(vp)]
         L.ba_batch_upload_profiles.argtypes = [vp, C.POINTER(BaConfig), sz, vp, vp, vp, C.POINTER(vp)]
         L.ba_batch_run.argtypes = [vp, C.POINTER(BaStats)]

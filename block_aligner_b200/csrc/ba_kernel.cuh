@@ -934,7 +934,8 @@ BA_DEV void finish_alignment(const Params& P, const AlnState& st, const WarpMem&
     else sv = (int)w.Dr[st.rlen - st.sj];
     res.score = st.off + sv - kZero; res.query_idx = st.qlen; res.reference_idx = st.rlen;
   }
-  res.rect_n = st.ridx; res.warp = slot;
+  res.rect_n = st.ridx; res.warp = slot | P.retry_bit;
+  if (TRACE && P.slot_pair && lane == 0) P.slot_pair[slot] = st.pair;
   if (TRACE && !st.overflow && P.cigar_stream) {
     const uint8_t* q = P.seq + P.q_off[st.pair];
     const uint8_t* r = (SCORING == kProfile) ? nullptr : P.seq + P.r_off[st.pair];
@@ -1325,7 +1326,12 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
 // the trace of pair `pair` is still in the arena of the slot that aligned it.
 BA_DEV void warp_traceback(const Params& P, const uint8_t* lut, uint32_t pair, uint32_t qi, uint32_t rj, bool eq, DevResult* out1) {
   DevResult res = P.out[pair];
-  const uint32_t slot = res.warp;
+  const uint32_t slot = res.warp & ~kRetrySlotBit;
+  if (P.slot_pair && P.slot_pair[slot] != pair) {     // a later pair of the batch has reused the slot's arena
+    res.status = (uint32_t)kTraceGone; res.cigar_n = 0;
+    if (wp::lane_id() == 0) *out1 = res;
+    return;
+  }
   const uint32_t* words = P.trace_words + (size_t)slot * P.trace_words_per_warp;
   const Rect* rects = P.rects + (size_t)slot * P.rects_per_warp;
   uint32_t* runs = P.run_scratch;   // single-warp launch: warp 0's scratch

@@ -11,47 +11,20 @@
 #include <string.h>
 #include <algorithm>
 #include <chrono>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include "../../include/block_aligner_b200.h"
 #include "ba_host.h"
+#include "ba_dev.h"
 #include "ba_kernel.cuh"
 
 using namespace ba;
 
-// -------------------------------------------------------------------------------------------------
-// device abstraction
-// -------------------------------------------------------------------------------------------------
-static thread_local std::string g_last_error;
-static int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
-
-#ifdef BA_EMU
-typedef int dev_stream_t;
-static int dmalloc(void** p, size_t n) { *p = malloc(n ? n : 1); if (!*p) return 1; memset(*p, 0xCD, n); return 0; }
-static void dfree(void* p) { free(p); }
-static int h2d(void* d, const void* s, size_t n, dev_stream_t) { if (n) memcpy(d, s, n); return 0; }
-static int d2h(void* d, const void* s, size_t n, dev_stream_t) { if (n) memcpy(d, s, n); return 0; }
-static int dzero(void* d, size_t n, dev_stream_t) { if (n) memset(d, 0, n); return 0; }
-static int dsync(dev_stream_t) { return 0; }
-#define CUDA_OK(x) (x)
-#else
-#include <cuda_runtime.h>
-typedef cudaStream_t dev_stream_t;
-static int cuda_fail(cudaError_t e, const char* what) {
-  g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
-  return 1;
-}
-#define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return cuda_fail(_e, #x); } while (0)
-static int dmalloc(void** p, size_t n) { CK(cudaMalloc(p, n ? n : 1)); return 0; }
-static void dfree(void* p) { if (p) cudaFree(p); }
-static int h2d(void* d, const void* s, size_t n, dev_stream_t st) { if (n) CK(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, st)); return 0; }
-static int d2h(void* d, const void* s, size_t n, dev_stream_t st) { if (n) CK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, st)); return 0; }
-static int dzero(void* d, size_t n, dev_stream_t st) { if (n) CK(cudaMemsetAsync(d, 0, n, st)); return 0; }
-static int dsync(dev_stream_t st) { CK(cudaStreamSynchronize(st)); return 0; }
-#define CUDA_OK(x) (x)
-#endif
+namespace ba { std::string& last_error_ref() { static thread_local std::string e; return e; } }
+#define g_last_error (ba::last_error_ref())
 
 // -------------------------------------------------------------------------------------------------
 // kernels
@@ -138,12 +111,6 @@ static void pack_all(const PackArgs& a) {
       for (uint32_t t = 0; t < a.pad; t++) dst[1 + len + t] = nul;
     }
 }
-struct EmuLaunch { const Params* P; unsigned char* smem; uint32_t wg; };
-template <int SCORING, int FLAGS, int FR>
-static void emu_warp_entry(void* arg) {
-  auto* l = (EmuLaunch*)arg;
-  warp_main<SCORING, FLAGS, FR>(*l->P, l->smem, 0, l->wg);
-}
 struct EmuTb { const Params* P; uint32_t pair, qi, rj; int eq; DevResult* out1; };
 static void emu_tb_entry(void* arg) {
   auto* t = (EmuTb*)arg;
@@ -154,22 +121,6 @@ static void emu_tb_entry(void* arg) {
 static int launch_traceback(const Params& P, uint32_t pair, uint32_t qi, uint32_t rj, int eq, DevResult* out1, dev_stream_t) {
   EmuTb t{&P, pair, qi, rj, eq, out1};
   emu::run_warp(&emu_tb_entry, &t);
-  return 0;
-}
-template <int SCORING, int FLAGS, int FR>
-static int launch_align(const Params& P, int blocks, int wpb, size_t smem_bytes, dev_stream_t) {
-  (void)wpb;
-  for (int b = 0; b < blocks; b++) {
-    std::vector<unsigned char> smem(smem_bytes + 64, 0xAB);
-    const int nm = SCORING == kNuc ? 128 : (SCORING == kAA ? 864 : 0);
-    for (int i = 0; i < nm; i++) smem[i] = (unsigned char)P.matrix[i];
-    stage_tables<SCORING>(smem.data(), 0, 1);
-    EmuLaunch l{&P, smem.data(), (uint32_t)b};
-    emu::run_warp(&emu_warp_entry<SCORING, FLAGS, FR>, &l);
-    // guard: the device code must stay inside the shared memory it was given
-    for (size_t i = smem_bytes; i < smem_bytes + 64; i++)
-      if (smem[i] != 0xAB) { fprintf(stderr, "emu: shared memory overrun at byte %zu (limit %zu)\n", i, smem_bytes); abort(); }
-  }
   return 0;
 }
 #else
@@ -209,28 +160,6 @@ __global__ void ba_profile_build_kernel(ProfBuildArgs a) {
   if (bad) atomicOr(a.err, 1u);
 }
 
-// 128 threads per block, at least 4 blocks per SM: caps the kernel at 128 registers/thread. Measured on
-// B200 (C2 workload): uncapped (207 regs, 8 warps/SM) 476 GCUPS, 160 regs 580, 128 regs 634, 96 regs 596.
-#ifndef BA_LB_BLOCKS
-#define BA_LB_BLOCKS 4
-#endif
-// TRACE kernels carry the trace-word accumulators on top of everything else: at 128 registers ptxas spills 390 bytes
-// per thread (local-memory round trips inside the column loop); BA_LB_BLOCKS_TRACE = 3 gives them 168.
-#ifndef BA_LB_BLOCKS_TRACE
-#define BA_LB_BLOCKS_TRACE BA_LB_BLOCKS
-#endif
-template <int SCORING, int FLAGS, int FR>
-__global__ void __launch_bounds__(128, (FLAGS & kTrace) ? BA_LB_BLOCKS_TRACE : BA_LB_BLOCKS) ba_align_kernel(const __grid_constant__ Params P) {
-  extern __shared__ __align__(16) unsigned char ba_smem[];
-  const int nm = SCORING == kNuc ? 128 : (SCORING == kAA ? 864 : 0);
-  for (int i = threadIdx.x; i < nm; i += blockDim.x) ba_smem[i] = (unsigned char)P.matrix[i];
-  __syncthreads();
-  stage_tables<SCORING>(ba_smem, (int)threadIdx.x, (int)blockDim.x);
-  __syncthreads();
-  const int wib = threadIdx.x >> 5;
-  warp_main<SCORING, FLAGS, FR>(P, ba_smem, wib, blockIdx.x * (blockDim.x >> 5) + wib);
-}
-
 __global__ void ba_traceback_kernel(const __grid_constant__ Params P, uint32_t pair, uint32_t qi, uint32_t rj, int eq, DevResult* out1) {
   __shared__ uint8_t lut[128];
   for (uint32_t i = threadIdx.x; i < 128; i += blockDim.x) lut[i] = tb_entry(i);
@@ -243,51 +172,7 @@ static int launch_traceback(const Params& P, uint32_t pair, uint32_t qi, uint32_
   return 0;
 }
 
-template <int SCORING, int FLAGS, int FR>
-static int launch_align(const Params& P, int blocks, int wpb, size_t smem_bytes, dev_stream_t st) {
-  CK(cudaFuncSetAttribute(ba_align_kernel<SCORING, FLAGS, FR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  ba_align_kernel<SCORING, FLAGS, FR><<<blocks, wpb * 32, smem_bytes, st>>>(P);
-  CK(cudaGetLastError());
-  return 0;
-}
-template <int SCORING, int FLAGS, int FR>
-static int occupancy(int wpb, size_t smem_bytes, int* blocks_per_sm) {
-  CK(cudaFuncSetAttribute(ba_align_kernel<SCORING, FLAGS, FR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ba_align_kernel<SCORING, FLAGS, FR>, wpb * 32, smem_bytes));
-  return 0;
-}
 #endif
-
-// kernel instantiations: scoring x flags x rows-per-lane of the fast phase (0 = generic phase only)
-// flags 4..7 = kExt | {TRACE, X_DROP}: LOCAL_START / FREE_QUERY_START_GAPS selected at run time, generic phase only
-// fast-phase modes 34 / 35 = 18 / 19 with the live borders in global memory (max block size >= 1024)
-#define BA_FOR_SEQ(X, S) X(S, 0, 0) X(S, 1, 0) X(S, 2, 0) X(S, 3, 0) X(S, 4, 0) X(S, 5, 0) X(S, 6, 0) X(S, 7, 0) \
-                         X(S, 0, 18) X(S, 1, 18) X(S, 2, 18) X(S, 3, 18) X(S, 0, 19) X(S, 1, 19) X(S, 2, 19) X(S, 3, 19) \
-                         X(S, 0, 34) X(S, 1, 34) X(S, 2, 34) X(S, 3, 34) X(S, 0, 35) X(S, 1, 35) X(S, 2, 35) X(S, 3, 35)
-#ifdef BA_MINIMAL   // tuning builds (tools/build_variant.sh): only the kernels of the C2 workload
-#define BA_FOR_KERNELS(X) X(kNuc, 2, 0) X(kNuc, 2, 18) X(kNuc, 3, 19) X(kNuc, 3, 35)
-#else
-#define BA_FOR_KERNELS(X) BA_FOR_SEQ(X, kNuc) BA_FOR_SEQ(X, kAA) BA_FOR_SEQ(X, kByte) \
-  X(kProfile, 0, 0) X(kProfile, 1, 0) X(kProfile, 2, 0) X(kProfile, 3, 0) \
-  X(kProfile, 4, 0) X(kProfile, 5, 0) X(kProfile, 6, 0) X(kProfile, 7, 0)
-#endif
-
-static int launch_dispatch(int scoring, int flags, int fr, const Params& P, int blocks, int wpb, size_t smem, dev_stream_t st) {
-#define X(S, F, R) if (scoring == S && flags == F && fr == R) return launch_align<S, F, R>(P, blocks, wpb, smem, st);
-  BA_FOR_KERNELS(X)
-#undef X
-  return fail(BA_ERR_ARG, "unsupported scoring/flags combination");
-}
-static int occupancy_dispatch(int scoring, int flags, int fr, int wpb, size_t smem, int* bps) {
-#ifdef BA_EMU
-  (void)scoring; (void)flags; (void)fr; (void)wpb; (void)smem; *bps = 1; return 0;
-#else
-#define X(S, F, R) if (scoring == S && flags == F && fr == R) return occupancy<S, F, R>(wpb, smem, bps);
-  BA_FOR_KERNELS(X)
-#undef X
-  return fail(BA_ERR_ARG, "unsupported scoring/flags combination");
-#endif
-}
 
 // -------------------------------------------------------------------------------------------------
 // objects
@@ -320,7 +205,13 @@ struct BaAligner {
   size_t pool_cached = 0;
   // pinned host staging for data the library has to re-pack before the upload (host AAProfile objects); grow-only
   uint8_t* h_stage = nullptr; size_t h_stage_cap = 0;
+  size_t pool_live_bytes = 0, pool_peak = 0;   // bytes handed out now / high-water mark since the cache was last trimmed
+  // Every public entry point that touches an aligner (or one of its batches) holds this lock for its whole body, so
+  // calls on one BaAligner from several host threads are serialised instead of racing on the pool / stream / staging
+  // bookkeeping (the Part 1 calls of all threads share one aligner). Recursive: ba_align_batch calls ba_batch_upload.
+  std::recursive_mutex mu;
 };
+typedef std::lock_guard<std::recursive_mutex> AlLock;
 
 static int stage_reserve(BaAligner* al, size_t n) {
   if (n <= al->h_stage_cap) return 0;
@@ -347,6 +238,10 @@ static int streams_acquire(BaAligner* al, StreamSet* ss) {
 }
 static void streams_release(BaAligner* al, const StreamSet& ss) { al->streams_free.push_back(ss); }
 
+static void pool_note_live(BaAligner* al, size_t sz) {
+  al->pool_live_bytes += sz;
+  if (al->pool_live_bytes > al->pool_peak) al->pool_peak = al->pool_live_bytes;
+}
 static int pool_alloc(BaAligner* al, void** p, size_t n) {
   if (n == 0) n = 1;
   int best = -1;
@@ -358,6 +253,7 @@ static int pool_alloc(BaAligner* al, void** p, size_t n) {
     *p = al->pool_free[best].first;
     al->pool_live.push_back(al->pool_free[best]);
     al->pool_cached -= al->pool_free[best].second;
+    pool_note_live(al, al->pool_free[best].second);
     al->pool_free.erase(al->pool_free.begin() + best);
     return 0;
   }
@@ -372,6 +268,7 @@ static int pool_alloc(BaAligner* al, void** p, size_t n) {
     if (rc) return rc;
   }
   al->pool_live.push_back({*p, n});
+  pool_note_live(al, n);
   return 0;
 }
 static void pool_release(BaAligner* al, void* p) {
@@ -380,10 +277,13 @@ static void pool_release(BaAligner* al, void* p) {
     if (al->pool_live[i].first == p) {
       const size_t sz = al->pool_live[i].second;
       al->pool_live.erase(al->pool_live.begin() + i);
-      // Keep up to 90 % of the device memory cached: the trace arenas of one TRACE batch alone are 55 % (measured on
-      // C5: with a 50 % cap some of them were cudaFree'd and cudaMalloc'ed again on every call, 400 ms each time).
-      // pool_alloc drops the cache and retries when a fresh allocation fails.
-      if (al->pool_cached + sz <= al->mem_total / 10 * 9) { al->pool_free.push_back({p, sz}); al->pool_cached += sz; }
+      al->pool_live_bytes -= std::min(al->pool_live_bytes, sz);
+      // The cache is bounded by what the caller's recent batches actually used: twice the high-water mark of live
+      // bytes (+ 64 MB), never more than 90 % of the device. A process that aligns one pair at a time keeps a few MB;
+      // C5 (trace arenas = 55 % of the device; with a 50 % cap some of them were cudaFree'd and cudaMalloc'ed again on
+      // every call, 400 ms each time) keeps its arenas. ba_trim() empties the cache and resets the mark.
+      const size_t cap = std::min<size_t>(al->mem_total / 10 * 9, 2 * al->pool_peak + ((size_t)64 << 20));
+      if (al->pool_cached + sz <= cap) { al->pool_free.push_back({p, sz}); al->pool_cached += sz; }
       else dfree(p);
       return;
     }
@@ -407,6 +307,8 @@ struct BaBatch {
   StepLog* d_steplog = nullptr; uint32_t* d_steplog_n = nullptr;
   uint32_t* d_overflow_list = nullptr; uint32_t* d_overflow_n = nullptr;
   uint32_t* d_zwords = nullptr;     // zero masks (TRACE && LOCAL_START)
+  uint32_t* d_slot_pair = nullptr; uint32_t* r_slot_pair = nullptr;   // TRACE: which pair's trace each slot arena holds
+  std::vector<uint32_t> h_qlen, h_rlen;   // lengths, kept for the bounds check of ba_batch_traceback
   // scratch of the overflow retry (worst-case trace arenas for the few alignments that did not fit the first-pass
   // arenas); kept until the next launch / free so that the trace of a retried pair can still be walked
   uint32_t* r_trace = nullptr; uint32_t* r_zwords = nullptr; Rect* r_rects = nullptr; int16_t* r_ckpt = nullptr; uint32_t* r_runs = nullptr;
@@ -505,8 +407,22 @@ extern "C" void ba_destroy(BaAligner* a) {
   delete a;
 }
 
+// Give the cached device buffers back to the driver (they are kept between batches because cudaMalloc / cudaFree of
+// GB-sized buffers cost more than the copies they serve) and forget the high-water mark that sizes the cache.
+extern "C" int ba_trim(BaAligner* a) {
+  if (!a) return fail(BA_ERR_ARG, "aligner is null");
+  AlLock lk(a->mu);
+#ifndef BA_EMU
+  if (cudaSetDevice(a->device) != cudaSuccess) return fail(BA_ERR_CUDA, "cudaSetDevice failed");
+#endif
+  for (auto& e : a->pool_free) dfree(e.first);
+  a->pool_free.clear(); a->pool_cached = 0; a->pool_peak = a->pool_live_bytes;
+  return BA_OK;
+}
+
 extern "C" void ba_batch_free(BaBatch* b) {
   if (!b) return;
+  AlLock lk(b->al->mu);
 #ifndef BA_EMU
   cudaSetDevice(b->al->device);
 #endif
@@ -514,7 +430,8 @@ extern "C" void ba_batch_free(BaBatch* b) {
   void* bufs[] = {b->d_seq, b->d_qoff, b->d_roff, b->d_qlen, b->d_rlen, b->d_order, b->d_matrix, b->d_profiles, b->d_prof_arena,
                   b->d_out, b->d_ticket, b->d_ckpt, b->d_trace, b->d_rects, b->d_runs, b->d_cigar, b->d_cigar_used,
                   b->d_steplog, b->d_steplog_n, b->d_tb_res, b->d_overflow_list, b->d_overflow_n, b->d_zwords,
-                  b->r_trace, b->r_zwords, b->r_rects, b->r_ckpt, b->r_runs, b->d_gborders, b->d_trace_pool, b->d_trace_pool_cursor};
+                  b->r_trace, b->r_zwords, b->r_rects, b->r_ckpt, b->r_runs, b->d_gborders, b->d_trace_pool, b->d_trace_pool_cursor,
+                  b->d_slot_pair, b->r_slot_pair};
   for (void* q : bufs) pool_release(al, q);
   if (b->has_ss) { dsync(b->ss.stream); streams_release(al, b->ss); }
   delete b;
@@ -553,6 +470,7 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
                          const uint8_t* r_bytes, const uint64_t* r_off, const AAProfile* const* profiles, const BaPssmBatch* pssm,
                          BaBatch** out) {
   if (!al || !out) return fail(BA_ERR_ARG, "null aligner/out");
+  AlLock lk(al->mu);
   uint32_t mn = 0, mx = 0;
   int rc = check_config(cfg, &mn, &mx);
   if (rc) return rc;
@@ -829,7 +747,7 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
   if (kSmemHeader + wpb * wbytes > al->smem_optin) { ba_batch_free(b); return fail(BA_ERR_SIZE, "max block size does not fit in shared memory"); }
   b->wpb = wpb; b->smem_bytes = kSmemHeader + wpb * wbytes;
   int bps = 1;
-  TRY(occupancy_dispatch(prof ? (int)kProfile : cfg->scoring, b->kflags, b->fast_rows, wpb, b->smem_bytes, &bps));
+  TRY(ba_occupancy_dispatch(prof ? (int)kProfile : cfg->scoring, b->kflags, b->fast_rows, wpb, b->smem_bytes, &bps));
   if (bps < 1) bps = 1;
   uint64_t max_blocks = (uint64_t)al->sm_count * bps;
 #ifdef BA_EMU
@@ -872,6 +790,10 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
     // retry pass. Not with LOCAL_START (the zero masks mirror the per-slot layout).
     if (!(cfg->flags & BA_LOCAL_START) && b->trace_words_per_warp < b->trace_words_bound && !getenv("BA_NO_TRACE_POOL")) {
       uint64_t pool_bytes = b->mem_budget / 10;
+      // ... but never more than the alignments that can be in flight could spill: a one-pair Part 1 call must not
+      // allocate (and then cache) gigabytes
+      const uint64_t est_slots = std::max<uint64_t>(1, std::min<uint64_t>(n, max_blocks * (uint64_t)wpb * spw));
+      pool_bytes = std::min<uint64_t>(pool_bytes, est_slots * (b->trace_words_bound - b->trace_words_per_warp) * 4 + 4096);
 #ifdef BA_EMU
       pool_bytes = std::min<uint64_t>(pool_bytes, (uint64_t)8 << 20);
 #endif
@@ -919,6 +841,8 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
     TRY(pool_alloc(al, (void**)&b->d_cigar_used, 8));
     TRY(pool_alloc(al, (void**)&b->d_overflow_list, std::max<size_t>(n, 1) * 4));
     TRY(pool_alloc(al, (void**)&b->d_overflow_n, 4));
+    TRY(pool_alloc(al, (void**)&b->d_slot_pair, nslots * 4));
+    b->h_qlen = ql; b->h_rlen = rl;
   }
   if (getenv("BA_STEP_LOG") && n == 1) {
     TRY(pool_alloc(al, (void**)&b->d_steplog, (size_t)(1 << 20) * sizeof(StepLog)));
@@ -977,10 +901,12 @@ static Params make_params(const BaBatch* b, bool retry = false) {
   P.cigar_stream = b->d_cigar; P.cigar_cap = b->cigar_cap; P.cigar_used = b->d_cigar_used;
   P.cigar_eq = b->cfg.cigar_eq ? 1u : 0u;
   P.overflow_list = b->d_overflow_list; P.overflow_n = b->d_overflow_n;
+  P.slot_pair = b->d_slot_pair; P.retry_bit = 0u;
   P.step_log = b->d_steplog; P.step_log_cap = b->d_steplog ? (1u << 20) : 0u; P.step_log_n = b->d_steplog_n;
   if (retry) {
     P.ckpt = b->r_ckpt; P.trace_words = b->r_trace; P.trace_words_per_warp = b->trace_words_bound; P.trace_zwords = b->r_zwords;
     P.rects = b->r_rects; P.rects_per_warp = b->rects_bound; P.run_scratch = b->r_runs;
+    P.slot_pair = b->r_slot_pair; P.retry_bit = kRetrySlotBit;
   }
   return P;
 }
@@ -989,6 +915,7 @@ static Params make_params(const BaBatch* b, bool retry = false) {
 static int batch_launch(BaBatch* b) {
   if (!b) return fail(BA_ERR_ARG, "batch is null");
   BaAligner* al = b->al;
+  AlLock lk(al->mu);
   dev_stream_t st = b->ss.stream;
 #ifndef BA_EMU
   if (cudaSetDevice(al->device) != cudaSuccess) return fail(BA_ERR_CUDA, "cudaSetDevice failed");
@@ -1006,7 +933,7 @@ static int batch_launch(BaBatch* b) {
 #ifndef BA_EMU
     cudaEventRecord(b->ss.ev0, st);
 #endif
-    int rc = launch_dispatch(P.scoring, P.flags, b->fast_rows, P, b->blocks, b->wpb, b->smem_bytes, st);
+    int rc = ba_launch_dispatch(P.scoring, P.flags, b->fast_rows, P, b->blocks, b->wpb, b->smem_bytes, st);
     if (rc) return rc == 1 ? BA_ERR_CUDA : rc;
     b->launches++;
   }
@@ -1019,6 +946,10 @@ static int batch_launch(BaBatch* b) {
 static int batch_wait(BaBatch* b, BaStats* stats) {
   if (!b || !b->launched) return fail(BA_ERR_ARG, "batch was not launched");
   BaAligner* al = b->al;
+  AlLock lk(al->mu);
+#ifndef BA_EMU
+  if (cudaSetDevice(al->device) != cudaSuccess) return fail(BA_ERR_CUDA, "cudaSetDevice failed");
+#endif
   dev_stream_t st = b->ss.stream;
   float ms = 0;
   int rc;
@@ -1041,20 +972,21 @@ static int batch_wait(BaBatch* b, BaStats* stats) {
         if (b->gb) blocks2 = std::min<uint64_t>(blocks2, (uint64_t)b->blocks);   // d_gborders is sized for the first pass
         const uint64_t nslots2 = blocks2 * b->wpb * spw;
         const size_t msz = b->max_size < 32 ? 32 : b->max_size;
-        void** rb[] = {(void**)&b->r_trace, (void**)&b->r_zwords, (void**)&b->r_rects, (void**)&b->r_ckpt, (void**)&b->r_runs};
+        void** rb[] = {(void**)&b->r_trace, (void**)&b->r_zwords, (void**)&b->r_rects, (void**)&b->r_ckpt, (void**)&b->r_runs, (void**)&b->r_slot_pair};
         for (void** q : rb) { pool_release(al, *q); *q = nullptr; }
         if (pool_alloc(al, (void**)&b->r_trace, nslots2 * b->trace_words_bound * 4)) return BA_ERR_NOMEM;
         if (b->d_zwords && pool_alloc(al, (void**)&b->r_zwords, nslots2 * b->trace_words_bound * 4)) return BA_ERR_NOMEM;
         if (pool_alloc(al, (void**)&b->r_rects, nslots2 * (uint64_t)b->rects_bound * sizeof(Rect))) return BA_ERR_NOMEM;
         if (pool_alloc(al, (void**)&b->r_ckpt, nslots2 * 4 * msz * sizeof(int16_t))) return BA_ERR_NOMEM;
         if (pool_alloc(al, (void**)&b->r_runs, blocks2 * b->wpb * (uint64_t)b->runs_per_warp * 4)) return BA_ERR_NOMEM;
+        if (pool_alloc(al, (void**)&b->r_slot_pair, nslots2 * 4)) return BA_ERR_NOMEM;
         b->retried = true;
         Params P2 = make_params(b, true);
         P2.order = b->d_overflow_list;     // the kernel appends to this list only on overflow, which cannot
         P2.n_pairs = n_over;               // happen with worst-case arenas, so reading it as the work list is safe
         P2.overflow_list = nullptr; P2.overflow_n = nullptr;
         if (dzero(b->d_ticket, 4, st)) return BA_ERR_CUDA;
-        rc = launch_dispatch(P2.scoring, P2.flags, b->fast_rows, P2, (int)blocks2, b->wpb, b->smem_bytes, st);
+        rc = ba_launch_dispatch(P2.scoring, P2.flags, b->fast_rows, P2, (int)blocks2, b->wpb, b->smem_bytes, st);
         if (rc) return rc == 1 ? BA_ERR_CUDA : rc;
         b->launches++;
       }
@@ -1083,6 +1015,7 @@ extern "C" int ba_batch_run(BaBatch* b, BaStats* stats) {
 extern "C" int ba_batch_download(BaBatch* b, AlignResult* out) {
   if (!b) return fail(BA_ERR_ARG, "batch is null");
   BaAligner* al = b->al;
+  AlLock lk(al->mu);
   dev_stream_t st = b->ss.stream;
 #ifndef BA_EMU
   if (cudaSetDevice(al->device) != cudaSuccess) return fail(BA_ERR_CUDA, "cudaSetDevice failed");
@@ -1141,6 +1074,7 @@ extern "C" void ba_emu_stats(uint64_t* out3, int reset) {
 // debug: fetch the per-step log of a single-pair batch run with BA_STEP_LOG=1
 extern "C" size_t ba_debug_step_log(BaBatch* b, StepLog* out, size_t cap) {
   if (!b || !b->d_steplog) return 0;
+  AlLock lk(b->al->mu);
   uint32_t n = 0;
   d2h(&n, b->d_steplog_n, 4, b->ss.stream); dsync(b->ss.stream);
   const size_t m = std::min<size_t>(std::min<size_t>(n, cap), 1u << 20);
@@ -1175,6 +1109,7 @@ static int align_batch_impl(BaAligner* a, const BaConfig* cfg, size_t n, const u
                             const uint8_t* r_bytes, const uint64_t* r_off, AlignResult* out, BaStats* stats, CigarOut* cg) {
   if (!a) return fail(BA_ERR_ARG, "aligner is null");
   if (n && (!q_off || !r_off)) return fail(BA_ERR_ARG, "null offsets");
+  AlLock lk(a->mu);
   const bool timing = getenv("BA_TIMING") != nullptr;
   const auto t0 = std::chrono::steady_clock::now();
   size_t K = 1;
@@ -1260,6 +1195,7 @@ extern "C" int ba_align_batch_exp(BaAligner* a, const BaConfig* cfg, size_t n, c
   uint32_t mn = 0, mx = 0;
   int rc = check_config(cfg, &mn, &mx);
   if (rc) return rc;
+  if (mn > mx) return fail(BA_ERR_SIZE, "min block size is larger than max block size");
   std::vector<size_t> active(n);
   for (size_t k = 0; k < n; k++) { active[k] = k; min_size_used[k] = 0; }
   BaStats tot; memset(&tot, 0, sizeof(tot));
@@ -1325,24 +1261,30 @@ static int align_uploaded_profiles(BaBatch* b, size_t n, AlignResult* out, BaSta
 }
 
 // Walk the stored trace of pair k back from an arbitrary end position (Trace::cigar / cigar_eq,
-// scan_block.rs:1469-1480). Only valid for the pair that ran last on its warp, i.e. batches of one
-// (the legacy block_cigar_* calls) or pair ids whose warp processed no later pair.
+// scan_block.rs:1469-1480). The trace of a pair stays resident until a later pair of the batch reuses its slot's
+// arena: always for batches of one (the legacy block_cigar_* calls), otherwise for the last pair each slot ran --
+// anything else is refused (BA_ERR_ARG) instead of walking somebody else's trace.
 extern "C" int ba_batch_traceback(BaBatch* b, size_t k, size_t query_idx, size_t reference_idx, int eq,
                                   const uint32_t** runs, size_t* n_runs) {
-  if (!b || !(b->cfg.flags & BA_TRACE) || k >= b->n || !b->downloaded) return fail(BA_ERR_ARG, "no trace available");
+  if (!b || !runs || !n_runs || !(b->cfg.flags & BA_TRACE) || k >= b->n || !b->downloaded) return fail(BA_ERR_ARG, "no trace available");
   if (eq && b->cfg.scoring == BA_SCORING_PROFILE) return fail(BA_ERR_ARG, "cigar_eq needs a reference sequence");
+  // "Traceback cigar end position must be in bounds!" (scan_block.rs:1483)
+  if (query_idx > b->h_qlen[k] || reference_idx > b->h_rlen[k]) return fail(BA_ERR_ARG, "Traceback cigar end position must be in bounds!");
+  if (b->h_out[k].status != kOk) return fail(BA_ERR_OVERFLOW, "the alignment of this pair did not complete");
   BaAligner* al = b->al;
+  AlLock lk(al->mu);
   dev_stream_t st = b->ss.stream;
 #ifndef BA_EMU
   if (cudaSetDevice(al->device) != cudaSuccess) return fail(BA_ERR_CUDA, "cudaSetDevice failed");
 #endif
-  Params P = make_params(b, b->retried && b->n == 1);
+  Params P = make_params(b, (b->h_out[k].warp & kRetrySlotBit) != 0);
   if (!b->d_tb_res && pool_alloc(al, (void**)&b->d_tb_res, sizeof(DevResult))) return BA_ERR_CUDA;
   if (dzero(b->d_cigar_used, 8, st)) return BA_ERR_CUDA;
   if (launch_traceback(P, (uint32_t)k, (uint32_t)query_idx, (uint32_t)reference_idx, eq, b->d_tb_res, st)) return BA_ERR_CUDA;
   DevResult res;
   if (d2h(&res, b->d_tb_res, sizeof(res), st) || dsync(st)) return BA_ERR_CUDA;
-  if (res.status != kOk) return fail(BA_ERR_OVERFLOW, "traceback failed (trace no longer resident or buffer overflow)");
+  if (res.status == kTraceGone) return fail(BA_ERR_ARG, "the trace of this pair is no longer resident (a later pair of the batch reused its arena)");
+  if (res.status != kOk) return fail(BA_ERR_OVERFLOW, "traceback failed (buffer overflow or an end position the alignment never reached)");
   b->h_tb.resize(res.cigar_n);
   if (d2h(b->h_tb.data(), b->d_cigar + res.cigar_off, (size_t)res.cigar_n * 4, st) || dsync(st)) return BA_ERR_CUDA;
   *runs = b->h_tb.data(); *n_runs = res.cigar_n;
@@ -1393,6 +1335,7 @@ static int measure_int_peak(BaAligner* al, bool packed, double* giga_ops_per_s) 
   (void)al; (void)packed; *giga_ops_per_s = 0; return BA_OK;
 #else
   if (!al || !giga_ops_per_s) return fail(BA_ERR_ARG, "null");
+  AlLock lk(al->mu);
   if (cudaSetDevice(al->device) != cudaSuccess) return fail(BA_ERR_CUDA, "cudaSetDevice failed");
   int* d = nullptr;
   if (dmalloc((void**)&d, 4)) return BA_ERR_CUDA;

@@ -22,7 +22,9 @@ enum Scoring : int { kNuc = 0, kAA = 1, kByte = 2, kProfile = 3 };
 enum Dir : int { kRight = 0, kDown = 1, kGrow = 2 };
 
 // per-pair status written by the kernel
-enum Status : uint32_t { kOk = 0, kNotRun = 1, kTraceOverflow = 2, kRectOverflow = 3, kCigarOverflow = 4 };
+enum Status : uint32_t { kOk = 0, kNotRun = 1, kTraceOverflow = 2, kRectOverflow = 3, kCigarOverflow = 4, kTraceGone = 5 };
+// DevResult::warp: slot index, bit 31 set when the pair ran in the overflow-retry pass (its trace lives in the retry scratch)
+constexpr uint32_t kRetrySlotBit = 0x80000000u;
 
 // Device-side view of one AAProfile (reference: src/scores.rs:454-468). `pos_aa` is the only score
 // layout kept on the device (row per position, 32 i8 each); the reference's transposed `aa_pos`
@@ -126,6 +128,8 @@ struct Params {
   uint32_t cigar_eq;
   // pairs whose trace arena overflowed (they are re-run with worst-case arenas)
   uint32_t* overflow_list; uint32_t* overflow_n;
+  // TRACE: pair whose trace a slot's arena holds (the last one that ran there); retry_bit = kRetrySlotBit in the retry pass
+  uint32_t* slot_pair; uint32_t retry_bit;
   // debug
   StepLog* step_log; uint32_t step_log_cap; uint32_t* step_log_n;   // only honoured for n_pairs == 1
 };

@@ -61,7 +61,7 @@ def align_sharded(aligner, cfg, q_arena, q_off, r_arena, r_off, want_cigars=Fals
     out = np.concatenate([p[:s].cpu().numpy() for p, s in zip(parts, sizes)], axis=0)
     assert out.shape == (n, 3)
     cigs = None
-    if want_cigars:
+    if want_cigars and (cfg.flags & api.TRACE):
         gathered = [None] * world
         dist.all_gather_object(gathered, cig)
         cigs = [c for part in gathered for c in part]

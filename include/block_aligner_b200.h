@@ -130,9 +130,13 @@ enum { BA_TRACE = 1, BA_XDROP = 2, BA_LOCAL_START = 4, BA_FREE_QUERY_START_GAPS 
         * for the profile side) */
        BA_REV_QUERY = 32, BA_REV_REFERENCE = 64 };
 
-typedef struct BaAligner BaAligner; /* one per GPU: streams + reusable device scratch. Not thread-safe: calls on one
-                                      * BaAligner (and its batches) must come from one host thread at a time, like a
-                                      * reference Block (src/scan_block.rs:1716: raw pointers, neither Send nor Sync) */
+typedef struct BaAligner BaAligner; /* one per GPU: streams + reusable device scratch. Calls on one BaAligner (and on
+                                      * its batches) may come from any number of host threads: the library serialises
+                                      * them on a per-aligner lock. A BaBatch handle itself is like a reference Block
+                                      * (src/scan_block.rs:1716: raw pointers, neither Send nor Sync): one thread at a
+                                      * time. Part 1 handles (BlockHandle, PaddedBytes, ...) follow the reference's
+                                      * contract -- not thread-safe per handle, safe across handles: every thread may
+                                      * own its Block even though all of them share one process-wide BaAligner. */
 typedef struct BaBatch BaBatch;     /* one uploaded batch: device-resident inputs and outputs */
 
 typedef struct BaConfig {
@@ -159,6 +163,9 @@ const char* ba_last_error_message(void);
 
 int ba_create(int device, BaAligner** out);
 void ba_destroy(BaAligner* a);
+/* Device buffers of freed batches are cached for the next batch (bounded by twice the largest footprint the aligner
+ * has seen, never above 90 % of the device); ba_trim returns the cache to the driver and resets that bound. */
+int ba_trim(BaAligner* a);
 
 /* Upload `n` (query, reference) pairs given as raw, unconverted bytes: sequence k of `q_bytes` is
  * q_bytes[q_off[k] .. q_off[k+1]). Conversion to the PaddedBytes layout (src/scan_block.rs:1829-1836)
@@ -196,8 +203,10 @@ int ba_batch_download(BaBatch* b, AlignResult* out);
 /* After ba_batch_download of a BA_TRACE batch: CIGAR of pair k as packed runs, (len << 4) | Operation,
  * in forward order. The pointer stays valid until ba_batch_free. */
 int ba_batch_cigar(const BaBatch* b, size_t k, const uint32_t** runs, size_t* n_runs);
-/* Trace::cigar / cigar_eq from an arbitrary end position (src/scan_block.rs:1469-1480). Valid while the
- * trace of pair k is still resident, i.e. for batches of one (what the Part 1 calls use). */
+/* Trace::cigar / cigar_eq from an arbitrary end position (src/scan_block.rs:1469-1480). BA_ERR_ARG when the end
+ * position lies outside the pair ("Traceback cigar end position must be in bounds!", :1483) or when the trace of
+ * pair k is no longer resident: a slot's arena holds the trace of the last pair that ran in it, so batches of one
+ * (what the Part 1 calls use) always qualify and larger batches only for those pairs. */
 int ba_batch_traceback(BaBatch* b, size_t k, size_t query_idx, size_t reference_idx, int eq,
                        const uint32_t** runs, size_t* n_runs);
 int ba_batch_total_stats(const BaBatch* b, BaStats* stats);

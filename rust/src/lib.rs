@@ -244,7 +244,7 @@ impl<const TRACE: bool, const X_DROP: bool, const LOCAL_START: bool, const FREE_
     /// scan_block.rs:884-902
     pub fn align_exp<M: Matrix>(&mut self, query: &PaddedBytes, reference: &PaddedBytes, matrix: &M, gaps: Gaps, size: RangeInclusive<usize>,
                                 x_drop: i32, target_score: i32) -> Option<usize> {
-        let mut s = *size.start();
+        let mut s = (*size.start()).max(16);   // scan_block.rs:885: `cmp::max(*size.start(), L)`, L = 16 on AVX2
         while s <= *size.end() {
             self.align(query, reference, matrix, gaps, s..=*size.end(), x_drop);
             if self.res.score >= target_score { return Some(s); }

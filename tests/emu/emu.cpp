@@ -44,7 +44,7 @@ struct WarpCtx {
   void* arg;
   char* stacks;
 };
-WarpCtx* g = nullptr;
+thread_local WarpCtx* g = nullptr;
 
 void switch_to_next_from(int me, bool finished) {
   if (finished && g->ndone == kLanes) {
