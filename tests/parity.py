@@ -27,8 +27,13 @@ def pad_arena(scoring, arena, off, pad):
     return out, poff[:n], lens[:n]
 
 
-def oracle_batch(scoring, matrix, gaps, size, x_drop, flags, cigar_eq, qa, qo, ra, ro, profiles=None, threads=None):
-    """-> results (n x 3 int64), cells (uint64[n]), cigars (list of run arrays or None)"""
+_RES_DT = np.dtype([("score", np.int32), ("query_idx", np.uint64), ("reference_idx", np.uint64)], align=True)
+_OPLEN_DT = np.dtype([("op", np.uint8), ("len", np.uint64)], align=True)
+
+
+def oracle_batch(scoring, matrix, gaps, size, x_drop, flags, cigar_eq, qa, qo, ra, ro, profiles=None, threads=None,
+                 cigars_as_arrays=True):
+    """-> results (n x 3 int64), cells (uint64[n]), cigars (list of run arrays (len << 4 | op, uint64) or None)"""
     L = ora.lib()
     n = len(qo) - 1
     pad = max(size[1], 16) + 32
@@ -60,7 +65,8 @@ def oracle_batch(scoring, matrix, gaps, size, x_drop, flags, cigar_eq, qa, qo, r
         b.gap_open, b.gap_extend = gaps
     b.min_size, b.max_size = size
     b.x_drop, b.flags, b.cigar_eq = x_drop, flags, int(bool(cigar_eq))
-    out = (ora.Result * max(n, 1))()
+    assert _RES_DT.itemsize == C.sizeof(ora.Result) and _OPLEN_DT.itemsize == C.sizeof(ora.OpLen)
+    out = np.zeros(max(n, 1), dtype=_RES_DT)
     cells = np.zeros(max(n, 1), dtype=np.uint64)
     trace = bool(flags & api.TRACE)
     coff = clen = carena = None
@@ -68,21 +74,41 @@ def oracle_batch(scoring, matrix, gaps, size, x_drop, flags, cigar_eq, qa, qo, r
         caps = ql.astype(np.uint64) + rl.astype(np.uint64) + 5
         coff = np.zeros(n + 1, dtype=np.uint64)
         np.cumsum(caps, out=coff[1:])
-        carena = (ora.OpLen * int(coff[-1] + 1))()
+        carena = np.zeros(int(coff[-1] + 1), dtype=_OPLEN_DT)
         clen = np.zeros(max(n, 1), dtype=np.uint32)
     threads = threads or ora.lib().ora_hw_threads()
-    e = L.ora_batch_align(C.byref(b), threads, out, cells.ctypes.data, carena, coff.ctypes.data if trace else None,
-                          clen.ctypes.data if trace else None)
+    e = L.ora_batch_align(C.byref(b), threads, out.ctypes.data, cells.ctypes.data, carena.ctypes.data if trace else None,
+                          coff.ctypes.data if trace else None, clen.ctypes.data if trace else None)
     if e:
         raise ValueError(f"oracle batch error {e}")
-    res = np.array([[out[k].score, out[k].query_idx, out[k].reference_idx] for k in range(n)], dtype=np.int64).reshape(n, 3)
+    res = np.stack([out["score"][:n].astype(np.int64), out["query_idx"][:n].astype(np.int64),
+                    out["reference_idx"][:n].astype(np.int64)], axis=1).reshape(n, 3)
     cigs = None
     if trace:
-        cigs = []
-        for k in range(n):
-            base = int(coff[k])
-            cigs.append(np.array([(carena[base + t].len << 4) | carena[base + t].op for t in range(int(clen[k]))], dtype=np.uint64))
+        packed = (carena["len"] << np.uint64(4)) | carena["op"].astype(np.uint64)
+        cigs = [packed[int(coff[k]):int(coff[k]) + int(clen[k])] for k in range(n)]
     return res, cells[:n], cigs
+
+
+def make_ora_profiles(ra, ro, block_size, gap_open, gap_extend, seed):
+    """The C4 profiles of workloads.make_pssm_batch / make_lib_profiles for the oracle: same numbers, same rng order
+    (PSSM = BLOSUM62 row of the consensus + noise; gaps for positions 1..=len, position 0 keeps the -128 defaults)."""
+    b62 = np.asarray(ora.builtin("BLOSUM62"), dtype=np.int8)
+    rng = np.random.default_rng(seed)
+    L = ora.lib()
+    out = []
+    for k in range(len(ro) - 1):
+        cons = ra[int(ro[k]):int(ro[k + 1])].tobytes()
+        o = ora.Profile.new(len(cons), block_size, gap_extend)
+        if len(cons):
+            sc = workloads.pssm_scores(b62, cons, rng)
+            assert L.ora_profile_set_all(o.h, workloads.MAP20, 20, sc.ctypes.data, sc.size, 0, 0, 0) == 0
+        assert L.ora_profile_set_all_gap_open_C(o.h, gap_open) == 0
+        assert L.ora_profile_set_all_gap_close_C(o.h, 0) == 0
+        assert L.ora_profile_set_all_gap_open_R(o.h, gap_open) == 0
+        o.set_gap_open_C(0, -128); o.set_gap_close_C(0, -128); o.set_gap_open_R(0, -128)
+        out.append(o)
+    return out
 
 
 def make_profiles(lib, b62, ra, ro, block_size, gap_open, gap_extend, seed):
@@ -221,3 +247,50 @@ def check_reversed(lib, al, n, rev, seed=5):
     got = run_lib(lib, al, w["scoring"], m, w["gaps"], (32, 256), 50, flags | rev, True, qa, qo, ra, ro)
     exp = oracle_batch(w["scoring"], m, w["gaps"], (32, 256), 50, flags, True, qh, qo, rh, ro)
     return compare(f"rev{rev}", got, exp)
+
+
+# ---- the one-call entry points (ba_align_batch*), as a C caller uses them ---------------------------------------
+ABI_RES_DT = np.dtype([("score", np.int32), ("q", np.uint64), ("r", np.uint64)], align=True)
+
+
+def abi_align_batch(lib, al, cfg, qa, qo, ra, ro):
+    """ba_align_batch -> (results n x 3 int64, BaStats)"""
+    n = len(qo) - 1
+    out = np.zeros(max(n, 1), dtype=ABI_RES_DT)
+    st = api.BaStats()
+    lib.check(lib.L.ba_align_batch(al.h, C.byref(cfg), n, qa.ctypes.data, qo.ctypes.data, ra.ctypes.data, ro.ctypes.data,
+                                   out.ctypes.data, C.byref(st)))
+    return np.stack([out["score"][:n].astype(np.int64), out["q"][:n].astype(np.int64), out["r"][:n].astype(np.int64)], axis=1), st
+
+
+def abi_align_batch_cigar(lib, al, cfg, qa, qo, ra, ro):
+    """ba_align_batch_cigar -> (results, list of run arrays, BaStats)"""
+    n = len(qo) - 1
+    out = np.zeros(max(n, 1), dtype=ABI_RES_DT)
+    cap = int(qo[-1] - qo[0] + ro[-1] - ro[0]) + 5 * n + 8
+    runs = np.zeros(cap, dtype=np.uint32)
+    off = np.zeros(max(n, 1), dtype=np.uint64)
+    ln = np.zeros(max(n, 1), dtype=np.uint32)
+    used = C.c_size_t()
+    st = api.BaStats()
+    lib.check(lib.L.ba_align_batch_cigar(al.h, C.byref(cfg), n, qa.ctypes.data, qo.ctypes.data, ra.ctypes.data, ro.ctypes.data,
+                                         out.ctypes.data, runs.ctypes.data, cap, off.ctypes.data, ln.ctypes.data,
+                                         C.byref(used), C.byref(st)))
+    assert used.value == int(ln[:n].sum())
+    cigs = [runs[int(off[k]):int(off[k]) + int(ln[k])].astype(np.uint64) for k in range(n)]
+    return np.stack([out["score"][:n].astype(np.int64), out["q"][:n].astype(np.int64), out["r"][:n].astype(np.int64)], axis=1), cigs, st
+
+
+def compare_abi(tag, res, cigs, st, exp):
+    """results (+ CIGARs) of a one-call entry point against oracle_batch's tuple; also the cell total of BaStats"""
+    res_e, cells_e, cig_e = exp
+    bad = int((res != res_e).any(axis=1).sum())
+    if cigs is not None:
+        bad += sum(1 for k in range(len(res_e)) if len(cigs[k]) != len(cig_e[k]) or not (cigs[k] == cig_e[k]).all())
+    if st is not None and int(st.cells) != int(cells_e.sum()):
+        print(f"[{tag}] cells {int(st.cells)} != oracle {int(cells_e.sum())}")
+        bad += 1
+    if bad:
+        k = int(np.argmax((res != res_e).any(axis=1)))
+        print(f"[{tag}] {bad} mismatches; first differing result: pair {k} got {res[k].tolist()} expected {res_e[k].tolist()}")
+    return bad
