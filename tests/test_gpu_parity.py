@@ -91,7 +91,7 @@ def test_C1_full(env):
 
 
 def test_C2_sample_full_length(env):
-    assert parity.check_workload(*env, workloads.WORKLOADS["C2_nanopore_xdrop_10k"], 1500) == 0
+    assert parity.check_workload(*env, workloads.WORKLOADS["C2_nanopore_xdrop_10k"], 10000) == 0
 
 
 def test_C2_with_trace(env):
@@ -99,15 +99,28 @@ def test_C2_with_trace(env):
 
 
 def test_C3_sample(env):
-    assert parity.check_workload(*env, workloads.WORKLOADS["C3_uniclust_protein_global"], 30000) == 0
+    assert parity.check_workload(*env, workloads.WORKLOADS["C3_uniclust_protein_global"], 100000) == 0
 
 
 def test_C4_sample(env):
     assert parity.check_workload(*env, workloads.WORKLOADS["C4_seq_to_profile_xdrop"], 1500) == 0
 
 
+def test_C4_large_sample_device_built_profiles(env):
+    """20 000 C4 pairs through the PSSM batch (profiles built on the device) against the oracle"""
+    lib, al = env
+    w = workloads.WORKLOADS["C4_seq_to_profile_xdrop"]
+    n = 20000
+    qa, qo, ra, ro = workloads.generate(w["gen"], n, seed=1234, stream=w["stream"])
+    pb = workloads.make_pssm_batch(lib, ra, ro, seed=11)
+    got = parity.run_lib(lib, al, api.SCORING_PROFILE, None, None, w["size"], w["x_drop"], w["flags"], False, qa, qo, ra, ro, pb)
+    op = parity.make_ora_profiles(ra, ro, w["size"][1], -10, -1, 11)
+    exp = parity.oracle_batch(api.SCORING_PROFILE, None, None, w["size"], w["x_drop"], w["flags"], False, qa, qo, ra, ro, op)
+    assert parity.compare("C4-20k", got, exp) == 0
+
+
 def test_C5_sample_long_reads_with_trace(env):
-    assert parity.check_workload(*env, workloads.WORKLOADS["C5_longread_trace_50k"], 24) == 0
+    assert parity.check_workload(*env, workloads.WORKLOADS["C5_longread_trace_50k"], 512) == 0
 
 
 def test_results_independent_of_batch_order_and_reuse(env):
