@@ -92,7 +92,7 @@ PART1_DATA = ["NW1", "BLOSUM45", "BLOSUM50", "BLOSUM62", "BLOSUM80", "BLOSUM90",
 PART2_FUNCTIONS = ["ba_error_string", "ba_last_error_message", "ba_create", "ba_destroy", "ba_trim", "ba_batch_upload",
                    "ba_batch_upload_profiles", "ba_batch_upload_pssm", "ba_align_batch_pssm", "ba_batch_run", "ba_batch_download", "ba_batch_cigar",
                    "ba_batch_traceback", "ba_batch_total_stats", "ba_batch_pair_stats", "ba_batch_free",
-                   "ba_align_batch", "ba_align_batch_cigar", "ba_align_batch_exp", "ba_align_batch_profiles", "ba_new_simple_nucmatrix", "ba_set_nucmatrix", "ba_free_nucmatrix",
+                   "ba_align_batch", "ba_align_batch_cigar", "ba_align_batch_exp", "ba_align_batch_exp_profiles", "ba_align_batch_exp_pssm", "ba_align_batch_profiles", "ba_new_simple_nucmatrix", "ba_set_nucmatrix", "ba_free_nucmatrix",
                    "ba_percent_len", "ba_cigar_format", "ba_measure_int_peak", "ba_measure_int_peak_packed"]
 
 
@@ -126,6 +126,8 @@ class Library:
         L.ba_align_batch.argtypes = [vp, C.POINTER(BaConfig), sz, vp, vp, vp, vp, vp, C.POINTER(BaStats)]
         L.ba_align_batch_exp.argtypes = [vp, C.POINTER(BaConfig), sz, vp, vp, vp, vp, vp, vp, vp, C.POINTER(BaStats)]
         L.ba_align_batch_profiles.argtypes = [vp, C.POINTER(BaConfig), sz, vp, vp, vp, vp, C.POINTER(BaStats)]
+        L.ba_align_batch_exp_profiles.argtypes = [vp, C.POINTER(BaConfig), sz, vp, vp, vp, vp, vp, vp, C.POINTER(BaStats)]
+        L.ba_align_batch_exp_pssm.argtypes = [vp, C.POINTER(BaConfig), sz, vp, vp, C.POINTER(BaPssmBatch), vp, vp, vp, C.POINTER(BaStats)]
         L.ba_align_batch_cigar.argtypes = [vp, C.POINTER(BaConfig), sz, vp, vp, vp, vp, vp, vp, sz, vp, vp, C.POINTER(sz),
                                            C.POINTER(BaStats)]
         L.ba_batch_upload_pssm.argtypes = [vp, C.POINTER(BaConfig), sz, vp, vp, C.POINTER(BaPssmBatch), C.POINTER(vp)]
@@ -292,20 +294,30 @@ class Aligner:
             b.free()
 
 
-def align_batch_exp(al, queries, references, scoring, matrix, gaps, size, target_scores, x_drop=0, flags=0):
-    """Block::align_exp for a batch -> (results, min_size_used with None where the target was never reached)"""
+def align_batch_exp(al, queries, references, scoring, matrix, gaps, size, target_scores, x_drop=0, flags=0, profiles=None):
+    """Block::align_exp / align_profile_exp for a batch -> (results, min_size_used with None where the target was never
+    reached, BaStats). `profiles`: a PssmBatch or a list of AAProfile (then `references` is ignored)."""
     qa, qo = concat(queries)
-    ra, ro = concat(references)
     n = len(queries)
     cfg = al.config(scoring, matrix, gaps, size, x_drop, flags, False)
-    out = np.zeros(n, dtype=np.dtype([("score", np.int32), ("query_idx", np.uint64), ("reference_idx", np.uint64)], align=True))
-    used = np.zeros(n, dtype=np.uint64)
+    out = np.zeros(max(n, 1), dtype=np.dtype([("score", np.int32), ("query_idx", np.uint64), ("reference_idx", np.uint64)], align=True))
+    used = np.zeros(max(n, 1), dtype=np.uint64)
     tgt = np.ascontiguousarray(target_scores, dtype=np.int32)
     st = BaStats()
-    al.lib.check(al.lib.L.ba_align_batch_exp(al.h, C.byref(cfg), n, qa.ctypes.data, qo.ctypes.data, ra.ctypes.data, ro.ctypes.data,
-                                             tgt.ctypes.data, out.ctypes.data, used.ctypes.data, C.byref(st)))
-    res = [(int(r["score"]), int(r["query_idx"]), int(r["reference_idx"])) for r in out]
-    return res, [int(u) if u else None for u in used]
+    L = al.lib.L
+    if isinstance(profiles, PssmBatch):
+        al.lib.check(L.ba_align_batch_exp_pssm(al.h, C.byref(cfg), n, qa.ctypes.data, qo.ctypes.data, C.byref(profiles.c),
+                                               tgt.ctypes.data, out.ctypes.data, used.ctypes.data, C.byref(st)))
+    elif profiles is not None:
+        arr = (C.c_void_p * n)(*[p.h for p in profiles])
+        al.lib.check(L.ba_align_batch_exp_profiles(al.h, C.byref(cfg), n, qa.ctypes.data, qo.ctypes.data, arr,
+                                                   tgt.ctypes.data, out.ctypes.data, used.ctypes.data, C.byref(st)))
+    else:
+        ra, ro = concat(references)
+        al.lib.check(L.ba_align_batch_exp(al.h, C.byref(cfg), n, qa.ctypes.data, qo.ctypes.data, ra.ctypes.data, ro.ctypes.data,
+                                          tgt.ctypes.data, out.ctypes.data, used.ctypes.data, C.byref(st)))
+    res = [(int(r["score"]), int(r["query_idx"]), int(r["reference_idx"])) for r in out[:n]]
+    return res, [int(u) if u else None for u in used[:n]], st
 
 
 class PssmBatch:

@@ -334,6 +334,8 @@ struct BaBatch {
   bool downloaded = false;
   StreamSet ss; bool has_ss = false;
   bool launched = false; uint32_t launches = 0;
+  // ba_align_batch_exp*: the work list of the current round (pair ids still below their target score)
+  const uint32_t* d_active = nullptr; uint32_t n_active = 0; bool use_active = false;
 };
 
 static bool pow2(uint64_t x) { return x && !(x & (x - 1)); }
@@ -461,6 +463,152 @@ static int check_config(const BaConfig* cfg, uint32_t* mn, uint32_t* mx) {
   // our limit: the lane-ordered argmax of this mode is computed with the whole block in one 256-row chunk
   if ((cfg->flags & BA_FREE_QUERY_END_GAPS) && a > 256) return fail(BA_ERR_SIZE, "FREE_QUERY_END_GAPS supports min block sizes up to 256");
   *mn = (uint32_t)a; *mx = (uint32_t)b;
+  return BA_OK;
+}
+
+// Launch geometry and per-slot scratch of a resident batch for min block size `mn` (the max size is fixed by the
+// upload: sequences are padded for it). Called by the upload and again by ba_align_batch_exp* for every doubled min
+// size, so whatever an earlier configuration allocated is released first.
+#define CFG_TRY(x) do { int _r = (x); if (_r) return _r == 1 ? BA_ERR_CUDA : _r; } while (0)
+static int batch_configure(BaBatch* b, uint32_t mn) {
+  BaAligner* al = b->al;
+  const BaConfig* cfg = &b->cfg;
+  const uint32_t mx = b->max_size;
+  const size_t n = b->n;
+  const bool prof = cfg->scoring == BA_SCORING_PROFILE;
+  b->min_size = mn;
+  {
+    void** old[] = {(void**)&b->d_ckpt, (void**)&b->d_gborders, (void**)&b->d_trace_pool, (void**)&b->d_trace_pool_cursor, (void**)&b->d_trace,
+                    (void**)&b->d_zwords, (void**)&b->d_rects, (void**)&b->d_runs, (void**)&b->d_slot_pair};
+    for (void** q : old) { pool_release(al, *q); *q = nullptr; }
+    b->trace_pool_units = 0;
+  }
+  // launch geometry and per-slot scratch
+  // fast phase: four alignments per warp while the block sits at its minimum size (32 or 64)
+  const bool ext = (cfg->flags & (BA_LOCAL_START | BA_FREE_QUERY_START_GAPS | BA_FREE_QUERY_END_GAPS)) != 0;
+  b->kflags = (cfg->flags & 3) | (ext ? kExt : 0);
+  // fast-phase mode (third kernel template argument): 4 / 8 = s32 rows per lane (TRACE), 16 + LGT = packed, 0 = none
+  b->fast_rows = (!prof && !ext && !getenv("BA_NO_FAST")) ? (mn == 32 ? 4 : (mn == 64 ? 8 : 0)) : 0;
+  b->slots_per_warp = b->fast_rows ? 4 : 1;
+  if (b->fast_rows && !b->pk_enable) b->fast_rows = 0;
+  if (b->fast_rows) {
+    const int lgt = mn == 32 ? 2 : 3;
+    b->fast_rows = 16 + lgt;
+    b->slots_per_warp = 32u >> lgt;
+  }
+  // max block >= 1024: the four live borders (8-32 KB per warp) move to global memory so that shared memory does not
+  // cap the SM at 8 warps or fewer (C5: 64..=2048)
+  const bool gb = b->fast_rows >= 16 && mx >= 1024 && !getenv("BA_NO_GLOBAL_BORDERS");
+  if (gb) b->fast_rows += 16;
+  b->gb = gb;
+  const size_t wbytes = warp_smem_bytes(mx, gb);
+  int wpb = 4;
+  while (wpb > 1 && kSmemHeader + wpb * wbytes > al->smem_optin - 1024) wpb >>= 1;
+  if (kSmemHeader + wpb * wbytes > al->smem_optin) { return fail(BA_ERR_SIZE, "max block size does not fit in shared memory"); }
+  b->wpb = wpb; b->smem_bytes = kSmemHeader + wpb * wbytes;
+  int bps = 1;
+  CFG_TRY(ba_occupancy_dispatch(prof ? (int)kProfile : cfg->scoring, b->kflags, b->fast_rows, wpb, b->smem_bytes, &bps));
+  if (bps < 1) bps = 1;
+  uint64_t max_blocks = (uint64_t)al->sm_count * bps;
+#ifdef BA_EMU
+  max_blocks = al->emu_warps; b->wpb = wpb = 1;
+#endif
+  const bool trace = (cfg->flags & BA_TRACE) != 0;
+  const size_t ms = mx < 32 ? 32 : mx;
+  const uint64_t spw = b->slots_per_warp;
+  b->max_blocks_hw = max_blocks;
+  if (trace) {
+    // Worst case per alignment = the reference's Trace::new (scan_block.rs:1364-1369): the block sits at its
+    // maximum size all the time. Real alignments spend most steps at the minimum size, so the first pass runs
+    // with arenas sized for 2x the all-minimum-size path plus one maximum-size grow; alignments that overflow
+    // are re-run with worst-case arenas (ba_batch_run).
+    const uint64_t len = (uint64_t)b->max_pair_len + 2;
+    uint64_t words = 2 * (uint64_t)(mx / 16) * (len + 2 * (uint64_t)mx);
+    if (mn == 16) words *= 2;   // 16-row rectangles still occupy a 32-lane word group
+    // FREE_QUERY_END_GAPS: every rectangle is laid out with 8 rows per lane (one 256-row chunk): 32 words per column
+    if (cfg->flags & BA_FREE_QUERY_END_GAPS) words = std::max<uint64_t>(words, 32 * (len + 2 * (uint64_t)mx));
+    if (words + 64 >= ((uint64_t)1 << 32)) { return fail(BA_ERR_SIZE, "trace arena of one alignment exceeds 2^32 words"); }
+    b->trace_words_bound = words + 64;
+    uint64_t first = 2 * len * (uint64_t)std::max<uint32_t>(mn, 32) / 8 + (uint64_t)mx * mx / 4 + 4096;
+    if (getenv("BA_TRACE_WORST_CASE") || (cfg->flags & BA_FREE_QUERY_END_GAPS)) first = b->trace_words_bound;
+    b->trace_words_per_warp = std::min<uint64_t>(b->trace_words_bound, first);
+    bool arena_forced = false;
+    if (const char* e = getenv("BA_TRACE_ARENA_WORDS")) {   // tests: tiny slot arenas exercise the pool / parking paths
+      b->trace_words_per_warp = std::min<uint64_t>(b->trace_words_bound, std::max<uint64_t>(64, (uint64_t)atoll(e)));
+      arena_forced = true;
+    }
+    b->arena_forced = arena_forced;
+    // one record per step (len / 8 shift steps; grow retries pop theirs again): the first pass gets twice that
+    b->rects_bound = (uint32_t)std::min<uint64_t>(len * 2 + 8, 0x7fffffffu);
+    b->rects_per_warp = b->trace_words_per_warp < b->trace_words_bound ? (uint32_t)std::min<uint64_t>(len / 4 + 1024, b->rects_bound) : b->rects_bound;
+    b->runs_per_warp = (uint32_t)std::min<uint64_t>(len + 8, 0x7fffffffu);
+    const uint64_t zmul = (cfg->flags & BA_LOCAL_START) ? 2 : 1;
+    const uint64_t per_warp = spw * (zmul * b->trace_words_per_warp * 4 + (uint64_t)b->rects_per_warp * sizeof(Rect)) + (uint64_t)b->runs_per_warp * 4;
+    b->mem_budget = (uint64_t)(al->mem_total * al->budget_frac);
+    // A tenth of the budget is a batch-wide overflow pool (trace_push): rectangles that do not fit a slot's own arena
+    // are bump-allocated there, so the rare alignment that sits at a large block size for long does not need the
+    // retry pass. Not with LOCAL_START (the zero masks mirror the per-slot layout).
+    if (!(cfg->flags & BA_LOCAL_START) && b->trace_words_per_warp < b->trace_words_bound && !getenv("BA_NO_TRACE_POOL")) {
+      uint64_t pool_bytes = b->mem_budget / 10;
+      // ... but never more than the alignments that can be in flight could spill: a one-pair Part 1 call must not
+      // allocate (and then cache) gigabytes
+      const uint64_t est_slots = std::max<uint64_t>(1, std::min<uint64_t>(n, max_blocks * (uint64_t)wpb * spw));
+      pool_bytes = std::min<uint64_t>(pool_bytes, est_slots * (b->trace_words_bound - b->trace_words_per_warp) * 4 + 4096);
+#ifdef BA_EMU
+      pool_bytes = std::min<uint64_t>(pool_bytes, (uint64_t)8 << 20);
+#endif
+      if (const char* e = getenv("BA_TRACE_POOL_BYTES")) pool_bytes = (uint64_t)atoll(e);   // tests: force exhaustion
+      b->trace_pool_units = pool_bytes / 64;
+      b->mem_budget -= b->trace_pool_units * 64;
+    }
+    const uint64_t fit_warps = std::max<uint64_t>(1, b->mem_budget / std::max<uint64_t>(per_warp, 1));
+    max_blocks = std::max<uint64_t>(1, std::min<uint64_t>(max_blocks, fit_warps / wpb));
+  }
+  uint64_t want = (n + wpb * spw - 1) / (wpb * spw);
+  if (want < 1) want = 1;
+  b->blocks = (int)std::min<uint64_t>(want, max_blocks);
+  const uint64_t nwarps = (uint64_t)b->blocks * wpb;
+  const uint64_t nslots = nwarps * spw;
+  if (trace && b->trace_words_per_warp < b->trace_words_bound && !b->arena_forced) {
+    // The retry pass of an overflowed alignment runs almost alone on the GPU (measured on C5: one retried 50 kbp pair
+    // costs 90 ms), so once the number of slots is fixed the first-pass arenas take what is left of the budget, up to
+    // twice the initial estimate (4x the all-minimum-size path).
+    const uint64_t zmul = (cfg->flags & BA_LOCAL_START) ? 2 : 1;
+    const uint64_t fixed = nslots * (uint64_t)b->rects_per_warp * sizeof(Rect) + nwarps * (uint64_t)b->runs_per_warp * 4;
+    const uint64_t len = (uint64_t)b->max_pair_len + 2;
+    const uint64_t cap = std::min<uint64_t>(b->trace_words_bound, 4 * len * (uint64_t)std::max<uint32_t>(mn, 32) / 8 + (uint64_t)mx * mx / 4 + 4096);
+    if (b->mem_budget > fixed) {
+      const uint64_t fit = (b->mem_budget - fixed) / (nslots * zmul * 4);
+      b->trace_words_per_warp = std::max<uint64_t>(b->trace_words_per_warp, std::min<uint64_t>(cap, fit));
+    }
+  }
+  CFG_TRY(pool_alloc(al, (void**)&b->d_ckpt, nslots * 4 * ms * sizeof(int16_t)));
+  if (b->gb) CFG_TRY(pool_alloc(al, (void**)&b->d_gborders, nwarps * 4 * ms * sizeof(int16_t)));
+  if (trace) {
+    if (b->trace_pool_units) {
+      CFG_TRY(pool_alloc(al, (void**)&b->d_trace_pool, b->trace_pool_units * 64));
+      CFG_TRY(pool_alloc(al, (void**)&b->d_trace_pool_cursor, 4));
+    }
+    CFG_TRY(pool_alloc(al, (void**)&b->d_trace, nslots * b->trace_words_per_warp * 4));
+    if (cfg->flags & BA_LOCAL_START) CFG_TRY(pool_alloc(al, (void**)&b->d_zwords, nslots * b->trace_words_per_warp * 4));
+    CFG_TRY(pool_alloc(al, (void**)&b->d_rects, nslots * (uint64_t)b->rects_per_warp * sizeof(Rect)));
+    CFG_TRY(pool_alloc(al, (void**)&b->d_runs, nwarps * (uint64_t)b->runs_per_warp * 4));
+    if (!b->d_cigar) {
+      uint64_t cap = 0;
+      for (size_t k = 0; k < n; k++) cap += (uint64_t)b->h_qlen[k] + b->h_rlen[k] + 5;
+      const uint64_t limit = (uint64_t)(al->mem_total * 0.15) / 4;
+      b->cigar_cap = std::min<uint64_t>(cap, std::max<uint64_t>(limit, 1024));
+      CFG_TRY(pool_alloc(al, (void**)&b->d_cigar, b->cigar_cap * 4));
+      CFG_TRY(pool_alloc(al, (void**)&b->d_cigar_used, 8));
+      CFG_TRY(pool_alloc(al, (void**)&b->d_overflow_list, std::max<size_t>(n, 1) * 4));
+      CFG_TRY(pool_alloc(al, (void**)&b->d_overflow_n, 4));
+    }
+    CFG_TRY(pool_alloc(al, (void**)&b->d_slot_pair, nslots * 4));
+  }
+  if (getenv("BA_STEP_LOG") && n == 1 && !b->d_steplog) {
+    CFG_TRY(pool_alloc(al, (void**)&b->d_steplog, (size_t)(1 << 20) * sizeof(StepLog)));
+    CFG_TRY(pool_alloc(al, (void**)&b->d_steplog_n, 4));
+  }
   return BA_OK;
 }
 
@@ -723,131 +871,8 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
   }
   if (herr) { ba_batch_free(b); return fail(BA_ERR_CHAR, "sequence byte outside the alphabet of the scoring matrix"); }
 
-  // launch geometry and per-slot scratch
-  // fast phase: four alignments per warp while the block sits at its minimum size (32 or 64)
-  const bool ext = (cfg->flags & (BA_LOCAL_START | BA_FREE_QUERY_START_GAPS | BA_FREE_QUERY_END_GAPS)) != 0;
-  b->kflags = (cfg->flags & 3) | (ext ? kExt : 0);
-  // fast-phase mode (third kernel template argument): 4 / 8 = s32 rows per lane (TRACE), 16 + LGT = packed, 0 = none
-  b->fast_rows = (!prof && !ext && !getenv("BA_NO_FAST")) ? (mn == 32 ? 4 : (mn == 64 ? 8 : 0)) : 0;
-  b->slots_per_warp = b->fast_rows ? 4 : 1;
-  if (b->fast_rows && !b->pk_enable) b->fast_rows = 0;
-  if (b->fast_rows) {
-    const int lgt = mn == 32 ? 2 : 3;
-    b->fast_rows = 16 + lgt;
-    b->slots_per_warp = 32u >> lgt;
-  }
-  // max block >= 1024: the four live borders (8-32 KB per warp) move to global memory so that shared memory does not
-  // cap the SM at 8 warps or fewer (C5: 64..=2048)
-  const bool gb = b->fast_rows >= 16 && mx >= 1024 && !getenv("BA_NO_GLOBAL_BORDERS");
-  if (gb) b->fast_rows += 16;
-  b->gb = gb;
-  const size_t wbytes = warp_smem_bytes(mx, gb);
-  int wpb = 4;
-  while (wpb > 1 && kSmemHeader + wpb * wbytes > al->smem_optin - 1024) wpb >>= 1;
-  if (kSmemHeader + wpb * wbytes > al->smem_optin) { ba_batch_free(b); return fail(BA_ERR_SIZE, "max block size does not fit in shared memory"); }
-  b->wpb = wpb; b->smem_bytes = kSmemHeader + wpb * wbytes;
-  int bps = 1;
-  TRY(ba_occupancy_dispatch(prof ? (int)kProfile : cfg->scoring, b->kflags, b->fast_rows, wpb, b->smem_bytes, &bps));
-  if (bps < 1) bps = 1;
-  uint64_t max_blocks = (uint64_t)al->sm_count * bps;
-#ifdef BA_EMU
-  max_blocks = al->emu_warps; b->wpb = wpb = 1;
-#endif
-  const bool trace = (cfg->flags & BA_TRACE) != 0;
-  const size_t ms = mx < 32 ? 32 : mx;
-  const uint64_t spw = b->slots_per_warp;
-  b->max_blocks_hw = max_blocks;
-  if (trace) {
-    // Worst case per alignment = the reference's Trace::new (scan_block.rs:1364-1369): the block sits at its
-    // maximum size all the time. Real alignments spend most steps at the minimum size, so the first pass runs
-    // with arenas sized for 2x the all-minimum-size path plus one maximum-size grow; alignments that overflow
-    // are re-run with worst-case arenas (ba_batch_run).
-    const uint64_t len = (uint64_t)b->max_pair_len + 2;
-    uint64_t words = 2 * (uint64_t)(mx / 16) * (len + 2 * (uint64_t)mx);
-    if (mn == 16) words *= 2;   // 16-row rectangles still occupy a 32-lane word group
-    // FREE_QUERY_END_GAPS: every rectangle is laid out with 8 rows per lane (one 256-row chunk): 32 words per column
-    if (cfg->flags & BA_FREE_QUERY_END_GAPS) words = std::max<uint64_t>(words, 32 * (len + 2 * (uint64_t)mx));
-    if (words + 64 >= ((uint64_t)1 << 32)) { ba_batch_free(b); return fail(BA_ERR_SIZE, "trace arena of one alignment exceeds 2^32 words"); }
-    b->trace_words_bound = words + 64;
-    uint64_t first = 2 * len * (uint64_t)std::max<uint32_t>(mn, 32) / 8 + (uint64_t)mx * mx / 4 + 4096;
-    if (getenv("BA_TRACE_WORST_CASE") || (cfg->flags & BA_FREE_QUERY_END_GAPS)) first = b->trace_words_bound;
-    b->trace_words_per_warp = std::min<uint64_t>(b->trace_words_bound, first);
-    bool arena_forced = false;
-    if (const char* e = getenv("BA_TRACE_ARENA_WORDS")) {   // tests: tiny slot arenas exercise the pool / parking paths
-      b->trace_words_per_warp = std::min<uint64_t>(b->trace_words_bound, std::max<uint64_t>(64, (uint64_t)atoll(e)));
-      arena_forced = true;
-    }
-    b->arena_forced = arena_forced;
-    // one record per step (len / 8 shift steps; grow retries pop theirs again): the first pass gets twice that
-    b->rects_bound = (uint32_t)std::min<uint64_t>(len * 2 + 8, 0x7fffffffu);
-    b->rects_per_warp = b->trace_words_per_warp < b->trace_words_bound ? (uint32_t)std::min<uint64_t>(len / 4 + 1024, b->rects_bound) : b->rects_bound;
-    b->runs_per_warp = (uint32_t)std::min<uint64_t>(len + 8, 0x7fffffffu);
-    const uint64_t zmul = (cfg->flags & BA_LOCAL_START) ? 2 : 1;
-    const uint64_t per_warp = spw * (zmul * b->trace_words_per_warp * 4 + (uint64_t)b->rects_per_warp * sizeof(Rect)) + (uint64_t)b->runs_per_warp * 4;
-    b->mem_budget = (uint64_t)(al->mem_total * al->budget_frac);
-    // A tenth of the budget is a batch-wide overflow pool (trace_push): rectangles that do not fit a slot's own arena
-    // are bump-allocated there, so the rare alignment that sits at a large block size for long does not need the
-    // retry pass. Not with LOCAL_START (the zero masks mirror the per-slot layout).
-    if (!(cfg->flags & BA_LOCAL_START) && b->trace_words_per_warp < b->trace_words_bound && !getenv("BA_NO_TRACE_POOL")) {
-      uint64_t pool_bytes = b->mem_budget / 10;
-      // ... but never more than the alignments that can be in flight could spill: a one-pair Part 1 call must not
-      // allocate (and then cache) gigabytes
-      const uint64_t est_slots = std::max<uint64_t>(1, std::min<uint64_t>(n, max_blocks * (uint64_t)wpb * spw));
-      pool_bytes = std::min<uint64_t>(pool_bytes, est_slots * (b->trace_words_bound - b->trace_words_per_warp) * 4 + 4096);
-#ifdef BA_EMU
-      pool_bytes = std::min<uint64_t>(pool_bytes, (uint64_t)8 << 20);
-#endif
-      if (const char* e = getenv("BA_TRACE_POOL_BYTES")) pool_bytes = (uint64_t)atoll(e);   // tests: force exhaustion
-      b->trace_pool_units = pool_bytes / 64;
-      b->mem_budget -= b->trace_pool_units * 64;
-    }
-    const uint64_t fit_warps = std::max<uint64_t>(1, b->mem_budget / std::max<uint64_t>(per_warp, 1));
-    max_blocks = std::max<uint64_t>(1, std::min<uint64_t>(max_blocks, fit_warps / wpb));
-  }
-  uint64_t want = (n + wpb * spw - 1) / (wpb * spw);
-  if (want < 1) want = 1;
-  b->blocks = (int)std::min<uint64_t>(want, max_blocks);
-  const uint64_t nwarps = (uint64_t)b->blocks * wpb;
-  const uint64_t nslots = nwarps * spw;
-  if (trace && b->trace_words_per_warp < b->trace_words_bound && !b->arena_forced) {
-    // The retry pass of an overflowed alignment runs almost alone on the GPU (measured on C5: one retried 50 kbp pair
-    // costs 90 ms), so once the number of slots is fixed the first-pass arenas take what is left of the budget, up to
-    // twice the initial estimate (4x the all-minimum-size path).
-    const uint64_t zmul = (cfg->flags & BA_LOCAL_START) ? 2 : 1;
-    const uint64_t fixed = nslots * (uint64_t)b->rects_per_warp * sizeof(Rect) + nwarps * (uint64_t)b->runs_per_warp * 4;
-    const uint64_t len = (uint64_t)b->max_pair_len + 2;
-    const uint64_t cap = std::min<uint64_t>(b->trace_words_bound, 4 * len * (uint64_t)std::max<uint32_t>(mn, 32) / 8 + (uint64_t)mx * mx / 4 + 4096);
-    if (b->mem_budget > fixed) {
-      const uint64_t fit = (b->mem_budget - fixed) / (nslots * zmul * 4);
-      b->trace_words_per_warp = std::max<uint64_t>(b->trace_words_per_warp, std::min<uint64_t>(cap, fit));
-    }
-  }
-  TRY(pool_alloc(al, (void**)&b->d_ckpt, nslots * 4 * ms * sizeof(int16_t)));
-  if (b->gb) TRY(pool_alloc(al, (void**)&b->d_gborders, nwarps * 4 * ms * sizeof(int16_t)));
-  if (trace) {
-    if (b->trace_pool_units) {
-      TRY(pool_alloc(al, (void**)&b->d_trace_pool, b->trace_pool_units * 64));
-      TRY(pool_alloc(al, (void**)&b->d_trace_pool_cursor, 4));
-    }
-    TRY(pool_alloc(al, (void**)&b->d_trace, nslots * b->trace_words_per_warp * 4));
-    if (cfg->flags & BA_LOCAL_START) TRY(pool_alloc(al, (void**)&b->d_zwords, nslots * b->trace_words_per_warp * 4));
-    TRY(pool_alloc(al, (void**)&b->d_rects, nslots * (uint64_t)b->rects_per_warp * sizeof(Rect)));
-    TRY(pool_alloc(al, (void**)&b->d_runs, nwarps * (uint64_t)b->runs_per_warp * 4));
-    uint64_t cap = 0;
-    for (size_t k = 0; k < n; k++) cap += (uint64_t)ql[k] + rl[k] + 5;
-    const uint64_t limit = (uint64_t)(al->mem_total * 0.15) / 4;
-    b->cigar_cap = std::min<uint64_t>(cap, std::max<uint64_t>(limit, 1024));
-    TRY(pool_alloc(al, (void**)&b->d_cigar, b->cigar_cap * 4));
-    TRY(pool_alloc(al, (void**)&b->d_cigar_used, 8));
-    TRY(pool_alloc(al, (void**)&b->d_overflow_list, std::max<size_t>(n, 1) * 4));
-    TRY(pool_alloc(al, (void**)&b->d_overflow_n, 4));
-    TRY(pool_alloc(al, (void**)&b->d_slot_pair, nslots * 4));
-    b->h_qlen = ql; b->h_rlen = rl;
-  }
-  if (getenv("BA_STEP_LOG") && n == 1) {
-    TRY(pool_alloc(al, (void**)&b->d_steplog, (size_t)(1 << 20) * sizeof(StepLog)));
-    TRY(pool_alloc(al, (void**)&b->d_steplog_n, 4));
-  }
+  b->h_qlen = ql; b->h_rlen = rl;
+  TRY(batch_configure(b, mn));
   *out = b;
   return BA_OK;
 }
@@ -875,6 +900,7 @@ static Params make_params(const BaBatch* b, bool retry = false) {
   memset(&P, 0, sizeof(P));
   const bool prof = b->cfg.scoring == BA_SCORING_PROFILE;
   P.n_pairs = (uint32_t)b->n; P.order = b->d_order; P.seq = b->d_seq;
+  if (b->use_active) { P.n_pairs = b->n_active; P.order = b->d_active; }
   P.q_off = b->d_qoff; P.q_len = b->d_qlen; P.r_off = b->d_roff; P.r_len = b->d_rlen;
   P.profiles = b->d_profiles; P.matrix = b->d_matrix;
   P.gap_open = b->cfg.gaps.open; P.gap_extend = b->cfg.gaps.extend;
@@ -929,7 +955,7 @@ static int batch_launch(BaBatch* b) {
   b->downloaded = false;
   b->launches = 0;
   b->retried = false;
-  if (b->n) {
+  if (P.n_pairs) {
 #ifndef BA_EMU
     cudaEventRecord(b->ss.ev0, st);
 #endif
@@ -953,7 +979,7 @@ static int batch_wait(BaBatch* b, BaStats* stats) {
   dev_stream_t st = b->ss.stream;
   float ms = 0;
   int rc;
-  if (b->n) {
+  if (b->use_active ? b->n_active : b->n) {
     if (b->d_overflow_n && b->trace_words_per_warp < b->trace_words_bound) {
       uint32_t n_over = 0;
       if (d2h(&n_over, b->d_overflow_n, 4, st) || dsync(st)) return BA_ERR_CUDA;
@@ -1185,51 +1211,147 @@ static int align_batch_impl(BaAligner* a, const BaConfig* cfg, size_t n, const u
   return rc;
 }
 
-// Block::align_exp (scan_block.rs:884-902) for a batch: every pair is aligned with min block size s = min, 2 min, ...
-// <= max until its score reaches target_score[k]. min_size_used[k] = the size that reached it, 0 = the reference's
-// None; out[k] = the result of the last attempt (what Block::res() returns afterwards).
-extern "C" int ba_align_batch_exp(BaAligner* a, const BaConfig* cfg, size_t n, const uint8_t* q_bytes, const uint64_t* q_off,
-                                  const uint8_t* r_bytes, const uint64_t* r_off, const int32_t* target_score,
-                                  AlignResult* out, uintptr_t* min_size_used, BaStats* stats) {
+// Block::align_exp / align_profile_exp (scan_block.rs:884-902, 974-992) for a batch: every pair is aligned with min
+// block size s = max(min, 16), 2s, ... <= max until its score reaches target_score[k]. min_size_used[k] = the size that
+// reached it, 0 = the reference's None; out[k] = the result of the pair's last attempt (what Block::res() returns
+// afterwards). The batch is uploaded ONCE and stays resident: after every round a device-side filter compacts the
+// ids of the pairs still below their target into the next round's work list (order preserved, so the longest-first
+// schedule survives), and only the length of that list crosses the bus.
+struct ExpArgs {
+  const DevResult* out; const int32_t* target; const uint32_t* in_list; uint32_t n_in;
+  uint32_t* out_list; uint32_t* out_n; uint32_t* used; uint32_t sz;
+  unsigned long long* totals;    // [0] cells, [1] steps, [2] failed pairs of all rounds
+};
+#ifdef BA_EMU
+static void exp_filter(const ExpArgs& a, dev_stream_t) {
+  uint32_t m = 0;
+  for (uint32_t i = 0; i < a.n_in; i++) {
+    const uint32_t pair = a.in_list[i];
+    const DevResult& r = a.out[pair];
+    a.totals[0] += r.cells; a.totals[1] += r.steps; a.totals[2] += r.status ? 1 : 0;
+    if (r.score >= a.target[pair]) a.used[pair] = a.sz; else a.out_list[m++] = pair;
+  }
+  *a.out_n = m;
+}
+#else
+__global__ void __launch_bounds__(1024) ba_exp_filter_kernel(ExpArgs a) {
+  __shared__ uint32_t wsum[32];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t base = 0, failed = 0;
+  unsigned long long cells = 0, steps = 0;
+  for (uint32_t i0 = 0; i0 < a.n_in; i0 += 1024) {
+    const uint32_t i = i0 + threadIdx.x;
+    bool keep = false; uint32_t pair = 0;
+    if (i < a.n_in) {
+      pair = a.in_list[i];
+      const DevResult r = a.out[pair];
+      cells += r.cells; steps += r.steps; failed += r.status ? 1u : 0u;
+      if (r.score >= a.target[pair]) a.used[pair] = a.sz; else keep = true;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) wsum[warp] = (uint32_t)__popc(m);
+    __syncthreads();
+    uint32_t woff = 0, tot = 0;
+    for (uint32_t w = 0; w < 32; w++) { const uint32_t c = wsum[w]; if (w < warp) woff += c; tot += c; }
+    if (keep) a.out_list[base + woff + (uint32_t)__popc(m & ((1u << lane) - 1u))] = pair;
+    base += tot;
+    __syncthreads();
+  }
+  atomicAdd(a.totals + 0, cells); atomicAdd(a.totals + 1, steps); atomicAdd(a.totals + 2, (unsigned long long)failed);
+  if (threadIdx.x == 0) *a.out_n = base;
+}
+static void exp_filter(const ExpArgs& a, dev_stream_t st) { ba_exp_filter_kernel<<<1, 1024, 0, st>>>(a); }
+#endif
+
+static int align_exp_resident(BaBatch* b, size_t n, const int32_t* target_score, AlignResult* out, uintptr_t* min_size_used, BaStats* stats) {
+  BaAligner* al = b->al;
+  dev_stream_t st = b->ss.stream;
+  const uint32_t mn = b->min_size, mx = b->max_size;
+  int32_t* d_target = nullptr; uint32_t* d_used = nullptr; uint32_t* d_list[2] = {nullptr, nullptr}; uint32_t* d_n = nullptr;
+  unsigned long long* d_tot = nullptr;
+  auto cleanup = [&]() { pool_release(al, d_target); pool_release(al, d_used); pool_release(al, d_list[0]); pool_release(al, d_list[1]);
+                         pool_release(al, d_n); pool_release(al, d_tot); };
+#define EXP_TRY(x) do { int _r = (x); if (_r) { cleanup(); ba_batch_free(b); return _r == 1 ? BA_ERR_CUDA : _r; } } while (0)
+  EXP_TRY(pool_alloc(al, (void**)&d_target, n * 4)); EXP_TRY(pool_alloc(al, (void**)&d_used, n * 4));
+  EXP_TRY(pool_alloc(al, (void**)&d_list[0], n * 4)); EXP_TRY(pool_alloc(al, (void**)&d_list[1], n * 4));
+  EXP_TRY(pool_alloc(al, (void**)&d_n, 4)); EXP_TRY(pool_alloc(al, (void**)&d_tot, 24));
+  EXP_TRY(h2d(d_target, target_score, n * 4, st)); EXP_TRY(dzero(d_used, n * 4, st)); EXP_TRY(dzero(d_tot, 24, st));
+  BaStats tot; memset(&tot, 0, sizeof(tot));
+  const uint32_t* cur = b->d_order; uint32_t n_cur = (uint32_t)n;
+  int flip = 0;
+  for (uint64_t sz = mn; sz <= mx && n_cur; sz *= 2) {
+    if (sz != mn) EXP_TRY(batch_configure(b, (uint32_t)sz));
+    b->use_active = true; b->d_active = cur; b->n_active = n_cur;
+    BaStats st1;
+    EXP_TRY(batch_launch(b));
+    EXP_TRY(batch_wait(b, &st1));
+    tot.kernel_ms += st1.kernel_ms; tot.kernel_launches += st1.kernel_launches + 1;
+    ExpArgs ea{b->d_out, d_target, cur, n_cur, d_list[flip], d_n, d_used, (uint32_t)sz, d_tot};
+    exp_filter(ea, st);
+    uint32_t n_next = 0;
+    EXP_TRY(d2h(&n_next, d_n, 4, st)); EXP_TRY(dsync(st));
+    cur = d_list[flip]; n_cur = n_next; flip ^= 1;
+  }
+  b->use_active = false;
+  std::vector<uint32_t> used(n);
+  unsigned long long totals[3] = {0, 0, 0};
+  EXP_TRY(d2h(used.data(), d_used, n * 4, st)); EXP_TRY(d2h(totals, d_tot, 24, st)); EXP_TRY(dsync(st));
+  for (size_t k = 0; k < n; k++) min_size_used[k] = used[k];
+  cleanup();
+  b->cigar_skip = true;
+  int rc = ba_batch_download(b, out);
+  tot.cells = totals[0]; tot.steps = totals[1]; tot.n_failed = (uint32_t)totals[2]; tot.pack_ms = b->pack_ms;
+  tot.kernel_launches += n ? 1 : 0;   // convert/pad
+  if (stats) *stats = tot;
+  ba_batch_free(b);
+  return rc;
+#undef EXP_TRY
+}
+static int exp_check(const BaConfig* cfg, const int32_t* target_score, AlignResult* out, uintptr_t* min_size_used) {
   if (!cfg || !target_score || !out || !min_size_used) return fail(BA_ERR_ARG, "null argument");
   uint32_t mn = 0, mx = 0;
   int rc = check_config(cfg, &mn, &mx);
   if (rc) return rc;
   if (mn > mx) return fail(BA_ERR_SIZE, "min block size is larger than max block size");
-  std::vector<size_t> active(n);
-  for (size_t k = 0; k < n; k++) { active[k] = k; min_size_used[k] = 0; }
-  BaStats tot; memset(&tot, 0, sizeof(tot));
-  for (uint64_t sz = mn; sz <= mx && !active.empty(); sz *= 2) {
-    // compact copy of the still-active pairs
-    const size_t m = active.size();
-    std::vector<uint64_t> qo(m + 1, 0), ro(m + 1, 0);
-    for (size_t t = 0; t < m; t++) {
-      qo[t + 1] = qo[t] + (q_off[active[t] + 1] - q_off[active[t]]);
-      ro[t + 1] = ro[t] + (r_off[active[t] + 1] - r_off[active[t]]);
-    }
-    std::vector<uint8_t> qa(qo[m] + 1), ra(ro[m] + 1);
-    for (size_t t = 0; t < m; t++) {
-      memcpy(qa.data() + qo[t], q_bytes + q_off[active[t]], qo[t + 1] - qo[t]);
-      memcpy(ra.data() + ro[t], r_bytes + r_off[active[t]], ro[t + 1] - ro[t]);
-    }
-    BaConfig c2 = *cfg;
-    c2.size.min = sz; c2.size.max = mx;
-    std::vector<AlignResult> res(m);
-    BaStats st1;
-    rc = ba_align_batch(a, &c2, m, qa.data(), qo.data(), ra.data(), ro.data(), res.data(), &st1);
-    if (rc) return rc;
-    tot.cells += st1.cells; tot.steps += st1.steps; tot.kernel_ms += st1.kernel_ms; tot.pack_ms += st1.pack_ms;
-    tot.kernel_launches += st1.kernel_launches; tot.n_failed += st1.n_failed;
-    std::vector<size_t> next;
-    for (size_t t = 0; t < m; t++) {
-      out[active[t]] = res[t];
-      if (res[t].score >= target_score[active[t]]) min_size_used[active[t]] = (uintptr_t)sz;
-      else next.push_back(active[t]);
-    }
-    active.swap(next);
-  }
-  if (stats) *stats = tot;
   return BA_OK;
+}
+extern "C" int ba_align_batch_exp(BaAligner* a, const BaConfig* cfg, size_t n, const uint8_t* q_bytes, const uint64_t* q_off,
+                                  const uint8_t* r_bytes, const uint64_t* r_off, const int32_t* target_score,
+                                  AlignResult* out, uintptr_t* min_size_used, BaStats* stats) {
+  int rc = exp_check(cfg, target_score, out, min_size_used);
+  if (rc) return rc;
+  if (!a) return fail(BA_ERR_ARG, "aligner is null");
+  AlLock lk(a->mu);
+  BaBatch* b = nullptr;
+  rc = ba_batch_upload(a, cfg, n, q_bytes, q_off, r_bytes, r_off, &b);
+  if (rc) return rc;
+  return align_exp_resident(b, n, target_score, out, min_size_used, stats);
+}
+// Block::align_profile_exp (scan_block.rs:974-992) for a batch, profiles as host AAProfile objects ...
+extern "C" int ba_align_batch_exp_profiles(BaAligner* a, const BaConfig* cfg, size_t n, const uint8_t* q_bytes, const uint64_t* q_off,
+                                           const AAProfile* const* profiles, const int32_t* target_score,
+                                           AlignResult* out, uintptr_t* min_size_used, BaStats* stats) {
+  int rc = exp_check(cfg, target_score, out, min_size_used);
+  if (rc) return rc;
+  if (!a) return fail(BA_ERR_ARG, "aligner is null");
+  AlLock lk(a->mu);
+  BaBatch* b = nullptr;
+  rc = ba_batch_upload_profiles(a, cfg, n, q_bytes, q_off, profiles, &b);
+  if (rc) return rc;
+  return align_exp_resident(b, n, target_score, out, min_size_used, stats);
+}
+// ... and as raw PSSM rows the library turns into profiles on the device
+extern "C" int ba_align_batch_exp_pssm(BaAligner* a, const BaConfig* cfg, size_t n, const uint8_t* q_bytes, const uint64_t* q_off,
+                                       const BaPssmBatch* pssm, const int32_t* target_score,
+                                       AlignResult* out, uintptr_t* min_size_used, BaStats* stats) {
+  int rc = exp_check(cfg, target_score, out, min_size_used);
+  if (rc) return rc;
+  if (!a) return fail(BA_ERR_ARG, "aligner is null");
+  AlLock lk(a->mu);
+  BaBatch* b = nullptr;
+  rc = ba_batch_upload_pssm(a, cfg, n, q_bytes, q_off, pssm, &b);
+  if (rc) return rc;
+  return align_exp_resident(b, n, target_score, out, min_size_used, stats);
 }
 
 // sequence-to-profile counterpart of ba_align_batch (no chunking: profiles are uploaded as one arena)

@@ -230,11 +230,19 @@ int ba_align_batch_cigar(BaAligner* a, const BaConfig* cfg, size_t n,
                          AlignResult* out, uint32_t* runs, size_t runs_cap, uint64_t* run_off, uint32_t* run_len,
                          size_t* runs_used, BaStats* stats);
 
-/* Block::align_exp (src/scan_block.rs:884-902) for a batch: retry with doubled min block size until
- * score >= target_score[k]. min_size_used[k] = the min size that reached the target, 0 = None. */
+/* Block::align_exp / align_profile_exp (src/scan_block.rs:884-902, 974-992) for a batch: retry with doubled min block
+ * size (starting at max(size.min, 16)) until score >= target_score[k]. min_size_used[k] = the min size that reached the
+ * target, 0 = the reference's None; out[k] = the result of pair k's last attempt. The batch is uploaded once and stays
+ * on the device; between rounds only the list of pair ids still below their target is rebuilt (on the device). */
 int ba_align_batch_exp(BaAligner* a, const BaConfig* cfg, size_t n,
                        const uint8_t* q_bytes, const uint64_t* q_off, const uint8_t* r_bytes, const uint64_t* r_off,
                        const int32_t* target_score, AlignResult* out, uintptr_t* min_size_used, BaStats* stats);
+int ba_align_batch_exp_profiles(BaAligner* a, const BaConfig* cfg, size_t n,
+                                const uint8_t* q_bytes, const uint64_t* q_off, const struct AAProfile* const* profiles,
+                                const int32_t* target_score, AlignResult* out, uintptr_t* min_size_used, BaStats* stats);
+int ba_align_batch_exp_pssm(BaAligner* a, const BaConfig* cfg, size_t n,
+                            const uint8_t* q_bytes, const uint64_t* q_off, const BaPssmBatch* pssm,
+                            const int32_t* target_score, AlignResult* out, uintptr_t* min_size_used, BaStats* stats);
 int ba_align_batch_profiles(BaAligner* a, const BaConfig* cfg, size_t n,
                             const uint8_t* q_bytes, const uint64_t* q_off,
                             const struct AAProfile* const* profiles, AlignResult* out, BaStats* stats);

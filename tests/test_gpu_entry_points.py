@@ -150,7 +150,7 @@ def test_align_batch_exp_against_oracle_loop(env, flags):
     full, _, _ = al.align_batch(qs, rs, api.SCORING_NUC, nw1, (-2, -1), (512, 512), 10000, flags)
     targets = [f[0] for f in full]
     targets[7] = 10 ** 6          # unreachable: min_size_used = None, result of the last attempt
-    res, used = api.align_batch_exp(al, qs, rs, api.SCORING_NUC, nw1, (-2, -1), (32, 512), targets, x_drop=10000, flags=flags)
+    res, used, _ = api.align_batch_exp(al, qs, rs, api.SCORING_NUC, nw1, (-2, -1), (32, 512), targets, x_drop=10000, flags=flags)
     exp = _exp_loop_oracle(ora.NUC, ora.nw1(), (-2, -1), (32, 512), 10000, flags, qs, rs, targets)
     assert [(tuple(r), u) for r, u in zip(res, used)] == [(tuple(e[0]), e[1]) for e in exp]
     assert used[7] is None and len(set(used)) >= (3 if flags == 0 else 2), "test inputs should need retries at several sizes"

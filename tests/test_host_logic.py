@@ -119,7 +119,7 @@ def test_align_exp_matches_reference_loop(env):
     # targets: the score a 256-wide block finds (so small blocks often miss it)
     full, _, _ = al.align_batch(qs, rs, api.SCORING_NUC, nw1, (-2, -1), (256, 256))
     targets = [f[0] for f in full]
-    res, used = api.align_batch_exp(al, qs, rs, api.SCORING_NUC, nw1, (-2, -1), (32, 256), targets)
+    res, used, _ = api.align_batch_exp(al, qs, rs, api.SCORING_NUC, nw1, (-2, -1), (32, 256), targets)
     for k in range(16):
         ob = ora.Block(len(qs[k]), len(rs[k]), 256, 0)
         q, r = ora.Padded(ora.NUC, qs[k], 256), ora.Padded(ora.NUC, rs[k], 256)
@@ -168,3 +168,48 @@ def test_align_batch_cigar_delivers_runs_into_caller_buffer(env, monkeypatch):
     rc = lib.L.ba_align_batch_cigar(al.h, C.byref(cfg), n, qa.ctypes.data, qo.ctypes.data, ra.ctypes.data, ro.ctypes.data,
                                     out.ctypes.data, small.ctypes.data, 8, off.ctypes.data, ln.ctypes.data, C.byref(used), C.byref(st))
     assert rc == api.ERR_OVERFLOW if hasattr(api, "ERR_OVERFLOW") else rc != 0
+
+
+def test_align_profile_exp_matches_reference_loop(env):
+    """ba_align_batch_exp_pssm / _profiles vs the reference's align_profile_exp loop (scan_block.rs:974-992) on the oracle"""
+    import ora
+    import parity
+    from block_aligner_b200 import workloads
+    lib, al = env
+    w = workloads.WORKLOADS["C4_seq_to_profile_xdrop"]
+    n = 20
+    gen = workloads.params(alphabet=1, len_dist=0, len_min=300, len_max=700, sub_rate=0.3, ins_rate=0.03, del_rate=0.03,
+                           big_indel_prob=1.0, big_indel_min=60, big_indel_max=120)
+    qa, qo, ra, ro = workloads.generate(gen, n, seed=3, stream=4)
+    qs = [qa[int(qo[k]):int(qo[k + 1])].tobytes() for k in range(n)]
+    pb = workloads.make_pssm_batch(lib, ra, ro, seed=21)
+    oprofs = parity.make_ora_profiles(ra, ro, 256, -10, -1, 21)
+    # targets: what a 256-wide block finds
+    exp_full = parity.oracle_batch(api.SCORING_PROFILE, None, None, (256, 256), 0, 0, False, qa, qo, ra, ro, profiles=oprofs)
+    targets = [int(x) for x in exp_full[0][:, 0]]
+    targets[3] = 10 ** 6
+    res, used, st = api.align_batch_exp(al, qs, None, api.SCORING_PROFILE, None, None, (32, 256), targets, profiles=pb)
+    lprofs = workloads.make_lib_profiles(lib, ra, ro, 256, seed=21)
+    res2, used2, _ = api.align_batch_exp(al, qs, None, api.SCORING_PROFILE, None, None, (32, 256), targets, profiles=lprofs)
+    assert res == res2 and used == used2
+    cells = 0
+    for k in range(n):
+        ob = ora.Block(len(qs[k]), len(oprofs[k]), 256, 0)
+        q = ora.Padded(ora.AA, qs[k], 256)
+        exp_used, exp_res, mn = None, None, 32
+        while mn <= 256:
+            exp_res = ob.align_profile(q, oprofs[k], (mn, 256), 0)
+            cells += ob.cells()
+            if exp_res[0] >= targets[k]:
+                exp_used = mn
+                break
+            mn *= 2
+        assert res[k] == exp_res and used[k] == exp_used, (k, res[k], exp_res, used[k], exp_used)
+    assert used[3] is None and st.cells == cells and st.n_failed == 0
+    assert any(u not in (32, None) for u in used), "test inputs should need at least one retry"
+
+
+def test_align_exp_rejects_min_above_max(env):
+    lib, al = env
+    with pytest.raises(api.BlockAlignerError, match="larger than max"):
+        api.align_batch_exp(al, [b"ACGT"], [b"ACGT"], api.SCORING_NUC, api.nuc_matrix(1, -1), (-2, -1), (64, 32), [1])
