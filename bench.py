@@ -245,31 +245,56 @@ def measure(name, n, steps, warmup, ctx, cpu_seconds, want_cpu, pageable_once=Fa
         cig = dict(cap=cap, runs=torch.empty(cap, dtype=torch.int32).pin_memory(), off=np.zeros(n, dtype=np.uint64),
                    len=np.zeros(n, dtype=np.uint32), used=C.c_size_t())
     path = "ba_align_batch_cigar" if trace else ("ba_align_batch_pssm" if profiles is not None else "ba_align_batch")
+    # Nucleotide workloads: the end-to-end leg hands the library BAM-style 4-bit codes (BA_INPUT_NUC4, two bases per byte;
+    # packed once, outside the timed region: it is the caller's input format) -- half the bytes cross PCIe. The same call
+    # with one ASCII byte per base is timed next to it (e2e.ascii_input).
+    nuc4 = w["scoring"] == api.SCORING_NUC and not os.environ.get("BA_BENCH_NO_NUC4")
+    cfg_main = cfg
+    if nuc4:
+        pq, _ = api.pack_nuc4(lib, qa, qo)
+        pr, _ = api.pack_nuc4(lib, ra, ro)
+        (pq, kq), (pr, kr) = pin(pq), pin(pr)
+        keep += [kq, kr]
+        cfg_main = al.config(w["scoring"], matrix, w["gaps"], w["size"], w["x_drop"], w["flags"] | api.INPUT_NUC4, bool(w.get("cigar_eq")))
 
-    def e2e_once(q_arena, r_arena):
+    def e2e_once(q_arena, r_arena, c=None):
+        c = c or cfg
         if trace:
-            lib.check(lib.L.ba_align_batch_cigar(al.h, C.byref(cfg), n, q_arena.ctypes.data, qo.ctypes.data, r_arena.ctypes.data,
+            lib.check(lib.L.ba_align_batch_cigar(al.h, C.byref(c), n, q_arena.ctypes.data, qo.ctypes.data, r_arena.ctypes.data,
                                                  ro.ctypes.data, out.ctypes.data, cig["runs"].data_ptr(), cig["cap"],
                                                  cig["off"].ctypes.data, cig["len"].ctypes.data, C.byref(cig["used"]), C.byref(st)))
         elif profiles is not None:
-            lib.check(lib.L.ba_align_batch_pssm(al.h, C.byref(cfg), n, q_arena.ctypes.data, qo.ctypes.data, C.byref(profiles.c),
+            lib.check(lib.L.ba_align_batch_pssm(al.h, C.byref(c), n, q_arena.ctypes.data, qo.ctypes.data, C.byref(profiles.c),
                                                 out.ctypes.data, C.byref(st)))
         else:
-            lib.check(lib.L.ba_align_batch(al.h, C.byref(cfg), n, q_arena.ctypes.data, qo.ctypes.data, r_arena.ctypes.data,
+            lib.check(lib.L.ba_align_batch(al.h, C.byref(c), n, q_arena.ctypes.data, qo.ctypes.data, r_arena.ctypes.data,
                                            ro.ctypes.data, out.ctypes.data, C.byref(st)))
-    e2e_error, e2e_launches, pageable_s = None, 0, None
+    e2e_error, e2e_launches, pageable_s, ascii_s = None, 0, None, None
     try:
-        for _ in range(min(warmup, 2)):
+        if nuc4:      # the ASCII-input variant first (same entry point, one byte per base)
             e2e_once(qa, ra)
+            barrier()
+            t1 = time.perf_counter()
+            for _ in range(steps):
+                out[:] = 0
+                e2e_once(qa, ra)
+            barrier()
+            ascii_s = time.perf_counter() - t1
+            ascii_out = out.copy()
+        mq, mr = (pq, pr) if nuc4 else (qa, ra)
+        for _ in range(min(warmup, 2)):
+            e2e_once(mq, mr, cfg_main)
         barrier()
         t1 = time.perf_counter()
         for _ in range(steps):
             out[:] = 0
-            e2e_once(qa, ra)
+            e2e_once(mq, mr, cfg_main)
             e2e_launches += int(st.kernel_launches)      # alignment + convert/pad (+ profile build) launches of this call
         barrier()
         e2e_s = time.perf_counter() - t1
         e2e_out = out.copy()
+        if nuc4 and not (ascii_out == e2e_out).all():
+            e2e_error = "4-bit and ASCII inputs returned different results"
         if pageable_once and profiles is None:
             # the same call from ordinary (pageable) caller memory, once: what a drop-in user who does not pin gets
             qp, rp = np.array(qa, copy=True), np.array(ra, copy=True)
@@ -286,16 +311,17 @@ def measure(name, n, steps, warmup, ctx, cpu_seconds, want_cpu, pageable_once=Fa
         e2e_s = float("inf")
         e2e_out = out
     sampler.stop_flag = True
-    h2d = int(qa.nbytes + 2 * qo.nbytes + n * (8 + 8 + 4 + 4 + 4) + (profiles.nbytes() if profiles is not None else ra.nbytes))
-    d2h = int(n * 56) + (int(cig["used"].value) * 4 if trace else 0)
+    seq_bytes = int(pq.nbytes + pr.nbytes) if nuc4 else int(qa.nbytes + (profiles.nbytes() if profiles is not None else ra.nbytes))
+    h2d = int(seq_bytes + 2 * qo.nbytes + n * (8 + 8 + 4 + 4 + 4))
+    d2h = int(n * 48) + (int(cig["used"].value) * 4 if trace else 0)
 
     # ---- max over ranks ----
-    vals = torch.tensor([dev_s, e2e_s, wall], dtype=torch.float64, device="cuda")
+    vals = torch.tensor([dev_s, e2e_s, wall, ascii_s or 0.0], dtype=torch.float64, device="cuda")
     cells_t = torch.tensor([cells_step], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(cells_t, op=dist.ReduceOp.SUM)
-    dev_s, e2e_s, wall = [float(x) for x in vals.tolist()]
+    dev_s, e2e_s, wall, ascii_s = [float(x) for x in vals.tolist()]
     cells_all = float(cells_t.item())
     if rank != 0:
         return None
@@ -309,7 +335,7 @@ def measure(name, n, steps, warmup, ctx, cpu_seconds, want_cpu, pageable_once=Fa
     ops = OPS_PER_CELL[w["flags"] & 3]
     achieved = cells_step * steps / (sum(kernel_ms) / 1e3) * ops / 1e9     # this rank's kernel
     peaks = ctx["peaks"]
-    alg_bytes = float(qa.nbytes + (profiles.nbytes() if profiles is not None else ra.nbytes) + n * 56)
+    alg_bytes = float(qa.nbytes + (profiles.nbytes() if profiles is not None else ra.nbytes) + n * 48)
     traffic, traffic_src = newest_traffic(name.split("_")[0], n)
     res = {
         "metric": "GCUPS (computed DP cells / s / 1e9)", "value": gcups, "unit": "GCUPS", "n_gpus": world,
@@ -323,7 +349,8 @@ def measure(name, n, steps, warmup, ctx, cpu_seconds, want_cpu, pageable_once=Fa
         "alignments_per_s": n * world * steps / dev_s,
         "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s / steps * 1e3, "alignments_per_s": n * world * steps / e2e_s, "entry_point": path,
-                "caller_buffers": "pinned host memory"},
+                "caller_buffers": "pinned host memory",
+                "input_format": "BAM 4-bit base codes, two per byte (BA_INPUT_NUC4)" if nuc4 else "one byte per residue"},
         # launches of this library's kernels inside the two timed regions (counted by the library, BaStats)
         "gpu_launches": value_launches + e2e_launches,
         "gpu_launches_detail": {"value_region": value_launches, "e2e_region": e2e_launches},
@@ -338,6 +365,10 @@ def measure(name, n, steps, warmup, ctx, cpu_seconds, want_cpu, pageable_once=Fa
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"}},
         "clocks": sampler.summary(), "n_failed_pairs": n_failed, "wall_s_timed_region": wall,
     }
+    if nuc4 and ascii_s:
+        res["e2e"]["ascii_input"] = {"value": cells_all * steps / ascii_s / 1e9, "unit": "GCUPS", "ms_per_step": ascii_s / steps * 1e3,
+                                     "h2d_bytes_per_step": int(qa.nbytes + ra.nbytes + 2 * qo.nbytes + n * 28),
+                                     "note": "same entry point, one ASCII byte per base (the reference's own input format)"}
     if pageable_s is not None:
         res["e2e"]["pageable_caller_buffers"] = {"value": cells_step / pageable_s / 1e9, "unit": "GCUPS", "ms_per_step": pageable_s * 1e3,
                                                  "steps": 1, "note": "same call, inputs in ordinary malloc'ed memory (this rank only)"}
@@ -350,6 +381,43 @@ def measure(name, n, steps, warmup, ctx, cpu_seconds, want_cpu, pageable_once=Fa
         if not e2e_error:
             res["parity"] = parity_of(cb, e2e_out, cig, path)
     del keep
+    return res
+
+
+def strong_scaling(lib, al, name, n, n_gpus, steps, cb):
+    """ONE batch of the workload's full size over n_gpus GPUs in ONE call (ba_align_batch_multi): host buffers in, results
+    in the caller's order out, wall clock around the call. Run by rank 0 alone after the per-rank (weak-scaling) part."""
+    from block_aligner_b200 import api, workloads
+    w = load_workload(name)
+    n = n or w["n"]
+    lib.check(lib.L.ba_trim(al.h))
+    qa, qo, ra, ro, keep = gen_shard(w, n, first=0, pinned=True)
+    pq, _ = api.pack_nuc4(lib, qa, qo)
+    pr, _ = api.pack_nuc4(lib, ra, ro)
+    (pq, kq), (pr, kr) = pin(pq), pin(pr)
+    matrix = workloads.matrix_of(lib, w)
+    cfg = al.config(w["scoring"], matrix, w["gaps"], w["size"], w["x_drop"], w["flags"] | api.INPUT_NUC4, False)
+    out = np.zeros(n, dtype=RES_DT)
+    st = api.BaStats()
+
+    def once():
+        lib.check(lib.L.ba_align_batch_multi(None, n_gpus, C.byref(cfg), n, pq.ctypes.data, qo.ctypes.data, pr.ctypes.data, ro.ctypes.data,
+                                             out.ctypes.data, C.byref(st)))
+    once()
+    once()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out[:] = 0
+        once()
+    dt = (time.perf_counter() - t0) / steps
+    res = {"n_gpus": n_gpus, "pairs": n, "entry_point": "ba_align_batch_multi", "value": int(st.cells) / dt / 1e9, "unit": "GCUPS",
+           "ms_per_step": dt * 1e3, "steps": steps, "scaling": "strong",
+           "note": "one batch, one call, all GPUs: contiguous shards of equal sum(|q|+|r|), one host thread per GPU, "
+                   "results written in the caller's order; wall clock incl. H2D (4-bit input) and D2H"}
+    if cb is not None:
+        res["parity"] = parity_of(cb, out, None, "ba_align_batch_multi")
+    lib.L.ba_multi_release()
+    del keep, kq, kr
     return res
 
 
@@ -435,6 +503,13 @@ def main():
             bad += line["parity"]["mismatches"]
     line.pop("_e2e_out", None)
     line.pop("_cig", None)
+    if args.workload == HEADLINE and not os.environ.get("BA_BENCH_NO_STRONG"):
+        try:
+            line["strong_scaling"] = strong_scaling(lib, al, args.workload, args.pairs, max(1, args.gpus), max(2, args.steps // 2),
+                                                    cb if want_cpu else None)
+            bad += line["strong_scaling"].get("parity", {}).get("mismatches", 0)
+        except Exception as e:
+            line["strong_scaling"] = {"error": repr(e)}
     if world == 1 and not args.no_configs and args.workload == HEADLINE and not args.pairs:
         ctx1 = dict(ctx, world=1)
         line["configs"] = {}

@@ -17,6 +17,7 @@ DEFAULT_LIB = os.path.join(_HERE, "libblock_aligner_b200.so")
 SCORING_NUC, SCORING_AA, SCORING_BYTE, SCORING_PROFILE = 0, 1, 2, 3
 TRACE, XDROP, LOCAL_START, FREE_QUERY_START_GAPS, FREE_QUERY_END_GAPS = 1, 2, 4, 8, 16
 REV_QUERY, REV_REFERENCE = 32, 64      # PaddedBytes::set_bytes_rev for the whole batch (done on the device)
+INPUT_NUC4 = 128                       # arenas hold BAM 4-bit codes, offsets count nibbles
 OPS = {0: "?", 1: "M", 2: "=", 3: "X", 4: "I", 5: "D"}
 
 
@@ -93,7 +94,8 @@ PART2_FUNCTIONS = ["ba_error_string", "ba_last_error_message", "ba_create", "ba_
                    "ba_batch_upload_profiles", "ba_batch_upload_pssm", "ba_align_batch_pssm", "ba_batch_run", "ba_batch_download", "ba_batch_cigar",
                    "ba_batch_traceback", "ba_batch_total_stats", "ba_batch_pair_stats", "ba_batch_free",
                    "ba_align_batch", "ba_align_batch_cigar", "ba_align_batch_exp", "ba_align_batch_exp_profiles", "ba_align_batch_exp_pssm", "ba_align_batch_profiles", "ba_new_simple_nucmatrix", "ba_set_nucmatrix", "ba_free_nucmatrix",
-                   "ba_percent_len", "ba_cigar_format", "ba_measure_int_peak", "ba_measure_int_peak_packed"]
+                   "ba_device_count", "ba_multi_release", "ba_align_batch_multi", "ba_align_batch_multi_cigar", "ba_align_batch_multi_pssm",
+                   "ba_percent_len", "ba_pack_nuc4", "ba_cigar_format", "ba_measure_int_peak", "ba_measure_int_peak_packed"]
 
 
 class Library:
@@ -136,6 +138,14 @@ class Library:
         L.ba_new_simple_nucmatrix.argtypes = [i8, i8]
         L.ba_set_nucmatrix.argtypes = [vp, u8, u8, i8]
         L.ba_free_nucmatrix.argtypes = [vp]
+        L.ba_device_count.restype = C.c_int
+        L.ba_multi_release.restype = None
+        L.ba_align_batch_multi.argtypes = [vp, C.c_int, C.POINTER(BaConfig), sz, vp, vp, vp, vp, vp, C.POINTER(BaStats)]
+        L.ba_align_batch_multi_cigar.argtypes = [vp, C.c_int, C.POINTER(BaConfig), sz, vp, vp, vp, vp, vp, vp, sz, vp, vp, C.POINTER(sz),
+                                                 C.POINTER(BaStats)]
+        L.ba_align_batch_multi_pssm.argtypes = [vp, C.c_int, C.POINTER(BaConfig), sz, vp, vp, C.POINTER(BaPssmBatch), vp, C.POINTER(BaStats)]
+        L.ba_pack_nuc4.restype = sz
+        L.ba_pack_nuc4.argtypes = [vp, sz, vp, C.c_uint64]
         L.ba_percent_len.restype = sz
         L.ba_percent_len.argtypes = [sz, C.c_float]
         L.ba_cigar_format.restype = sz
@@ -233,6 +243,18 @@ def concat(seqs):
         off[1:] = np.cumsum([len(s) for s in seqs], dtype=np.uint64)
     arena = np.frombuffer(b"".join(seqs), dtype=np.uint8) if seqs else np.zeros(0, dtype=np.uint8)
     return np.ascontiguousarray(arena), off
+
+
+def pack_nuc4(lib, arena, off):
+    """ASCII arena + byte offsets -> (BAM-nibble arena, the same offsets read as nibble offsets) for INPUT_NUC4:
+    the concatenation stays dense, sequence k = nibbles [off[k], off[k+1])."""
+    arena = np.ascontiguousarray(arena, dtype=np.uint8)
+    total = int(off[-1])
+    packed = np.zeros((total + 1) // 2 + 1, dtype=np.uint8)
+    bad = lib.L.ba_pack_nuc4(arena.ctypes.data, total, packed.ctypes.data, 0)
+    if bad:
+        raise BlockAlignerError(f"byte {bad - 1} is not a nucleotide code")
+    return packed, np.ascontiguousarray(off, dtype=np.uint64)
 
 
 def runs_to_string(runs):

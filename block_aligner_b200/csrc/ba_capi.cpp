@@ -234,6 +234,22 @@ void block_set_bytes_padded_aa(PaddedBytes* p, const uint8_t* s, uintptr_t len, 
 void block_set_bytes_rev_padded_aa(PaddedBytes* p, const uint8_t* s, uintptr_t len, uintptr_t max_size) { set_bytes(p, s, len, max_size, true); }
 void block_free_padded_aa(PaddedBytes* p) { delete p; }
 
+// ---- BA_INPUT_NUC4 host helper: ASCII -> BAM nibble codes ("=ACMGRSVTWYHKDBN") ---------------------------------
+size_t ba_pack_nuc4(const uint8_t* ascii, size_t len, uint8_t* packed, uint64_t nibble_off) {
+  static const char code[] = "=ACMGRSVTWYHKDBN";
+  uint8_t lut[256];
+  memset(lut, 0, sizeof(lut));
+  for (int c = 1; c < 16; c++) { lut[(uint8_t)code[c]] = (uint8_t)c; lut[(uint8_t)(code[c] + 32)] = (uint8_t)c; }
+  for (size_t k = 0; k < len; k++) {
+    const uint8_t v = lut[ascii[k]];
+    if (!v) return k + 1;
+    const uint64_t nb = nibble_off + k;
+    uint8_t& b = packed[nb >> 1];
+    b = (nb & 1) ? (uint8_t)((b & 0xf0u) | v) : (uint8_t)((b & 0x0fu) | (v << 4));
+  }
+  return 0;
+}
+
 // ---- lib.rs:109-111 --------------------------------------------------------------------------------
 uintptr_t ba_percent_len(uintptr_t len, float p) {
   // Rust's f32::round rounds half away from zero, like roundf

@@ -36,7 +36,14 @@ struct PackArgs {
   uint8_t* seq; const uint64_t* pq_off; const uint64_t* pr_off;
   uint32_t n; uint32_t pad; int32_t scoring; uint32_t* err;
   uint32_t rev_q, rev_r;      // PaddedBytes::set_bytes_rev (scan_block.rs:1815-1822)
+  uint32_t nuc4;              // BA_INPUT_NUC4: raw arenas hold 4-bit codes, raw offsets count nibbles (high nibble first)
 };
+// BAM / htslib nibble codes -> the ASCII letter the reference would have been given ("=ACMGRSVTWYHKDBN"); code 0 ('=') is
+// not a base and is reported as a bad character
+BA_HD uint8_t nuc4_letter(uint32_t code) {
+  const uint64_t lo = 0x565352474d434100ull, hi = 0x4e42444b48595754ull;   // bytes: \0 A C M G R S V | T W Y H K D B N
+  return (uint8_t)(((code & 8u) ? hi : lo) >> (8u * (code & 7u)));
+}
 
 // One padded device profile (ProfBuild, ba_types.h). `tid` / `nthreads`: the calling thread's share of the profile.
 // Layout written: pos_aa [curr_len][32] i8, then gap_open_C, gap_close_C, gap_open_R [curr_len] i16.
@@ -107,6 +114,16 @@ static void pack_all(const PackArgs& a) {
       const uint8_t nul = host::null_code(a.scoring);
       dst[0] = nul;
       const bool rev = which ? a.rev_r != 0 : a.rev_q != 0;
+      if (a.nuc4) {
+        const uint8_t* arena = which ? a.raw_r : a.raw_q;
+        const uint64_t o0 = which ? a.raw_r_off[k] : a.raw_q_off[k];
+        for (uint64_t t = 0; t < len; t++) {
+          const uint64_t nb = o0 + (rev ? len - 1 - t : t);
+          const uint32_t code = (nb & 1) ? (arena[nb >> 1] & 15u) : (arena[nb >> 1] >> 4);
+          dst[1 + t] = nuc4_letter(code);
+          if (code == 0) *a.err = 1;
+        }
+      } else
       for (uint64_t t = 0; t < len; t++) { bool ok; dst[1 + t] = host::convert_char(a.scoring, src[rev ? len - 1 - t : t], &ok); if (!ok) *a.err = 1; }
       for (uint32_t t = 0; t < a.pad; t++) dst[1 + len + t] = nul;
     }
@@ -139,6 +156,17 @@ __global__ void ba_pack_kernel(PackArgs a) {
     uint8_t* dst = a.seq + (which ? a.pr_off[k] : a.pq_off[k]);
     if (lane == 0) dst[0] = nul;
     const bool rev = which ? a.rev_r != 0 : a.rev_q != 0;
+    if (a.nuc4) {
+      const uint8_t* arena = which ? a.raw_r : a.raw_q;
+      const uint64_t o0 = which ? a.raw_r_off[k] : a.raw_q_off[k];
+      for (uint64_t t = lane; t < len; t += 32) {
+        const uint64_t nb = o0 + (rev ? len - 1 - t : t);
+        const uint32_t byte = arena[nb >> 1];
+        const uint32_t code = (nb & 1) ? (byte & 15u) : (byte >> 4);
+        if (code == 0) bad = true;
+        dst[1 + t] = nuc4_letter(code);
+      }
+    } else
     for (uint64_t t = lane; t < len; t += 32) {
       uint8_t c = src[rev ? len - 1 - t : t];
       if (a.scoring != kByte) {
@@ -443,8 +471,9 @@ extern "C" void ba_batch_free(BaBatch* b) {
 static int check_config(const BaConfig* cfg, uint32_t* mn, uint32_t* mx) {
   if (!cfg) return fail(BA_ERR_ARG, "cfg is null");
   if (cfg->scoring < 0 || cfg->scoring > 3) return fail(BA_ERR_ARG, "bad scoring kind");
-  if (cfg->flags & ~(BA_TRACE | BA_XDROP | BA_LOCAL_START | BA_FREE_QUERY_START_GAPS | BA_FREE_QUERY_END_GAPS | BA_REV_QUERY | BA_REV_REFERENCE))
+  if (cfg->flags & ~(BA_TRACE | BA_XDROP | BA_LOCAL_START | BA_FREE_QUERY_START_GAPS | BA_FREE_QUERY_END_GAPS | BA_REV_QUERY | BA_REV_REFERENCE | BA_INPUT_NUC4))
     return fail(BA_ERR_ARG, "unsupported flags");
+  if ((cfg->flags & BA_INPUT_NUC4) && cfg->scoring != BA_SCORING_NUC) return fail(BA_ERR_ARG, "BA_INPUT_NUC4 needs BA_SCORING_NUC");
   if ((cfg->flags & BA_XDROP) && (cfg->flags & BA_FREE_QUERY_END_GAPS))
     return fail(BA_ERR_ARG, "Cannot set both X_DROP and FREE_QUERY_END_GAPS!");   // scan_block.rs:861
   if ((cfg->flags & BA_LOCAL_START) && (cfg->flags & BA_FREE_QUERY_START_GAPS))
@@ -691,8 +720,12 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
   const uint64_t seq_bytes = pos + 512;   // slack: the fast phase touches up to B + 136 bytes past the position it reads (pk_fast_step)
   const auto tu1 = std::chrono::steady_clock::now();
 
-  const uint64_t qraw = n ? q_off[n] - q_off[0] : 0;
-  const uint64_t rraw = (!prof && n) ? r_off[n] - r_off[0] : 0;
+  // BA_INPUT_NUC4: offsets count nibbles; the bytes that hold nibbles [off[0], off[n]) are copied and the offsets are
+  // rebased to the first copied byte (off[0] rounded down to even)
+  const bool nuc4 = (cfg->flags & BA_INPUT_NUC4) != 0;
+  const uint64_t qb0 = n ? (nuc4 ? q_off[0] >> 1 : q_off[0]) : 0, rb0 = (!prof && n) ? (nuc4 ? r_off[0] >> 1 : r_off[0]) : 0;
+  const uint64_t qraw = n ? (nuc4 ? ((q_off[n] + 1) >> 1) - qb0 : q_off[n] - q_off[0]) : 0;
+  const uint64_t rraw = (!prof && n) ? (nuc4 ? ((r_off[n] + 1) >> 1) - rb0 : r_off[n] - r_off[0]) : 0;
   uint8_t *d_rawq = nullptr, *d_rawr = nullptr; uint64_t *d_rawqoff = nullptr, *d_rawroff = nullptr; uint32_t* d_err = nullptr;
   auto free_tmp = [&]() { pool_release(al, d_rawq); pool_release(al, d_rawr); pool_release(al, d_rawqoff); pool_release(al, d_rawroff); pool_release(al, d_err); };
 #define TRY2(x) do { int _r = (x); if (_r) { free_tmp(); ba_batch_free(b); return _r == 1 ? BA_ERR_CUDA : _r; } } while (0)
@@ -709,10 +742,13 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
   const auto tu2 = std::chrono::steady_clock::now();
   // offsets are rebased so that the raw arenas start at 0
   std::vector<uint64_t> qo(n + 1), ro(n + 1);
-  for (size_t k = 0; k <= n && n; k++) { qo[k] = q_off[k] - q_off[0]; if (!prof) ro[k] = r_off[k] - r_off[0]; }
+  for (size_t k = 0; k <= n && n; k++) {
+    qo[k] = q_off[k] - (nuc4 ? qb0 * 2 : q_off[0]);
+    if (!prof) ro[k] = r_off[k] - (nuc4 ? rb0 * 2 : r_off[0]);
+  }
   if (n) {
-    TRY2(h2d(d_rawq, q_bytes + q_off[0], qraw, st)); TRY2(h2d(d_rawqoff, qo.data(), (n + 1) * 8, st));
-    if (!prof) { TRY2(h2d(d_rawr, r_bytes + r_off[0], rraw, st)); TRY2(h2d(d_rawroff, ro.data(), (n + 1) * 8, st)); }
+    TRY2(h2d(d_rawq, q_bytes + qb0, qraw, st)); TRY2(h2d(d_rawqoff, qo.data(), (n + 1) * 8, st));
+    if (!prof) { TRY2(h2d(d_rawr, r_bytes + rb0, rraw, st)); TRY2(h2d(d_rawroff, ro.data(), (n + 1) * 8, st)); }
     TRY2(h2d(b->d_qoff, pq.data(), n * 8, st)); TRY2(h2d(b->d_qlen, ql.data(), n * 4, st));
     if (!prof) TRY2(h2d(b->d_roff, pr.data(), n * 8, st));
     TRY2(h2d(b->d_rlen, rl.data(), n * 4, st));
@@ -843,6 +879,7 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
   pa.seq = b->d_seq; pa.pq_off = b->d_qoff; pa.pr_off = b->d_roff; pa.n = (uint32_t)n; pa.pad = pad;
   pa.scoring = prof ? (int)kAA : cfg->scoring; pa.err = d_err;
   pa.rev_q = (cfg->flags & BA_REV_QUERY) ? 1u : 0u; pa.rev_r = (cfg->flags & BA_REV_REFERENCE) ? 1u : 0u;
+  pa.nuc4 = nuc4 ? 1u : 0u;
   if (n) {
 #ifdef BA_EMU
     pack_all(pa);
@@ -1380,6 +1417,166 @@ static int align_uploaded_profiles(BaBatch* b, size_t n, AlignResult* out, BaSta
   }
   ba_batch_free(b);
   return rc;
+}
+
+// -------------------------------------------------------------------------------------------------
+// In-library multi-GPU entry points (SURVEY.md 8b "Needed extension" / 8e): one call, one batch, several GPUs of the
+// box. Pairs are independent (Block::align touches only its own scratch, scan_block.rs:847-878), so the batch is cut
+// into one contiguous shard per device with equal sum(|q| + |r|) -- the block aligner's work per pair is proportional
+// to its path length times the block sizes it visits --, every shard runs on its own host thread through the same
+// pipelined path as ba_align_batch (own aligner, own streams), and each thread writes its results straight into the
+// caller's arrays at the shard's offset: original order, no gather step, no collective.
+// -------------------------------------------------------------------------------------------------
+static std::mutex g_multi_mu;
+static std::vector<BaAligner*> g_multi;      // process-wide aligners of the multi-GPU entry points, index = device
+
+static BaAligner* multi_aligner(int dev, int* rc) {
+  std::lock_guard<std::mutex> lk(g_multi_mu);
+  if (dev < 0) { *rc = fail(BA_ERR_ARG, "negative device index"); return nullptr; }
+  if ((size_t)dev >= g_multi.size()) g_multi.resize((size_t)dev + 1, nullptr);
+  if (!g_multi[dev]) { *rc = ba_create(dev, &g_multi[dev]); if (*rc) return nullptr; }
+  *rc = BA_OK;
+  return g_multi[dev];
+}
+extern "C" int ba_device_count(void) {
+#ifdef BA_EMU
+  const char* e = getenv("BA_EMU_DEVICES");
+  return e ? std::max(1, atoi(e)) : 1;
+#else
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+#endif
+}
+// destroys the aligners the multi-GPU entry points created (they are otherwise kept for the life of the process)
+extern "C" void ba_multi_release(void) {
+  std::lock_guard<std::mutex> lk(g_multi_mu);
+  for (BaAligner* a : g_multi) if (a) ba_destroy(a);
+  g_multi.clear();
+}
+
+struct MultiShard { size_t lo = 0, hi = 0; int dev = 0; int rc = 0; BaStats st; std::string err; };
+
+// cut [0, n) into `parts` contiguous ranges of equal sum(|q| + |r| + 64)
+static std::vector<size_t> multi_cuts(size_t n, const uint64_t* q_off, const uint64_t* r_off, size_t parts) {
+  std::vector<size_t> cut(parts + 1, n);
+  cut[0] = 0;
+  auto work = [&](size_t k) { return (q_off[k] - q_off[0]) + (r_off ? r_off[k] - r_off[0] : 0) + 64 * (uint64_t)k; };
+  const uint64_t total = n ? work(n) : 0;
+  for (size_t c = 1, k = 0; c < parts; c++) {
+    const uint64_t target = total / parts * c;
+    while (k < n && work(k) < target) k++;
+    cut[c] = k;
+  }
+  return cut;
+}
+
+template <class F, class G>
+static int multi_run(const int* devices, int n_dev, size_t n, const uint64_t* q_off, const uint64_t* r_off, BaStats* stats,
+                     std::vector<MultiShard>& sh, F body, G prepare) {
+  const int avail = ba_device_count();
+  if (n_dev <= 0) n_dev = avail;
+  if (n_dev <= 0) return fail(BA_ERR_CUDA, "no CUDA device available; this library has no CPU fallback");
+  if (n && !q_off) return fail(BA_ERR_ARG, "null offsets");
+  sh.assign((size_t)n_dev, MultiShard());
+  std::vector<BaAligner*> als((size_t)n_dev, nullptr);
+  for (int d = 0; d < n_dev; d++) {
+    sh[d].dev = devices ? devices[d] : d;
+    for (int e = 0; e < d; e++) if (sh[e].dev == sh[d].dev) return fail(BA_ERR_ARG, "device listed twice");
+    int rc = 0;
+    als[d] = multi_aligner(sh[d].dev, &rc);
+    if (rc) return rc;
+  }
+  const std::vector<size_t> cut = multi_cuts(n, q_off, r_off, (size_t)n_dev);
+  for (int d = 0; d < n_dev; d++) { sh[d].lo = cut[d]; sh[d].hi = cut[d + 1]; }
+  prepare(sh);
+  auto worker = [&](int d) {
+    memset(&sh[d].st, 0, sizeof(BaStats));
+    if (sh[d].hi == sh[d].lo) { sh[d].rc = BA_OK; return; }
+    sh[d].rc = body(als[d], sh[d], d);
+    if (sh[d].rc) sh[d].err = g_last_error;
+  };
+  std::vector<std::thread> th;
+  for (int d = 1; d < n_dev; d++) th.emplace_back(worker, d);
+  worker(0);
+  for (auto& t : th) t.join();
+  BaStats tot; memset(&tot, 0, sizeof(tot));
+  int rc = BA_OK;
+  for (int d = 0; d < n_dev; d++) {
+    if (sh[d].rc && !rc) { rc = sh[d].rc; g_last_error = "device " + std::to_string(sh[d].dev) + ": " + sh[d].err; }
+    tot.cells += sh[d].st.cells; tot.steps += sh[d].st.steps; tot.kernel_launches += sh[d].st.kernel_launches; tot.n_failed += sh[d].st.n_failed;
+    tot.kernel_ms = std::max(tot.kernel_ms, sh[d].st.kernel_ms); tot.pack_ms = std::max(tot.pack_ms, sh[d].st.pack_ms);
+  }
+  if (stats) *stats = tot;
+  return rc;
+}
+
+extern "C" int ba_align_batch_multi(const int* devices, int n_dev, const BaConfig* cfg, size_t n,
+                                    const uint8_t* q_bytes, const uint64_t* q_off, const uint8_t* r_bytes, const uint64_t* r_off,
+                                    AlignResult* out, BaStats* stats) {
+  if (n && !r_off) return fail(BA_ERR_ARG, "null offsets");
+  if (!n) { if (stats) memset(stats, 0, sizeof(*stats)); return BA_OK; }
+  std::vector<MultiShard> sh;
+  return multi_run(devices, n_dev, n, q_off, r_off, stats, sh, [&](BaAligner* a, MultiShard& s, int) {
+    return align_batch_impl(a, cfg, s.hi - s.lo, q_bytes, q_off + s.lo, r_bytes, r_off + s.lo, out ? out + s.lo : nullptr, &s.st, nullptr);
+  }, [](std::vector<MultiShard>&) {});
+}
+
+// CIGARs included (BA_TRACE): like ba_align_batch_cigar, but run_off[k] is an absolute index into `runs` and the shards'
+// regions of `runs` are not contiguous with each other -- each device gets a slice of the buffer in proportion to its
+// shard's worst case sum(|q| + |r| + 5). *runs_used = words written in total.
+extern "C" int ba_align_batch_multi_cigar(const int* devices, int n_dev, const BaConfig* cfg, size_t n,
+                                          const uint8_t* q_bytes, const uint64_t* q_off, const uint8_t* r_bytes, const uint64_t* r_off,
+                                          AlignResult* out, uint32_t* runs, size_t runs_cap, uint64_t* run_off, uint32_t* run_len,
+                                          size_t* runs_used, BaStats* stats) {
+  if (!cfg || !(cfg->flags & BA_TRACE)) return fail(BA_ERR_ARG, "ba_align_batch_multi_cigar needs BA_TRACE");
+  if (n && (!runs || !run_off || !run_len || !r_off)) return fail(BA_ERR_ARG, "null CIGAR output");
+  if (!n) { if (stats) memset(stats, 0, sizeof(*stats)); if (runs_used) *runs_used = 0; return BA_OK; }
+  std::vector<MultiShard> sh;
+  std::vector<size_t> base, used;
+  const int rc = multi_run(devices, n_dev, n, q_off, r_off, stats, sh, [&](BaAligner* a, MultiShard& s, int d) {
+    if (base.empty()) return fail(BA_ERR_ARG, "internal: shard table not ready");
+    CigarOut cg{runs + base[d], base[d + 1] - base[d], run_off + s.lo, run_len + s.lo, 0};
+    const int r = align_batch_impl(a, cfg, s.hi - s.lo, q_bytes, q_off + s.lo, r_bytes, r_off + s.lo, out ? out + s.lo : nullptr, &s.st, &cg);
+    used[d] = cg.used;
+    if (!r) for (size_t k = s.lo; k < s.hi; k++) run_off[k] += base[d];
+    return r;
+  }, [&](std::vector<MultiShard>& shards) {
+    // slice the caller's buffer: worst case per shard when it fits, proportional shares otherwise
+    const size_t nd = shards.size();
+    std::vector<uint64_t> worst(nd, 0);
+    uint64_t wsum = 0;
+    for (size_t d = 0; d < nd; d++) {
+      const MultiShard& s = shards[d];
+      worst[d] = (q_off[s.hi] - q_off[s.lo]) + (r_off[s.hi] - r_off[s.lo]) + 5 * (uint64_t)(s.hi - s.lo);
+      wsum += worst[d];
+    }
+    base.assign(nd + 1, 0); used.assign(nd, 0);
+    for (size_t d = 0; d < nd; d++) {
+      const uint64_t share = wsum <= runs_cap ? worst[d] : (uint64_t)((long double)runs_cap * worst[d] / std::max<uint64_t>(wsum, 1));
+      base[d + 1] = base[d] + (size_t)share;
+    }
+  });
+  size_t tot = 0;
+  for (size_t u : used) tot += u;
+  if (runs_used) *runs_used = tot;
+  return rc;
+}
+
+// sequence-to-profile batches (profiles built on every device from its shard of the raw PSSM rows)
+extern "C" int ba_align_batch_multi_pssm(const int* devices, int n_dev, const BaConfig* cfg, size_t n,
+                                         const uint8_t* q_bytes, const uint64_t* q_off, const BaPssmBatch* pssm,
+                                         AlignResult* out, BaStats* stats) {
+  if (!pssm || (n && !pssm->score_off)) return fail(BA_ERR_ARG, "pssm is null");
+  if (!n) { if (stats) memset(stats, 0, sizeof(*stats)); return BA_OK; }
+  std::vector<MultiShard> sh;
+  // profile positions dominate the work of a pair: balance on |q| + 20 * len
+  return multi_run(devices, n_dev, n, q_off, pssm->score_off, stats, sh, [&](BaAligner* a, MultiShard& s, int) {
+    BaPssmBatch p = *pssm;
+    p.score_off = pssm->score_off + s.lo;
+    if (pssm->gap_off) p.gap_off = pssm->gap_off + s.lo;
+    return ba_align_batch_pssm(a, cfg, s.hi - s.lo, q_bytes, q_off + s.lo, &p, out ? out + s.lo : nullptr, &s.st);
+  }, [](std::vector<MultiShard>&) {});
 }
 
 // Walk the stored trace of pair k back from an arbitrary end position (Trace::cigar / cigar_eq,

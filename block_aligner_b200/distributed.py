@@ -1,7 +1,9 @@
 """Multi-GPU use: one process per GPU, pairs sharded across ranks, no collective on the data path.
 
 Every pair is an independent alignment (the reference's `Block::align` touches only its own scratch), so
-the only communication is the host-side gather of the 24-byte AlignResults (plus CIGAR strings when asked).
+the only communication is the host-side gather of the 24-byte AlignResults (plus CIGAR strings when asked), done over
+a gloo (CPU) group. A single process that owns several GPUs does not need this module: `ba_align_batch_multi` in the
+C ABI shards one batch over the GPUs of the box and delivers the results in order.
 Shards are contiguous ranges balanced by total sequence length, so that results concatenate in the original
 order.
 """
@@ -51,18 +53,34 @@ def align_sharded(aligner, cfg, q_arena, q_off, r_arena, r_off, want_cigars=Fals
     if world == 1:
         return mine, cig
     n = len(q_off) - 1
-    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    # host-side gather of the 24-byte results (and CIGAR strings): always over a gloo (CPU) group -- results are already
+    # in host memory, and the data path must not depend on NCCL (pairs are independent, there is nothing to exchange)
+    group = _host_group()
     sizes = (bounds[1:] - bounds[:-1]).tolist()
     pad = max(sizes)
-    buf = torch.zeros((pad, 3), dtype=torch.int64, device=dev)
-    buf[:hi - lo] = torch.from_numpy(mine).to(dev)
+    buf = torch.zeros((pad, 3), dtype=torch.int64)
+    buf[:hi - lo] = torch.from_numpy(mine)
     parts = [torch.zeros_like(buf) for _ in range(world)]
-    dist.all_gather(parts, buf)
-    out = np.concatenate([p[:s].cpu().numpy() for p, s in zip(parts, sizes)], axis=0)
+    dist.all_gather(parts, buf, group=group)
+    out = np.concatenate([p[:s].numpy() for p, s in zip(parts, sizes)], axis=0)
     assert out.shape == (n, 3)
     cigs = None
     if want_cigars and (cfg.flags & api.TRACE):
         gathered = [None] * world
-        dist.all_gather_object(gathered, cig)
+        dist.all_gather_object(gathered, cig, group=group)
         cigs = [c for part in gathered for c in part]
     return out, cigs
+
+
+_HOST_GROUP = None
+
+
+def _host_group():
+    """A gloo group over all ranks (the default group itself when that already is gloo)."""
+    global _HOST_GROUP
+    import torch.distributed as dist
+    if dist.get_backend() == "gloo":
+        return None
+    if _HOST_GROUP is None:
+        _HOST_GROUP = dist.new_group(backend="gloo")
+    return _HOST_GROUP

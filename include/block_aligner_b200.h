@@ -128,7 +128,14 @@ enum { BA_TRACE = 1, BA_XDROP = 2, BA_LOCAL_START = 4, BA_FREE_QUERY_START_GAPS 
        /* PaddedBytes::set_bytes_rev (src/scan_block.rs:1815-1822) for the whole batch: the queries / references are
         * reversed while they are converted and padded on the device (reverse-extension pipelines; with BaPssmBatch.rev
         * for the profile side) */
-       BA_REV_QUERY = 32, BA_REV_REFERENCE = 64 };
+       BA_REV_QUERY = 32, BA_REV_REFERENCE = 64,
+       /* Input format of nucleotide batches: q_bytes / r_bytes hold 4-bit base codes, two per byte, high nibble first,
+        * in the BAM / htslib encoding "=ACMGRSVTWYHKDBN" (what bam_get_seq returns), and q_off / r_off count NIBBLES:
+        * sequence k = nibbles [off[k], off[k+1]) of the arena (sequences need not start on a byte boundary). The
+        * library expands the codes to the letters the reference would have been given while it converts and pads on
+        * the device, so results are identical to the ASCII input and half the bytes cross the bus. BA_SCORING_NUC only;
+        * code 0 ('=') is BA_ERR_CHAR. ba_pack_nuc4 packs ASCII on the host. */
+       BA_INPUT_NUC4 = 128 };
 
 typedef struct BaAligner BaAligner; /* one per GPU: streams + reusable device scratch. Calls on one BaAligner (and on
                                       * its batches) may come from any number of host threads: the library serialises
@@ -251,6 +258,28 @@ int ba_align_batch_pssm(BaAligner* a, const BaConfig* cfg, size_t n,
                         const uint8_t* q_bytes, const uint64_t* q_off,
                         const BaPssmBatch* pssm, AlignResult* out, BaStats* stats);
 
+/* One batch over several GPUs of the box in one call: the batch is cut into one contiguous shard
+ * per device with equal sum(|q| + |r|), every shard runs on its own host thread through the pipelined path of
+ * ba_align_batch, and results land in the caller's arrays in the original order (pairs are independent: no collective,
+ * no gather step). `devices` lists n_dev CUDA device indices (NULL: devices 0 .. n_dev-1; n_dev <= 0: every visible
+ * device). The library keeps one aligner per device for the life of the process (ba_multi_release destroys them).
+ * BaStats: cells / steps / launches summed, kernel_ms = the slowest device.
+ * _cigar: run_off[k] indexes `runs` absolutely; every device fills its own slice of the buffer (worst case
+ * sum(|q| + |r| + 5) of its shard when runs_cap allows, a proportional share otherwise), so the used regions are not
+ * contiguous; *runs_used = words written in total. */
+int ba_device_count(void);
+void ba_multi_release(void);
+int ba_align_batch_multi(const int* devices, int n_dev, const BaConfig* cfg, size_t n,
+                         const uint8_t* q_bytes, const uint64_t* q_off, const uint8_t* r_bytes, const uint64_t* r_off,
+                         AlignResult* out, BaStats* stats);
+int ba_align_batch_multi_cigar(const int* devices, int n_dev, const BaConfig* cfg, size_t n,
+                               const uint8_t* q_bytes, const uint64_t* q_off, const uint8_t* r_bytes, const uint64_t* r_off,
+                               AlignResult* out, uint32_t* runs, size_t runs_cap, uint64_t* run_off, uint32_t* run_len,
+                               size_t* runs_used, BaStats* stats);
+int ba_align_batch_multi_pssm(const int* devices, int n_dev, const BaConfig* cfg, size_t n,
+                              const uint8_t* q_bytes, const uint64_t* q_off, const BaPssmBatch* pssm,
+                              AlignResult* out, BaStats* stats);
+
 /* Measured integer-ALU roofline denominators for this device (giga add/max operations per second); see DESIGN.md.
  * ba_measure_int_peak: DPX add-max / max3 on one 32-bit value per lane (the exact path);
  * ba_measure_int_peak_packed: the same instructions on two i16 values per lane (VIADDMNMX.S16x2, the packed path). */
@@ -261,6 +290,10 @@ int ba_measure_int_peak_packed(BaAligner* a, double* giga_ops_per_s);
 struct NucMatrix* ba_new_simple_nucmatrix(int8_t match_score, int8_t mismatch_score); /* src/scores.rs:150-164 */
 void ba_set_nucmatrix(struct NucMatrix* m, uint8_t a, uint8_t b, int8_t score);       /* src/scores.rs:174-183 */
 void ba_free_nucmatrix(struct NucMatrix* m);
+/* ASCII bases -> BAM nibble codes for BA_INPUT_NUC4: writes `len` nibbles into `packed` starting at nibble index
+ * `nibble_off` (high nibble of a byte first; the other nibble of a shared byte is preserved). Returns 0, or 1 + the
+ * index of the first byte that is not one of "ACMGRSVTWYHKDBN" (case-insensitive). */
+size_t ba_pack_nuc4(const uint8_t* ascii, size_t len, uint8_t* packed, uint64_t nibble_off);
 uintptr_t ba_percent_len(uintptr_t len, float p);                                     /* src/lib.rs:109-111 */
 /* format packed runs as a CIGAR string ("9=2I4=1I"); returns the length written (excluding NUL) */
 size_t ba_cigar_format(const uint32_t* runs, size_t n_runs, char* out, size_t cap);   /* src/cigar.rs:147-163 */
