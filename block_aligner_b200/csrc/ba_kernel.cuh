@@ -28,7 +28,7 @@
 
 #ifdef BA_EMU
 // coverage counters of the emulated build (tests assert that the packed path really ran)
-namespace emu_stats { inline uint64_t pk_cells = 0, exact_cells = 0, fast_steps = 0; }
+namespace emu_stats { inline uint64_t pk_cells = 0, exact_cells = 0, fast_steps = 0, big_cells = 0; }
 #endif
 
 namespace ba {
@@ -671,8 +671,7 @@ BA_DEV void apply_grow(AlnState& st, const WarpMem& w, bool trace) {
 // Is the pending step (st.dir already chosen, st.si/sj already moved) a plain block-32 shift that the
 // fast phase can execute? (no early break: scan_block.rs:1216-1224)
 template <int SCORING, bool XDROP>
-BA_DEV bool fast_eligible(const Params& P, const AlnState& st) {
-  const int FB = (int)P.fast_block;     // 0 (fast phase off), 32 or 64 == min block size
+BA_DEV bool shift_eligible(const AlnState& st, int FB) {
   if (SCORING == kProfile || FB == 0) return false;
   if (st.B != FB || st.dir == kGrow) return false;
   if (!XDROP) {
@@ -681,6 +680,10 @@ BA_DEV bool fast_eligible(const Params& P, const AlnState& st) {
     if (vec_base + (uint32_t)FB > vec_len && col_base + 7 > col_len) return false;
   }
   return true;
+}
+template <int SCORING, bool XDROP>
+BA_DEV bool fast_eligible(const Params& P, const AlnState& st) {
+  return shift_eligible<SCORING, XDROP>(st, (int)P.fast_block);     // 0 (fast phase off), 32 or 64 == min block size
 }
 
 // The packed fast phase keeps its newest checkpoint in shared memory (pk_fast_step); the generic phase reads and
@@ -722,8 +725,82 @@ BA_DEV bool pk_borders_ok(const Params& P, const AlnState& st, const WarpMem& w)
   return wp::ballot(!ok) == 0u;
 }
 
+enum { kStFast = 0, kStNeedGeneric = 1, kStNeedGrow = 2, kStDone = 3, kStEmpty = 4, kStNeedShrink = 5 };
+struct PkFast { uint32_t aD[4], aC[4], oD[4], oR[4]; };
+
+template <int LGT>
+BA_DEV void pk_fast_load(PkFast& f, const WarpMem& w, int dir, bool mine) {
+  constexpr int G = 1 << LGT;
+  const int lg = wp::lane_id() & (G - 1);
+  const int16_t *ad = dir == kRight ? w.Dc : w.Dr, *ac = dir == kRight ? w.Cc : w.Rr;
+  const int16_t *od = dir == kRight ? w.Dr : w.Dc, *orr = dir == kRight ? w.Rr : w.Cc;
+  if (mine) { pk_load4(ad, lg, G, f.aD); pk_load4(ac, lg, G, f.aC); pk_load4(od, lg, G, f.oD); pk_load4(orr, lg, G, f.oR); }
+}
+template <int LGT>
+BA_DEV void pk_fast_spill(const PkFast& f, const WarpMem& w, int dir, bool mine) {
+  constexpr int G = 1 << LGT;
+  const int lg = wp::lane_id() & (G - 1);
+  int16_t *ad = dir == kRight ? w.Dc : w.Dr, *ac = dir == kRight ? w.Cc : w.Rr;
+  int16_t *od = dir == kRight ? w.Dr : w.Dc, *orr = dir == kRight ? w.Rr : w.Cc;
+  wp::syncwarp();
+  if (mine) {
+    pk_store4(ad, lg, G, f.aD); pk_store4(ac, lg, G, f.aC); pk_store4(od, lg, G, f.oD); pk_store4(orr, lg, G, f.oR);
+    // temp_buf1/2 hold the 8 fresh values of the last shift = the last 8 entries of the orthogonal border
+    if (lg >= G - 2) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        w.t1[4 * (lg - (G - 2)) + k] = (int16_t)wp::h_hi(f.oD[k]);
+        w.t2[4 * (lg - (G - 2)) + k] = (int16_t)wp::h_hi(f.oR[k]);
+      }
+    }
+  }
+  wp::syncwarp();
+}
+
+template <int SCORING, int FLAGS, int LGT, bool BIG>
+BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast& f, int& status,
+                         const uint8_t* qp, const uint8_t* rp, uint32_t my_slot);
+BA_DEV void bcast_state(AlnState& d, const AlnState& s, int src);
+
+// Register-resident shift steps for a block above the minimum size (64 / 128 / 256 rows; the unrelated tails of X-drop
+// alignments sit at the maximum size for dozens of steps): the alignment being serviced by the generic phase runs
+// pk_fast_step with 1 << LGT lanes until a step needs something else. Returns the status that ended the loop; borders
+// are back in shared memory, the newest checkpoint in the slot's global checkpoint.
+#ifndef BA_BIG_LOOP_INLINE
+#define BA_BIG_LOOP_FN BA_DEV_NOINLINE     // own register allocation: inlined into run_generic it made the whole kernel spill
+#else
+#define BA_BIG_LOOP_FN BA_DEV
+#endif
+template <int SCORING, int FLAGS, int LGT>
+BA_BIG_LOOP_FN int big_loop(const Params& P, AlnState* stp, const WarpMem* wp_, uint32_t slot) {
+  // by-value working copies: the caller's state and pointers stay in registers on its side of the call (only the
+  // temporaries it passes are address-taken), and this function keeps its own copies in registers
+  AlnState st = *stp;
+  const WarpMem w = *wp_;
+  constexpr int G = 1 << LGT;
+  const int lane = wp::lane_id();
+  const bool mine = lane < G;
+  PkFast f;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { f.aD[k] = 0; f.aC[k] = 0; f.oD[k] = 0; f.oR[k] = 0; }
+  pk_fast_load<LGT>(f, w, st.dir, mine);
+  const uint8_t* qp = P.seq + P.q_off[st.pair];
+  const uint8_t* rp = P.seq + P.r_off[st.pair];
+  int status = mine ? kStFast : kStEmpty;
+  for (;;) {
+    pk_fast_step<SCORING, FLAGS, LGT, true>(P, w, st, f, status, qp, rp, slot);
+    if (wp::shfl_idx(status, 0) != kStFast) break;
+  }
+  status = wp::shfl_idx(status, 0);
+  if (G < 32) bcast_state(st, st, 0);
+  // the registers are laid out for the step executed last (= prev_dir)
+  pk_fast_spill<LGT>(f, w, st.prev_dir, mine);
+  *stp = st;
+  return status;
+}
+
 template <int SCORING, int FLAGS>
-BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const SlotMem& sm) {
+BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const SlotMem& sm, uint32_t slot) {
   constexpr bool TRACE = (FLAGS & kTrace) != 0, XDROP = (FLAGS & kXDrop) != 0, EXT = (FLAGS & kExt) != 0;
   constexpr bool PROF = SCORING == kProfile;
   const bool m_local = EXT && (P.ext_flags & kLocalStart), m_fqs = EXT && (P.ext_flags & kFreeQueryStartGaps);
@@ -742,14 +819,48 @@ BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const Sl
   if (SCORING == kByte) { sc.b_match = (int)P.matrix[0]; sc.b_mismatch = (int)P.matrix[1]; }
   const int min_size = (int)P.min_size, max_size = (int)P.max_size;
 
+  bool resume_shrink = false;
   for (;;) {
-    if (fast_eligible<SCORING, XDROP>(P, st) && (!TRACE || trace_room(st, sm.words_cap, sm.rects_cap, st.B)) &&
-        (!P.pk_fast || pk_borders_ok(P, st, w))) return kRunFast;
-    const int prev_off = st.off;
     int bv = 0, gbv = 0; unsigned bkey = 15u << 27, gbkey = 15u << 27;
-    int right_max, down_max;
+    int right_max = 0, down_max = 0, mx = 0;
     const int B = st.B;
     const uint32_t si = st.si, sj = st.sj;
+    if (!resume_shrink) {
+    if (fast_eligible<SCORING, XDROP>(P, st) && (!TRACE || trace_room(st, sm.words_cap, sm.rects_cap, st.B)) &&
+        (!P.pk_fast || pk_borders_ok(P, st, w))) return kRunFast;
+#ifdef BA_BIG_LOOP
+    // Shift steps of a block above the minimum size in a register-resident loop (big_loop). OFF: measured on B200 / C2
+    // (100 k pairs) the kernel fell from 1150 GCUPS to 913-1021 in every variant (all sizes / 256 only, inlined /
+    // noinline): inlined, the extra copies of the step code push the kernel from 93 KB to 158 KB and 371 spill
+    // instructions; as a separate function the ~60 live registers of the caller are saved around every call. The
+    // instruction cache and the 128-register cap, not the instruction count of the tail steps, decide.
+#ifndef BA_BIG_SIZES
+#define BA_BIG_SIZES (64 | 128 | 256)     // block sizes served by big_loop (tuning: every size is one more copy of the step code)
+#endif
+    if (!PROF && !EXT && P.pk_fast && (B == 64 || B == 128 || B == 256) && (B & BA_BIG_SIZES) && B > (int)P.fast_block && !st.overflow &&
+        shift_eligible<SCORING, XDROP>(st, B) && (!TRACE || trace_room(st, sm.words_cap, sm.rects_cap, B)) && pk_borders_ok(P, st, w)) {
+      int bs;
+      AlnState tst = st;       // temporaries for the call (see big_loop)
+      WarpMem tw = w;
+      if ((BA_BIG_SIZES & 256) && B == 256) bs = big_loop<SCORING, FLAGS, 5>(P, &tst, &tw, slot);
+      else if ((BA_BIG_SIZES & 128) && B == 128) bs = big_loop<SCORING, FLAGS, 4>(P, &tst, &tw, slot);
+      else if (BA_BIG_SIZES & 64) bs = big_loop<SCORING, FLAGS, 3>(P, &tst, &tw, slot);
+      else bs = kStNeedGeneric;
+      st = tst;
+      if (bs == kStDone) return kRunDone;
+      if (bs == kStNeedGrow) { apply_grow(st, w, TRACE); continue; }
+      if (bs == kStNeedShrink) { resume_shrink = true; continue; }
+      continue;    // kStNeedGeneric: the pending step fails one of the tests above and runs below
+    }
+#endif
+    }
+    if (resume_shrink) {
+      // a big_loop step found a new best with the maximum in the corner: resume after the grow test (scan_block.rs:505)
+      resume_shrink = false;
+      mx = st.off_max - st.off + kZero;
+      border_maxes(w.Dc, w.Dr, right_max, down_max);
+    } else {
+    const int prev_off = st.off;
     st.steps++;
     // One shift step computes one rectangle, a grow step two (down part, then right part). A single
     // place_rect call site serves all of them: the kernel has to stay small enough for the I-cache.
@@ -828,7 +939,7 @@ BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const Sl
     st.prev_dir = st.dir;
     const int D_max_max = wp::red_max(bv);
     const int grow_max = wp::red_max(gbv);
-    const int mx = wp::imax(D_max_max, grow_max);
+    mx = wp::imax(D_max_max, grow_max);
     st.off_max = st.off + mx - kZero;
     st.y_drop_iter++;
     bool grow_no_max = (this_dir == kGrow);
@@ -892,6 +1003,7 @@ BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const Sl
         continue;
       }
     }
+    }   // !resume_shrink
 
     if (B > min_size && st.y_drop_iter == 0) {
       const int smx = shrink_max(w.Dc, w.Dr, B);
@@ -957,46 +1069,15 @@ BA_DEV void finish_alignment(const Params& P, const AlnState& st, const WarpMem&
 // outside the packed path's exact range, end of the alignment) parks the group: its status changes and the generic
 // phase services it with the whole warp.
 // ---------------------------------------------------------------------------------------------
-enum { kStFast = 0, kStNeedGeneric = 1, kStNeedGrow = 2, kStDone = 3, kStEmpty = 4 };
-
 // ---------------------------------------------------------------------------------------------
 // Packed fast phase: 32 >> LGT alignments per warp, G = 1 << LGT lanes each (block size 8 * G == min_size),
 // borders in registers in the packed layout of ba_packed.cuh (entry e of a border: lane (e mod 4G) / 4,
 // register e mod 4, halfword e / 4G). The rectangle of a step is computed with
 // pk_cols8; a group whose values leave the packed path's exact range is parked for the generic phase.
 // ---------------------------------------------------------------------------------------------
-struct PkFast { uint32_t aD[4], aC[4], oD[4], oR[4]; };
-
-template <int LGT>
-BA_DEV void pk_fast_load(PkFast& f, const WarpMem& w, int dir, bool mine) {
-  constexpr int G = 1 << LGT;
-  const int lg = wp::lane_id() & (G - 1);
-  const int16_t *ad = dir == kRight ? w.Dc : w.Dr, *ac = dir == kRight ? w.Cc : w.Rr;
-  const int16_t *od = dir == kRight ? w.Dr : w.Dc, *orr = dir == kRight ? w.Rr : w.Cc;
-  if (mine) { pk_load4(ad, lg, G, f.aD); pk_load4(ac, lg, G, f.aC); pk_load4(od, lg, G, f.oD); pk_load4(orr, lg, G, f.oR); }
-}
-template <int LGT>
-BA_DEV void pk_fast_spill(const PkFast& f, const WarpMem& w, int dir, bool mine) {
-  constexpr int G = 1 << LGT;
-  const int lg = wp::lane_id() & (G - 1);
-  int16_t *ad = dir == kRight ? w.Dc : w.Dr, *ac = dir == kRight ? w.Cc : w.Rr;
-  int16_t *od = dir == kRight ? w.Dr : w.Dc, *orr = dir == kRight ? w.Rr : w.Cc;
-  wp::syncwarp();
-  if (mine) {
-    pk_store4(ad, lg, G, f.aD); pk_store4(ac, lg, G, f.aC); pk_store4(od, lg, G, f.oD); pk_store4(orr, lg, G, f.oR);
-    // temp_buf1/2 hold the 8 fresh values of the last shift = the last 8 entries of the orthogonal border
-    if (lg >= G - 2) {
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        w.t1[4 * (lg - (G - 2)) + k] = (int16_t)wp::h_hi(f.oD[k]);
-        w.t2[4 * (lg - (G - 2)) + k] = (int16_t)wp::h_hi(f.oR[k]);
-      }
-    }
-  }
-  wp::syncwarp();
-}
-
-template <int SCORING, int FLAGS, int LGT>
+// BIG: the block may be above the minimum size (big_loop): the checkpoint goes straight to the slot's global checkpoint
+// in the plain layout, and the shrink test of scan_block.rs:505-510 is evaluated (a shrink parks the group).
+template <int SCORING, int FLAGS, int LGT, bool BIG = false>
 BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast& f, int& status,
                          const uint8_t* qp, const uint8_t* rp, uint32_t my_slot) {
   // The slot's trace arena and rectangle stack are recomputed from the slot index where they are needed: carried
@@ -1079,6 +1160,12 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast
   const uint32_t pmm = wp::vmax2((uint32_t)wp::shfl_idx_w((int)pm, 0, G), (uint32_t)wp::shfl_idx_w((int)pm, 1, G));
   const int a_max = wp::h_lo(pmm), o_max = wp::h_hi(pmm);
   const int right_max = right ? a_max : o_max, down_max = right ? o_max : a_max;
+  // suffix_max over the last two entries of both borders (scan_block.rs:1030-1032): high halves of registers 2 and 3 of the last lane
+  int smx = 0;
+  if (BIG) {
+    const uint32_t sl = wp::vmax2(wp::vmax2(f.aD[2], f.aD[3]), wp::vmax2(f.oD[2], f.oD[3]));
+    smx = wp::h_hi((uint32_t)wp::shfl_idx_w((int)sl, G - 1, G));
+  }
   unsigned key = 0;
   if (XDROP) {
     key = pk_lane_key(m, mc, lg, G, mxv);
@@ -1099,7 +1186,7 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast
   // ---- post-step decisions (scan_block.rs:332-558 restricted to B == min_size, shift steps) ----
   if (active) {
 #ifdef BA_EMU
-    if (lg == 0) emu_stats::fast_steps++;
+    if (lg == 0) { if (BIG) emu_stats::big_cells += (uint64_t)kStep * B; else emu_stats::fast_steps++; }
 #endif
     st.off = off;
     st.steps++;
@@ -1120,11 +1207,16 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast
         st.i_ckpt = si; st.j_ckpt = sj; st.off_ckpt = off;
         // checkpoint copy of all four borders (scan_block.rs:413-420): kept in shared memory in the packed
         // layout, array order D_col, C_col, D_row, R_row; moved to the slot's global checkpoint when the group parks
-        uint4* ck = (uint4*)w.ck + (grp * 4) * G + lg;
-        const int ia = right ? 0 : 2 * G, io = right ? 2 * G : 0;
-        ck[ia] = make_uint4(f.aD[0], f.aD[1], f.aD[2], f.aD[3]); ck[ia + G] = make_uint4(f.aC[0], f.aC[1], f.aC[2], f.aC[3]);
-        ck[io] = make_uint4(f.oD[0], f.oD[1], f.oD[2], f.oD[3]); ck[io + G] = make_uint4(f.oR[0], f.oR[1], f.oR[2], f.oR[3]);
-        st.ck_pk = 1u;
+        if (BIG) {
+          int16_t *ad = right ? w.kDc : w.kDr, *ac = right ? w.kCc : w.kRr, *od = right ? w.kDr : w.kDc, *orr = right ? w.kRr : w.kCc;
+          pk_store4(ad, lg, G, f.aD); pk_store4(ac, lg, G, f.aC); pk_store4(od, lg, G, f.oD); pk_store4(orr, lg, G, f.oR);
+        } else {
+          uint4* ck = (uint4*)w.ck + (grp * 4) * G + lg;
+          const int ia = right ? 0 : 2 * G, io = right ? 2 * G : 0;
+          ck[ia] = make_uint4(f.aD[0], f.aD[1], f.aD[2], f.aD[3]); ck[ia + G] = make_uint4(f.aC[0], f.aC[1], f.aC[2], f.aC[3]);
+          ck[io] = make_uint4(f.oD[0], f.oD[1], f.oD[2], f.oD[3]); ck[io + G] = make_uint4(f.oR[0], f.oR[1], f.oR[2], f.oR[3]);
+          st.ck_pk = 1u;
+        }
         if (TRACE) { st.ck_widx = st.widx; st.ck_ridx = st.ridx; }
       }
       st.best_max = st.off_max;
@@ -1145,9 +1237,10 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast
       else if (sj + B > st.rlen) { st.si = si + kStep; st.dir = kDown; }
       else if (si + B > st.qlen) { st.sj = sj + kStep; st.dir = kRight; }
       else if (2 * B <= (int)P.max_size && st.y_drop_iter > (B / kStep) - 1) nstatus = kStNeedGrow;   // state left untouched
+      else if (BIG && B > (int)P.min_size && st.y_drop_iter == 0 && smx >= mxv) nstatus = kStNeedShrink;   // scan_block.rs:505-510, done by run_generic
       else if (down_max > right_max) { st.si = si + kStep; st.dir = kDown; }
       else { st.sj = sj + kStep; st.dir = kRight; }
-      if (nstatus == kStFast && !fast_eligible<SCORING, XDROP>(P, st)) nstatus = kStNeedGeneric;
+      if (nstatus == kStFast && !shift_eligible<SCORING, XDROP>(st, B)) nstatus = kStNeedGeneric;
       if (TRACE && nstatus == kStFast && !trace_room(st, sm.words_cap, sm.rects_cap, B)) nstatus = kStNeedGeneric;
     }
     status = nstatus;
@@ -1295,7 +1388,7 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
         if (sg == kStNeedGrow) apply_grow(gs, w, TRACE);
       }
       int r = kRunDone;
-      if (sg != kStDone) r = run_generic<SCORING, FLAGS>(P, gs, w, sm);
+      if (sg != kStDone) r = run_generic<SCORING, FLAGS>(P, gs, w, sm, slot);
       if (r == kRunDone) {
         finish_alignment<SCORING, FLAGS>(P, gs, w, sm, slot, warp_global);
         if (mine) status = kStEmpty;

@@ -1128,9 +1128,9 @@ extern "C" int ba_batch_pair_stats(const BaBatch* b, size_t k, uint64_t* cells, 
 }
 
 #ifdef BA_EMU
-extern "C" void ba_emu_stats(uint64_t* out3, int reset) {
-  out3[0] = emu_stats::pk_cells; out3[1] = emu_stats::exact_cells; out3[2] = emu_stats::fast_steps;
-  if (reset) { emu_stats::pk_cells = 0; emu_stats::exact_cells = 0; emu_stats::fast_steps = 0; }
+extern "C" void ba_emu_stats(uint64_t* out4, int reset) {
+  out4[0] = emu_stats::pk_cells; out4[1] = emu_stats::exact_cells; out4[2] = emu_stats::fast_steps; out4[3] = emu_stats::big_cells;
+  if (reset) { emu_stats::pk_cells = 0; emu_stats::exact_cells = 0; emu_stats::fast_steps = 0; emu_stats::big_cells = 0; }
 }
 #endif
 

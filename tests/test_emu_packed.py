@@ -26,9 +26,9 @@ def env():
 
 
 def stats(lib, reset=True):
-    out = (C.c_uint64 * 3)()
+    out = (C.c_uint64 * 4)()
     lib.L.ba_emu_stats(out, int(reset))
-    return dict(pk_cells=out[0], exact_cells=out[1], fast_steps=out[2])
+    return dict(pk_cells=out[0], exact_cells=out[1], fast_steps=out[2], big_cells=out[3])
 
 
 @pytest.mark.parametrize("flags", [0, api.XDROP])
@@ -42,7 +42,7 @@ def test_dna_packed_coverage(env, flags, size):
     assert parity.check_workload(lib, al, w, 10, seed=31 + flags) == 0
     s = stats(lib)
     fast_cells = s["fast_steps"] * 8 * size[0] if size[0] in (32, 64) else 0
-    packed = s["pk_cells"] + fast_cells
+    packed = s["pk_cells"] + fast_cells + s["big_cells"]
     if size[1] <= 256:
         assert packed > 4 * s["exact_cells"], s      # the packed path carries the bulk of the work
     else:
