@@ -484,7 +484,7 @@ def main():
         pass
     ctx = dict(lib=lib, al=al, rank=rank, world=world, local_rank=local_rank, barrier=barrier, dist=dist, peaks=peaks,
                peak_s32=al.int_peak_gops(False), peak_s16x2=al.int_peak_gops(True),
-               packed_profiles=bool(getattr(lib, "packed_profiles", False)))
+               packed_profiles=not os.environ.get("BA_NO_FAST"))
     want_cpu = not args.no_cpu_baseline
     line = measure(args.workload, args.pairs, args.steps, args.warmup, ctx, args.cpu_seconds, False, pageable_once=(world == 1))
     # every rank is past its last collective: ranks > 0 are done, rank 0 goes on alone (CPU leg, other configs)

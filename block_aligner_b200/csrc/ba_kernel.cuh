@@ -672,7 +672,7 @@ BA_DEV void apply_grow(AlnState& st, const WarpMem& w, bool trace) {
 // fast phase can execute? (no early break: scan_block.rs:1216-1224)
 template <int SCORING, bool XDROP>
 BA_DEV bool shift_eligible(const AlnState& st, int FB) {
-  if (SCORING == kProfile || FB == 0) return false;
+  if (FB == 0) return false;
   if (st.B != FB || st.dir == kGrow) return false;
   if (!XDROP) {
     const uint32_t vec_base = st.dir == kRight ? st.si : st.sj, vec_len = st.dir == kRight ? st.qlen : st.rlen;
@@ -710,6 +710,7 @@ BA_DEV bool pk_borders_ok(const Params& P, const AlnState& st, const WarpMem& w)
   const int lane = wp::lane_id();
   int GL, GH;
   pk_bounds(kStep, P.gap_open, P.gap_extend, P.pk_smax, GL, GH);
+  if (P.scoring == kProfile) { GL = kPkpGL; GH = kPkpGH; }
   const int noa = clamp16(st.off - st.off_max);
   const int lo_b = wp::imax(GL - noa, kI16Min), hi_b = wp::imin(GH - noa, kI16Max);
   bool ok = lo_b <= hi_b && noa >= -1024 && noa <= 1024;
@@ -1092,6 +1093,7 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast
   }
   constexpr bool XDROP = (FLAGS & kXDrop) != 0, TRACE = (FLAGS & kTrace) != 0;
   constexpr int KIND = (SCORING == kProfile) ? kAA : SCORING;
+  constexpr bool PROF = SCORING == kProfile;
   constexpr int G = 1 << LGT;
   constexpr int B = 8 * G;
   const int lane = wp::lane_id(), lg = lane & (G - 1), grp = lane >> LGT;
@@ -1110,9 +1112,38 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast
   const uint32_t oa2 = pk2(off_add);
 
   PkScorer<KIND> sc;
-  sc.init(w.smem0, P);
-  sc.rows(*(const uint32_t*)(vec + vec_base + 4 * lg), *(const uint32_t*)(vec + vec_base + 4 * G + 4 * lg));
-  const uint2 cw = *(const uint2*)(col + col_base);
+  PkpOps po;
+  uint2 cw = make_uint2(0u, 0u);
+  if (!PROF) {
+    sc.init(w.smem0, P);
+    sc.rows(*(const uint32_t*)(vec + vec_base + 4 * lg), *(const uint32_t*)(vec + vec_base + 4 * G + 4 * lg));
+    cw = *(const uint2*)(col + col_base);
+  } else {
+    // sequence-to-profile: qp is the query, the profile plays the reference (rows of a down step, columns of a right step)
+    const ProfileDev* pd = P.profiles + st.pair;
+    const int8_t* tp = pd->tp;
+    po.right = right; po.tlen = pd->tlen; po.hi_off = 4u * G;
+    po.gp = pd->gp + 4 * (size_t)col_base;
+    po.rres[0] = 0; po.rres[1] = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { po.Bc[k] = 0; po.oR[k] = 0; po.cR[k] = 0; }
+    if (right) {
+      po.tpc = tp + col_base;
+      po.rres[0] = *(const uint32_t*)(qp + vec_base + 4 * lg);
+      po.rres[1] = *(const uint32_t*)(qp + vec_base + 4 * G + 4 * lg);
+    } else {
+      po.tpc = tp + vec_base + 4 * lg;
+      cw = *(const uint2*)(qp + col_base);
+      const int ge = P.gap_extend;
+      const uint32_t r0 = vec_base + 4 * lg, r1 = r0 + 4 * G;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {   // get_gap_open_down_C / _R, get_gap_close_down (scan_block.rs:671-676)
+        po.Bc[k] = (uint32_t)(((int)wp::ldg(pd->gap_open_R + r0 + k) + ge) + 65536 * ((int)wp::ldg(pd->gap_open_R + r1 + k) + ge));
+        po.oR[k] = (uint32_t)((int)wp::ldg(pd->gap_open_C + r0 + k) + 65536 * (int)wp::ldg(pd->gap_open_C + r1 + k));
+        po.cR[k] = wp::h_pack((int)wp::ldg(pd->gap_close_C + r0 + k), (int)wp::ldg(pd->gap_close_C + r1 + k));
+      }
+    }
+  }
   // (Tried: touching the next 128-byte line of both sequences every step so that the token loads never leave L1 --
   // 89 % of the kernel's long-scoreboard samples sit at the first use of cw. Measured on B200 it costs 10 % on C2
   // (1156 -> 1042 GCUPS) and 16 % on C3: the extra loads hurt more than the misses they hide. BA_SEQ_PREFETCH re-enables.)
@@ -1127,7 +1158,8 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast
   uint32_t* fr = w.fr + grp * 8;
   uint32_t* tw = nullptr;
   if (TRACE && active) tw = trace_push_local(st, sm, right ? si : si + (B - kStep), right ? sj + (B - kStep) : sj, kStep, B, right, lg == 0, 3);
-  pk_cols8<KIND, XDROP, LGT, TRACE>(sc, P.kc, LGT, lg, cw.x, cw.y, D, C, (uint32_t)corner & 0xffffu, 0, m, mc, fr, lg == G - 1, tw, TRACE && active);
+  if (PROF) pkp_cols8<XDROP, LGT>(po, P.kc, lg, cw.x, cw.y, D, C, (uint32_t)corner & 0xffffu, m, mc, fr, lg == G - 1);
+  else pk_cols8<KIND, XDROP, LGT, TRACE>(sc, P.kc, LGT, lg, cw.x, cw.y, D, C, (uint32_t)corner & 0xffffu, 0, m, mc, fr, lg == G - 1, tw, TRACE && active);
   wp::syncwarp();
 
   // ---- borders after the step ----
@@ -1249,6 +1281,7 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast
   {
     int GL, GH;
     pk_bounds(kStep, P.gap_open, P.gap_extend, P.pk_smax, GL, GH);
+    if (PROF) { GL = kPkpGL; GH = kPkpGH; }
     const int noa = clamp16(st.off - st.off_max);
     const int lo_b = wp::imax(GL - noa, kI16Min), hi_b = wp::imin(GH - noa, kI16Max);
     // Only the D registers need the test: C <= D and R <= D bound the gap tables from above, and from below they
@@ -1400,7 +1433,7 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
       if (mine) {
         st = gs; status = kStFast;
         qp = P.seq + P.q_off[gs.pair];
-        rp = P.seq + P.r_off[gs.pair];
+        if (SCORING != kProfile) rp = P.seq + P.r_off[gs.pair];
       }
       wp::syncwarp();
     }

@@ -103,7 +103,8 @@ static int occupancy(int wpb, size_t smem_bytes, int* blocks_per_sm) {
 #else
 #define BA_FOR_KERNELS(X) BA_FOR_SEQ(X, kNuc) BA_FOR_SEQ(X, kAA) BA_FOR_SEQ(X, kByte) \
   X(kProfile, 0, 0) X(kProfile, 1, 0) X(kProfile, 2, 0) X(kProfile, 3, 0) \
-  X(kProfile, 4, 0) X(kProfile, 5, 0) X(kProfile, 6, 0) X(kProfile, 7, 0)
+  X(kProfile, 4, 0) X(kProfile, 5, 0) X(kProfile, 6, 0) X(kProfile, 7, 0) \
+  X(kProfile, 0, 18) X(kProfile, 2, 18) X(kProfile, 0, 19) X(kProfile, 2, 19)
 #endif
 
 #ifndef BA_TU_TOP
@@ -138,8 +139,8 @@ int BA_CAT3(ba_launch_tu_, BA_TU_S, BA_TU_G)(int scoring, int flags, int fr, con
 }
 int BA_CAT3(ba_occupancy_tu_, BA_TU_S, BA_TU_G)(int scoring, int flags, int fr, int wpb, size_t smem, int* bps) { return tu_occupancy<0>(scoring, flags, fr, wpb, smem, bps); }
 #else
-// the (scoring kind, group) units the product build compiles: sequence kinds 0..2 x groups 0..2, profiles (3) x group 0
-#define BA_FOR_TUS(Y) Y(0, 0) Y(0, 1) Y(0, 2) Y(1, 0) Y(1, 1) Y(1, 2) Y(2, 0) Y(2, 1) Y(2, 2) Y(3, 0)
+// the (scoring kind, group) units the product build compiles: sequence kinds 0..2 x groups 0..2, profiles (3) x groups 0..1
+#define BA_FOR_TUS(Y) Y(0, 0) Y(0, 1) Y(0, 2) Y(1, 0) Y(1, 1) Y(1, 2) Y(2, 0) Y(2, 1) Y(2, 2) Y(3, 0) Y(3, 1)
 #define Y(S, G) int ba_launch_tu_##S##_##G(int, int, int, const ba::Params&, int, int, size_t, dev_stream_t); \
                 int ba_occupancy_tu_##S##_##G(int, int, int, int, size_t, int*);
 BA_FOR_TUS(Y)

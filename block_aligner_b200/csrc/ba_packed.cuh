@@ -258,6 +258,111 @@ BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int LGr, int l
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Sequence-to-profile (place_block_profile_right / _down, scan_block.rs:612-783) on the packed datapath, for the fast
+// phase. One body serves both directions; the operands of the direction that does not apply are zero:
+//   right (vectors = query rows, columns = profile positions): per column  A = gap_open_C + ext, cl = gap_close_C,
+//         oRc = gap_open_R  (one 16-byte load of ProfileDev::gp), scores = 8 words of ProfileDev::tp per four columns
+//         (row of the lane's query residue, the four positions), one PRMT per pair of cells;
+//   down  (vectors = profile positions, columns = query residues): per row  Bc = gap_open_R + ext, oR = gap_open_C,
+//         cR = gap_close_C (the reference swaps the roles, scan_block.rs:671-676), scores = two words of tp per column
+//         (row of the column's residue, the lane's four + four positions).
+// Recurrence per cell (T space: the open cost varies per row or column, so the U-space trick of pk_cols8 does not apply):
+//   C11 = max(C10 + ext, D10 + A + Bc);  D' = max(D00 + s, C11 + cl);  x = D' + oRc + oR;  T = max(T_up + ext, x);
+//   D = max(D', T + cR).  Plain 32-bit adds stand in for packed adds wherever a negative operand is added to halves that
+// the range guard keeps >= its magnitude (no borrow between the halves); operands of those adds are "v * 65537".
+// Exact while every border value lies in [kPkpGL, kPkpGH] (pk_fast_step's guard): per column D falls by at most
+// |open| + |ext| + |close| <= 384 and rises by at most score + close_C + close_R <= 381, whatever the profile holds.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kPkpGL = 8 * 384 + 128 + 128, kPkpGH = kI16Max - 8 * 381;
+struct PkpOps {
+  bool right;
+  const uint32_t* gp;              // right: gp + 4 * (first column position)
+  const int8_t* tpc;               // right: tp + first column position; down: tp + first row position of the lane (low half)
+  uint32_t tlen, hi_off;           // row stride of tp; down: byte offset of the lane's high-half rows (4 * G)
+  uint32_t rres[2];                // right: query residues of the lane's rows (low / high half), one per byte
+  uint32_t Bc[4], oR[4], cR[4];    // down: per-row operands (Bc, oR: v * 65537 form; cR: packed halves); right: 0
+};
+
+template <bool XDROP, int LGT>
+BA_DEV void pkp_cols8(const PkpOps& o, const PkConst& kc, int lg, uint32_t cw0, uint32_t cw1,
+                      uint32_t (&D)[4], uint32_t (&C)[4], uint32_t corner_lo, uint32_t (&m)[4], uint32_t (&mc)[kMcN],
+                      uint32_t* fr, bool writer) {
+  constexpr int G = 1 << LGT;
+  const uint32_t z = wp::opaque_zero();
+  const uint32_t ge2 = kc.ge2 + z;
+  const uint32_t kge1 = kc.kge[1] + z, kge2 = kc.kge[2] + z, kge3 = kc.kge[3] + z;
+  const uint32_t lanedec = (uint32_t)lg * kc.lane1 + (lg ? 0x10000u : 0u);   // packed 4 * lg * gap_extend
+  uint64_t cwq = ((uint64_t)cw1 << 32) | cw0;
+  uint32_t w[8] = {};
+#pragma unroll 1
+  for (int cidx = 0; cidx < 8; cidx++) {
+    uint32_t A = 0, cl = 0, oRc = 0, wl = 0, wh = 0;
+    if (o.right) {
+      if ((cidx & 3) == 0) {
+        // the lane's eight rows x four columns: row r of tp is the residue of query row r
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          w[k] = *(const uint32_t*)(o.tpc + (size_t)((o.rres[0] >> (8 * k)) & 0xffu) * o.tlen + cidx);
+          w[4 + k] = *(const uint32_t*)(o.tpc + (size_t)((o.rres[1] >> (8 * k)) & 0xffu) * o.tlen + cidx);
+        }
+      }
+      const uint4 g = *(const uint4*)(o.gp + 4 * cidx);
+      A = g.x; cl = g.y; oRc = g.z;
+    } else {
+      const int8_t* row = o.tpc + (size_t)((uint32_t)cwq & 0xffu) * o.tlen;
+      wl = *(const uint32_t*)row;
+      wh = *(const uint32_t*)(row + o.hi_off);
+    }
+    cwq >>= 8;
+    // selector of column (cidx & 3): byte c of the low word sign-extended into the low half, of the high word into the high half
+    const uint32_t c4 = (uint32_t)(cidx & 3);
+    const uint32_t selc = (c4 | ((8u | c4) << 4) | ((4u | c4) << 8) | ((12u | c4) << 12));
+    uint32_t up = (uint32_t)wp::shfl_idx_w((int)D[3], lg - 1, G);
+    if (lg == 0) up = (up << 16) | (cidx == 0 ? corner_lo : 0u);
+    uint32_t dd[4], c11[4], tt[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t selk = ((uint32_t)k | ((8u | (uint32_t)k) << 4) | ((4u | (uint32_t)k) << 8) | ((12u | (uint32_t)k) << 12));
+      const uint32_t s2 = o.right ? wp::prmt_sx(w[k], w[4 + k], selc) : wp::prmt_sx(wl, wh, selk);
+      const uint32_t d00 = k ? D[k - 1] : up;
+      const uint32_t c11o = D[k] + A + o.Bc[k];
+      c11[k] = wp::viaddmax2(C[k], ge2, c11o);
+      dd[k] = wp::viaddmax2(d00, s2, c11[k] + cl);
+      const uint32_t x = dd[k] + oRc + o.oR[k];
+      tt[k] = k ? wp::viaddmax2(tt[k - 1], ge2, x) : x;
+    }
+    uint32_t inc = tt[3];
+#pragma unroll
+    for (int s = 0; s < LGT; s++) {
+      const uint32_t u = (uint32_t)wp::shfl_up_w((int)inc, 1 << s, G);
+      inc = wp::viaddmax2(u, s == 0 ? kge3 : kc.dec[s] + z, inc);
+    }
+    const uint32_t tl = (uint32_t)wp::shfl_idx_w((int)inc, G - 1, G);
+    uint32_t ex = (uint32_t)wp::shfl_up_w((int)inc, 1, G);
+    if (lg == 0) ex = 0u;
+    const uint32_t cin = wp::viaddmax2(tl << 16, lanedec, ex);
+    uint32_t Tn3 = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t Tn = wp::viaddmax2(cin, k == 0 ? ge2 : (k == 1 ? kge1 : (k == 2 ? kge2 : kge3)), tt[k]);
+      const uint32_t Dn = wp::viaddmax2(Tn, o.cR[k], dd[k]);
+      if (k == 3) Tn3 = Tn;
+      if (XDROP) {
+        bool ph, pl;
+        m[k] = wp::vibmax2(Dn, m[k], ph, pl);
+        const uint32_t c1 = (uint32_t)(cidx + 1) + wp::opaque_zero();
+        if (pl) mc[k] = wp::prmt(mc[k], c1, 0x3254u);
+        if (ph) mc[k] = wp::prmt(mc[k], c1, 0x5410u);
+      } else {
+        m[0] = wp::vmax2(m[0], Dn);
+      }
+      D[k] = Dn; C[k] = c11[k];
+    }
+    if (writer) fr[cidx] = wp::prmt(Tn3, D[3], 0x7632u);   // T.hi | D.hi << 16
+  }
+}
+
 // Best cell of the lane under the reference's order: value desc, AVX lane (row mod 16) asc, column desc, row desc
 // (scan_block.rs:1194-1201, avx2.rs:271-274). pk_lane_key: key of the lane's best cell among those equal to M
 // (0 if none); key format as in place_rect_r: (15 - class) << 27 | (column + 1) << 13 | row. Every row has seen

@@ -98,10 +98,46 @@ BA_HD void prof_build_one(const ProfBuildArgs& a, uint32_t k, uint32_t tid, uint
   }
 }
 
+// byte offsets of the derived layouts inside a profile's arena slot, and the slot size
+BA_HD uint64_t prof_tlen(uint64_t cl) { return (cl + 15) & ~(uint64_t)15; }
+BA_HD uint64_t prof_gp_off(uint64_t cl) { return (cl * 38 + 15) & ~(uint64_t)15; }
+BA_HD uint64_t prof_tp_off(uint64_t cl) { return prof_gp_off(cl) + cl * 16; }
+BA_HD uint64_t prof_slot_bytes(uint64_t cl, bool derive) { return ((derive ? prof_tp_off(cl) + 32 * prof_tlen(cl) : cl * 38) + 63) & ~(uint64_t)63; }
+// second pass over a built profile (after a barrier): the transposed scores and the packed per-position gap operands
+BA_HD void prof_derive_one(const ProfBuildArgs& a, uint32_t k, uint32_t tid, uint32_t nthreads) {
+  const ProfBuild d = a.desc[k];
+  if (!d.derive) return;
+  uint8_t* base = a.arena + d.dst_off;
+  const uint32_t cl = d.curr_len, tlen = (uint32_t)prof_tlen(cl);
+  const int8_t* pos_aa = (const int8_t*)base;
+  const int16_t* oc = (const int16_t*)(base + (uint64_t)cl * 32);
+  const int16_t* cc = oc + cl;
+  const int16_t* orr = cc + cl;
+  uint32_t* gp = (uint32_t*)(base + prof_gp_off(cl));
+  int8_t* tp = (int8_t*)(base + prof_tp_off(cl));
+  for (uint32_t t = tid; t < cl; t += nthreads) {
+    gp[4 * t + 0] = (uint32_t)(((int)oc[t] + d.gap_extend) * 65537);
+    gp[4 * t + 1] = (uint32_t)((int)cc[t] * 65537);
+    gp[4 * t + 2] = (uint32_t)((int)orr[t] * 65537);
+    gp[4 * t + 3] = 0u;
+  }
+  // one 32-bit word = 4 consecutive positions of one residue
+  for (uint32_t t = tid; t < 32 * (tlen / 4); t += nthreads) {
+    const uint32_t res = t / (tlen / 4), p0 = (t % (tlen / 4)) * 4;
+    uint32_t word = 0;
+    for (uint32_t e = 0; e < 4; e++) {
+      const uint32_t pos = p0 + e;
+      const int8_t v = pos < cl ? pos_aa[(uint64_t)pos * 32 + res] : (int8_t)-128;
+      word |= (uint32_t)(uint8_t)v << (8 * e);
+    }
+    ((uint32_t*)tp)[t] = word;
+  }
+}
+
 #ifdef BA_EMU
 static void prof_build_all(const ProfBuildArgs& a) {
   bool bad = false;
-  for (uint32_t k = 0; k < a.n; k++) prof_build_one(a, k, 0, 1, bad);
+  for (uint32_t k = 0; k < a.n; k++) { prof_build_one(a, k, 0, 1, bad); prof_derive_one(a, k, 0, 1); }
   if (bad) *a.err = 1;
 }
 static void pack_all(const PackArgs& a) {
@@ -184,7 +220,11 @@ __global__ void ba_pack_kernel(PackArgs a) {
 // one CTA per profile (grid-stride): coalesced 32-bit stores over the whole padded profile
 __global__ void ba_profile_build_kernel(ProfBuildArgs a) {
   bool bad = false;
-  for (uint32_t k = blockIdx.x; k < a.n; k += gridDim.x) prof_build_one(a, k, threadIdx.x, blockDim.x, bad);
+  for (uint32_t k = blockIdx.x; k < a.n; k += gridDim.x) {
+    prof_build_one(a, k, threadIdx.x, blockDim.x, bad);
+    __syncthreads();
+    prof_derive_one(a, k, threadIdx.x, blockDim.x);
+  }
   if (bad) atomicOr(a.err, 1u);
 }
 
@@ -344,6 +384,7 @@ struct BaBatch {
   uint32_t rects_bound = 0;         // worst-case rectangle records per alignment
   int kflags = 0;                   // template FLAGS of the kernel: (flags & 3) | kExt
   int pk_smax = 0; uint32_t pk_enable = 0;   // packed 2 x i16 path (ba_packed.cuh): largest matrix entry, on/off
+  bool prof_fast = false; int prof_ge = -1;  // profile batch served by the packed fast phase; its (uniform) gap_extend
   uint64_t trace_words_bound = 0;   // worst case per alignment (the reference's Trace::new size)
   uint64_t mem_budget = 0; uint64_t max_blocks_hw = 1;
   // launch geometry
@@ -518,8 +559,9 @@ static int batch_configure(BaBatch* b, uint32_t mn) {
   b->kflags = (cfg->flags & 3) | (ext ? kExt : 0);
   // fast-phase mode (third kernel template argument): 4 / 8 = s32 rows per lane (TRACE), 16 + LGT = packed, 0 = none
   b->fast_rows = (!prof && !ext && !getenv("BA_NO_FAST")) ? (mn == 32 ? 4 : (mn == 64 ? 8 : 0)) : 0;
+  if (prof && b->prof_fast) b->fast_rows = mn == 32 ? 4 : (mn == 64 ? 8 : 0);
   b->slots_per_warp = b->fast_rows ? 4 : 1;
-  if (b->fast_rows && !b->pk_enable) b->fast_rows = 0;
+  if (b->fast_rows && !b->pk_enable && !prof) b->fast_rows = 0;
   if (b->fast_rows) {
     const int lgt = mn == 32 ? 2 : 3;
     b->fast_rows = 16 + lgt;
@@ -527,7 +569,7 @@ static int batch_configure(BaBatch* b, uint32_t mn) {
   }
   // max block >= 1024: the four live borders (8-32 KB per warp) move to global memory so that shared memory does not
   // cap the SM at 8 warps or fewer (C5: 64..=2048)
-  const bool gb = b->fast_rows >= 16 && mx >= 1024 && !getenv("BA_NO_GLOBAL_BORDERS");
+  const bool gb = b->fast_rows >= 16 && mx >= 1024 && !prof && !getenv("BA_NO_GLOBAL_BORDERS");
   if (gb) b->fast_rows += 16;
   b->gb = gb;
   const size_t wbytes = warp_smem_bytes(mx, gb);
@@ -769,11 +811,24 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
     // PSSM rows of a BaPssmBatch); ba_profile_build_kernel expands them and writes the -128 padding on the device.
     std::vector<ProfileDev> pd(n);
     std::vector<ProfBuild> bd(n);
+    // The packed fast phase serves profile batches without TRACE / extended modes at min block 32 / 64 when every
+    // profile of the batch has the same gap_extend (the constants of the packed scan are per batch); it needs the
+    // derived layouts (ProfileDev::tp / gp), built on the device behind the base arrays.
+    bool prof_fast = !(cfg->flags & (BA_TRACE | BA_LOCAL_START | BA_FREE_QUERY_START_GAPS | BA_FREE_QUERY_END_GAPS)) && (mn == 32 || mn == 64) &&
+                     !getenv("BA_NO_FAST") && !getenv("BA_NO_PACKED") && n > 0;
+    if (prof_fast && !pssm) {
+      const int ge0 = host::profile_gap_extend(profiles[0]);
+      for (size_t k = 1; k < n && prof_fast; k++) prof_fast = host::profile_gap_extend(profiles[k]) == ge0;
+    }
+    b->prof_fast = prof_fast;
+    b->prof_ge = n ? (pssm ? (int)pssm->gap_extend : host::profile_gap_extend(profiles[0])) : -1;
     uint64_t ppos = 0, spos = 0;
     for (size_t k = 0; k < n; k++) {
       const uint64_t cl = pssm ? (uint64_t)rl[k] + mx + 1 : host::profile_curr_len(profiles[k]);
       bd[k].dst_off = ppos; bd[k].curr_len = (uint32_t)cl;
-      ppos += ((cl * 32 + cl * 6) + 63) & ~(uint64_t)63;
+      bd[k].gap_extend = pssm ? (int32_t)pssm->gap_extend : host::profile_gap_extend(profiles[k]);
+      bd[k].derive = prof_fast ? 1u : 0u;
+      ppos += prof_slot_bytes(cl, prof_fast);
       if (pssm) {
         bd[k].np = rl[k];
         bd[k].src_off = pssm->score_off[k] - pssm->score_off[0];
@@ -796,7 +851,10 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
       pd[k].gap_close_C = (const int16_t*)(dbase + cl * 34);
       pd[k].gap_open_R = (const int16_t*)(dbase + cl * 36);
       pd[k].len = rl[k];
-      pd[k].gap_extend = pssm ? (int32_t)pssm->gap_extend : host::profile_gap_extend(profiles[k]);
+      pd[k].gap_extend = bd[k].gap_extend;
+      pd[k].tp = prof_fast ? (const int8_t*)(dbase + prof_tp_off(cl)) : nullptr;
+      pd[k].gp = prof_fast ? (const uint32_t*)(dbase + prof_gp_off(cl)) : nullptr;
+      pd[k].tlen = (uint32_t)prof_tlen(cl); pd[k].pad_ = 0;
     }
     ProfBuildArgs ba;
     memset(&ba, 0, sizeof(ba));
@@ -941,12 +999,13 @@ static Params make_params(const BaBatch* b, bool retry = false) {
   P.q_off = b->d_qoff; P.q_len = b->d_qlen; P.r_off = b->d_roff; P.r_len = b->d_rlen;
   P.profiles = b->d_profiles; P.matrix = b->d_matrix;
   P.gap_open = b->cfg.gaps.open; P.gap_extend = b->cfg.gaps.extend;
+  if (prof) { P.gap_open = 0; P.gap_extend = b->prof_ge; }   // per-position gap opens; the (uniform) extend cost of the fast phase
   P.min_size = b->min_size; P.max_size = b->max_size; P.x_drop = b->cfg.x_drop;
   P.flags = b->kflags; P.scoring = prof ? (int)kProfile : b->cfg.scoring;
   P.pk_smax = b->pk_smax; P.pk_enable = b->pk_enable;
   {
     auto pk2h = [](int v) { return ((uint32_t)v & 0xffffu) | ((uint32_t)v << 16); };
-    const int go = b->cfg.gaps.open, ge = b->cfg.gaps.extend;
+    const int go = prof ? 0 : b->cfg.gaps.open, ge = prof ? b->prof_ge : b->cfg.gaps.extend;
     P.kc.ge2 = pk2h(ge); P.kc.go1 = (uint32_t)go * 65537u; P.kc.or2 = pk2h(go - ge);
     for (int k = 0; k < 4; k++) P.kc.kge[k] = pk2h((k + 1) * ge);
     for (int s2 = 0; s2 < 5; s2++) P.kc.dec[s2] = pk2h((4 << s2) * ge);

@@ -36,6 +36,12 @@ struct ProfileDev {
   const int16_t* gap_open_R;     // [curr_len]
   uint32_t len;                  // str_len
   int32_t gap_extend;
+  // derived layouts for the packed fast phase (built on the device next to the arrays above; null when not built):
+  // tp: the scores transposed, row per residue, [32][tlen] i8 (the numbers of the reference's aa_pos, scores.rs:457):
+  //     the 4 / 8 consecutive positions a step needs for one residue are one 32-bit / 64-bit load;
+  // gp: per position {gap_open_C + gap_extend, gap_close_C, gap_open_R} as 32-bit "v * 65537" operands of the packed
+  //     recurrence, 16 bytes per position = one load per rectangle column
+  const int8_t* tp; const uint32_t* gp; uint32_t tlen; uint32_t pad_;
 };
 
 // Construction of one padded device profile (ba_profile_build_kernel): AAProfile::new's -128 defaults
@@ -48,6 +54,8 @@ struct ProfBuild {
   uint64_t dst_off;      // byte offset inside the profile arena (64-byte aligned)
   uint32_t np;           // kind 0: staged positions; kind 1: len
   uint32_t curr_len;     // positions of the padded device profile
+  int32_t gap_extend;
+  uint32_t derive;       // also build the derived layouts (ProfileDev::tp / gp) behind the base arrays
 };
 struct ProfBuildArgs {
   const ProfBuild* desc; uint32_t n; int32_t kind;

@@ -15,6 +15,7 @@
 struct alignas(8) uint2 { unsigned x, y; };
 struct alignas(16) uint4 { unsigned x, y, z, w; };
 inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r; r.x = x; r.y = y; return r; }
 namespace ba { namespace wp {
 inline int lane_id() { return emu::lane(); }
 inline int shfl_up(int v, int d) { const uint32_t* a = emu::exchange((uint32_t)v); int l = emu::lane(); return l >= d ? (int)a[l - d] : v; }
@@ -45,6 +46,7 @@ inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   for (int i = 0; i < 4; i++) { const uint32_t n = (sel >> (4 * i)) & 0xfu; uint32_t byte = (uint32_t)(src >> (8 * (n & 7))) & 0xffu; if (n & 8) byte = (byte & 0x80u) ? 0xffu : 0u; r |= byte << (8 * i); }
   return r;
 }
+inline uint32_t prmt_sx(uint32_t a, uint32_t b, uint32_t sel) { return prmt(a, b, sel); }
 inline uint32_t opaque_zero() { return 0u; }
 inline int red_max(int v) { const uint32_t* a = emu::exchange((uint32_t)v); int m = (int)a[0]; for (int i = 1; i < 32; i++) m = (int)a[i] > m ? (int)a[i] : m; return m; }
 inline unsigned red_max_u(unsigned v) { const uint32_t* a = emu::exchange(v); unsigned m = a[0]; for (int i = 1; i < 32; i++) m = a[i] > m ? a[i] : m; return m; }
@@ -89,6 +91,9 @@ BA_DEV uint32_t viaddmax2(uint32_t a, uint32_t b, uint32_t c) { return __viaddma
 BA_DEV uint32_t viaddmin2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_s16x2(a, b, c); }
 BA_DEV uint32_t vibmax2(uint32_t a, uint32_t b, bool& ph, bool& pl) { return __vibmax_s16x2(a, b, &ph, &pl); }
 BA_DEV uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+// PRMT with sign replication (selector nibbles with bit 3 set copy the sign of the selected byte into all eight bits):
+// spelled in PTX, the documented form of that mode
+BA_DEV uint32_t prmt_sx(uint32_t a, uint32_t b, uint32_t sel) { uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel)); return d; }
 // always 0 (blocks are one-dimensional) but thread-varying for the compiler: keeps a value out of the uniform datapath
 BA_DEV uint32_t opaque_zero() { return threadIdx.y; }
 BA_DEV int red_max(int v) { return __reduce_max_sync(kFull, v); }

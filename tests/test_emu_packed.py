@@ -94,3 +94,17 @@ def test_range_guard_long_score_drift(env):
     assert parity.check_workload(lib, al, w, 3, seed=3) == 0
     s = stats(lib)
     assert s["fast_steps"] * 8 * 32 > 20 * s["exact_cells"], s
+
+
+@pytest.mark.parametrize("flags", [0, api.XDROP])
+@pytest.mark.parametrize("size", [(32, 256), (64, 128)])
+def test_profile_fast_phase_coverage(env, flags, size):
+    """sequence-to-profile batches without TRACE run their shift steps in the packed fast phase (pkp_cols8)"""
+    lib, al = env
+    stats(lib)
+    assert parity.check_pssm(lib, al, 24, 5 + flags, False, (0, 0), False, size=size, flags=flags) == 0
+    s = stats(lib)
+    assert s["fast_steps"] * 8 * size[0] > s["exact_cells"], s
+    stats(lib)
+    assert parity.check_pssm(lib, al, 12, 9, True, (1, 0), True, size=size, flags=flags | api.TRACE) == 0
+    assert stats(lib)["fast_steps"] == 0      # TRACE profile batches stay on the exact path
