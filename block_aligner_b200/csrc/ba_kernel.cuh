@@ -1029,7 +1029,7 @@ BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const Sl
 
 // result (scan_block.rs:567-592) + traceback. Borders must be in shared memory.
 template <int SCORING, int FLAGS>
-BA_DEV void finish_alignment(const Params& P, const AlnState& st, const WarpMem& w, const SlotMem& sm, uint32_t slot, uint32_t warp_global) {
+BA_DEV void finish_alignment(const Params& P, const AlnState& st, const WarpMem& w, uint32_t slot) {
   constexpr bool TRACE = (FLAGS & kTrace) != 0, XDROP = (FLAGS & kXDrop) != 0;
   const int lane = wp::lane_id();
   wp::syncwarp();
@@ -1047,15 +1047,8 @@ BA_DEV void finish_alignment(const Params& P, const AlnState& st, const WarpMem&
     else sv = (int)w.Dr[st.rlen - st.sj];
     res.score = st.off + sv - kZero; res.query_idx = st.qlen; res.reference_idx = st.rlen;
   }
-  res.rect_n = st.ridx; res.warp = slot | P.retry_bit;
-  if (TRACE && P.slot_pair && lane == 0) P.slot_pair[slot] = st.pair;
-  if (TRACE && !st.overflow && P.cigar_stream) {
-    const uint8_t* q = P.seq + P.q_off[st.pair];
-    const uint8_t* r = (SCORING == kProfile) ? nullptr : P.seq + P.r_off[st.pair];
-    uint32_t* runs = P.run_scratch + (size_t)warp_global * P.runs_per_warp;
-    emit_cigar(P, w.smem0 + kMatBytes + kPkTabBytes, sm.words, (P.ext_flags & kLocalStart) ? sm.zwords : nullptr, (P.ext_flags & kFreeQueryStartGaps) != 0,
-               sm.rects, st.ridx, res.query_idx, res.reference_idx, q, r, P.cigar_eq != 0, runs, res);
-  }
+  res.rect_n = st.ridx; res.warp = TRACE ? P.arena_of[st.pair] : slot;
+  // TRACE: the trace stays in the pair's arena; ba_traceback_batch_kernel walks it (one walk per lane) after this kernel
   if (lane == 0) {
     P.out[st.pair] = res;
     if (TRACE && st.overflow && P.overflow_list) P.overflow_list[wp::atomic_add(P.overflow_n, 1u)] = st.pair;
@@ -1085,10 +1078,11 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast
   // across the loop they are 11 more live registers in kernels that already spill (TRACE, 128-register cap).
   SlotMem sm;
   sm.kDc = sm.kCc = sm.kDr = sm.kRr = nullptr; sm.words = nullptr; sm.words_cap = 0; sm.zwords = nullptr; sm.rects = nullptr; sm.rects_cap = 0;
-  if ((FLAGS & kTrace) != 0) {
-    sm.words = P.trace_words + (size_t)my_slot * P.trace_words_per_warp;
+  if ((FLAGS & kTrace) != 0 && status == kStFast) {
+    const uint32_t arena = P.arena_of[st.pair];
+    sm.words = P.trace_words + (size_t)arena * P.trace_words_per_warp;
     sm.words_cap = P.trace_words_per_warp;
-    sm.rects = P.rects + (size_t)my_slot * P.rects_per_warp;
+    sm.rects = P.rects + (size_t)arena * P.rects_per_warp;
     sm.rects_cap = P.rects_per_warp;
   }
   constexpr bool XDROP = (FLAGS & kXDrop) != 0, TRACE = (FLAGS & kTrace) != 0;
@@ -1337,13 +1331,16 @@ BA_DEV void bind_slot(const Params& P, uint32_t slot, WarpMem& w, SlotMem& sm, b
   sm.kDc = g; sm.kCc = g + ms; sm.kDr = g + 2 * ms; sm.kRr = g + 3 * ms;
   w.kDc = sm.kDc; w.kCc = sm.kCc; w.kDr = sm.kDr; w.kRr = sm.kRr;
   sm.words = nullptr; sm.words_cap = 0; sm.zwords = nullptr; sm.rects = nullptr; sm.rects_cap = 0;
-  if (trace) {
-    sm.words = P.trace_words + (size_t)slot * P.trace_words_per_warp;
-    sm.words_cap = P.trace_words_per_warp;
-    if (P.trace_zwords) sm.zwords = P.trace_zwords + (size_t)slot * P.trace_words_per_warp;
-    sm.rects = P.rects + (size_t)slot * P.rects_per_warp;
-    sm.rects_cap = P.rects_per_warp;
-  }
+  (void)trace;
+}
+// the trace arena of the pair being serviced
+BA_DEV void bind_trace(const Params& P, uint32_t pair, SlotMem& sm) {
+  const uint32_t arena = P.arena_of[pair];
+  sm.words = P.trace_words + (size_t)arena * P.trace_words_per_warp;
+  sm.words_cap = P.trace_words_per_warp;
+  sm.zwords = P.trace_zwords ? P.trace_zwords + (size_t)arena * P.trace_words_per_warp : nullptr;
+  sm.rects = P.rects + (size_t)arena * P.rects_per_warp;
+  sm.rects_cap = P.rects_per_warp;
 }
 
 // FM selects the fast phase: 0 = none (every step in the generic phase), 16 + LGT = packed fast phase with
@@ -1411,8 +1408,10 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
         t = (uint32_t)wp::shfl_idx((int)t, 0);
         if (t >= P.n_pairs) { tickets_left = false; continue; }
         init_alignment<SCORING, FLAGS>(P, gs, P.order ? P.order[t] : t, w);
+        if (TRACE) bind_trace(P, gs.pair, sm);
       } else {
         bcast_state(gs, st, g * GW);
+        if (TRACE) bind_trace(P, gs.pair, sm);
         // a parked group's registers are still laid out for the step it executed last (= prev_dir)
         if (PKF) {
           pk_fast_spill<LGT>(pf, w, gs.prev_dir, mine);
@@ -1423,7 +1422,7 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
       int r = kRunDone;
       if (sg != kStDone) r = run_generic<SCORING, FLAGS>(P, gs, w, sm, slot);
       if (r == kRunDone) {
-        finish_alignment<SCORING, FLAGS>(P, gs, w, sm, slot, warp_global);
+        finish_alignment<SCORING, FLAGS>(P, gs, w, slot);
         if (mine) status = kStEmpty;
         g--;            // try to refill this slot right away
         continue;
@@ -1452,21 +1451,157 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
 // the trace of pair `pair` is still in the arena of the slot that aligned it.
 BA_DEV void warp_traceback(const Params& P, const uint8_t* lut, uint32_t pair, uint32_t qi, uint32_t rj, bool eq, DevResult* out1) {
   DevResult res = P.out[pair];
-  const uint32_t slot = res.warp & ~kRetrySlotBit;
-  if (P.slot_pair && P.slot_pair[slot] != pair) {     // a later pair of the batch has reused the slot's arena
-    res.status = (uint32_t)kTraceGone; res.cigar_n = 0;
-    if (wp::lane_id() == 0) *out1 = res;
-    return;
-  }
+  const uint32_t slot = P.arena_of[pair];
   const uint32_t* words = P.trace_words + (size_t)slot * P.trace_words_per_warp;
   const Rect* rects = P.rects + (size_t)slot * P.rects_per_warp;
-  uint32_t* runs = P.run_scratch;   // single-warp launch: warp 0's scratch
+  uint32_t* runs = P.run_scratch + (size_t)slot * P.runs_per_warp;
   const uint8_t* q = P.seq + P.q_off[pair];
   const uint8_t* r = P.profiles ? nullptr : P.seq + P.r_off[pair];
   res.status = (uint32_t)kOk;
   const uint32_t* zwords = ((P.ext_flags & kLocalStart) && P.trace_zwords) ? P.trace_zwords + (size_t)slot * P.trace_words_per_warp : nullptr;
   emit_cigar(P, lut, words, zwords, (P.ext_flags & kFreeQueryStartGaps) != 0, rects, res.rect_n, qi, rj, q, r, eq, runs, res);
   if (wp::lane_id() == 0) *out1 = res;
+}
+
+// Batch traceback: lane `t` of the launch walks the trace of pair list[t] from the end position of its result
+// (Trace::cigar / cigar_eq, scan_block.rs:1469-1480): 32 independent dependent-load chains per warp instead of one.
+// The runs come out reversed (Cigar::add order, cigar.rs:71-79) into the arena's scratch; the warp then copies each
+// lane's list forward into the output stream (space claimed with one atomicAdd per alignment).
+// Prefetch distance in rectangle records, into L2: with 128 walks per SM the windows of an L1 prefetch (8 sectors per
+// rectangle) do not fit the L1 (measured: no gain); in L2 (126 MB) the windows of every walk of the batch do.
+constexpr uint32_t kTbLaneAhead = 8;
+BA_DEV void lanes_traceback(const Params& P, const uint8_t* lut, const uint32_t* list, uint32_t n, uint32_t t) {
+  const int lane = wp::lane_id();
+  const bool have = t < n;
+  uint32_t pair = 0, nruns = 0, ok = 0;
+  DevResult res;
+  res.score = 0; res.query_idx = 0; res.reference_idx = 0; res.status = (uint32_t)kNotRun; res.cells = 0; res.steps = 0;
+  res.cigar_n = 0; res.cigar_off = 0; res.rect_n = 0; res.warp = 0;
+  const uint32_t* runs = nullptr;
+  bool active_walk = false, fqs_ = false;
+  const uint32_t *words_ = nullptr, *zwords_ = nullptr;
+  const Rect* rects_ = nullptr;
+  uint32_t* rs_ = nullptr;
+  const uint8_t *q_ = nullptr, *r_ = nullptr;
+  WalkState s;
+  s.i = 0; s.j = 0; s.ridx = 0; s.table = 0; s.cur_op = 0; s.cur_len = 0; s.nruns = 0; s.bad = 0; s.stop = 0;
+  if (have) {
+    pair = list ? list[t] : t;
+    res = P.out[pair];
+    res.cigar_n = 0; res.cigar_off = 0;
+    if (res.status == (uint32_t)kOk) {
+      const uint32_t arena = P.arena_of[pair];
+      const uint32_t* words = P.trace_words + (size_t)arena * P.trace_words_per_warp;
+      const uint32_t* zwords = ((P.ext_flags & kLocalStart) && P.trace_zwords) ? P.trace_zwords + (size_t)arena * P.trace_words_per_warp : nullptr;
+      const Rect* rects = P.rects + (size_t)arena * P.rects_per_warp;
+      uint32_t* rs = P.run_scratch + (size_t)arena * P.runs_per_warp;
+      const uint8_t* q = P.seq + P.q_off[pair];
+      const uint8_t* r = P.profiles ? nullptr : P.seq + P.r_off[pair];
+      const bool fqs = (P.ext_flags & kFreeQueryStartGaps) != 0;
+      active_walk = true;
+      words_ = words; zwords_ = zwords; rects_ = rects; rs_ = rs; q_ = q; r_ = r; fqs_ = fqs;
+      s.i = res.query_idx; s.j = res.reference_idx; s.ridx = res.rect_n;
+    }
+  }
+  // Flat loop, one iteration = one record fetch or one cell step of every lane: nested per-lane loops would let the 32
+  // walks drift apart and serialise (measured: 116 ms for 10 k walks of ~90 k steps, i.e. ~2400 cycles per step).
+  {
+    Rect rc;
+    rc.row = 0xffffffffu; rc.col = 0xffffffffu; rc.h = 0; rc.w = 0; rc.right = 0; rc.word_off = 0;   // "no rectangle yet"
+    const uint32_t* tw = nullptr;
+    const bool eq = P.cigar_eq != 0;
+    const uint32_t cap = P.runs_per_warp;
+    for (;;) {
+      const bool go = active_walk && (s.i > 0 || s.j > 0) && !s.bad && !s.stop;
+      if (wp::ballot(go) == 0u) break;
+      if (go) {
+        if (!(s.i >= rc.row && s.j >= rc.col)) {
+          // the newest rectangle containing (i, j) (scan_block.rs:1578-1590): one record per iteration
+          if (s.ridx == 0) s.bad = 1u;
+          else {
+            s.ridx--;
+            rc = rects_[s.ridx];
+            tw = rect_words_ptr(words_, P.trace_pool, rc);
+            // the walk is a chain of dependent loads over words written long ago: fetch the words of the rectangle
+            // kTbLaneAhead records down the stack (the walk visits the stack in order) and, further ahead, the records
+            if (s.ridx >= kTbLaneAhead) {
+              const Rect pr = rects_[s.ridx - kTbLaneAhead];
+              const uint32_t* pw = rect_words_ptr(words_, P.trace_pool, pr);
+              // a missing load brings in one 32-byte sector: touch every sector of a shift rectangle (one per column at
+              // block size 64), the first eight of anything larger
+              const uint32_t nw = (uint32_t)(pr.h >> 3) * pr.w;
+#pragma unroll
+              for (uint32_t u = 0; u < 64u; u += 8u) if (u < nw) wp::touch_l2(pw + u);
+              if (s.ridx >= 4 * kTbLaneAhead && (s.ridx & 1u) == 0u) wp::touch_l2(rects_ + (s.ridx - 4 * kTbLaneAhead));
+            }
+          }
+        } else if (fqs_ && (rc.right & 1u) && s.i == 0) {
+          s.stop = 1u;      // FREE_QUERY_START_GAPS: stop on row 0, which always lies in right rectangles (scan_block.rs:1597-1600)
+        } else {
+          const bool rc_right = (rc.right & 1u) != 0;
+          const uint32_t layout = (rc.right >> 1) & 3u;
+          const uint32_t v = rc_right ? s.i - rc.row : s.j - rc.col;
+          const uint32_t c = rc_right ? s.j - rc.col : s.i - rc.row;
+          uint32_t nib;
+          bool zstop = false;
+          if (layout == 3u) {
+            const uint32_t hh = (uint32_t)rc.h >> 1, G = (uint32_t)rc.h >> 3;
+            const uint32_t half = v >= hh ? 1u : 0u, vv = v - half * hh;
+            nib = (tw[(size_t)c * G + (vv >> 2)] >> (16u * half + 4u * (vv & 3u))) & 15u;
+          } else {
+            const uint32_t R = layout == 1u ? 8u : (uint32_t)rect_rows_per_lane(rc.h);
+            const uint32_t CH = 32u * R, ngroups = (uint32_t)rc.w >> 3;
+            const uint32_t ch = v / CH, ln = (v % CH) / R, k = v % R;
+            const size_t widx = (((size_t)ch * ngroups + (c >> 3)) * R + k) * 32 + ln;
+            // LOCAL_START: the alignment starts at a cell equal to relative_zero (scan_block.rs:1606-1612)
+            if (zwords_ && s.table == 0 && ((zwords_[rc.word_off + widx] >> (c & 7)) & 1u)) zstop = true;
+            nib = (tw[widx] >> (4 * (c & 7))) & 15u;
+          }
+          if (zstop) s.stop = 1u;
+          else {
+            const uint32_t e = lut[(rc_right ? 64u : 0u) | (s.table << 4) | nib];
+            uint32_t op = e & 7u;
+            const uint32_t di = (e >> 3) & 1u, dj = (e >> 4) & 1u;
+            if (op == 1u && eq) op = (q_[s.i] == r_[s.j]) ? 2u : 3u;   // scan_block.rs:1620-1628
+            if ((di && s.i == 0) || (dj && s.j == 0)) s.bad = 1u;
+            else {
+              s.i -= di; s.j -= dj; s.table = e >> 5;
+              if (op == s.cur_op) s.cur_len++;
+              else {
+                if (s.cur_len) { if (s.nruns < cap) rs_[s.nruns] = (s.cur_len << 4) | s.cur_op; s.nruns++; }
+                s.cur_op = op; s.cur_len = 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  if (active_walk) {
+    if (s.cur_len) { if (s.nruns < P.runs_per_warp) rs_[s.nruns] = (s.cur_len << 4) | s.cur_op; s.nruns++; }
+    nruns = s.nruns; runs = rs_;
+    ok = (!s.bad && s.nruns <= P.runs_per_warp) ? 1u : 0u;
+    if (!ok) res.status = (uint32_t)kCigarOverflow;
+  }
+  wp::syncwarp();
+  for (int l = 0; l < 32; l++) {
+    if (!wp::shfl_idx((int)ok, l)) continue;
+    const uint32_t nl = (uint32_t)wp::shfl_idx((int)nruns, l);
+    const uint64_t rp = (uint64_t)(uintptr_t)runs;
+    const uint32_t plo = (uint32_t)wp::shfl_idx((int)(uint32_t)(rp & 0xffffffffu), l), phi = (uint32_t)wp::shfl_idx((int)(uint32_t)(rp >> 32), l);
+    const uint32_t* src = (const uint32_t*)(uintptr_t)(((uint64_t)phi << 32) | plo);
+    unsigned long long base = 0;
+    if (lane == 0) base = wp::atomic_add64(P.cigar_used, (unsigned long long)nl);
+    const uint32_t blo = (uint32_t)wp::shfl_idx((int)(uint32_t)(base & 0xffffffffu), 0), bhi = (uint32_t)wp::shfl_idx((int)(uint32_t)(base >> 32), 0);
+    base = ((unsigned long long)bhi << 32) | blo;
+    const bool fits = base + nl <= P.cigar_cap;
+    if (fits) for (uint32_t u = (uint32_t)lane; u < nl; u += 32) P.cigar_stream[base + u] = src[nl - 1 - u];
+    if (lane == l) {
+      if (fits) { res.cigar_n = nl; res.cigar_off = base; }
+      else res.status = (uint32_t)kCigarOverflow;
+    }
+  }
+  if (have) P.out[pair] = res;
 }
 
 }  // namespace ba

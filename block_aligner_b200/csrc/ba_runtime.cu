@@ -176,6 +176,17 @@ static int launch_traceback(const Params& P, uint32_t pair, uint32_t qi, uint32_
   emu::run_warp(&emu_tb_entry, &t);
   return 0;
 }
+struct EmuTbBatch { const Params* P; const uint32_t* list; uint32_t n, warp; };
+static void emu_tb_batch_entry(void* arg) {
+  auto* t = (EmuTbBatch*)arg;
+  static uint8_t lut[128];
+  for (uint32_t i = 0; i < 128; i++) lut[i] = tb_entry(i);
+  lanes_traceback(*t->P, lut, t->list, t->n, t->warp * 32 + (uint32_t)wp::lane_id());
+}
+static int launch_traceback_batch(const Params& P, const uint32_t* list, uint32_t n, dev_stream_t) {
+  for (uint32_t wi = 0; wi * 32 < n; wi++) { EmuTbBatch t{&P, list, n, wi}; emu::run_warp(&emu_tb_batch_entry, &t); }
+  return 0;
+}
 #else
 __global__ void ba_pack_kernel(PackArgs a) {
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -236,6 +247,30 @@ __global__ void ba_traceback_kernel(const __grid_constant__ Params P, uint32_t p
 }
 static int launch_traceback(const Params& P, uint32_t pair, uint32_t qi, uint32_t rj, int eq, DevResult* out1, dev_stream_t st) {
   ba_traceback_kernel<<<1, 32, 0, st>>>(P, pair, qi, rj, eq, out1);
+  CK(cudaGetLastError());
+  return 0;
+}
+// one walk per lane over the pairs of a launch whose traces are resident (list = the launch's work list)
+// `stride`: every stride-th lane walks (32 / stride walks per warp, see launch_traceback_batch)
+__global__ void __launch_bounds__(128) ba_traceback_batch_kernel(const __grid_constant__ Params P, const uint32_t* list, uint32_t n, uint32_t stride) {
+  __shared__ uint8_t lut[128];
+  for (uint32_t i = threadIdx.x; i < 128; i += blockDim.x) lut[i] = tb_entry(i);
+  __syncthreads();
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  lanes_traceback(P, lut, list, n, (t % stride) ? 0xffffffffu : t / stride);
+}
+static int launch_traceback_batch(const Params& P, const uint32_t* list, uint32_t n, dev_stream_t st) {
+  if (!n) return 0;
+  // Walks per warp. Every walk is a chain of dependent loads through its own pages (trace arena, sequences, records,
+  // run scratch), and the walks of one warp share every load instruction: measured on B200 with 10 k walks of ~90 k
+  // steps (C5), 32 walks per warp take 106 ms, 16: 87, 8: 66, 4: 55, 2: 74 (more resident warps per SM than the memory
+  // system serves well), 1: 84. So: four walks per warp while the launch still fits the GPU at once, more as the batch grows.
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  uint32_t stride = (uint32_t)std::min<uint64_t>(8, std::max<uint64_t>(1, (uint64_t)sms * 1024 / n));
+  if (const char* e = getenv("BA_TB_STRIDE")) stride = (uint32_t)std::max(1, atoi(e));
+  const uint64_t threads = (uint64_t)n * stride;
+  ba_traceback_batch_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(P, list, n, stride);
   CK(cudaGetLastError());
   return 0;
 }
@@ -375,23 +410,25 @@ struct BaBatch {
   StepLog* d_steplog = nullptr; uint32_t* d_steplog_n = nullptr;
   uint32_t* d_overflow_list = nullptr; uint32_t* d_overflow_n = nullptr;
   uint32_t* d_zwords = nullptr;     // zero masks (TRACE && LOCAL_START)
-  uint32_t* d_slot_pair = nullptr; uint32_t* r_slot_pair = nullptr;   // TRACE: which pair's trace each slot arena holds
+  // TRACE: every pair of a launch owns one trace arena; a wave = the pairs of one launch (their arenas fit the budget)
+  struct Wave { uint32_t t0 = 0, n = 0; uint64_t words = 0; uint32_t rects = 0, runs = 0; };
+  std::vector<Wave> waves;              // first pass, over the processing order
+  Wave cur;                             // geometry of the wave that ran last (its traces are the resident ones)
+  std::vector<uint32_t> h_order;        // processing order (pair ids, longest first)
+  std::vector<uint32_t> h_arena_of;     // pair -> arena index inside its wave
+  std::vector<uint8_t> resident;        // pairs whose trace is still in an arena (ba_batch_traceback)
+  uint32_t* d_arena_of = nullptr; bool h_arena_of_dirty = false;
+  uint64_t cap_trace = 0, cap_rects = 0, cap_runs = 0;   // bytes allocated for the arenas
   std::vector<uint32_t> h_qlen, h_rlen;   // lengths, kept for the bounds check of ba_batch_traceback
-  // scratch of the overflow retry (worst-case trace arenas for the few alignments that did not fit the first-pass
-  // arenas); kept until the next launch / free so that the trace of a retried pair can still be walked
-  uint32_t* r_trace = nullptr; uint32_t* r_zwords = nullptr; Rect* r_rects = nullptr; int16_t* r_ckpt = nullptr; uint32_t* r_runs = nullptr;
-  bool retried = false; bool arena_forced = false;
-  uint32_t rects_bound = 0;         // worst-case rectangle records per alignment
+  bool arena_forced = false;
   int kflags = 0;                   // template FLAGS of the kernel: (flags & 3) | kExt
   int pk_smax = 0; uint32_t pk_enable = 0;   // packed 2 x i16 path (ba_packed.cuh): largest matrix entry, on/off
   bool prof_fast = false; int prof_ge = -1;  // profile batch served by the packed fast phase; its (uniform) gap_extend
-  uint64_t trace_words_bound = 0;   // worst case per alignment (the reference's Trace::new size)
   uint64_t mem_budget = 0; uint64_t max_blocks_hw = 1;
   // launch geometry
   int blocks = 0, wpb = 0; size_t smem_bytes = 0; uint32_t slots_per_warp = 1; int fast_rows = 0; bool gb = false;
   int16_t* d_gborders = nullptr;
   uint32_t* d_trace_pool = nullptr; uint32_t* d_trace_pool_cursor = nullptr; uint64_t trace_pool_units = 0;
-  uint64_t trace_words_per_warp = 0; uint32_t rects_per_warp = 0, runs_per_warp = 0;
   // host results
   std::vector<DevResult> h_out;
   std::vector<uint32_t> h_cigar;
@@ -501,8 +538,7 @@ extern "C" void ba_batch_free(BaBatch* b) {
   void* bufs[] = {b->d_seq, b->d_qoff, b->d_roff, b->d_qlen, b->d_rlen, b->d_order, b->d_matrix, b->d_profiles, b->d_prof_arena,
                   b->d_out, b->d_ticket, b->d_ckpt, b->d_trace, b->d_rects, b->d_runs, b->d_cigar, b->d_cigar_used,
                   b->d_steplog, b->d_steplog_n, b->d_tb_res, b->d_overflow_list, b->d_overflow_n, b->d_zwords,
-                  b->r_trace, b->r_zwords, b->r_rects, b->r_ckpt, b->r_runs, b->d_gborders, b->d_trace_pool, b->d_trace_pool_cursor,
-                  b->d_slot_pair, b->r_slot_pair};
+                  b->d_gborders, b->d_trace_pool, b->d_trace_pool_cursor, b->d_arena_of};
   for (void* q : bufs) pool_release(al, q);
   if (b->has_ss) { dsync(b->ss.stream); streams_release(al, b->ss); }
   delete b;
@@ -540,6 +576,14 @@ static int check_config(const BaConfig* cfg, uint32_t* mn, uint32_t* mx) {
 // upload: sequences are padded for it). Called by the upload and again by ba_align_batch_exp* for every doubled min
 // size, so whatever an earlier configuration allocated is released first.
 #define CFG_TRY(x) do { int _r = (x); if (_r) return _r == 1 ? BA_ERR_CUDA : _r; } while (0)
+// worst-case trace words of one alignment of total length `len` = the reference's Trace::new (scan_block.rs:1364-1369)
+static uint64_t trace_bound_words(int flags, uint32_t mn, uint32_t mx, uint64_t len) {
+  uint64_t words = 2 * (uint64_t)(mx / 16) * (len + 2 * (uint64_t)mx);
+  if (mn == 16) words *= 2;   // 16-row rectangles still occupy a 32-lane word group
+  // FREE_QUERY_END_GAPS: every rectangle is laid out with 8 rows per lane (one 256-row chunk): 32 words per column
+  if (flags & BA_FREE_QUERY_END_GAPS) words = std::max<uint64_t>(words, 32 * (len + 2 * (uint64_t)mx));
+  return words + 64;
+}
 static int batch_configure(BaBatch* b, uint32_t mn) {
   BaAligner* al = b->al;
   const BaConfig* cfg = &b->cfg;
@@ -549,7 +593,7 @@ static int batch_configure(BaBatch* b, uint32_t mn) {
   b->min_size = mn;
   {
     void** old[] = {(void**)&b->d_ckpt, (void**)&b->d_gborders, (void**)&b->d_trace_pool, (void**)&b->d_trace_pool_cursor, (void**)&b->d_trace,
-                    (void**)&b->d_zwords, (void**)&b->d_rects, (void**)&b->d_runs, (void**)&b->d_slot_pair};
+                    (void**)&b->d_zwords, (void**)&b->d_rects, (void**)&b->d_runs, (void**)&b->d_arena_of};
     for (void** q : old) { pool_release(al, *q); *q = nullptr; }
     b->trace_pool_units = 0;
   }
@@ -588,82 +632,83 @@ static int batch_configure(BaBatch* b, uint32_t mn) {
   const size_t ms = mx < 32 ? 32 : mx;
   const uint64_t spw = b->slots_per_warp;
   b->max_blocks_hw = max_blocks;
-  if (trace) {
-    // Worst case per alignment = the reference's Trace::new (scan_block.rs:1364-1369): the block sits at its
-    // maximum size all the time. Real alignments spend most steps at the minimum size, so the first pass runs
-    // with arenas sized for 2x the all-minimum-size path plus one maximum-size grow; alignments that overflow
-    // are re-run with worst-case arenas (ba_batch_run).
-    const uint64_t len = (uint64_t)b->max_pair_len + 2;
-    uint64_t words = 2 * (uint64_t)(mx / 16) * (len + 2 * (uint64_t)mx);
-    if (mn == 16) words *= 2;   // 16-row rectangles still occupy a 32-lane word group
-    // FREE_QUERY_END_GAPS: every rectangle is laid out with 8 rows per lane (one 256-row chunk): 32 words per column
-    if (cfg->flags & BA_FREE_QUERY_END_GAPS) words = std::max<uint64_t>(words, 32 * (len + 2 * (uint64_t)mx));
-    if (words + 64 >= ((uint64_t)1 << 32)) { return fail(BA_ERR_SIZE, "trace arena of one alignment exceeds 2^32 words"); }
-    b->trace_words_bound = words + 64;
-    uint64_t first = 2 * len * (uint64_t)std::max<uint32_t>(mn, 32) / 8 + (uint64_t)mx * mx / 4 + 4096;
-    if (getenv("BA_TRACE_WORST_CASE") || (cfg->flags & BA_FREE_QUERY_END_GAPS)) first = b->trace_words_bound;
-    b->trace_words_per_warp = std::min<uint64_t>(b->trace_words_bound, first);
-    bool arena_forced = false;
-    if (const char* e = getenv("BA_TRACE_ARENA_WORDS")) {   // tests: tiny slot arenas exercise the pool / parking paths
-      b->trace_words_per_warp = std::min<uint64_t>(b->trace_words_bound, std::max<uint64_t>(64, (uint64_t)atoll(e)));
-      arena_forced = true;
-    }
-    b->arena_forced = arena_forced;
-    // one record per step (len / 8 shift steps; grow retries pop theirs again): the first pass gets twice that
-    b->rects_bound = (uint32_t)std::min<uint64_t>(len * 2 + 8, 0x7fffffffu);
-    b->rects_per_warp = b->trace_words_per_warp < b->trace_words_bound ? (uint32_t)std::min<uint64_t>(len / 4 + 1024, b->rects_bound) : b->rects_bound;
-    b->runs_per_warp = (uint32_t)std::min<uint64_t>(len + 8, 0x7fffffffu);
-    const uint64_t zmul = (cfg->flags & BA_LOCAL_START) ? 2 : 1;
-    const uint64_t per_warp = spw * (zmul * b->trace_words_per_warp * 4 + (uint64_t)b->rects_per_warp * sizeof(Rect)) + (uint64_t)b->runs_per_warp * 4;
-    b->mem_budget = (uint64_t)(al->mem_total * al->budget_frac);
-    // A tenth of the budget is a batch-wide overflow pool (trace_push): rectangles that do not fit a slot's own arena
-    // are bump-allocated there, so the rare alignment that sits at a large block size for long does not need the
-    // retry pass. Not with LOCAL_START (the zero masks mirror the per-slot layout).
-    if (!(cfg->flags & BA_LOCAL_START) && b->trace_words_per_warp < b->trace_words_bound && !getenv("BA_NO_TRACE_POOL")) {
-      uint64_t pool_bytes = b->mem_budget / 10;
-      // ... but never more than the alignments that can be in flight could spill: a one-pair Part 1 call must not
-      // allocate (and then cache) gigabytes
-      const uint64_t est_slots = std::max<uint64_t>(1, std::min<uint64_t>(n, max_blocks * (uint64_t)wpb * spw));
-      pool_bytes = std::min<uint64_t>(pool_bytes, est_slots * (b->trace_words_bound - b->trace_words_per_warp) * 4 + 4096);
-#ifdef BA_EMU
-      pool_bytes = std::min<uint64_t>(pool_bytes, (uint64_t)8 << 20);
-#endif
-      if (const char* e = getenv("BA_TRACE_POOL_BYTES")) pool_bytes = (uint64_t)atoll(e);   // tests: force exhaustion
-      b->trace_pool_units = pool_bytes / 64;
-      b->mem_budget -= b->trace_pool_units * 64;
-    }
-    const uint64_t fit_warps = std::max<uint64_t>(1, b->mem_budget / std::max<uint64_t>(per_warp, 1));
-    max_blocks = std::max<uint64_t>(1, std::min<uint64_t>(max_blocks, fit_warps / wpb));
-  }
   uint64_t want = (n + wpb * spw - 1) / (wpb * spw);
   if (want < 1) want = 1;
   b->blocks = (int)std::min<uint64_t>(want, max_blocks);
   const uint64_t nwarps = (uint64_t)b->blocks * wpb;
   const uint64_t nslots = nwarps * spw;
-  if (trace && b->trace_words_per_warp < b->trace_words_bound && !b->arena_forced) {
-    // The retry pass of an overflowed alignment runs almost alone on the GPU (measured on C5: one retried 50 kbp pair
-    // costs 90 ms), so once the number of slots is fixed the first-pass arenas take what is left of the budget, up to
-    // twice the initial estimate (4x the all-minimum-size path).
-    const uint64_t zmul = (cfg->flags & BA_LOCAL_START) ? 2 : 1;
-    const uint64_t fixed = nslots * (uint64_t)b->rects_per_warp * sizeof(Rect) + nwarps * (uint64_t)b->runs_per_warp * 4;
-    const uint64_t len = (uint64_t)b->max_pair_len + 2;
-    const uint64_t cap = std::min<uint64_t>(b->trace_words_bound, 4 * len * (uint64_t)std::max<uint32_t>(mn, 32) / 8 + (uint64_t)mx * mx / 4 + 4096);
-    if (b->mem_budget > fixed) {
-      const uint64_t fit = (b->mem_budget - fixed) / (nslots * zmul * 4);
-      b->trace_words_per_warp = std::max<uint64_t>(b->trace_words_per_warp, std::min<uint64_t>(cap, fit));
-    }
-  }
   CFG_TRY(pool_alloc(al, (void**)&b->d_ckpt, nslots * 4 * ms * sizeof(int16_t)));
   if (b->gb) CFG_TRY(pool_alloc(al, (void**)&b->d_gborders, nwarps * 4 * ms * sizeof(int16_t)));
   if (trace) {
-    if (b->trace_pool_units) {
-      CFG_TRY(pool_alloc(al, (void**)&b->d_trace_pool, b->trace_pool_units * 64));
-      CFG_TRY(pool_alloc(al, (void**)&b->d_trace_pool_cursor, 4));
+    // Trace memory. Every pair of a launch owns one arena (trace words + rectangle records + run scratch), indexed by
+    // arena_of[pair], so the traces of a whole launch are resident when its alignment kernel ends and the traceback
+    // runs as a second kernel with one walk per lane. The worst case per alignment is the reference's Trace::new
+    // (scan_block.rs:1364-1369: the block sits at its maximum size all the time); real alignments spend most steps
+    // at the minimum size, so the first pass gives every pair twice its all-minimum-size path and lets the rare
+    // rectangle that does not fit borrow from a batch-wide overflow pool (trace_push). Pairs that still overflow are
+    // re-run with worst-case arenas (batch_wait). The processing order is longest-first, so a wave (the pairs of one
+    // launch) is a run of similar lengths and uniform arenas sized by its first pair waste little.
+    const uint64_t zmul = (cfg->flags & BA_LOCAL_START) ? 2 : 1;
+    b->mem_budget = (uint64_t)(al->mem_total * al->budget_frac);
+    const bool want_pool = !(cfg->flags & BA_LOCAL_START) && !getenv("BA_NO_TRACE_POOL") && !getenv("BA_TRACE_WORST_CASE") &&
+                           !(cfg->flags & BA_FREE_QUERY_END_GAPS);
+    auto pair_len = [&](uint32_t t) { return (uint64_t)b->h_qlen[b->h_order[t]] + b->h_rlen[b->h_order[t]]; };
+    b->waves.clear();
+    b->arena_forced = getenv("BA_TRACE_ARENA_WORDS") != nullptr;
+    uint64_t spill_max = 0;
+    for (uint32_t t = 0; t < n;) {
+      const uint64_t len = (((pair_len(t) >> 6) + 1) << 6) + 2;      // the order is sorted in buckets of 64
+      const uint64_t bound = trace_bound_words(cfg->flags, mn, mx, len);
+      if (bound >= ((uint64_t)1 << 32)) return fail(BA_ERR_SIZE, "trace arena of one alignment exceeds 2^32 words");
+      uint64_t words = 2 * len * (uint64_t)std::max<uint32_t>(mn, 32) / 8 + 4096 + (want_pool ? 0 : (uint64_t)mx * mx / 4);
+      if (!want_pool && (getenv("BA_TRACE_WORST_CASE") || (cfg->flags & BA_FREE_QUERY_END_GAPS))) words = bound;
+      if (const char* e = getenv("BA_TRACE_ARENA_WORDS")) words = std::max<uint64_t>(64, (uint64_t)atoll(e));   // tests: tiny arenas
+      words = std::min(words, bound);
+      BaBatch::Wave wv;
+      wv.t0 = t; wv.words = words;
+      wv.rects = (uint32_t)std::min<uint64_t>(words < bound ? len / 4 + 1024 : len * 2 + 8, 0x7fffffffu);
+      wv.runs = (uint32_t)std::min<uint64_t>(len + 8, 0x7fffffffu);
+      const uint64_t per = zmul * words * 4 + (uint64_t)wv.rects * sizeof(Rect) + (uint64_t)wv.runs * 4;
+      const uint64_t room = b->mem_budget - (want_pool ? b->mem_budget / 10 : 0);
+      wv.n = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n - t, room / std::max<uint64_t>(per, 1)));
+      if (b->waves.empty() && wv.n == n && !b->arena_forced && words < bound) {
+        // one wave holds everything: the arenas take what is left of the budget, up to 4x the all-minimum-size path
+        // (an overflow retry costs far more than the memory)
+        const uint64_t fixed = (uint64_t)n * ((uint64_t)wv.rects * sizeof(Rect) + (uint64_t)wv.runs * 4);
+        const uint64_t cap = std::min<uint64_t>(bound, 4 * len * (uint64_t)std::max<uint32_t>(mn, 32) / 8 + 4096);
+        if (room > fixed) wv.words = std::max<uint64_t>(words, std::min<uint64_t>(cap, (room - fixed) / ((uint64_t)n * zmul * 4)));
+      }
+      spill_max = std::max<uint64_t>(spill_max, (uint64_t)wv.n * (bound - std::min(bound, wv.words)));
+      b->cap_trace = std::max<uint64_t>(b->cap_trace, (uint64_t)wv.n * wv.words * 4);
+      b->cap_rects = std::max<uint64_t>(b->cap_rects, (uint64_t)wv.n * wv.rects * sizeof(Rect));
+      b->cap_runs = std::max<uint64_t>(b->cap_runs, (uint64_t)wv.n * wv.runs * 4);
+      b->waves.push_back(wv);
+      t += wv.n;
     }
-    CFG_TRY(pool_alloc(al, (void**)&b->d_trace, nslots * b->trace_words_per_warp * 4));
-    if (cfg->flags & BA_LOCAL_START) CFG_TRY(pool_alloc(al, (void**)&b->d_zwords, nslots * b->trace_words_per_warp * 4));
-    CFG_TRY(pool_alloc(al, (void**)&b->d_rects, nslots * (uint64_t)b->rects_per_warp * sizeof(Rect)));
-    CFG_TRY(pool_alloc(al, (void**)&b->d_runs, nwarps * (uint64_t)b->runs_per_warp * 4));
+    b->h_arena_of.assign(n, 0);
+    for (const BaBatch::Wave& wv : b->waves)
+      for (uint32_t t = 0; t < wv.n; t++) b->h_arena_of[b->h_order[wv.t0 + t]] = t;
+    if (want_pool && spill_max) {
+      // a tenth of the budget, but never more than the alignments of a wave could spill: a one-pair Part 1 call must
+      // not allocate (and then cache) gigabytes
+      uint64_t pool_bytes = std::min<uint64_t>(b->mem_budget / 10, spill_max * 4 + 4096);
+#ifdef BA_EMU
+      pool_bytes = std::min<uint64_t>(pool_bytes, (uint64_t)8 << 20);
+#endif
+      if (const char* e = getenv("BA_TRACE_POOL_BYTES")) pool_bytes = (uint64_t)atoll(e);   // tests: force exhaustion
+      b->trace_pool_units = pool_bytes / 64;
+      if (b->trace_pool_units) {
+        CFG_TRY(pool_alloc(al, (void**)&b->d_trace_pool, b->trace_pool_units * 64));
+        CFG_TRY(pool_alloc(al, (void**)&b->d_trace_pool_cursor, 4));
+      }
+    }
+    CFG_TRY(pool_alloc(al, (void**)&b->d_trace, b->cap_trace));
+    if (cfg->flags & BA_LOCAL_START) CFG_TRY(pool_alloc(al, (void**)&b->d_zwords, b->cap_trace));
+    CFG_TRY(pool_alloc(al, (void**)&b->d_rects, b->cap_rects));
+    CFG_TRY(pool_alloc(al, (void**)&b->d_runs, b->cap_runs));
+    CFG_TRY(pool_alloc(al, (void**)&b->d_arena_of, std::max<size_t>(n, 1) * 4));
+    CFG_TRY(h2d(b->d_arena_of, b->h_arena_of.data(), n * 4, b->ss.stream));
+    CFG_TRY(dsync(b->ss.stream));
     if (!b->d_cigar) {
       uint64_t cap = 0;
       for (size_t k = 0; k < n; k++) cap += (uint64_t)b->h_qlen[k] + b->h_rlen[k] + 5;
@@ -674,7 +719,8 @@ static int batch_configure(BaBatch* b, uint32_t mn) {
       CFG_TRY(pool_alloc(al, (void**)&b->d_overflow_list, std::max<size_t>(n, 1) * 4));
       CFG_TRY(pool_alloc(al, (void**)&b->d_overflow_n, 4));
     }
-    CFG_TRY(pool_alloc(al, (void**)&b->d_slot_pair, nslots * 4));
+    b->resident.assign(n, 0);
+    if (!b->waves.empty()) b->cur = b->waves[0];
   }
   if (getenv("BA_STEP_LOG") && n == 1 && !b->d_steplog) {
     CFG_TRY(pool_alloc(al, (void**)&b->d_steplog, (size_t)(1 << 20) * sizeof(StepLog)));
@@ -966,7 +1012,7 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
   }
   if (herr) { ba_batch_free(b); return fail(BA_ERR_CHAR, "sequence byte outside the alphabet of the scoring matrix"); }
 
-  b->h_qlen = ql; b->h_rlen = rl;
+  b->h_qlen = ql; b->h_rlen = rl; b->h_order = order;
   TRY(batch_configure(b, mn));
   *out = b;
   return BA_OK;
@@ -990,7 +1036,7 @@ extern "C" int ba_batch_upload_pssm(BaAligner* a, const BaConfig* cfg, size_t n,
   return upload_common(a, cfg, n, q_bytes, q_off, nullptr, nullptr, nullptr, pssm, out);
 }
 
-static Params make_params(const BaBatch* b, bool retry = false) {
+static Params make_params(const BaBatch* b) {
   Params P;
   memset(&P, 0, sizeof(P));
   const bool prof = b->cfg.scoring == BA_SCORING_PROFILE;
@@ -1016,24 +1062,39 @@ static Params make_params(const BaBatch* b, bool retry = false) {
   P.ckpt = b->d_ckpt; P.slots_per_warp = b->slots_per_warp; P.gborders = b->d_gborders;
   P.fast_block = b->fast_rows >= 16 ? (8u << (b->fast_rows & 15)) : (uint32_t)(8 * b->fast_rows);
   P.pk_fast = b->fast_rows >= 16 ? 1u : 0u;
-  P.trace_words = b->d_trace; P.trace_words_per_warp = b->trace_words_per_warp;
+  P.trace_words = b->d_trace; P.trace_words_per_warp = b->cur.words; P.arena_of = b->d_arena_of;
   P.trace_pool = b->d_trace_pool; P.trace_pool_cursor = b->d_trace_pool_cursor; P.trace_pool_units = b->trace_pool_units;
-  P.rects = b->d_rects; P.rects_per_warp = b->rects_per_warp;
-  P.run_scratch = b->d_runs; P.runs_per_warp = b->runs_per_warp;
+  P.rects = b->d_rects; P.rects_per_warp = b->cur.rects;
+  P.run_scratch = b->d_runs; P.runs_per_warp = b->cur.runs;
   P.cigar_stream = b->d_cigar; P.cigar_cap = b->cigar_cap; P.cigar_used = b->d_cigar_used;
   P.cigar_eq = b->cfg.cigar_eq ? 1u : 0u;
   P.overflow_list = b->d_overflow_list; P.overflow_n = b->d_overflow_n;
-  P.slot_pair = b->d_slot_pair; P.retry_bit = 0u;
   P.step_log = b->d_steplog; P.step_log_cap = b->d_steplog ? (1u << 20) : 0u; P.step_log_n = b->d_steplog_n;
-  if (retry) {
-    P.ckpt = b->r_ckpt; P.trace_words = b->r_trace; P.trace_words_per_warp = b->trace_words_bound; P.trace_zwords = b->r_zwords;
-    P.rects = b->r_rects; P.rects_per_warp = b->rects_bound; P.run_scratch = b->r_runs;
-    P.slot_pair = b->r_slot_pair; P.retry_bit = kRetrySlotBit;
-  }
   return P;
 }
 
-// Launch the alignment kernel of a resident batch on the batch's own stream (no host synchronisation).
+// One launch of the alignment kernel over a work list, followed -- for TRACE batches -- by the traceback kernel over
+// the same list (the list's traces are resident in their arenas then). Stream-ordered, no host synchronisation.
+static int launch_wave(BaBatch* b, Params& P, const uint32_t* list, uint32_t n_list, const BaBatch::Wave& wv, int blocks) {
+  dev_stream_t st = b->ss.stream;
+  const bool trace = (b->cfg.flags & BA_TRACE) != 0;
+  P.order = list; P.n_pairs = n_list;
+  if (trace) { P.trace_words_per_warp = wv.words; P.rects_per_warp = wv.rects; P.runs_per_warp = wv.runs; b->cur = wv; }
+  if (!n_list) return BA_OK;
+  if (dzero(b->d_ticket, 4, st)) return BA_ERR_CUDA;
+  if (b->d_trace_pool_cursor && dzero(b->d_trace_pool_cursor, 4, st)) return BA_ERR_CUDA;
+  int rc = ba_launch_dispatch(P.scoring, P.flags, b->fast_rows, P, blocks, b->wpb, b->smem_bytes, st);
+  if (rc) return rc == 1 ? BA_ERR_CUDA : rc;
+  b->launches++;
+  if (trace && P.cigar_stream) {
+    if (launch_traceback_batch(P, list, n_list, st)) return BA_ERR_CUDA;
+    b->launches++;
+  }
+  return BA_OK;
+}
+
+// Launch a resident batch on its own stream (no host synchronisation): one wave, or -- TRACE batches whose arenas do not
+// fit the memory budget at once -- several in a row.
 static int batch_launch(BaBatch* b) {
   if (!b) return fail(BA_ERR_ARG, "batch is null");
   BaAligner* al = b->al;
@@ -1043,28 +1104,44 @@ static int batch_launch(BaBatch* b) {
   if (cudaSetDevice(al->device) != cudaSuccess) return fail(BA_ERR_CUDA, "cudaSetDevice failed");
 #endif
   Params P = make_params(b);
-  if (dzero(b->d_ticket, 4, st)) return BA_ERR_CUDA;
   if (b->d_cigar_used && dzero(b->d_cigar_used, 8, st)) return BA_ERR_CUDA;
   if (b->d_overflow_n && dzero(b->d_overflow_n, 4, st)) return BA_ERR_CUDA;
-  if (b->d_trace_pool_cursor && dzero(b->d_trace_pool_cursor, 4, st)) return BA_ERR_CUDA;
   if (b->d_steplog_n && dzero(b->d_steplog_n, 4, st)) return BA_ERR_CUDA;
   b->downloaded = false;
   b->launches = 0;
-  b->retried = false;
-  if (P.n_pairs) {
+  const bool trace = (b->cfg.flags & BA_TRACE) != 0;
+  const uint32_t n_run = b->use_active ? b->n_active : (uint32_t)b->n;
 #ifndef BA_EMU
-    cudaEventRecord(b->ss.ev0, st);
+  if (n_run) cudaEventRecord(b->ss.ev0, st);
 #endif
-    int rc = ba_launch_dispatch(P.scoring, P.flags, b->fast_rows, P, b->blocks, b->wpb, b->smem_bytes, st);
-    if (rc) return rc == 1 ? BA_ERR_CUDA : rc;
-    b->launches++;
+  if (!trace || b->use_active) {
+    BaBatch::Wave none;
+    int rc = launch_wave(b, P, b->use_active ? b->d_active : b->d_order, n_run, none, b->blocks);
+    if (rc) return rc;
+  } else {
+    if (b->h_arena_of_dirty) {     // a retry pass of the previous run re-assigned arenas
+      for (const BaBatch::Wave& wv : b->waves)
+        for (uint32_t t = 0; t < wv.n; t++) b->h_arena_of[b->h_order[wv.t0 + t]] = t;
+      if (h2d(b->d_arena_of, b->h_arena_of.data(), b->n * 4, st) || dsync(st)) return BA_ERR_CUDA;
+      b->h_arena_of_dirty = false;
+    }
+    std::fill(b->resident.begin(), b->resident.end(), 0);
+    for (const BaBatch::Wave& wv : b->waves) {
+      int rc = launch_wave(b, P, b->d_order + wv.t0, wv.n, wv, b->blocks);
+      if (rc) return rc;
+    }
+    if (!b->waves.empty()) {
+      const BaBatch::Wave& wv = b->waves.back();
+      for (uint32_t t = 0; t < wv.n; t++) b->resident[b->h_order[wv.t0 + t]] = 1;
+    }
   }
   b->launched = true;
   return BA_OK;
 }
 
-// Wait for a launched batch; re-run alignments whose (deliberately small) trace arena overflowed with
-// worst-case arenas; report the device time between the first launch and the last completion.
+// Wait for a launched batch; re-run alignments whose (deliberately small) trace arena overflowed with worst-case arenas
+// -- in the same buffers, as many at a time as fit --; report the device time between the first launch and the last
+// completion.
 static int batch_wait(BaBatch* b, BaStats* stats) {
   if (!b || !b->launched) return fail(BA_ERR_ARG, "batch was not launched");
   BaAligner* al = b->al;
@@ -1074,43 +1151,53 @@ static int batch_wait(BaBatch* b, BaStats* stats) {
 #endif
   dev_stream_t st = b->ss.stream;
   float ms = 0;
-  int rc;
   if (b->use_active ? b->n_active : b->n) {
-    if (b->d_overflow_n && b->trace_words_per_warp < b->trace_words_bound) {
+    if (b->d_overflow_n && !b->use_active) {
       uint32_t n_over = 0;
       if (d2h(&n_over, b->d_overflow_n, 4, st) || dsync(st)) return BA_ERR_CUDA;
-      if (getenv("BA_TIMING")) fprintf(stderr, "batch_wait: %zu pairs, %d blocks x %d warps, %u slots/warp, trace words/slot %llu (bound %llu), %u overflowed\n",
-                                       b->n, b->blocks, b->wpb, b->slots_per_warp, (unsigned long long)b->trace_words_per_warp,
-                                       (unsigned long long)b->trace_words_bound, n_over);
+      if (getenv("BA_TIMING")) fprintf(stderr, "batch_wait: %zu pairs, %d blocks x %d warps, %u slots/warp, %zu wave(s), trace words/arena %llu, %u overflowed\n",
+                                       b->n, b->blocks, b->wpb, b->slots_per_warp, b->waves.size(), (unsigned long long)b->cur.words, n_over);
       if (n_over) {
-        // second pass over the overflowed pairs only, with worst-case arenas in separate scratch (the first-pass
-        // arenas stay as they are, so the batch can be run again)
-        const uint64_t spw = b->slots_per_warp;
+        std::vector<uint32_t> over(n_over);
+        if (d2h(over.data(), b->d_overflow_list, (size_t)n_over * 4, st) || dsync(st)) return BA_ERR_CUDA;
         const uint64_t zmul = b->d_zwords ? 2 : 1;
-        const uint64_t per_warp = spw * (zmul * b->trace_words_bound * 4 + (uint64_t)b->rects_bound * sizeof(Rect)) + (uint64_t)b->runs_per_warp * 4;
-        const uint64_t fit_warps = std::max<uint64_t>(1, (uint64_t)(b->mem_budget * 0.6) / std::max<uint64_t>(per_warp, 1));
-        uint64_t blocks2 = std::max<uint64_t>(1, std::min<uint64_t>(b->max_blocks_hw, fit_warps / b->wpb));
-        blocks2 = std::min<uint64_t>(blocks2, (n_over + b->wpb * spw - 1) / (b->wpb * spw));
-        if (b->gb) blocks2 = std::min<uint64_t>(blocks2, (uint64_t)b->blocks);   // d_gborders is sized for the first pass
-        const uint64_t nslots2 = blocks2 * b->wpb * spw;
-        const size_t msz = b->max_size < 32 ? 32 : b->max_size;
-        void** rb[] = {(void**)&b->r_trace, (void**)&b->r_zwords, (void**)&b->r_rects, (void**)&b->r_ckpt, (void**)&b->r_runs, (void**)&b->r_slot_pair};
-        for (void** q : rb) { pool_release(al, *q); *q = nullptr; }
-        if (pool_alloc(al, (void**)&b->r_trace, nslots2 * b->trace_words_bound * 4)) return BA_ERR_NOMEM;
-        if (b->d_zwords && pool_alloc(al, (void**)&b->r_zwords, nslots2 * b->trace_words_bound * 4)) return BA_ERR_NOMEM;
-        if (pool_alloc(al, (void**)&b->r_rects, nslots2 * (uint64_t)b->rects_bound * sizeof(Rect))) return BA_ERR_NOMEM;
-        if (pool_alloc(al, (void**)&b->r_ckpt, nslots2 * 4 * msz * sizeof(int16_t))) return BA_ERR_NOMEM;
-        if (pool_alloc(al, (void**)&b->r_runs, blocks2 * b->wpb * (uint64_t)b->runs_per_warp * 4)) return BA_ERR_NOMEM;
-        if (pool_alloc(al, (void**)&b->r_slot_pair, nslots2 * 4)) return BA_ERR_NOMEM;
-        b->retried = true;
-        Params P2 = make_params(b, true);
-        P2.order = b->d_overflow_list;     // the kernel appends to this list only on overflow, which cannot
-        P2.n_pairs = n_over;               // happen with worst-case arenas, so reading it as the work list is safe
-        P2.overflow_list = nullptr; P2.overflow_n = nullptr;
-        if (dzero(b->d_ticket, 4, st)) return BA_ERR_CUDA;
-        rc = ba_launch_dispatch(P2.scoring, P2.flags, b->fast_rows, P2, (int)blocks2, b->wpb, b->smem_bytes, st);
-        if (rc) return rc == 1 ? BA_ERR_CUDA : rc;
-        b->launches++;
+        uint64_t len = 0;
+        for (uint32_t k : over) len = std::max<uint64_t>(len, (uint64_t)b->h_qlen[k] + b->h_rlen[k] + 2);
+        BaBatch::Wave wv;
+        wv.words = trace_bound_words(b->cfg.flags, b->min_size, b->max_size, len);
+        wv.rects = (uint32_t)std::min<uint64_t>(len * 2 + 8, 0x7fffffffu);
+        wv.runs = (uint32_t)std::min<uint64_t>(len + 8, 0x7fffffffu);
+        // the worst-case arenas live in the first pass's buffers (grown if not even one fits)
+        auto fit = [&]() { return std::min<uint64_t>(std::min<uint64_t>(b->cap_trace / (wv.words * 4), b->cap_rects / ((uint64_t)wv.rects * sizeof(Rect))),
+                                                     b->cap_runs / ((uint64_t)wv.runs * 4)); };
+        if (fit() == 0) {
+          void** bufs[] = {(void**)&b->d_trace, (void**)&b->d_zwords, (void**)&b->d_rects, (void**)&b->d_runs};
+          const bool had_z = b->d_zwords != nullptr;
+          for (void** q : bufs) { pool_release(al, *q); *q = nullptr; }
+          b->cap_trace = std::max<uint64_t>(b->cap_trace, wv.words * 4);
+          b->cap_rects = std::max<uint64_t>(b->cap_rects, (uint64_t)wv.rects * sizeof(Rect));
+          b->cap_runs = std::max<uint64_t>(b->cap_runs, (uint64_t)wv.runs * 4);
+          if (pool_alloc(al, (void**)&b->d_trace, b->cap_trace)) return BA_ERR_NOMEM;
+          if (had_z && pool_alloc(al, (void**)&b->d_zwords, b->cap_trace)) return BA_ERR_NOMEM;
+          if (pool_alloc(al, (void**)&b->d_rects, b->cap_rects)) return BA_ERR_NOMEM;
+          if (pool_alloc(al, (void**)&b->d_runs, b->cap_runs)) return BA_ERR_NOMEM;
+        }
+        (void)zmul;
+        const uint64_t per_wave = std::max<uint64_t>(1, fit());
+        Params P2 = make_params(b);
+        P2.overflow_list = nullptr; P2.overflow_n = nullptr;     // cannot overflow with worst-case arenas
+        std::fill(b->resident.begin(), b->resident.end(), 0);
+        for (uint32_t t0 = 0; t0 < n_over; t0 += (uint32_t)per_wave) {
+          wv.t0 = t0; wv.n = (uint32_t)std::min<uint64_t>(per_wave, n_over - t0);
+          for (uint32_t t = 0; t < wv.n; t++) b->h_arena_of[over[t0 + t]] = t;
+          if (h2d(b->d_arena_of, b->h_arena_of.data(), b->n * 4, st) || dsync(st)) return BA_ERR_CUDA;
+          b->h_arena_of_dirty = true;
+          const uint64_t spw = b->slots_per_warp;
+          const int blocks2 = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)b->blocks, (wv.n + b->wpb * spw - 1) / (b->wpb * spw)));
+          int rc = launch_wave(b, P2, b->d_overflow_list + t0, wv.n, wv, blocks2);
+          if (rc) return rc;
+          if (t0 + wv.n >= n_over) for (uint32_t t = 0; t < wv.n; t++) b->resident[over[t0 + t]] = 1;
+        }
       }
     }
 #ifndef BA_EMU
@@ -1419,7 +1506,8 @@ extern "C" int ba_align_batch_exp(BaAligner* a, const BaConfig* cfg, size_t n, c
   if (!a) return fail(BA_ERR_ARG, "aligner is null");
   AlLock lk(a->mu);
   BaBatch* b = nullptr;
-  rc = ba_batch_upload(a, cfg, n, q_bytes, q_off, r_bytes, r_off, &b);
+  BaConfig c2 = *cfg; c2.flags &= ~BA_TRACE;     // only results are returned: the trace is not needed (it does not change them)
+  rc = ba_batch_upload(a, &c2, n, q_bytes, q_off, r_bytes, r_off, &b);
   if (rc) return rc;
   return align_exp_resident(b, n, target_score, out, min_size_used, stats);
 }
@@ -1432,7 +1520,8 @@ extern "C" int ba_align_batch_exp_profiles(BaAligner* a, const BaConfig* cfg, si
   if (!a) return fail(BA_ERR_ARG, "aligner is null");
   AlLock lk(a->mu);
   BaBatch* b = nullptr;
-  rc = ba_batch_upload_profiles(a, cfg, n, q_bytes, q_off, profiles, &b);
+  BaConfig c2 = *cfg; c2.flags &= ~BA_TRACE;
+  rc = ba_batch_upload_profiles(a, &c2, n, q_bytes, q_off, profiles, &b);
   if (rc) return rc;
   return align_exp_resident(b, n, target_score, out, min_size_used, stats);
 }
@@ -1445,7 +1534,8 @@ extern "C" int ba_align_batch_exp_pssm(BaAligner* a, const BaConfig* cfg, size_t
   if (!a) return fail(BA_ERR_ARG, "aligner is null");
   AlLock lk(a->mu);
   BaBatch* b = nullptr;
-  rc = ba_batch_upload_pssm(a, cfg, n, q_bytes, q_off, pssm, &b);
+  BaConfig c2 = *cfg; c2.flags &= ~BA_TRACE;
+  rc = ba_batch_upload_pssm(a, &c2, n, q_bytes, q_off, pssm, &b);
   if (rc) return rc;
   return align_exp_resident(b, n, target_score, out, min_size_used, stats);
 }
@@ -1655,13 +1745,13 @@ extern "C" int ba_batch_traceback(BaBatch* b, size_t k, size_t query_idx, size_t
 #ifndef BA_EMU
   if (cudaSetDevice(al->device) != cudaSuccess) return fail(BA_ERR_CUDA, "cudaSetDevice failed");
 #endif
-  Params P = make_params(b, (b->h_out[k].warp & kRetrySlotBit) != 0);
+  if (!b->resident[k]) return fail(BA_ERR_ARG, "the trace of this pair is no longer resident (a later launch of the batch reused its arena)");
+  Params P = make_params(b);
   if (!b->d_tb_res && pool_alloc(al, (void**)&b->d_tb_res, sizeof(DevResult))) return BA_ERR_CUDA;
   if (dzero(b->d_cigar_used, 8, st)) return BA_ERR_CUDA;
   if (launch_traceback(P, (uint32_t)k, (uint32_t)query_idx, (uint32_t)reference_idx, eq, b->d_tb_res, st)) return BA_ERR_CUDA;
   DevResult res;
   if (d2h(&res, b->d_tb_res, sizeof(res), st) || dsync(st)) return BA_ERR_CUDA;
-  if (res.status == kTraceGone) return fail(BA_ERR_ARG, "the trace of this pair is no longer resident (a later pair of the batch reused its arena)");
   if (res.status != kOk) return fail(BA_ERR_OVERFLOW, "traceback failed (buffer overflow or an end position the alignment never reached)");
   b->h_tb.resize(res.cigar_n);
   if (d2h(b->h_tb.data(), b->d_cigar + res.cigar_off, (size_t)res.cigar_n * 4, st) || dsync(st)) return BA_ERR_CUDA;

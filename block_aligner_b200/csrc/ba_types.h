@@ -23,8 +23,6 @@ enum Dir : int { kRight = 0, kDown = 1, kGrow = 2 };
 
 // per-pair status written by the kernel
 enum Status : uint32_t { kOk = 0, kNotRun = 1, kTraceOverflow = 2, kRectOverflow = 3, kCigarOverflow = 4, kTraceGone = 5 };
-// DevResult::warp: slot index, bit 31 set when the pair ran in the overflow-retry pass (its trace lives in the retry scratch)
-constexpr uint32_t kRetrySlotBit = 0x80000000u;
 
 // Device-side view of one AAProfile (reference: src/scores.rs:454-468). `pos_aa` is the only score
 // layout kept on the device (row per position, 32 i8 each); the reference's transposed `aa_pos`
@@ -85,7 +83,7 @@ struct DevResult {
   uint32_t cigar_n;              // number of runs written for this pair
   uint64_t cigar_off;            // offset (in runs) into the cigar stream
   uint32_t rect_n;               // rectangles on the trace stack at the end (TRACE)
-  uint32_t warp;                 // slot that ran this pair (its trace arena holds the trace)
+  uint32_t warp;                 // trace arena that holds this pair's trace (TRACE)
 };
 
 // one record per step, debug builds only (mirrors ora_step in oracle/ba_oracle.h)
@@ -121,23 +119,26 @@ struct Params {
   DevResult* out;
   uint32_t* ticket;              // work counter
   // per-warp scratch in global memory
-  // a "slot" is one alignment in flight: 1 per warp, or 4 per warp when the block-32 fast phase is on
+  // a "slot" is one alignment in flight: 1 per warp, or 4 / 8 per warp when the packed fast phase is on
   uint32_t slots_per_warp;
   uint32_t fast_block;           // 0: fast phase off; 32 / 64: block size served by the fast phase (== min_size)
   int16_t* ckpt;                 // 4 * max(max_size, 32) int16 per slot: checkpoint borders
   int16_t* gborders;             // kernels with global live borders (FM >= 32): 4 * max(max_size, 32) int16 per warp
-  uint32_t* trace_words; uint64_t trace_words_per_warp;   // per slot (name kept: per-"warp" arena of v0)
+  // TRACE: every pair of a launch owns one trace arena (words + rectangle records + run scratch), arena_of[pair] = its
+  // index. The trace stays resident after the alignment, so the CIGARs are produced by a second kernel with one walk per
+  // lane (ba_traceback_batch_kernel) instead of one walk per warp inside the alignment kernel.
+  const uint32_t* arena_of;
+  uint32_t* trace_words; uint64_t trace_words_per_warp;   // per arena (names kept from the per-warp arenas of v0)
   // shared overflow pool for rectangles that do not fit a slot's own arena: bump-allocated in units of 16 words
   uint32_t* trace_pool; uint32_t* trace_pool_cursor; uint64_t trace_pool_units;
-  Rect* rects; uint32_t rects_per_warp;                   // per slot
-  uint32_t* run_scratch; uint32_t runs_per_warp;  // reversed CIGAR runs while walking back
+  Rect* rects; uint32_t rects_per_warp;                   // per arena
+  uint32_t* run_scratch; uint32_t runs_per_warp;  // per arena: reversed CIGAR runs while walking back
   // cigar output stream: runs packed as (len << 4) | op, allocated with atomicAdd on *cigar_used
   uint32_t* cigar_stream; uint64_t cigar_cap; unsigned long long* cigar_used;
   uint32_t cigar_eq;
   // pairs whose trace arena overflowed (they are re-run with worst-case arenas)
   uint32_t* overflow_list; uint32_t* overflow_n;
-  // TRACE: pair whose trace a slot's arena holds (the last one that ran there); retry_bit = kRetrySlotBit in the retry pass
-  uint32_t* slot_pair; uint32_t retry_bit;
+
   // debug
   StepLog* step_log; uint32_t step_log_cap; uint32_t* step_log_n;   // only honoured for n_pairs == 1
 };

@@ -60,6 +60,7 @@ inline int imax(int a, int b) { return a > b ? a : b; }
 inline int imin(int a, int b) { return a < b ? a : b; }
 template <class T> inline T ldg(const T* p) { return *p; }
 inline void touch(const void*) {}
+inline void touch_l2(const void*) {}
 }}  // namespace ba::wp
 #else
 #define BA_DEV __device__ __forceinline__
@@ -109,6 +110,9 @@ BA_DEV int imax(int a, int b) { return max(a, b); }
 BA_DEV int imin(int a, int b) { return min(a, b); }
 template <class T> BA_DEV T ldg(const T* p) { return __ldg(p); }
 // bring the 128-byte line of p into L1 / L2 without waiting for it (a load whose result is never used)
-BA_DEV void touch(const void* p) { unsigned d; asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(d) : "l"(p)); (void)d; }
+// (a prefetch instruction, not a load into a dummy register: the register of an outstanding load is scoreboarded, and
+// the next instruction the compiler gives that register to waits for the data -- measured in the batch traceback)
+BA_DEV void touch(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+BA_DEV void touch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 }}  // namespace ba::wp
 #endif

@@ -94,7 +94,8 @@ def test_trace_arena_overflow_is_retried(env, pool, monkeypatch):
     qa, qo, ra, ro = workloads.generate(w["gen"], 6, stream=31)
     m = workloads.matrix_of(lib, w)
     got = parity.run_lib(lib, al, w["scoring"], m, w["gaps"], w["size"], 0, api.TRACE, True, qa, qo, ra, ro)
-    assert got[3].kernel_launches == (1 if pool else 2), "expected the overflow pool / the retry pass to be used"
+    nl = got[3].kernel_launches       # an alignment and a traceback kernel per pass; the retry pass may take several waves
+    assert (nl == 2) if pool else (nl >= 4 and nl % 2 == 0), "expected the overflow pool / the retry pass to be used"
     exp = parity.oracle_batch(w["scoring"], m, w["gaps"], w["size"], 0, api.TRACE, True, qa, qo, ra, ro)
     assert parity.compare("overflow-retry", got, exp) == 0
 
@@ -232,7 +233,7 @@ def test_batch_with_overflow_retry_can_run_again(env, monkeypatch):
     outs = []
     for _ in range(3):
         st = b.run()
-        assert st.kernel_launches == 2
+        assert st.kernel_launches >= 4      # first pass + retry pass(es), an alignment and a traceback kernel each
         r = b.download()
         outs.append((r.copy(), [b.cigar_string(k) for k in range(len(qo) - 1)]))
     b.free()
@@ -248,7 +249,7 @@ def test_trace_pool_exhaustion_falls_back_to_retry(env, monkeypatch):
     qa, qo, ra, ro = workloads.generate(w["gen"], 6, stream=31)
     m = workloads.matrix_of(lib, w)
     got = parity.run_lib(lib, al, w["scoring"], m, w["gaps"], w["size"], 0, api.TRACE, True, qa, qo, ra, ro)
-    assert got[3].kernel_launches == 2
+    assert got[3].kernel_launches >= 4
     exp = parity.oracle_batch(w["scoring"], m, w["gaps"], w["size"], 0, api.TRACE, True, qa, qo, ra, ro)
     assert parity.compare("pool-exhausted", got, exp) == 0
 
@@ -270,6 +271,6 @@ def test_full_slot_arena_parks_fast_phase_and_spills_to_pool(env, size, monkeypa
     qa, qo, ra, ro = workloads.generate(w["gen"], 10, stream=51)
     m = workloads.matrix_of(lib, w)
     got = parity.run_lib(lib, al, w["scoring"], m, w["gaps"], size, 80, w["flags"], True, qa, qo, ra, ro)
-    assert got[3].kernel_launches == 1
+    assert got[3].kernel_launches == 2
     exp = parity.oracle_batch(w["scoring"], m, w["gaps"], size, 80, w["flags"], True, qa, qo, ra, ro)
     assert parity.compare("tiny-arena", got, exp) == 0
