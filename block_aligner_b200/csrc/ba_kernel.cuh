@@ -324,7 +324,7 @@ BA_DEV void place_rect_r(const SeqScorer<(SCORING == kProfile ? kAA : SCORING)>&
           const int v = trk[k] >> 14;
           const unsigned c1 = (unsigned)(trk[k] & 16383);
           const unsigned cls = (unsigned)((lane * R + k) & 15);
-          const unsigned key = ((15u - cls) << 27) | (c1 << 13) | (unsigned)(v0 + k);
+          const unsigned key = ((15u - cls) << kKeyClsShift) | (c1 << kKeyColShift) | (unsigned)(v0 + k);
           if (c1 != 0 && (v > bv || (v == bv && key > bkey))) { bv = v; bkey = key; }
         }
       }
@@ -344,7 +344,7 @@ BA_DEV void place_rect(const SeqScorer<(SCORING == kProfile ? kAA : SCORING)>& s
                        const RectArgs& a, const WarpMem& w, int& bv, unsigned& bkey) {
   constexpr bool RT = (SCORING == kProfile) ? RIGHT : true;
   bv = 0;                // D_max starts at MIN = 0 (scan_block.rs:1101)
-  bkey = 15u << 27;      // "no cell": AVX lane 0 with argmax (0, 0)
+  bkey = 15u << kKeyClsShift;      // "no cell": AVX lane 0 with argmax (0, 0)
   if (a.W == 0 || a.H == 0) return;   // scan_block.rs:1105-1107
   // FREE_QUERY_END_GAPS needs the whole rectangle in one chunk (cell order matters): 8 rows per lane up to 256 rows
   if (a.H >= 256 || (EXT && a.fqe)) place_rect_r<SCORING, RT, 8, TRACE, XDROP, EXT>(sc, pa, a, w, bv, bkey);
@@ -822,7 +822,7 @@ BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const Sl
 
   bool resume_shrink = false;
   for (;;) {
-    int bv = 0, gbv = 0; unsigned bkey = 15u << 27, gbkey = 15u << 27;
+    int bv = 0, gbv = 0; unsigned bkey = 15u << kKeyClsShift, gbkey = 15u << kKeyClsShift;
     int right_max = 0, down_max = 0, mx = 0;
     const int B = st.B;
     const uint32_t si = st.si, sj = st.sj;
@@ -911,7 +911,7 @@ BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const Sl
       }
       add_cells(st, (uint32_t)(a.W * a.H));
       sc.vec = rect_right ? q : r; sc.col = rect_right ? r : q;
-      int pbv = 0; unsigned pkey = 15u << 27;
+      int pbv = 0; unsigned pkey = 15u << kKeyClsShift;
       if (!st.overflow) {
         const bool done = pk_ok;
         if (pk_ok) place_rect_pk<(PROF ? kAA : SCORING), XDROP, TRACE>(w.smem0, P, P.kc, sc.vec, sc.col, a, w.fr, pbv, pkey);
@@ -967,8 +967,8 @@ BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const Sl
         const int tv = use_right ? bv : gbv;
         const unsigned tk = use_right ? bkey : gbkey;
         const unsigned key = wp::red_max_u(tv == m ? tk : 0u);
-        const unsigned cp1 = (key >> 13) & 0x3fffu;
-        uint32_t v = key & 0x1fffu, c = 0;
+        const unsigned cp1 = (key >> kKeyColShift) & 0x3fffu;
+        uint32_t v = key & kKeyRowMask, c = 0;
         if (cp1 == 0) v = 0; else c = cp1 - 1;
         if (this_dir == kRight) { st.best_i = si + v; st.best_j = sj + (uint32_t)(B - kStep) + c; }
         else if (this_dir == kDown) { st.best_i = si + (uint32_t)(B - kStep) + c; st.best_j = sj + v; }
@@ -1223,8 +1223,8 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast
     st.y_drop_iter++;
     if (st.off_max > st.best_max) {
       if (XDROP) {
-        const unsigned cp1 = (key >> 13) & 0x3fffu;
-        uint32_t v = key & 0x1fffu, c = 0;
+        const unsigned cp1 = (key >> kKeyColShift) & 0x3fffu;
+        uint32_t v = key & kKeyRowMask, c = 0;
         if (cp1 == 0) v = 0; else c = cp1 - 1;
         if (right) { st.best_i = si + v; st.best_j = sj + (B - kStep) + c; }
         else { st.best_i = si + (B - kStep) + c; st.best_j = sj + v; }

@@ -365,23 +365,23 @@ BA_DEV void pkp_cols8(const PkpOps& o, const PkConst& kc, int lg, uint32_t cw0, 
 
 // Best cell of the lane under the reference's order: value desc, AVX lane (row mod 16) asc, column desc, row desc
 // (scan_block.rs:1194-1201, avx2.rs:271-274). pk_lane_key: key of the lane's best cell among those equal to M
-// (0 if none); key format as in place_rect_r: (15 - class) << 27 | (column + 1) << 13 | row. Every row has seen
+// (0 if none); key format as in place_rect_r: (15 - class) << 28 | (column + 1) << 14 | row. Every row has seen
 // a cell >= 0 (guard), so there is no "no cell" case.
 BA_DEV unsigned pk_lane_key(const uint32_t (&m)[4], const uint32_t (&mc)[kMcN], int lg, int G, int M) {
   const uint32_t M2 = pk2(M);
-  const unsigned base0 = ((15u - (unsigned)((4 * lg) & 15)) << 27) | (unsigned)(4 * lg);
+  const unsigned base0 = ((15u - (unsigned)((4 * lg) & 15)) << kKeyClsShift) | (unsigned)(4 * lg);
   unsigned key = 0;
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     bool ph, pl;
     wp::vibmax2(m[k], M2, ph, pl);            // m >= M, i.e. m == M for M = the maximum
-    const unsigned base = base0 - ((unsigned)k << 27) + (unsigned)k;
+    const unsigned base = base0 - ((unsigned)k << kKeyClsShift) + (unsigned)k;
 #if BA_PK_SPLIT_MC
-    const unsigned klo = base | (mc[k] << 13);
-    const unsigned khi = (base + (unsigned)(4 * G)) | (mc[4 + k] << 13);
+    const unsigned klo = base | (mc[k] << kKeyColShift);
+    const unsigned khi = (base + (unsigned)(4 * G)) | (mc[4 + k] << kKeyColShift);
 #else
-    const unsigned klo = base | ((mc[k] & 0xffffu) << 13);
-    const unsigned khi = (base + (unsigned)(4 * G)) | ((mc[k] >> 16) << 13);
+    const unsigned klo = base | ((mc[k] & 0xffffu) << kKeyColShift);
+    const unsigned khi = (base + (unsigned)(4 * G)) | ((mc[k] >> 16) << kKeyColShift);
 #endif
     if (pl && klo > key) key = klo;
     if (ph && khi > key) key = khi;
@@ -469,7 +469,7 @@ BA_DEV void place_rect_pk(const unsigned char* smem, const Params& P, const PkCo
   uint32_t D[4], C[4];
   pk_load4(a.AD, lg, G, D);
   pk_load4(a.AC, lg, G, C);
-  bv = 0; bkey = 15u << 27;
+  bv = 0; bkey = 15u << kKeyClsShift;
   const uint32_t oa2 = pk2(a.off_add);
 #pragma unroll
   for (int k = 0; k < 4; k++) { D[k] = wp::vadd2(D[k], oa2); C[k] = wp::vadd2(C[k], oa2); }

@@ -563,7 +563,7 @@ static int check_config(const BaConfig* cfg, uint32_t* mn, uint32_t* mx) {
   uint64_t a = cfg->size.min < (uint64_t)kL ? kL : cfg->size.min, b = cfg->size.max < (uint64_t)kL ? kL : cfg->size.max;
   if (!(a < 65535 && b < 65535)) return fail(BA_ERR_SIZE, "Block sizes must be smaller than 2^16 - 1!");
   if (!(pow2(a) && pow2(b))) return fail(BA_ERR_SIZE, "Block sizes must be powers of two!");
-  if (b > (uint64_t)kMaxBlock) return fail(BA_ERR_SIZE, "max block size above 8192 is not supported by this build");
+  if (b > (uint64_t)kMaxBlock) return fail(BA_ERR_SIZE, "max block size above 16384 is not supported by this build");
   if ((cfg->flags & BA_XDROP) && cfg->x_drop < 0) return fail(BA_ERR_XDROP, "X-drop threshold amount must be nonnegative!");
   if (cfg->scoring == BA_SCORING_PROFILE && cfg->cigar_eq) return fail(BA_ERR_ARG, "cigar_eq needs a reference sequence");
   // our limit: the lane-ordered argmax of this mode is computed with the whole block in one 256-row chunk
@@ -1549,13 +1549,57 @@ extern "C" int ba_align_batch_profiles(BaAligner* a, const BaConfig* cfg, size_t
   if (rc) return rc;
   return align_uploaded_profiles(b, n, out, stats);
 }
-// the same for profiles built on the device from raw PSSM rows (BaPssmBatch)
+// the same for profiles built on the device from raw PSSM rows (BaPssmBatch). Large batches are cut into chunks on separate
+// streams like ba_align_batch: the upload + profile construction of chunk k + 1 overlaps the alignment kernel of chunk k.
 extern "C" int ba_align_batch_pssm(BaAligner* a, const BaConfig* cfg, size_t n, const uint8_t* q_bytes, const uint64_t* q_off,
                                    const BaPssmBatch* pssm, AlignResult* out, BaStats* stats) {
-  BaBatch* b = nullptr;
-  int rc = ba_batch_upload_pssm(a, cfg, n, q_bytes, q_off, pssm, &b);
-  if (rc) return rc;
-  return align_uploaded_profiles(b, n, out, stats);
+  if (!a || !pssm) return fail(BA_ERR_ARG, "null aligner / pssm");
+  AlLock lk(a->mu);
+  size_t K = 1;
+  const uint64_t bytes = (n && pssm->score_off) ? pssm->score_off[n] - pssm->score_off[0] : 0;
+  if (n >= 8192 && bytes >= ((uint64_t)32 << 20)) K = 4;
+  if (const char* e = getenv("BA_PIPELINE_CHUNKS")) K = std::max<size_t>(1, std::min<size_t>((size_t)atoi(e), 64));
+  if (K > n) K = n ? n : 1;
+  if (K == 1) {
+    BaBatch* b = nullptr;
+    int rc = ba_batch_upload_pssm(a, cfg, n, q_bytes, q_off, pssm, &b);
+    if (rc) return rc;
+    return align_uploaded_profiles(b, n, out, stats);
+  }
+  std::vector<size_t> cut(K + 1, n);
+  cut[0] = 0;
+  for (size_t c = 1, k = 0; c < K; c++) {
+    const uint64_t target = bytes * c / K;
+    while (k < n && pssm->score_off[k] - pssm->score_off[0] < target) k++;
+    cut[c] = k;
+  }
+  std::vector<BaBatch*> bs(K, nullptr);
+  int rc = BA_OK;
+  BaStats tot; memset(&tot, 0, sizeof(tot));
+  for (size_t c = 0; c < K && !rc; c++) {
+    const size_t lo = cut[c], hi = cut[c + 1];
+    BaPssmBatch p = *pssm;
+    p.score_off = pssm->score_off + lo;
+    if (pssm->gap_off) p.gap_off = pssm->gap_off + lo;
+    rc = ba_batch_upload_pssm(a, cfg, hi - lo, q_bytes, q_off + lo, &p, &bs[c]);
+    if (!rc) rc = batch_launch(bs[c]);
+  }
+  for (size_t c = 0; c < K; c++) {
+    if (!bs[c]) continue;
+    BaStats st1;
+    if (!rc) rc = batch_wait(bs[c], &st1);
+    if (!rc) rc = ba_batch_download(bs[c], out ? out + cut[c] : nullptr);
+    if (!rc) {
+      tot.kernel_ms += st1.kernel_ms; tot.pack_ms += st1.pack_ms; tot.kernel_launches += st1.kernel_launches + (bs[c]->n ? 2 : 0);
+      for (size_t k = 0; k < bs[c]->n; k++) {
+        tot.cells += bs[c]->h_out[k].cells; tot.steps += bs[c]->h_out[k].steps;
+        if (bs[c]->h_out[k].status) tot.n_failed++;
+      }
+    }
+    ba_batch_free(bs[c]);
+  }
+  if (stats) *stats = tot;
+  return rc;
 }
 static int align_uploaded_profiles(BaBatch* b, size_t n, AlignResult* out, BaStats* stats) {
   int rc = ba_batch_run(b, stats);

@@ -11,7 +11,13 @@ constexpr int kL = 16;             // AVX2 lanes: min block size clamp, argmax t
 constexpr int kZero = 1 << 14;     // stored i16 v  <->  true score off + v - kZero
 constexpr int kStep = 8;
 constexpr int kXDropIter = 2;
-constexpr int kMaxBlock = 8192;    // our cap (reference allows < 65535; > 16384 "not recommended")
+// Largest block size served: what percent_len can return (src/lib.rs:109-111). The reference itself accepts sizes below
+// 65535 (src/scan_block.rs:855), i.e. also 32768, which it does not recommend; 32768 rows + 16384 columns + the lane class
+// no longer fit the 32-bit argmax key below.
+constexpr int kMaxBlock = 16384;
+// X-drop argmax key (total order of src/scan_block.rs:1194-1201, src/avx2.rs:271-274): (15 - lane class) | column + 1 | row
+constexpr int kKeyClsShift = 28, kKeyColShift = 14;
+constexpr unsigned kKeyRowMask = 0x3fffu;
 
 // Block<TRACE, X_DROP, ...> const generics as bit flags (reference: src/scan_block.rs:89)
 enum Flags : int { kTrace = 1, kXDrop = 2, kLocalStart = 4, kFreeQueryStartGaps = 8, kFreeQueryEndGaps = 16 };

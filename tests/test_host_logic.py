@@ -30,8 +30,8 @@ def test_argument_rules(env):
         _run(al, b"ACGT", b"ACGT", size=(24, 32))
     with pytest.raises(api.BlockAlignerError, match="nonnegative"):
         _run(al, b"ACGT", b"ACGT", x_drop=-1, flags=api.XDROP)
-    with pytest.raises(api.BlockAlignerError, match="8192"):
-        _run(al, b"ACGT", b"ACGT", size=(32, 16384))
+    with pytest.raises(api.BlockAlignerError, match="16384"):
+        _run(al, b"ACGT", b"ACGT", size=(32, 32768))
     with pytest.raises(api.BlockAlignerError, match="larger than max"):      # our rule: the reference walks off its scratch here
         _run(al, b"ACGT", b"ACGT", size=(64, 32))
     assert _run(al, b"ACGT", b"ACGT", size=(4, 8)) == (4, 4, 4)     # sizes below L are clamped up to 16
@@ -213,3 +213,24 @@ def test_align_exp_rejects_min_above_max(env):
     lib, al = env
     with pytest.raises(api.BlockAlignerError, match="larger than max"):
         api.align_batch_exp(al, [b"ACGT"], [b"ACGT"], api.SCORING_NUC, api.nuc_matrix(1, -1), (-2, -1), (64, 32), [1])
+
+
+def test_align_batch_pssm_pipelined_chunks(env, monkeypatch):
+    """ba_align_batch_pssm cuts big batches into pipelined chunks; results must not depend on the cut."""
+    import parity
+    from block_aligner_b200 import workloads
+    lib, al = env
+    w = workloads.WORKLOADS["C4_seq_to_profile_xdrop"]
+    n = 23
+    qa, qo, ra, ro = workloads.generate(w["gen"], n, seed=8, stream=4)
+    cfg = al.config(api.SCORING_PROFILE, None, None, (32, 128), w["x_drop"], w["flags"], False)
+    exp = parity.oracle_batch(api.SCORING_PROFILE, None, None, (32, 128), w["x_drop"], w["flags"], False, qa, qo, ra, ro,
+                              profiles=parity.make_ora_profiles(ra, ro, 128, -10, -1, 77))
+    pb = workloads.make_pssm_batch(lib, ra, ro, seed=77)
+    for chunks in ("1", "2", "5"):
+        monkeypatch.setenv("BA_PIPELINE_CHUNKS", chunks)
+        out = np.zeros(n, dtype=parity.ABI_RES_DT)
+        st = api.BaStats()
+        lib.check(lib.L.ba_align_batch_pssm(al.h, C.byref(cfg), n, qa.ctypes.data, qo.ctypes.data, C.byref(pb.c), out.ctypes.data, C.byref(st)))
+        res = np.stack([out["score"].astype(np.int64), out["q"].astype(np.int64), out["r"].astype(np.int64)], axis=1)
+        assert parity.compare_abi(f"pssm-chunks{chunks}", res, None, st, exp) == 0
