@@ -726,8 +726,29 @@ BA_DEV bool pk_borders_ok(const Params& P, const AlnState& st, const WarpMem& w)
   return wp::ballot(!ok) == 0u;
 }
 
+// BA_PK_ORIGIN = 1: the first block of an alignment goes through the packed path (run_generic); 0: exact 32-bit path
+#ifndef BA_PK_ORIGIN
+#define BA_PK_ORIGIN 1
+#endif
 enum { kStFast = 0, kStNeedGeneric = 1, kStNeedGrow = 2, kStDone = 3, kStEmpty = 4, kStNeedShrink = 5 };
-struct PkFast { uint32_t aD[4], aC[4], oD[4], oR[4]; };
+// cw (BA_CW_PREFETCH = 1 only): the eight column tokens of the group's next step, loaded while the previous step's
+// epilogue runs -- the first use of that load is the largest single stall of the fast phase (3.7 % of the C2 kernel's
+// samples, ncu r02). OFF: measured on B200 / C2 the two registers it keeps alive across the step push three others
+// into local memory (6 LDL per step) and the kernel falls from 1195 to 1128 GCUPS.
+#ifndef BA_CW_PREFETCH
+#define BA_CW_PREFETCH 0
+#endif
+struct PkFast { uint32_t aD[4], aC[4], oD[4], oR[4]; uint2 cw; };
+
+// load the column tokens of the pending shift step (st.dir / st.si / st.sj already describe it)
+template <int SCORING, int LGT>
+BA_DEV void pk_fast_prefetch(PkFast& f, const AlnState& st, const uint8_t* qp, const uint8_t* rp) {
+  constexpr int B = 8 << LGT;
+  const bool right = st.dir == kRight;
+  if (SCORING == kProfile && right) return;     // a right step reads the profile's columns, not tokens
+  const uint8_t* col = right ? rp : qp;
+  f.cw = *(const uint2*)(col + (right ? st.sj : st.si) + (B - kStep));
+}
 
 template <int LGT>
 BA_DEV void pk_fast_load(PkFast& f, const WarpMem& w, int dir, bool mine) {
@@ -787,6 +808,8 @@ BA_BIG_LOOP_FN int big_loop(const Params& P, AlnState* stp, const WarpMem* wp_, 
   pk_fast_load<LGT>(f, w, st.dir, mine);
   const uint8_t* qp = P.seq + P.q_off[st.pair];
   const uint8_t* rp = P.seq + P.r_off[st.pair];
+  f.cw = make_uint2(0u, 0u);
+  if (BA_CW_PREFETCH) pk_fast_prefetch<SCORING, LGT>(f, st, qp, rp);
   int status = mine ? kStFast : kStEmpty;
   for (;;) {
     pk_fast_step<SCORING, FLAGS, LGT, true>(P, w, st, f, status, qp, rp, slot);
@@ -903,7 +926,27 @@ BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const Sl
       a.tw = nullptr; a.tz = nullptr;
       a.local = m_local; a.fqs0 = m_fqs && rect_right && a.vec_base == 0;
       a.fqe = m_fqe; a.fq_cls = (int)(qlen % kL); a.fq_row0 = (int)qlen - (int)a.vec_base;
-      const bool pk_ok = !PROF && !EXT && P.pk_enable && !st.overflow && pk_rect_ok(P, a);
+      // First block of an alignment on the packed path. Its input borders are Allocated::clear's MIN = 0 (scan_block.rs:
+      // 1322-1339), below the packed path's exact range. Every cell of that block is reachable from the forced origin
+      // cell (relative_zero = 16384) through gaps, so each maximum of the recurrence is won by a candidate that descends
+      // from the origin; candidates that descend from the borders ("garbage") only ever compare with each other (C of
+      // the first column, D' of the first column below row 0) before they lose. Max-plus is shift-equivariant, so
+      // starting all borders at S = GL instead of 0 leaves every such comparison, every origin-derived value, every trace
+      // bit and the four output borders unchanged -- provided garbage (<= S + W * max score) stays below the smallest
+      // origin-derived candidate (>= relative_zero - 3 |open| - (H + W) |extend|), which is tested here. The origin cell
+      // itself (scan_block.rs:1130-1132: D00 + score replaced by relative_zero) is the corner operand minus that score.
+      bool origin_pk = false;
+      if (!PROF && !EXT && P.pk_enable && BA_PK_ORIGIN && st.dir == kGrow && part == 1 && prev_size == 0 && a.vec_base == 0 && a.col_base == 0 && !st.overflow) {
+        int GL, GH;
+        pk_bounds(a.W, P.gap_open, P.gap_extend, P.pk_smax, GL, GH);
+        if (GL + a.W * P.pk_smax < a.rz + 3 * P.gap_open + (a.H + a.W) * P.gap_extend) {
+          sc.vec = q; sc.col = r;
+          a.off_add = GL; a.corner = a.rz - sc.score(sc.col_token(0), sc.row_token(0));
+          origin_pk = true;
+        }
+      }
+      const bool pk_ok = !PROF && !EXT && P.pk_enable && !st.overflow && pk_rect_ok(P, a, origin_pk);
+      if (origin_pk && !pk_ok) { a.off_add = 0; a.corner = 0; }
       if (TRACE && a.W > 0 && a.H >= 0) {
         const uint32_t woff = st.widx;
         if (m_local && sm.zwords) a.tz = sm.zwords + woff;
@@ -1111,7 +1154,7 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast
   if (!PROF) {
     sc.init(w.smem0, P);
     sc.rows(*(const uint32_t*)(vec + vec_base + 4 * lg), *(const uint32_t*)(vec + vec_base + 4 * G + 4 * lg));
-    cw = *(const uint2*)(col + col_base);
+    cw = BA_CW_PREFETCH ? f.cw : *(const uint2*)(col + col_base);
   } else {
     // sequence-to-profile: qp is the query, the profile plays the reference (rows of a down step, columns of a right step)
     const ProfileDev* pd = P.profiles + st.pair;
@@ -1127,7 +1170,7 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast
       po.rres[1] = *(const uint32_t*)(qp + vec_base + 4 * G + 4 * lg);
     } else {
       po.tpc = tp + vec_base + 4 * lg;
-      cw = *(const uint2*)(qp + col_base);
+      cw = BA_CW_PREFETCH ? f.cw : *(const uint2*)(qp + col_base);
       const int ge = P.gap_extend;
       const uint32_t r0 = vec_base + 4 * lg, r1 = r0 + 4 * G;
 #pragma unroll
@@ -1146,14 +1189,15 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast
   if (lg == 1) wp::touch(col + col_base + kStep + 128);
 #endif
 
-  uint32_t D[4], C[4], m[4], mc[kMcN] = {};
+  constexpr int MCN = PROF ? 4 : PkMc<TRACE, 4>::kN;
+  uint32_t D[4], C[4], m[4], mc[MCN] = {};
 #pragma unroll
   for (int k = 0; k < 4; k++) { D[k] = wp::vadd2(f.aD[k], oa2); C[k] = wp::vadd2(f.aC[k], oa2); m[k] = 0u; }
   uint32_t* fr = w.fr + grp * 8;
   uint32_t* tw = nullptr;
   if (TRACE && active) tw = trace_push_local(st, sm, right ? si : si + (B - kStep), right ? sj + (B - kStep) : sj, kStep, B, right, lg == 0, 3);
-  if (PROF) pkp_cols8<XDROP, LGT>(po, P.kc, lg, cw.x, cw.y, D, C, (uint32_t)corner & 0xffffu, m, mc, fr, lg == G - 1);
-  else pk_cols8<KIND, XDROP, LGT, TRACE>(sc, P.kc, LGT, lg, cw.x, cw.y, D, C, (uint32_t)corner & 0xffffu, 0, m, mc, fr, lg == G - 1, tw, TRACE && active);
+  if constexpr (PROF) pkp_cols8<XDROP, LGT, MCN>(po, P.kc, lg, cw.x, cw.y, D, C, (uint32_t)corner & 0xffffu, m, mc, fr, lg == G - 1);
+  else pk_cols8<KIND, XDROP, LGT, TRACE, 4>(sc, P.kc, G, lg, cw.x, cw.y, D, C, (uint32_t)corner & 0xffffu, 0, m, mc, fr, lg == G - 1, tw, TRACE && active);
   wp::syncwarp();
 
   // ---- borders after the step ----
@@ -1194,20 +1238,12 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast
   }
   unsigned key = 0;
   if (XDROP) {
-    key = pk_lane_key(m, mc, lg, G, mxv);
+    key = pk_lane_key<4, MCN>(m, mc, lg, G, mxv);
 #pragma unroll
     for (int s = 0; s < LGT; s++) { const unsigned u = (unsigned)wp::shfl_xor_w((int)key, 1 << s, G); key = u > key ? u : key; }
   }
 
-  if (P.step_log && active && lg == 0) {
-    const uint32_t n = *P.step_log_n;
-    if (n < P.step_log_cap) {
-      StepLog sl; sl.dir = st.dir; sl.i = si; sl.j = sj; sl.block_size = (uint32_t)B; sl.off = off;
-      sl.max = (int16_t)mxv; sl.right_max = (int16_t)right_max; sl.down_max = (int16_t)down_max;
-      P.step_log[n] = sl;
-    }
-    *P.step_log_n = n + 1;
-  }
+  // (no step log here: a batch that asks for it runs without a fast phase, ba_runtime.cu)
 
   // ---- post-step decisions (scan_block.rs:332-558 restricted to B == min_size, shift steps) ----
   if (active) {
@@ -1295,11 +1331,13 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast
   {
     const uint32_t flip = (status == kStFast && st.dir != st.prev_dir) ? 0xffffffffu : 0u;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      uint32_t t = (f.aD[k] ^ f.oD[k]) & flip; f.aD[k] ^= t; f.oD[k] ^= t;
-      t = (f.aC[k] ^ f.oR[k]) & flip; f.aC[k] ^= t; f.oR[k] ^= t;
+    for (int k = 0; k < 4; k++) {   // one bit-select (LOP3) per register
+      const uint32_t aD = f.aD[k], oD = f.oD[k], aC = f.aC[k], oR = f.oR[k];
+      f.aD[k] = (aD & ~flip) | (oD & flip); f.oD[k] = (oD & ~flip) | (aD & flip);
+      f.aC[k] = (aC & ~flip) | (oR & flip); f.oR[k] = (oR & ~flip) | (aC & flip);
     }
   }
+  if (BA_CW_PREFETCH && status == kStFast) pk_fast_prefetch<SCORING, LGT>(f, st, qp, rp);
 }
 
 BA_DEV void bcast_state(AlnState& d, const AlnState& s, int src) {
@@ -1385,6 +1423,7 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
   PkFast pf;
 #pragma unroll
   for (int k = 0; k < 4; k++) { pf.aD[k] = 0; pf.aC[k] = 0; pf.oD[k] = 0; pf.oR[k] = 0; }
+  pf.cw = make_uint2(0u, 0u);
   int status = kStEmpty;
   const uint8_t* qp = P.seq;
   const uint8_t* rp = P.seq;
@@ -1433,6 +1472,7 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
         st = gs; status = kStFast;
         qp = P.seq + P.q_off[gs.pair];
         if (SCORING != kProfile) rp = P.seq + P.r_off[gs.pair];
+        if (PKF && BA_CW_PREFETCH) pk_fast_prefetch<SCORING, LGT>(pf, st, qp, rp);
       }
       wp::syncwarp();
     }

@@ -34,17 +34,27 @@ BA_DEV uint32_t pk2(int v) { return wp::h_pack(v, v); }
 #define BA_PK_IMAD 0
 #endif
 #define BA_PK_ONE 1u
-// BA_PK_SPLIT_MC = 1: the X-drop column trackers of the two half-blocks live in separate registers (mc[k], mc[4 + k])
-// and are updated with predicated moves (ptxas emits SEL, the same pipe as PRMT); 0: both in one register, PRMT
+// BA_PK_SPLIT_MC = 1 (default): the X-drop column trackers of the two half-blocks live in separate registers
+// (mc[k], mc[K + k]) and are updated with SEL; 0: both in one register, updated with PRMT. Same pipe, but the split
+// form needs no (column + 1) operand in PRMT position: measured +1.5 % on B200 / C2 (1195 -> 1213 GCUPS, r02). TRACE
+// kernels (which spill at the 128-register cap) and the profile loop keep the four packed trackers.
 #ifndef BA_PK_SPLIT_MC
-#define BA_PK_SPLIT_MC 0
+#define BA_PK_SPLIT_MC 1
 #endif
-constexpr int kMcN = BA_PK_SPLIT_MC ? 8 : 4;
+// BA_PK_KVAR: rows-per-lane variants of the generic phase's packed rectangles (bit 0: one register per lane for 32 / 64
+// rows, bit 1: two registers per lane for 128 rows; 0: four registers per lane everywhere, fewer lanes busy). OFF:
+// the variants cut the executed instructions (C2 -9 %, C3 -19 %, ncu r02 k2) but add 2.5 KB of hot code each, and the
+// kernels sit at the edge of the SM's 32 KB instruction cache: sm__icc_request_hit_rate fell 96 -> 87 % (C2) and
+// 78 -> 68 % (C3), and both got slower on B200 (C2 1226 -> 1189 GCUPS, C3 635 -> 606, same box, profiles/r02_variants.txt)
+#ifndef BA_PK_KVAR
+#define BA_PK_KVAR 0
+#endif
+template <bool TRACE, int K> struct PkMc { static constexpr bool kSplit = BA_PK_SPLIT_MC && !TRACE; static constexpr int kN = kSplit ? 2 * K : K; };
 constexpr int kPkUnroll = BA_PK_UNROLL;    // 1, 2 or 4
 
 // shared-memory scoring tables of the packed path (one copy per CTA, built by stage_tables)
 constexpr int kMatBytes = 1024;            // raw matrix (exact path)
-constexpr int kPkTabBytes = 8192;          // kNuc: [8 classes][16][16] packed score pairs; kAA: [27][32] i16
+constexpr int kPkTabBytes = 8320;          // kNuc: packed score pairs, bank-spread layout (nuc_tab_index); kAA: [27][32] i16
 constexpr int kTbLutBytes = 128;           // traceback step table (tb_entry, ba_kernel.cuh)
 constexpr int kSmemHeader = kMatBytes + kPkTabBytes + kTbLutBytes;
 
@@ -67,19 +77,31 @@ BA_HD uint8_t tb_entry(uint32_t idx) {
 }
 
 template <int KIND> struct PkScorer;
-// NucMatrix (scores.rs:195-209): row (c & 7) * 16, column b & 15
+// NucMatrix (scores.rs:195-209): row (c & 7) * 16, column b & 15. One table word holds the scores of a pair of rows
+// (tokens lo, hi) against one column class. Layout (nuc_tab_index): word = class * 260 + r(lo, hi), where the low four
+// bits of r are bits 1-2 of the two row tokens -- the bits that tell A, C, G, T apart ('A' & 15 = 1, 'C' = 3, 'G' = 7,
+// 'T' = 4). With the plain [class][lo][hi] order the 32 lanes of a column step hit 8 of the 32 shared-memory banks
+// (6.1 wavefronts per LDS on random ACGT, ncu: 6.5 G bank conflicts per C2 launch); with this order 2.1.
+constexpr int kNucClsStride = 260;         // words per column class (256 + 4: neighbouring classes start 4 banks apart)
+BA_HD uint32_t nuc_row_index(uint32_t lo, uint32_t hi) {
+  return ((lo >> 1) & 3u) | (((hi >> 1) & 3u) << 2) | ((lo & 1u) << 4) | (((lo >> 3) & 1u) << 5) | ((hi & 1u) << 6) | (((hi >> 3) & 1u) << 7);
+}
+BA_HD uint32_t nuc_tab_index(uint32_t cls, uint32_t lo, uint32_t hi) { return cls * kNucClsStride + nuc_row_index(lo, hi); }
 template <> struct PkScorer<kNuc> {
-  const unsigned char* tab; uint32_t rt[4]; uint32_t one;
-  BA_DEV void init(const unsigned char* smem, const Params&) { tab = smem + kMatBytes; one = wp::opaque_zero() + BA_PK_ONE; }
+  const unsigned char* tab; uint32_t rt[4];
+  BA_DEV void init(const unsigned char* smem, const Params&) { tab = smem + kMatBytes; }
   BA_DEV void rows(uint32_t wlo, uint32_t whi) {
-    const uint32_t t = ((wlo & 0x0f0f0f0fu) << 4) | (whi & 0x0f0f0f0fu);
+    // nuc_row_index of the four (lo, hi) token pairs at once, one per byte
+    const uint32_t a = (wlo >> 1) & 0x03030303u, b = (whi << 1) & 0x0c0c0c0cu;
+    const uint32_t c = (wlo << 4) & 0x10101010u, d = (wlo << 2) & 0x20202020u;
+    const uint32_t e = (whi << 6) & 0x40404040u, f = (whi << 4) & 0x80808080u;
+    const uint32_t t = a | b | c | d | e | f;
 #pragma unroll
     for (int k = 0; k < 4; k++) rt[k] = ((t >> (8 * k)) & 0xffu) << 2;
   }
-  BA_DEV uint32_t colh(uint32_t cb) const { return (cb & 7u) << 10; }
-  // ch and rt[k] have no bits in common; with BA_PK_IMAD the OR is issued as an IMAD (ch * 1 + rt) on the FMA pipe: the
-  // ALU pipe is the kernel's bottleneck (ncu: pipe_alu 71 %, math_pipe_throttle), the FMA pipe is nearly idle
-  BA_DEV uint32_t score(uint32_t ch, int k) const { return *(const uint32_t*)(tab + (BA_PK_IMAD ? ch * one + rt[k] : (ch | rt[k]))); }
+  BA_DEV uint32_t colh(uint32_t cb) const { return cb & 7u; }
+  // class * stride + row offset: one IMAD (FMA pipe; the ALU pipe is the column loop's bottleneck)
+  BA_DEV uint32_t score(uint32_t ch, int k) const { return *(const uint32_t*)(tab + (ch * (uint32_t)(4 * kNucClsStride) + rt[k])); }
 };
 // AAMatrix (scores.rs:110-127): row c * 32, column b & 31
 template <> struct PkScorer<kAA> {
@@ -121,7 +143,7 @@ BA_DEV void stage_tables(unsigned char* smem, int tid, int nthreads) {
     uint32_t* t = (uint32_t*)(smem + kMatBytes);
     for (int i = tid; i < 2048; i += nthreads) {
       const int cls = i >> 8, a = (i >> 4) & 15, b = i & 15;
-      t[i] = wp::h_pack((int)mat[cls * 16 + a], (int)mat[cls * 16 + b]);
+      t[nuc_tab_index((uint32_t)cls, (uint32_t)a, (uint32_t)b)] = wp::h_pack((int)mat[cls * 16 + a], (int)mat[cls * 16 + b]);
     }
   } else if (SCORING == kAA) {
     int16_t* t = (int16_t*)(smem + kMatBytes);
@@ -148,18 +170,24 @@ BA_DEV void pk_bounds(int W, int go, int ge, int smax, int& GL, int& GH) {
 // per halfword 0xffff where y == x, else 0; needs x <= y (then y + ~x = y - x - 1 is -1 exactly for equal halves)
 BA_DEV uint32_t pk_eqmask(uint32_t y, uint32_t x) { return wp::viaddmin2(y, ~x, 0u); }
 
-template <int KIND, bool XDROP, int LGT, bool TRACE = false>
-BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int LGr, int lg, uint32_t cw0, uint32_t cw1,
-                     uint32_t (&D)[4], uint32_t (&C)[4], uint32_t corner_lo, int cbase, uint32_t (&m)[4], uint32_t (&mc)[kMcN],
+// K = registers per lane and array (4, 2 or 1): a rectangle of H rows is spread over G = H / (2 K) lanes, lane lg keeps
+// rows K lg + k in the low halfwords and rows K G + K lg + k in the high halfwords (k < K). K = 4 is the layout of the
+// fast phase and of 256-row rectangles; K = 2 / 1 put a 128 / 64-row rectangle on all 32 lanes (32 rows: 16 lanes)
+// instead of 16 / 8 / 4 of them -- the grow rectangles and the shift steps of blocks 64 and 128 (C3: 42 % of the
+// kernel's instructions ran in that loop at 1/4 of the lanes, ncu r02). NST = Kogge-Stone stages executed (>= log2 G;
+// a stage whose shuffle distance reaches G returns the lane's own value and changes nothing because extend < 0).
+template <int KIND, bool XDROP, int NST, bool TRACE = false, int K = 4>
+BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int G, int lg, uint32_t cw0, uint32_t cw1,
+                     uint32_t (&D)[K], uint32_t (&C)[K], uint32_t corner_lo, int cbase, uint32_t (&m)[K], uint32_t (&mc)[PkMc<TRACE, K>::kN],
                      uint32_t* fr, bool writer, uint32_t* tw = nullptr, bool tstore = false) {
-  const int LG = LGT ? LGT : LGr;
-  const int G = 1 << LG;
+  static_assert(!TRACE || K == 4, "trace words are laid out for four registers per lane");
+  constexpr bool SPLIT = PkMc<TRACE, K>::kSplit;
   // The uniform constants are copied into vector registers once per call (opaque_zero): ptxas otherwise rebuilds
   // every packed constant from its 16-bit halves at each use.
   const uint32_t z = wp::opaque_zero();
   const uint32_t ge2 = kc.ge2 + z, or2 = kc.or2 + z;
   const uint32_t kge1 = kc.kge[1] + z, kge2 = kc.kge[2] + z, kge3 = kc.kge[3] + z;
-  const uint32_t lanedec = (uint32_t)lg * kc.lane1 + (lg ? 0x10000u : 0u);   // packed 4 * lg * gap_extend
+  const uint32_t lanedec = (uint32_t)(lg * K) * kc.ge1 + (lg ? 0x10000u : 0u);   // packed K * lg * gap_extend
   const uint32_t one = z + BA_PK_ONE;
   // kPkUnroll columns per iteration of the rolled loop: the kernel's hot code has to stay inside the SM's
   // instruction cache (ncu: sm__icc_request_hit_rate), which a fully unrolled 8-column body does not
@@ -173,14 +201,14 @@ BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int LGr, int l
       const int cidx = h * kPkUnroll + cc;
       const uint32_t ch = sc.colh((cwh >> (8 * cc)) & 0xffu);
       // diagonal input of the lane's first rows: the previous column of the row above. Lane 0: low half = the
-      // rectangle's corner (first column only; MIN = 0 afterwards, scan_block.rs:1211), high half = row 4G - 1,
-      // which is the low half of the last lane's register 3.
-      uint32_t up = (uint32_t)wp::shfl_idx_w((int)D[3], lg - 1, G);
+      // rectangle's corner (first column only; MIN = 0 afterwards, scan_block.rs:1211), high half = row K G - 1,
+      // which is the low half of the last lane's last register.
+      uint32_t up = (uint32_t)wp::shfl_idx_w((int)D[K - 1], lg - 1, G);
       if (lg == 0) up = (up << 16) | ((cbase + cidx == 0) ? corner_lo : 0u);
-      uint32_t dd[4], c11[4], uu[4];
-      uint32_t acc[4];                            // trace nibbles of the lane's rows (TRACE)
+      uint32_t dd[K], c11[K], uu[K];
+      uint32_t acc[K];                            // trace nibbles of the lane's rows (TRACE)
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
+      for (int k = 0; k < K; k++) {
         const uint32_t s2 = sc.score(ch, k);
         const uint32_t d00 = k ? D[k - 1] : up;
         // packed add as one 32-bit add: no borrow, both halves >= |open| (guard)
@@ -190,29 +218,24 @@ BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int LGr, int l
         dd[k] = wp::viaddmax2(d00, s2, c11[k]);
         uu[k] = k ? wp::viaddmax2(uu[k - 1], ge2, dd[k]) : dd[0];
       }
-      // Kogge-Stone over the lane aggregates, both half-blocks at once
-      uint32_t inc = uu[3];
-      if (LGT) {
+      // Kogge-Stone over the lane aggregates, both half-blocks at once; stage s decays by (K << s) * extend
+      uint32_t inc = uu[K - 1];
 #pragma unroll
-        for (int s = 0; s < (LGT ? LGT : 1); s++) {
-          const uint32_t u = (uint32_t)wp::shfl_up_w((int)inc, 1 << s, G);
-          inc = wp::viaddmax2(u, s == 0 ? kge3 : kc.dec[s] + z, inc);
-        }
-      } else {
-        for (int s = 0; s < LG; s++) {
-          const uint32_t u = (uint32_t)wp::shfl_up_w((int)inc, 1 << s, G);
-          inc = wp::viaddmax2(u, kc.dec[s] + z, inc);
-        }
+      for (int s = 0; s < NST; s++) {
+        const uint32_t u = (uint32_t)wp::shfl_up_w((int)inc, 1 << s, G);
+        const int mult = K << s;                  // 1, 2, 3, 4 -> ge2 / kge[]; 4 << t -> dec[t]
+        const uint32_t dc = mult == 1 ? ge2 : (mult == 2 ? kge1 : (mult == 4 ? kge3 : kc.dec[s + (K == 4 ? 0 : (K == 2 ? -1 : -2))] + z));
+        inc = wp::viaddmax2(u, dc, inc);
       }
       // carry into the lane: the lanes above (same half) and, for the high half, the whole low half-block
       const uint32_t tl = (uint32_t)wp::shfl_idx_w((int)inc, G - 1, G);
       uint32_t ex = (uint32_t)wp::shfl_up_w((int)inc, 1, G);
       if (lg == 0) ex = 0u;
       const uint32_t cin = wp::viaddmax2(tl << 16, lanedec, ex);
-      uint32_t Un3 = 0;
+      uint32_t UnL = 0;
       uint32_t eprev = 0u;                        // "R gap opened at this row" (T == x) of the previous row of the lane
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
+      for (int k = 0; k < K; k++) {
         const uint32_t Un = wp::viaddmax2(cin, k == 0 ? ge2 : (k == 1 ? kge1 : (k == 2 ? kge2 : kge3)), uu[k]);
         uint32_t Dn;
         if (TRACE) {
@@ -225,20 +248,19 @@ BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int LGr, int l
         } else {
           Dn = wp::viaddmax2(Un, or2, dd[k]);
         }
-        if (k == 3) Un3 = Un;
+        if (k == K - 1) UnL = Un;
         if (XDROP) {
           bool ph, pl;
           m[k] = wp::vibmax2(Dn, m[k], ph, pl);
           // kept in a vector register (opaque_zero) so that PRMT can take its selector as an immediate
           const uint32_t c1 = (uint32_t)(cbase + cidx + 1) + wp::opaque_zero();
-#if BA_PK_SPLIT_MC
-          // column trackers of the two halves in separate registers: a predicated move (FMA pipe) instead of PRMT (ALU)
-          if (pl) mc[k] = c1;
-          if (ph) mc[4 + k] = c1;
-#else
-          if (pl) mc[k] = wp::prmt(mc[k], c1, 0x3254u);
-          if (ph) mc[k] = wp::prmt(mc[k], c1, 0x5410u);
-#endif
+          if (SPLIT) {
+            mc[k] = pl ? c1 : mc[k];
+            mc[PkMc<TRACE, K>::kN - K + k] = ph ? c1 : mc[PkMc<TRACE, K>::kN - K + k];
+          } else {
+            if (pl) mc[k] = wp::prmt(mc[k], c1, 0x3254u);
+            if (ph) mc[k] = wp::prmt(mc[k], c1, 0x5410u);
+          }
         } else {
           m[0] = wp::vmax2(m[0], Dn);
         }
@@ -250,10 +272,10 @@ BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int LGr, int l
         uint32_t eup = (uint32_t)wp::shfl_idx_w((int)eprev, lg - 1, G);
         if (lg == 0) eup <<= 16;
         acc[0] |= eup & 0x00080008u;
-        const uint32_t word = acc[0] | (acc[1] << 4) | (acc[2] << 8) | (acc[3] << 12);
+        const uint32_t word = acc[0] | (acc[1 % K] << 4) | (acc[2 % K] << 8) | (acc[3 % K] << 12);
         if (tstore) tw[(size_t)(cbase + cidx) * G + lg] = word;
       }
-      if (writer) fr[cidx] = wp::prmt(wp::vadd2(Un3, or2), D[3], 0x7632u);   // T.hi | D.hi << 16
+      if (writer) fr[cidx] = wp::prmt(wp::vadd2(UnL, or2), D[K - 1], 0x7632u);   // T.hi | D.hi << 16
     }
   }
 }
@@ -284,9 +306,9 @@ struct PkpOps {
   uint32_t Bc[4], oR[4], cR[4];    // down: per-row operands (Bc, oR: v * 65537 form; cR: packed halves); right: 0
 };
 
-template <bool XDROP, int LGT>
+template <bool XDROP, int LGT, int MC>      // MC >= 4: only mc[0..3] are used (both column trackers packed in one register)
 BA_DEV void pkp_cols8(const PkpOps& o, const PkConst& kc, int lg, uint32_t cw0, uint32_t cw1,
-                      uint32_t (&D)[4], uint32_t (&C)[4], uint32_t corner_lo, uint32_t (&m)[4], uint32_t (&mc)[kMcN],
+                      uint32_t (&D)[4], uint32_t (&C)[4], uint32_t corner_lo, uint32_t (&m)[4], uint32_t (&mc)[MC],
                       uint32_t* fr, bool writer) {
   constexpr int G = 1 << LGT;
   const uint32_t z = wp::opaque_zero();
@@ -366,47 +388,68 @@ BA_DEV void pkp_cols8(const PkpOps& o, const PkConst& kc, int lg, uint32_t cw0, 
 // Best cell of the lane under the reference's order: value desc, AVX lane (row mod 16) asc, column desc, row desc
 // (scan_block.rs:1194-1201, avx2.rs:271-274). pk_lane_key: key of the lane's best cell among those equal to M
 // (0 if none); key format as in place_rect_r: (15 - class) << 28 | (column + 1) << 14 | row. Every row has seen
-// a cell >= 0 (guard), so there is no "no cell" case.
-BA_DEV unsigned pk_lane_key(const uint32_t (&m)[4], const uint32_t (&mc)[kMcN], int lg, int G, int M) {
+// a cell >= 0 (guard), so there is no "no cell" case. The two rows of a register share their class (K G is a multiple
+// of 16). MC = K: both column trackers packed in mc[k]; MC = 2 K: low halves in mc[k], high halves in mc[K + k].
+template <int K, int MC>
+BA_DEV unsigned pk_lane_key(const uint32_t (&m)[K], const uint32_t (&mc)[MC], int lg, int G, int M) {
   const uint32_t M2 = pk2(M);
-  const unsigned base0 = ((15u - (unsigned)((4 * lg) & 15)) << kKeyClsShift) | (unsigned)(4 * lg);
+  const unsigned base0 = ((15u - (unsigned)((K * lg) & 15)) << kKeyClsShift) | (unsigned)(K * lg);
   unsigned key = 0;
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
+  for (int k = 0; k < K; k++) {
     bool ph, pl;
     wp::vibmax2(m[k], M2, ph, pl);            // m >= M, i.e. m == M for M = the maximum
     const unsigned base = base0 - ((unsigned)k << kKeyClsShift) + (unsigned)k;
-#if BA_PK_SPLIT_MC
-    const unsigned klo = base | (mc[k] << kKeyColShift);
-    const unsigned khi = (base + (unsigned)(4 * G)) | (mc[4 + k] << kKeyColShift);
-#else
-    const unsigned klo = base | ((mc[k] & 0xffffu) << kKeyColShift);
-    const unsigned khi = (base + (unsigned)(4 * G)) | ((mc[k] >> 16) << kKeyColShift);
-#endif
+    const unsigned clo = MC == K ? (mc[k] & 0xffffu) : mc[k];
+    const unsigned chi = MC == K ? (mc[k] >> 16) : mc[(MC == K ? 0 : K) + k];
+    const unsigned klo = base | (clo << kKeyColShift);
+    const unsigned khi = (base + (unsigned)(K * G)) | (chi << kKeyColShift);
     if (pl && klo > key) key = klo;
     if (ph && khi > key) key = khi;
   }
   return key;
 }
-BA_DEV int pk_lane_max(const uint32_t (&m)[4]) {
-  const uint32_t v = wp::vmax2(wp::vmax3_2(m[0], m[1], m[2]), m[3]);
+template <int K>
+BA_DEV int pk_lane_max(const uint32_t (&m)[K]) {
+  uint32_t v = m[0];
+#pragma unroll
+  for (int k = 1; k < K; k++) v = wp::vmax2(v, m[k]);
   return wp::imax(wp::h_lo(v), wp::h_hi(v));
 }
 
-// borders in shared memory <-> packed registers of lane lg (rows 4lg.. and 4G + 4lg..)
-BA_DEV void pk_load4(const int16_t* p, int lg, int G, uint32_t (&r)[4]) {
-  const uint2 lo = *(const uint2*)(p + 4 * lg);
-  const uint2 hi = *(const uint2*)(p + 4 * G + 4 * lg);
-  r[0] = wp::prmt(lo.x, hi.x, 0x5410u); r[1] = wp::prmt(lo.x, hi.x, 0x7632u);
-  r[2] = wp::prmt(lo.y, hi.y, 0x5410u); r[3] = wp::prmt(lo.y, hi.y, 0x7632u);
+// borders in shared memory <-> packed registers of lane lg (rows K lg.. and K G + K lg..)
+template <int K>
+BA_DEV void pk_loadk(const int16_t* p, int lg, int G, uint32_t (&r)[K]) {
+  if (K == 4) {
+    const uint2 lo = *(const uint2*)(p + 4 * lg);
+    const uint2 hi = *(const uint2*)(p + 4 * G + 4 * lg);
+    r[0] = wp::prmt(lo.x, hi.x, 0x5410u); r[1 % K] = wp::prmt(lo.x, hi.x, 0x7632u);
+    r[2 % K] = wp::prmt(lo.y, hi.y, 0x5410u); r[3 % K] = wp::prmt(lo.y, hi.y, 0x7632u);
+  } else if (K == 2) {
+    const uint32_t lo = *(const uint32_t*)(p + 2 * lg), hi = *(const uint32_t*)(p + 2 * G + 2 * lg);
+    r[0] = wp::prmt(lo, hi, 0x5410u); r[1 % K] = wp::prmt(lo, hi, 0x7632u);
+  } else {
+    r[0] = (uint32_t)(uint16_t)p[lg] | ((uint32_t)(uint16_t)p[G + lg] << 16);
+  }
 }
-BA_DEV void pk_store4(int16_t* p, int lg, int G, const uint32_t (&r)[4]) {
-  uint2 lo, hi;
-  lo.x = wp::prmt(r[0], r[1], 0x5410u); lo.y = wp::prmt(r[2], r[3], 0x5410u);
-  hi.x = wp::prmt(r[0], r[1], 0x7632u); hi.y = wp::prmt(r[2], r[3], 0x7632u);
-  *(uint2*)(p + 4 * lg) = lo;
-  *(uint2*)(p + 4 * G + 4 * lg) = hi;
+template <int K>
+BA_DEV void pk_storek(int16_t* p, int lg, int G, const uint32_t (&r)[K]) {
+  if (K == 4) {
+    uint2 lo, hi;
+    lo.x = wp::prmt(r[0], r[1 % K], 0x5410u); lo.y = wp::prmt(r[2 % K], r[3 % K], 0x5410u);
+    hi.x = wp::prmt(r[0], r[1 % K], 0x7632u); hi.y = wp::prmt(r[2 % K], r[3 % K], 0x7632u);
+    *(uint2*)(p + 4 * lg) = lo;
+    *(uint2*)(p + 4 * G + 4 * lg) = hi;
+  } else if (K == 2) {
+    *(uint32_t*)(p + 2 * lg) = wp::prmt(r[0], r[1 % K], 0x5410u);
+    *(uint32_t*)(p + 2 * G + 2 * lg) = wp::prmt(r[0], r[1 % K], 0x7632u);
+  } else {
+    p[lg] = (int16_t)(r[0] & 0xffffu);
+    p[G + lg] = (int16_t)(r[0] >> 16);
+  }
 }
+BA_DEV void pk_load4(const int16_t* p, int lg, int G, uint32_t (&r)[4]) { pk_loadk<4>(p, lg, G, r); }
+BA_DEV void pk_store4(int16_t* p, int lg, int G, const uint32_t (&r)[4]) { pk_storek<4>(p, lg, G, r); }
 
 // lane-local range test of the D registers of both borders (the packed fast phase's per-step guard)
 BA_DEV bool pk_in_range_d(const uint32_t (&a)[4], const uint32_t (&b)[4], int lo, int hi) {
@@ -436,64 +479,77 @@ BA_DEV bool pk_in_range(const uint32_t (&a)[N], const uint32_t (&b)[N], int lo, 
 
 // Can this rectangle go through the packed path? Shape (32..256 rows, whole 8-column groups, no early break, not
 // the forced origin cell) and value range of its inputs (pk_bounds). Nothing is modified.
-BA_DEV bool pk_rect_ok(const Params& P, const RectArgs& a) {
+BA_DEV bool pk_rect_ok(const Params& P, const RectArgs& a, bool origin_ok = false) {
   const int lane = wp::lane_id();
   const int H = a.H, W = a.W;
   if (!(H == 32 || H == 64 || H == 128 || H == 256) || W <= 0 || (W & 7) || W > 256 || a.ncols != W) return false;
-  if (a.vec_base == 0 && a.col_base == 0) return false;        // forced origin cell (scan_block.rs:1130-1132)
-  const int G = H >> 3;
-  const int lg = lane & (G - 1);
+  if (a.vec_base == 0 && a.col_base == 0 && !origin_ok) return false;   // forced origin cell (scan_block.rs:1130-1132): only as set up by run_generic
   int GL, GH;
   pk_bounds(W, P.gap_open, P.gap_extend, P.pk_smax, GL, GH);
   // raw border values v become v + off_add (saturating in the reference): exact and inside [GL, GH] iff
   // v is inside [GL - off_add, GH - off_add] (clipped to i16)
   const int lo_b = wp::imax(GL - a.off_add, kI16Min), hi_b = wp::imin(GH - a.off_add, kI16Max);
-  uint32_t D[4], C[4];
-  pk_load4(a.AD, lg, G, D);
-  pk_load4(a.AC, lg, G, C);
+  // every lane tests 8 consecutive entries of both input borders (entries >= H: lanes mirror the first ones)
+  const int e = (8 * lane) & (H - 1);
+  const uint4 d = *(const uint4*)(a.AD + e), c = *(const uint4*)(a.AC + e);
+  const uint32_t D[4] = {d.x, d.y, d.z, d.w}, C[4] = {c.x, c.y, c.z, c.w};
   const bool ok = lo_b <= hi_b && a.corner >= 0 && a.corner <= GH && pk_in_range<4>(D, C, lo_b, hi_b);
   return wp::ballot(!ok) == 0u;
 }
 
 // Packed replacement of place_rect for sequence-sequence rectangles with borders in shared memory (generic
 // phase, one alignment per warp; lanes >= G mirror lanes < G). Only for rectangles pk_rect_ok accepted.
-// TRACE: a.tw receives H / 8 words per column (Rect layout 3, see pk_cols8).
-template <int KIND, bool XDROP, bool TRACE>
-BA_DEV void place_rect_pk(const unsigned char* smem, const Params& P, const PkConst& kc, const uint8_t* vec, const uint8_t* col,
-                          const RectArgs& a, uint32_t* fr, int& bv, unsigned& bkey) {
+// TRACE: a.tw receives H / 8 words per column (Rect layout 3, see pk_cols8); TRACE keeps four registers per lane (its
+// trace words hold eight nibbles per lane), so rectangles below 256 rows use G < 32 lanes there. Without TRACE a
+// rectangle of 128 / 64 / 32 rows runs with 2 / 1 / 1 registers per lane on 32 / 32 / 16 lanes.
+template <int KIND, bool XDROP, bool TRACE, int K>
+BA_DEV void place_rect_pk_k(const unsigned char* smem, const Params& P, const PkConst& kc, const uint8_t* vec, const uint8_t* col,
+                            const RectArgs& a, uint32_t* fr, int& bv, unsigned& bkey) {
   const int lane = wp::lane_id();
   const int H = a.H, W = a.W;
-  const int G = H >> 3;
-  const int LG = H == 32 ? 2 : (H == 64 ? 3 : (H == 128 ? 4 : 5));
+  const int G = H / (2 * K);
   const int lg = lane & (G - 1);
-  uint32_t D[4], C[4];
-  pk_load4(a.AD, lg, G, D);
-  pk_load4(a.AC, lg, G, C);
+  uint32_t D[K], C[K];
+  pk_loadk<K>(a.AD, lg, G, D);
+  pk_loadk<K>(a.AC, lg, G, C);
   bv = 0; bkey = 15u << kKeyClsShift;
   const uint32_t oa2 = pk2(a.off_add);
 #pragma unroll
-  for (int k = 0; k < 4; k++) { D[k] = wp::vadd2(D[k], oa2); C[k] = wp::vadd2(C[k], oa2); }
+  for (int k = 0; k < K; k++) { D[k] = wp::vadd2(D[k], oa2); C[k] = wp::vadd2(C[k], oa2); }
 
   PkScorer<KIND> sc;
   sc.init(smem, P);
-  sc.rows(*(const uint32_t*)(vec + a.vec_base + 4 * lg), *(const uint32_t*)(vec + a.vec_base + 4 * G + 4 * lg));
-  uint32_t m[4] = {0u, 0u, 0u, 0u}, mc[kMcN] = {};
+  {
+    const uint8_t* vl = vec + a.vec_base + K * lg;
+    const uint8_t* vh = vl + K * G;
+    if (K == 4) sc.rows(*(const uint32_t*)vl, *(const uint32_t*)vh);
+    else if (K == 2) sc.rows(*(const uint16_t*)vl, *(const uint16_t*)vh);
+    else sc.rows(*vl, *vh);
+  }
+  uint32_t m[K], mc[PkMc<TRACE, K>::kN] = {};
+#pragma unroll
+  for (int k = 0; k < K; k++) m[k] = 0u;
   const bool writer = lane == G - 1;
   for (int cb = 0; cb < W; cb += 8) {
     const uint2 cw = *(const uint2*)(col + a.col_base + cb);
-#ifndef BA_PK_NO_LG5
-    if (LG == 5) pk_cols8<KIND, XDROP, 5, TRACE>(sc, kc, 5, lg, cw.x, cw.y, D, C, (uint32_t)a.corner & 0xffffu, cb, m, mc, fr, writer, a.tw, lane < G);
-    else
-#endif
-    pk_cols8<KIND, XDROP, 0, TRACE>(sc, kc, LG, lg, cw.x, cw.y, D, C, (uint32_t)a.corner & 0xffffu, cb, m, mc, fr, writer, a.tw, lane < G);
+    pk_cols8<KIND, XDROP, 5, TRACE, K>(sc, kc, G, lg, cw.x, cw.y, D, C, (uint32_t)a.corner & 0xffffu, cb, m, mc, fr, writer, a.tw, lane < G);
     wp::syncwarp();
     if (lane < 8) { const uint32_t v = fr[lane]; a.OD[cb + lane] = (int16_t)(v >> 16); a.OR_[cb + lane] = (int16_t)(v & 0xffffu); }
     wp::syncwarp();
   }
-  if (lane < G) { pk_store4(a.AD, lg, G, D); pk_store4(a.AC, lg, G, C); }
-  if (XDROP) { bv = pk_lane_max(m); bkey = pk_lane_key(m, mc, lg, G, bv); }
+  if (lane < G) { pk_storek<K>(a.AD, lg, G, D); pk_storek<K>(a.AC, lg, G, C); }
+  if (XDROP) { bv = pk_lane_max<K>(m); bkey = pk_lane_key<K, PkMc<TRACE, K>::kN>(m, mc, lg, G, bv); }
   else bv = wp::imax(bv, wp::imax(wp::h_lo(m[0]), wp::h_hi(m[0])));
   wp::syncwarp();
+}
+template <int KIND, bool XDROP, bool TRACE>
+BA_DEV void place_rect_pk(const unsigned char* smem, const Params& P, const PkConst& kc, const uint8_t* vec, const uint8_t* col,
+                          const RectArgs& a, uint32_t* fr, int& bv, unsigned& bkey) {
+  constexpr int K128 = (TRACE || !(BA_PK_KVAR & 2)) ? 4 : 2, K64 = (TRACE || !(BA_PK_KVAR & 1)) ? 4 : 1;
+  // (one call site per distinct K: every call is an inlined copy of the rectangle code)
+  if (K128 != 4 && a.H == 128) place_rect_pk_k<KIND, XDROP, TRACE, K128>(smem, P, kc, vec, col, a, fr, bv, bkey);
+  else if (K64 != 4 && a.H <= 64) place_rect_pk_k<KIND, XDROP, TRACE, K64>(smem, P, kc, vec, col, a, fr, bv, bkey);
+  else place_rect_pk_k<KIND, XDROP, TRACE, 4>(smem, P, kc, vec, col, a, fr, bv, bkey);
 }
 
 }  // namespace ba

@@ -604,6 +604,9 @@ static int batch_configure(BaBatch* b, uint32_t mn) {
   // fast-phase mode (third kernel template argument): 4 / 8 = s32 rows per lane (TRACE), 16 + LGT = packed, 0 = none
   b->fast_rows = (!prof && !ext && !getenv("BA_NO_FAST")) ? (mn == 32 ? 4 : (mn == 64 ? 8 : 0)) : 0;
   if (prof && b->prof_fast) b->fast_rows = mn == 32 ? 4 : (mn == 64 ? 8 : 0);
+  // the per-step debug log (BA_STEP_LOG, single pair) is only written by the generic phase: the fast step's code has to
+  // stay small (instruction cache), and the sequence of steps does not depend on which phase executes them
+  if (getenv("BA_STEP_LOG") && n == 1) b->fast_rows = 0;
   b->slots_per_warp = b->fast_rows ? 4 : 1;
   if (b->fast_rows && !b->pk_enable && !prof) b->fast_rows = 0;
   if (b->fast_rows) {
@@ -1056,6 +1059,7 @@ static Params make_params(const BaBatch* b) {
     for (int k = 0; k < 4; k++) P.kc.kge[k] = pk2h((k + 1) * ge);
     for (int s2 = 0; s2 < 5; s2++) P.kc.dec[s2] = pk2h((4 << s2) * ge);
     P.kc.lane1 = (uint32_t)(4 * ge) * 65537u;
+    P.kc.ge1 = (uint32_t)ge * 65537u;
   }
   P.ext_flags = (uint32_t)(b->cfg.flags & (BA_LOCAL_START | BA_FREE_QUERY_START_GAPS | BA_FREE_QUERY_END_GAPS)); P.trace_zwords = b->d_zwords;
   P.out = b->d_out; P.ticket = b->d_ticket;

@@ -102,6 +102,7 @@ struct PkConst {
   uint32_t kge[4];          // packed (k + 1) * gap_extend
   uint32_t dec[5];          // Kogge-Stone decays: packed (4 << s) * gap_extend
   uint32_t lane1;           // 4 * gap_extend * 65537: lane lg's packed decay 4 * lg * gap_extend = lg * lane1 + (lg ? 65536 : 0)
+  uint32_t ge1;             // gap_extend * 65537: the same decay for K rows per lane = (K * lg) * ge1 + (lg ? 65536 : 0)
 };
 
 struct Params {

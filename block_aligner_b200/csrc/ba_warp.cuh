@@ -48,6 +48,7 @@ inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 }
 inline uint32_t prmt_sx(uint32_t a, uint32_t b, uint32_t sel) { return prmt(a, b, sel); }
 inline uint32_t opaque_zero() { return 0u; }
+inline void pmov_fma(bool p, uint32_t& d, uint32_t s, uint32_t) { if (p) d = s; }
 inline int red_max(int v) { const uint32_t* a = emu::exchange((uint32_t)v); int m = (int)a[0]; for (int i = 1; i < 32; i++) m = (int)a[i] > m ? (int)a[i] : m; return m; }
 inline unsigned red_max_u(unsigned v) { const uint32_t* a = emu::exchange(v); unsigned m = a[0]; for (int i = 1; i < 32; i++) m = a[i] > m ? a[i] : m; return m; }
 inline unsigned ballot(bool p) { const uint32_t* a = emu::exchange(p ? 1u : 0u); unsigned m = 0; for (int i = 0; i < 32; i++) m |= (a[i] & 1u) << i; return m; }
@@ -97,6 +98,11 @@ BA_DEV uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(
 BA_DEV uint32_t prmt_sx(uint32_t a, uint32_t b, uint32_t sel) { uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel)); return d; }
 // always 0 (blocks are one-dimensional) but thread-varying for the compiler: keeps a value out of the uniform datapath
 BA_DEV uint32_t opaque_zero() { return threadIdx.y; }
+// if (p) d = s, issued as a predicated IMAD (s * one + 0, `one` = 1 but opaque to the compiler): the FMA pipe instead of
+// the ALU pipe, which PRMT / SEL / MOV would use and which bounds the packed column loop
+BA_DEV void pmov_fma(bool p, uint32_t& d, uint32_t s, uint32_t one) {
+  asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q mad.lo.u32 %0, %2, %3, 0;\n\t}" : "+r"(d) : "r"((uint32_t)p), "r"(s), "r"(one));
+}
 BA_DEV int red_max(int v) { return __reduce_max_sync(kFull, v); }
 BA_DEV unsigned red_max_u(unsigned v) { return __reduce_max_sync(kFull, v); }
 BA_DEV unsigned ballot(bool p) { return __ballot_sync(kFull, p); }

