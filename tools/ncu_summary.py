@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Append one capture to profiles/r01_ncu_align_kernel_summary.json from `ncu -i X.ncu-rep --page raw --csv` output.
+"""Append one capture to profiles/r02_ncu_kernel_summary.json (BA_NCU_SUMMARY overrides the file name) from `ncu -i X.ncu-rep --page raw --csv` output.
 
 usage: tools/ncu_summary.py raw.csv "<capture name>" <pairs in launch> "<note>"
 """
@@ -56,8 +56,8 @@ tu = units.get("gpu__time_duration.sum", "")
 tscale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(tu, None)
 if tscale is not None:
     cap["gpu__time_duration_ms"] = f("gpu__time_duration.sum") * tscale
-path = os.path.join(ROOT, "profiles", "r01_ncu_align_kernel_summary.json")
-doc = json.load(open(path))
+path = os.path.join(ROOT, "profiles", os.environ.get("BA_NCU_SUMMARY", "r02_ncu_kernel_summary.json"))
+doc = json.load(open(path)) if os.path.exists(path) else {"note": "one entry per ncu --set full capture (tools/ncu_job.sh); numbers under the profiler are not bench values", "captures": []}
 doc["captures"] = [c for c in doc["captures"] if c["capture"] != cap["capture"]] + [cap]
 json.dump(doc, open(path, "w"), indent=1)
 print(json.dumps(cap, indent=1))
