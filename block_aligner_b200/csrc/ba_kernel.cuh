@@ -28,7 +28,7 @@
 
 #ifdef BA_EMU
 // coverage counters of the emulated build (tests assert that the packed path really ran)
-namespace emu_stats { inline uint64_t pk_cells = 0, exact_cells = 0, fast_steps = 0, big_cells = 0; }
+namespace emu_stats { inline uint64_t pk_cells = 0, exact_cells = 0, fast_steps = 0, big_cells = 0, tb_staged = 0, tb_global = 0; }
 #endif
 
 namespace ba {
@@ -1510,7 +1510,19 @@ BA_DEV void warp_traceback(const Params& P, const uint8_t* lut, uint32_t pair, u
 // Prefetch distance in rectangle records, into L2: with 128 walks per SM the windows of an L1 prefetch (8 sectors per
 // rectangle) do not fit the L1 (measured: no gain); in L2 (126 MB) the windows of every walk of the batch do.
 constexpr uint32_t kTbLaneAhead = 8;
-BA_DEV void lanes_traceback(const Params& P, const uint8_t* lut, const uint32_t* list, uint32_t n, uint32_t t) {
+// STAGED: eight lanes per walk (t is valid in the first lane of each group of eight; launch_traceback_batch). The group
+// copies the trace words of the rectangle the walk will enter next into shared memory (`stage`: two buffers of
+// kTbStageWords words per group) with asynchronous copies while the walk is still inside the current rectangle, so
+// that a cell step reads its word from shared memory instead of following a chain of L2 / DRAM round trips (one per
+// column of every rectangle: 1200 cycles per cell step on C5, ncu r02: long_scoreboard 4.9 stalls per issue). Only
+// packed-path rectangles of at most kTbStageWords words are staged (shift steps of blocks 32 .. 128); anything larger is
+// read from global memory as before.
+constexpr uint32_t kTbStageWords = 128;
+BA_DEV bool tb_stageable(const Rect& rc, const uint32_t* pw) {
+  return ((rc.right >> 1) & 3u) == 3u && (uint32_t)(rc.h >> 3) * rc.w <= kTbStageWords && (((uintptr_t)pw) & 15u) == 0u;
+}
+template <bool STAGED>
+BA_DEV void lanes_traceback(const Params& P, const uint8_t* lut, const uint32_t* list, uint32_t n, uint32_t t, uint32_t* stage = nullptr) {
   const int lane = wp::lane_id();
   const bool have = t < n;
   uint32_t pair = 0, nruns = 0, ok = 0;
@@ -1551,11 +1563,100 @@ BA_DEV void lanes_traceback(const Params& P, const uint8_t* lut, const uint32_t*
     const uint32_t* tw = nullptr;
     const bool eq = P.cigar_eq != 0;
     const uint32_t cap = P.runs_per_warp;
+    // STAGED state: stg = the words of rc are in stage buffer `cur`; pend = index of the record whose words are being
+    // copied into the other buffer (0xffffffff: none), n_rec = that record
+    bool stg = false;
+    uint32_t cur = 0, pend = 0xffffffffu;
+    Rect n_rec = rc, nn_rec = rc;
+    uint32_t nn_idx = 0xffffffffu;
+    const int hl = lane & 7;
+    uint32_t* sbuf = STAGED ? stage + (size_t)(lane >> 3) * 2 * kTbStageWords : nullptr;
     for (;;) {
       const bool go = active_walk && (s.i > 0 || s.j > 0) && !s.bad && !s.stop;
       if (wp::ballot(go) == 0u) break;
-      if (go) {
-        if (!(s.i >= rc.row && s.j >= rc.col)) {
+      const bool in_rect = s.i >= rc.row && s.j >= rc.col;
+      if (STAGED) {
+        // ---- a walk needs its next record: the whole group of eight lanes takes part ----
+        const bool need = go && !in_rect;
+        const bool gneed = wp::shfl_idx_w((int)need, 0, 8) != 0;
+        if (wp::ballot(gneed) != 0u) {
+          {   // every lane of the warp runs this block (its shuffles use the full mask); groups without `need` copy nothing
+            // walker: the newest rectangle containing (i, j) (scan_block.rs:1578-1590), one record per iteration
+            uint32_t use_pend = 0, do_stage = 0, nw = 0;
+            const uint32_t* pw = nullptr;
+            if (need) {
+              if (s.ridx == 0) s.bad = 1u;
+              else {
+                s.ridx--;
+                use_pend = pend == s.ridx ? 1u : 0u;
+                rc = use_pend ? n_rec : rects_[s.ridx];
+                tw = rect_words_ptr(words_, P.trace_pool, rc);
+                if (s.i >= rc.row && s.j >= rc.col && tb_stageable(rc, tw)) { do_stage = 1u; pw = tw; nw = (uint32_t)(rc.h >> 3) * rc.w; }
+                stg = false;
+              }
+            }
+            do_stage = (uint32_t)wp::shfl_idx_w((int)do_stage, 0, 8);
+            use_pend = (uint32_t)wp::shfl_idx_w((int)use_pend, 0, 8);
+            // the group's copy in flight (if any) has landed: its buffer may be read or refilled. (Only the group with the
+            // event waits: the other groups' copies were issued moments ago.)
+            if (gneed) wp::cp_async_wait_all();
+            {
+              // not predicted (first rectangle of the walk, or records were skipped): copy now. (The shuffles are executed by
+              // every lane of the warp; only the copies depend on the group's flags.)
+              const uint64_t pa = (uint64_t)(uintptr_t)pw;
+              const uint32_t plo = (uint32_t)wp::shfl_idx_w((int)(uint32_t)pa, 0, 8), phi = (uint32_t)wp::shfl_idx_w((int)(uint32_t)(pa >> 32), 0, 8);
+              const uint32_t* src = (const uint32_t*)(uintptr_t)(((uint64_t)phi << 32) | plo);
+              nw = (uint32_t)wp::shfl_idx_w((int)nw, 0, 8);
+              const uint32_t gcur = (uint32_t)wp::shfl_idx_w((int)cur, 0, 8);
+              if (do_stage && !use_pend) {
+                for (uint32_t c4 = (uint32_t)hl; 4 * c4 < nw; c4 += 8) wp::cp_async16(sbuf + (gcur ^ 1u) * kTbStageWords + 4 * c4, src + 4 * c4);
+                wp::cp_async_commit();
+                wp::cp_async_wait_all();
+              }
+            }
+            // next record down the stack: its words go into the buffer the walk has just left. The record itself was
+            // loaded one event ago (nn_rec), the one after it is requested now: no load of this block is waited for here
+            uint32_t nstage = 0, nnw = 0;
+            const uint32_t* npw = nullptr;
+            if (need && !s.bad) {
+              if (do_stage) { cur ^= 1u; stg = true; }
+              pend = 0xffffffffu;
+              if (s.ridx > 0) {
+                n_rec = (nn_idx == s.ridx - 1) ? nn_rec : rects_[s.ridx - 1];
+                npw = rect_words_ptr(words_, P.trace_pool, n_rec);
+                if (tb_stageable(n_rec, npw)) { nstage = 1u; nnw = (uint32_t)(n_rec.h >> 3) * n_rec.w; pend = s.ridx - 1; }
+                nn_idx = 0xffffffffu;
+                if (s.ridx > 1) { nn_rec = rects_[s.ridx - 2]; nn_idx = s.ridx - 2; }
+                // further down: bring trace words and records from DRAM into L2. The stack is walked in order and shift
+                // rectangles lie back to back in the arena, so the words kTbLaneAhead rectangles down are (about) that many
+                // rectangle sizes below this one -- an address computed without loading that record
+                const uint32_t rw = (uint32_t)(rc.h >> 3) * rc.w;
+                if (!(rc.right & kRectPool) && rw <= kTbStageWords && rc.word_off >= (kTbLaneAhead + 1) * rw) {
+                  const uint32_t* ppw = tw - kTbLaneAhead * rw;
+#pragma unroll
+                  for (uint32_t u = 0; u < kTbStageWords; u += 8u) if (u < rw) wp::touch_l2(ppw + u);
+                }
+                if (s.ridx >= 4 * kTbLaneAhead && (s.ridx & 1u) == 0u) wp::touch_l2(rects_ + (s.ridx - 4 * kTbLaneAhead));
+              }
+            }
+            nstage = (uint32_t)wp::shfl_idx_w((int)nstage, 0, 8);
+            {
+              const uint64_t pa = (uint64_t)(uintptr_t)npw;
+              const uint32_t plo = (uint32_t)wp::shfl_idx_w((int)(uint32_t)pa, 0, 8), phi = (uint32_t)wp::shfl_idx_w((int)(uint32_t)(pa >> 32), 0, 8);
+              const uint32_t* src = (const uint32_t*)(uintptr_t)(((uint64_t)phi << 32) | plo);
+              nnw = (uint32_t)wp::shfl_idx_w((int)nnw, 0, 8);
+              const uint32_t gcur = (uint32_t)wp::shfl_idx_w((int)cur, 0, 8);
+              if (nstage) {
+                for (uint32_t c4 = (uint32_t)hl; 4 * c4 < nnw; c4 += 8) wp::cp_async16(sbuf + (gcur ^ 1u) * kTbStageWords + 4 * c4, src + 4 * c4);
+                wp::cp_async_commit();
+              }
+            }
+          }
+          wp::syncwarp();
+        }
+      }
+      if (go && (!STAGED || in_rect)) {
+        if (!in_rect) {
           // the newest rectangle containing (i, j) (scan_block.rs:1578-1590): one record per iteration
           if (s.ridx == 0) s.bad = 1u;
           else {
@@ -1587,7 +1688,12 @@ BA_DEV void lanes_traceback(const Params& P, const uint8_t* lut, const uint32_t*
           if (layout == 3u) {
             const uint32_t hh = (uint32_t)rc.h >> 1, G = (uint32_t)rc.h >> 3;
             const uint32_t half = v >= hh ? 1u : 0u, vv = v - half * hh;
-            nib = (tw[(size_t)c * G + (vv >> 2)] >> (16u * half + 4u * (vv & 3u))) & 15u;
+            const uint32_t wi = c * G + (vv >> 2);
+#ifdef BA_EMU
+            if (STAGED && stg) emu_stats::tb_staged++; else emu_stats::tb_global++;
+#endif
+            const uint32_t word = (STAGED && stg) ? sbuf[cur * kTbStageWords + wi] : tw[wi];
+            nib = (word >> (16u * half + 4u * (vv & 3u))) & 15u;
           } else {
             const uint32_t R = layout == 1u ? 8u : (uint32_t)rect_rows_per_lane(rc.h);
             const uint32_t CH = 32u * R, ngroups = (uint32_t)rc.w >> 3;

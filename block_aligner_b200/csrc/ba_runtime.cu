@@ -181,10 +181,15 @@ static void emu_tb_batch_entry(void* arg) {
   auto* t = (EmuTbBatch*)arg;
   static uint8_t lut[128];
   for (uint32_t i = 0; i < 128; i++) lut[i] = tb_entry(i);
-  lanes_traceback(*t->P, lut, t->list, t->n, t->warp * 32 + (uint32_t)wp::lane_id());
+  // BA_TB_STAGED: the shape of the staged launch (eight lanes per walk, four walks per warp)
+  static uint32_t stage[4 * 2 * kTbStageWords];
+  const uint32_t lane = (uint32_t)wp::lane_id();
+  if (!getenv("BA_TB_STAGED")) lanes_traceback<false>(*t->P, lut, t->list, t->n, t->warp * 32 + lane);
+  else lanes_traceback<true>(*t->P, lut, t->list, t->n, (lane & 7u) ? 0xffffffffu : t->warp * 4 + (lane >> 3), stage);
 }
 static int launch_traceback_batch(const Params& P, const uint32_t* list, uint32_t n, dev_stream_t) {
-  for (uint32_t wi = 0; wi * 32 < n; wi++) { EmuTbBatch t{&P, list, n, wi}; emu::run_warp(&emu_tb_batch_entry, &t); }
+  const uint32_t per = !getenv("BA_TB_STAGED") ? 32u : 4u;
+  for (uint32_t wi = 0; wi * per < n; wi++) { EmuTbBatch t{&P, list, n, wi}; emu::run_warp(&emu_tb_batch_entry, &t); }
   return 0;
 }
 #else
@@ -257,7 +262,19 @@ __global__ void __launch_bounds__(128) ba_traceback_batch_kernel(const __grid_co
   for (uint32_t i = threadIdx.x; i < 128; i += blockDim.x) lut[i] = tb_entry(i);
   __syncthreads();
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  lanes_traceback(P, lut, list, n, (t % stride) ? 0xffffffffu : t / stride);
+  lanes_traceback<false>(P, lut, list, n, (t % stride) ? 0xffffffffu : t / stride);
+}
+// eight lanes per walk; the seven lanes that do not walk help to stage the next rectangle's trace words in shared memory
+__global__ void __launch_bounds__(128) ba_traceback_staged_kernel(const __grid_constant__ Params P, const uint32_t* list, uint32_t n) {
+  __shared__ uint8_t lut[128];
+  __shared__ __align__(16) uint32_t stage[4 * 4 * 2 * kTbStageWords];     // 4 warps x 4 walks x 2 buffers
+  for (uint32_t i = threadIdx.x; i < 128; i += blockDim.x) lut[i] = tb_entry(i);
+  __syncthreads();
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t ngroups = (gridDim.x * blockDim.x) >> 3;
+  // the grid holds fewer groups than there are walks (launch_traceback_batch): every group takes walks t, t + ngroups, ...
+  for (uint32_t base = 0; base < n; base += ngroups)
+    lanes_traceback<true>(P, lut, list, n, (t & 7u) ? 0xffffffffu : base + (t >> 3), stage + (threadIdx.x >> 5) * (4 * 2 * kTbStageWords));
 }
 static int launch_traceback_batch(const Params& P, const uint32_t* list, uint32_t n, dev_stream_t st) {
   if (!n) return 0;
@@ -267,6 +284,20 @@ static int launch_traceback_batch(const Params& P, const uint32_t* list, uint32_
   // system serves well), 1: 84. So: four walks per warp while the launch still fits the GPU at once, more as the batch grows.
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  // BA_TB_STAGED=1: eight lanes per walk, the seven idle ones copy the next rectangle's trace words into shared memory
+  // with asynchronous copies (ba_traceback_staged_kernel), BA_TB_WALKS = walks in flight. Kept for the record, OFF: on
+  // B200 / C5 the staged walk takes 57.8 ms against 55.2 ms, and with fewer walks in flight the time grows in proportion
+  // (4096: +76 ms, 2048: +160 ms) -- a walk is not held by the latency of its trace words but by its own chain of ~90
+  // dependent instructions per cell step (ncu r02: 23 G warp instructions, issue slots 40 % busy with 4 warps per
+  // scheduler; profiles/r02_traceback_experiments.txt).
+  if (getenv("BA_TB_STAGED")) {
+    uint32_t walks = 1u << 20;
+    if (const char* e = getenv("BA_TB_WALKS")) walks = (uint32_t)std::max(16, atoi(e));
+    const uint64_t threads8 = (uint64_t)std::min<uint32_t>(n, walks) * 8;
+    ba_traceback_staged_kernel<<<(unsigned)((threads8 + 127) / 128), 128, 0, st>>>(P, list, n);
+    CK(cudaGetLastError());
+    return 0;
+  }
   uint32_t stride = (uint32_t)std::min<uint64_t>(8, std::max<uint64_t>(1, (uint64_t)sms * 1024 / n));
   if (const char* e = getenv("BA_TB_STRIDE")) stride = (uint32_t)std::max(1, atoi(e));
   const uint64_t threads = (uint64_t)n * stride;
@@ -681,6 +712,7 @@ static int batch_configure(BaBatch* b, uint32_t mn) {
         const uint64_t cap = std::min<uint64_t>(bound, 4 * len * (uint64_t)std::max<uint32_t>(mn, 32) / 8 + 4096);
         if (room > fixed) wv.words = std::max<uint64_t>(words, std::min<uint64_t>(cap, (room - fixed) / ((uint64_t)n * zmul * 4)));
       }
+      wv.words = (wv.words + 31) & ~(uint64_t)31;    // arenas start on 128-byte lines (16-byte asynchronous copies of the batch traceback)
       spill_max = std::max<uint64_t>(spill_max, (uint64_t)wv.n * (bound - std::min(bound, wv.words)));
       b->cap_trace = std::max<uint64_t>(b->cap_trace, (uint64_t)wv.n * wv.words * 4);
       b->cap_rects = std::max<uint64_t>(b->cap_rects, (uint64_t)wv.n * wv.rects * sizeof(Rect));
@@ -1280,7 +1312,8 @@ extern "C" int ba_batch_pair_stats(const BaBatch* b, size_t k, uint64_t* cells, 
 #ifdef BA_EMU
 extern "C" void ba_emu_stats(uint64_t* out4, int reset) {
   out4[0] = emu_stats::pk_cells; out4[1] = emu_stats::exact_cells; out4[2] = emu_stats::fast_steps; out4[3] = emu_stats::big_cells;
-  if (reset) { emu_stats::pk_cells = 0; emu_stats::exact_cells = 0; emu_stats::fast_steps = 0; emu_stats::big_cells = 0; }
+  if (getenv("BA_EMU_TB_STATS")) fprintf(stderr, "traceback cell steps: %llu staged, %llu from global memory\n", (unsigned long long)emu_stats::tb_staged, (unsigned long long)emu_stats::tb_global);
+  if (reset) { emu_stats::tb_staged = 0; emu_stats::tb_global = 0; emu_stats::pk_cells = 0; emu_stats::exact_cells = 0; emu_stats::fast_steps = 0; emu_stats::big_cells = 0; }
 }
 #endif
 

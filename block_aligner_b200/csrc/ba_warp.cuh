@@ -62,6 +62,9 @@ inline int imin(int a, int b) { return a < b ? a : b; }
 template <class T> inline T ldg(const T* p) { return *p; }
 inline void touch(const void*) {}
 inline void touch_l2(const void*) {}
+inline void cp_async16(void* dst, const void* src) { __builtin_memcpy(dst, src, 16); }
+inline void cp_async_commit() {}
+inline void cp_async_wait_all() {}
 }}  // namespace ba::wp
 #else
 #define BA_DEV __device__ __forceinline__
@@ -120,5 +123,11 @@ template <class T> BA_DEV T ldg(const T* p) { return __ldg(p); }
 // the next instruction the compiler gives that register to waits for the data -- measured in the batch traceback)
 BA_DEV void touch(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 BA_DEV void touch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+// asynchronous 16-byte copy global -> shared (LDGSTS, bypassing L1): the issuing thread does not wait for the data
+BA_DEV void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+BA_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+BA_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 }}  // namespace ba::wp
 #endif
