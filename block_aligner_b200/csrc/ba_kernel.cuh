@@ -96,6 +96,7 @@ struct RectArgs {
   int off_add;                   // just_offset folded into the load of AD/AC
   int rz;                        // relative_zero
   uint32_t* tw;                  // trace words of this rectangle (TRACE only)
+  int key_thr;                   // X_DROP, packed path: the argmax key is only needed if the block maximum exceeds this
   // extended modes (Block<_, _, LOCAL_START, FREE_QUERY_START_GAPS>; only read by EXT instantiations)
   bool local;                    // LOCAL_START: every cell is floored at relative_zero (scan_block.rs:1134-1136)
   bool fqs0;                     // FREE_QUERY_START_GAPS and this rectangle's vectors start at row 0 (:1130)
@@ -358,12 +359,40 @@ namespace ba {
 // ---------------------------------------------------------------------------------------------
 // Border helpers
 // ---------------------------------------------------------------------------------------------
+#ifndef BA_SHIFT_VEC
+#define BA_SHIFT_VEC 1
+#endif
 // shift_and_offset (scan_block.rs:1040-1061): slide by STEP, re-offset the kept part, append the
 // 8 fresh values from temp (not re-offset). Returns old buf1[STEP-1] + off_add.
+BA_DEV uint32_t sat_add_pair(uint32_t p, int off_add) {   // both halfwords: _mm256_adds_epi16 with a scalar
+  return wp::h_pack(sat_add(wp::h_lo(p), off_add), sat_add(wp::h_hi(p), off_add));
+}
 BA_DEV int shift_and_offset(int B, int16_t* b1, int16_t* b2, const int16_t* t1, const int16_t* t2, int off_add) {
   const int lane = wp::lane_id();
   const int corner = sat_add((int)b1[kStep - 1], off_add);
   wp::syncwarp();
+#if BA_SHIFT_VEC
+  // eight entries (16 bytes) per lane and pass: chunk ch of the result is chunk ch + 1 of the input, re-offset; the last
+  // chunk is the fresh one. A pass reads chunks [32 it + 1, 32 it + 33) and then writes [32 it, 32 it + 32): nothing is
+  // overwritten before it has been read.
+  const int nch = B / kStep;
+  for (int it = 0; it * 32 < nch; it++) {
+    const int ch = it * 32 + lane;
+    uint4 v1 = make_uint4(0u, 0u, 0u, 0u), v2 = v1;
+    if (ch < nch) {
+      if (ch < nch - 1) {
+        v1 = *(const uint4*)(b1 + kStep * (ch + 1)); v2 = *(const uint4*)(b2 + kStep * (ch + 1));
+        v1.x = sat_add_pair(v1.x, off_add); v1.y = sat_add_pair(v1.y, off_add); v1.z = sat_add_pair(v1.z, off_add); v1.w = sat_add_pair(v1.w, off_add);
+        v2.x = sat_add_pair(v2.x, off_add); v2.y = sat_add_pair(v2.y, off_add); v2.z = sat_add_pair(v2.z, off_add); v2.w = sat_add_pair(v2.w, off_add);
+      } else {
+        v1 = *(const uint4*)t1; v2 = *(const uint4*)t2;
+      }
+    }
+    wp::syncwarp();
+    if (ch < nch) { *(uint4*)(b1 + kStep * ch) = v1; *(uint4*)(b2 + kStep * ch) = v2; }
+    wp::syncwarp();
+  }
+#else
   for (int base = 0; base < B; base += 32) {
     const int idx = base + lane;
     int v1 = 0, v2 = 0;
@@ -380,6 +409,7 @@ BA_DEV int shift_and_offset(int B, int16_t* b1, int16_t* b2, const int16_t* t1, 
     if (idx < B) { b1[idx] = (int16_t)v1; b2[idx] = (int16_t)v2; }
     wp::syncwarp();
   }
+#endif
   return corner;
 }
 
@@ -387,12 +417,14 @@ BA_DEV void copy4(int n, int16_t* d0, int16_t* d1, int16_t* d2, int16_t* d3,
                   const int16_t* s0, const int16_t* s1, const int16_t* s2, const int16_t* s3, int src_off) {
   const int lane = wp::lane_id();
   wp::syncwarp();
-  for (int base = 0; base < n; base += 32) {
-    const int idx = base + lane;
-    int16_t a = 0, b = 0, c = 0, d = 0;
-    if (idx < n) { a = s0[idx + src_off]; b = s1[idx + src_off]; c = s2[idx + src_off]; d = s3[idx + src_off]; }
+  // n and src_off are multiples of 8 entries (block sizes are powers of two >= 16) and the arrays start on 16-byte
+  // boundaries: eight entries per lane and pass. Source and destination may be the same arrays with src_off = n (shrink).
+  for (int base = 0; base < n; base += 8 * 32) {
+    const int idx = base + 8 * lane;
+    uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a, c = a, d = a;
+    if (idx < n) { a = *(const uint4*)(s0 + idx + src_off); b = *(const uint4*)(s1 + idx + src_off); c = *(const uint4*)(s2 + idx + src_off); d = *(const uint4*)(s3 + idx + src_off); }
     wp::syncwarp();
-    if (idx < n) { d0[idx] = a; d1[idx] = b; d2[idx] = c; d3[idx] = d; }
+    if (idx < n) { *(uint4*)(d0 + idx) = a; *(uint4*)(d1 + idx) = b; *(uint4*)(d2 + idx) = c; *(uint4*)(d3 + idx) = d; }
   }
   wp::syncwarp();
 }
@@ -644,9 +676,10 @@ BA_DEV void init_alignment(const Params& P, AlnState& st, uint32_t pair, const W
   st.qlen = P.q_len[pair];
   st.rlen = (SCORING == kProfile) ? P.profiles[pair].len : P.r_len[pair];
   // Allocated::clear (scan_block.rs:1322-1339): every border starts at MIN = 0
-  for (int idx = lane; idx < (int)P.max_size; idx += 32) {
-    w.Dc[idx] = 0; w.Cc[idx] = 0; w.Dr[idx] = 0; w.Rr[idx] = 0;
-    w.kDc[idx] = 0; w.kCc[idx] = 0; w.kDr[idx] = 0; w.kRr[idx] = 0;
+  const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+  for (int idx = 8 * lane; idx < (int)P.max_size; idx += 8 * 32) {      // max_size is a multiple of 16 entries
+    *(uint4*)(w.Dc + idx) = z4; *(uint4*)(w.Cc + idx) = z4; *(uint4*)(w.Dr + idx) = z4; *(uint4*)(w.Rr + idx) = z4;
+    *(uint4*)(w.kDc + idx) = z4; *(uint4*)(w.kCc + idx) = z4; *(uint4*)(w.kDr + idx) = z4; *(uint4*)(w.kRr + idx) = z4;
   }
   if (lane < 16) { w.t1[lane] = 0; w.t2[lane] = 0; }
   wp::syncwarp();
@@ -924,6 +957,9 @@ BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const Sl
         if (lim + 1 < a.ncols) a.ncols = lim + 1;
       }
       a.tw = nullptr; a.tz = nullptr;
+      // a shift step finds a new best only if off + max - ZERO > best_max (scan_block.rs:346): below that the argmax of the
+      // rectangle is never looked at (the unrelated tails of X-drop alignments: most steps of a block at its maximum size)
+      a.key_thr = st.dir == kGrow ? kI16Min - 1 : st.best_max - st.off + kZero;
       a.local = m_local; a.fqs0 = m_fqs && rect_right && a.vec_base == 0;
       a.fqe = m_fqe; a.fq_cls = (int)(qlen % kL); a.fq_row0 = (int)qlen - (int)a.vec_base;
       // First block of an alignment on the packed path. Its input borders are Allocated::clear's MIN = 0 (scan_block.rs:

@@ -47,7 +47,7 @@ BA_DEV uint32_t pk2(int v) { return wp::h_pack(v, v); }
 // kernels sit at the edge of the SM's 32 KB instruction cache: sm__icc_request_hit_rate fell 96 -> 87 % (C2) and
 // 78 -> 68 % (C3), and both got slower on B200 (C2 1226 -> 1189 GCUPS, C3 635 -> 606, same box, profiles/r02_variants.txt)
 #ifndef BA_PK_KVAR
-#define BA_PK_KVAR 0
+#define BA_PK_KVAR 1
 #endif
 template <bool TRACE, int K> struct PkMc { static constexpr bool kSplit = BA_PK_SPLIT_MC && !TRACE; static constexpr int kN = kSplit ? 2 * K : K; };
 constexpr int kPkUnroll = BA_PK_UNROLL;    // 1, 2 or 4
@@ -538,7 +538,10 @@ BA_DEV void place_rect_pk_k(const unsigned char* smem, const Params& P, const Pk
     wp::syncwarp();
   }
   if (lane < G) { pk_storek<K>(a.AD, lg, G, D); pk_storek<K>(a.AC, lg, G, C); }
-  if (XDROP) { bv = pk_lane_max<K>(m); bkey = pk_lane_key<K, PkMc<TRACE, K>::kN>(m, mc, lg, G, bv); }
+  if (XDROP) {
+    bv = pk_lane_max<K>(m);
+    if (wp::red_max(bv) > a.key_thr) bkey = pk_lane_key<K, PkMc<TRACE, K>::kN>(m, mc, lg, G, bv);   // warp-uniform
+  }
   else bv = wp::imax(bv, wp::imax(wp::h_lo(m[0]), wp::h_hi(m[0])));
   wp::syncwarp();
 }
