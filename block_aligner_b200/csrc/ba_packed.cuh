@@ -179,7 +179,9 @@ BA_DEV uint32_t pk_eqmask(uint32_t y, uint32_t x) { return wp::viaddmin2(y, ~x, 
 template <int KIND, bool XDROP, int NST, bool TRACE = false, int K = 4>
 BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int G, int lg, uint32_t cw0, uint32_t cw1,
                      uint32_t (&D)[K], uint32_t (&C)[K], uint32_t corner_lo, int cbase, uint32_t (&m)[K], uint32_t (&mc)[PkMc<TRACE, K>::kN],
-                     uint32_t* fr, bool writer, uint32_t* tw = nullptr, bool tstore = false) {
+                     uint32_t* fr, bool writer, uint32_t* tw = nullptr, bool tstore = false, int ncol8 = 8) {
+  // ncol8 < 8: global-mode early break inside this group of eight columns (scan_block.rs:1216-1224): only the first
+  // ncol8 columns exist; D / C then hold the last computed column, like the reference's D_col / C_col after its break
   static_assert(!TRACE || K == 4, "trace words are laid out for four registers per lane");
   constexpr bool SPLIT = PkMc<TRACE, K>::kSplit;
   // The uniform constants are copied into vector registers once per call (opaque_zero): ptxas otherwise rebuilds
@@ -193,7 +195,7 @@ BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int G, int lg,
   // instruction cache (ncu: sm__icc_request_hit_rate), which a fully unrolled 8-column body does not
   uint64_t cwq = ((uint64_t)cw1 << 32) | cw0;
 #pragma unroll 1
-  for (int h = 0; h < 8 / kPkUnroll; h++) {
+  for (int h = 0; h < ncol8 / kPkUnroll; h++) {
     const uint32_t cwh = (uint32_t)cwq;
     cwq >>= 8 * kPkUnroll;
 #pragma unroll
@@ -477,12 +479,12 @@ BA_DEV bool pk_in_range(const uint32_t (&a)[N], const uint32_t (&b)[N], int lo, 
   return p0 && p1 && p2 && p3;
 }
 
-// Can this rectangle go through the packed path? Shape (32..256 rows, whole 8-column groups, no early break, not
-// the forced origin cell) and value range of its inputs (pk_bounds). Nothing is modified.
+// Can this rectangle go through the packed path? Shape (32..256 rows, whole 8-column groups, not the forced origin
+// cell unless run_generic set it up) and value range of its inputs (pk_bounds). Nothing is modified.
 BA_DEV bool pk_rect_ok(const Params& P, const RectArgs& a, bool origin_ok = false) {
   const int lane = wp::lane_id();
   const int H = a.H, W = a.W;
-  if (!(H == 32 || H == 64 || H == 128 || H == 256) || W <= 0 || (W & 7) || W > 256 || a.ncols != W) return false;
+  if (!(H == 32 || H == 64 || H == 128 || H == 256) || W <= 0 || (W & 7) || W > 256 || a.ncols <= 0) return false;
   if (a.vec_base == 0 && a.col_base == 0 && !origin_ok) return false;   // forced origin cell (scan_block.rs:1130-1132): only as set up by run_generic
   int GL, GH;
   pk_bounds(W, P.gap_open, P.gap_extend, P.pk_smax, GL, GH);
@@ -530,11 +532,12 @@ BA_DEV void place_rect_pk_k(const unsigned char* smem, const Params& P, const Pk
 #pragma unroll
   for (int k = 0; k < K; k++) m[k] = 0u;
   const bool writer = lane == G - 1;
-  for (int cb = 0; cb < W; cb += 8) {
+  for (int cb = 0; cb < a.ncols; cb += 8) {      // a.ncols < W: early break (run_generic), the remaining columns do not exist
     const uint2 cw = *(const uint2*)(col + a.col_base + cb);
-    pk_cols8<KIND, XDROP, 5, TRACE, K>(sc, kc, G, lg, cw.x, cw.y, D, C, (uint32_t)a.corner & 0xffffu, cb, m, mc, fr, writer, a.tw, lane < G);
+    const int n8 = wp::imin(8, a.ncols - cb);
+    pk_cols8<KIND, XDROP, 5, TRACE, K>(sc, kc, G, lg, cw.x, cw.y, D, C, (uint32_t)a.corner & 0xffffu, cb, m, mc, fr, writer, a.tw, lane < G, n8);
     wp::syncwarp();
-    if (lane < 8) { const uint32_t v = fr[lane]; a.OD[cb + lane] = (int16_t)(v >> 16); a.OR_[cb + lane] = (int16_t)(v & 0xffffu); }
+    if (lane < n8) { const uint32_t v = fr[lane]; a.OD[cb + lane] = (int16_t)(v >> 16); a.OR_[cb + lane] = (int16_t)(v & 0xffffu); }
     wp::syncwarp();
   }
   if (lane < G) { pk_storek<K>(a.AD, lg, G, D); pk_storek<K>(a.AC, lg, G, C); }
