@@ -1233,7 +1233,7 @@ BA_DEV void pk_fast_step(const Params& P, const WarpMem& w, AlnState& st, PkFast
   uint32_t* tw = nullptr;
   if (TRACE && active) tw = trace_push_local(st, sm, right ? si : si + (B - kStep), right ? sj + (B - kStep) : sj, kStep, B, right, lg == 0, 3);
   if constexpr (PROF) pkp_cols8<XDROP, LGT, MCN>(po, P.kc, lg, cw.x, cw.y, D, C, (uint32_t)corner & 0xffffu, m, mc, fr, lg == G - 1);
-  else pk_cols8<KIND, XDROP, LGT, TRACE, 4>(sc, P.kc, G, lg, cw.x, cw.y, D, C, (uint32_t)corner & 0xffffu, 0, m, mc, fr, lg == G - 1, tw, TRACE && active);
+  else pk_cols8<KIND, XDROP, LGT, TRACE, 4, G>(sc, P.kc, G, lg, cw.x, cw.y, D, C, (uint32_t)corner & 0xffffu, 0, m, mc, fr, lg == G - 1, tw, TRACE && active);
   wp::syncwarp();
 
   // ---- borders after the step ----

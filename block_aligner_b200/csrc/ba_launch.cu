@@ -64,8 +64,17 @@ static int occupancy(int, size_t, int* blocks_per_sm) { *blocks_per_sm = 1; retu
 #ifndef BA_LB_BLOCKS_TRACE
 #define BA_LB_BLOCKS_TRACE BA_LB_BLOCKS
 #endif
+// Protein kernels without X-drop or trace (C3) are held by instruction-cache misses and latency, not by the ALU pipe: a
+// fifth block per SM (102 registers, ~150 spill instructions, 20 warps) is worth +5 % there (753 -> 791 GCUPS; 3 blocks
+// 759, 6: 751, 8: 727), while the nucleotide X-drop kernel of C2 loses 7 % with it (1343 -> 1249).
+#ifndef BA_LB_BLOCKS_AA
+#define BA_LB_BLOCKS_AA 5
+#endif
+template <int SCORING, int FLAGS> constexpr int lb_blocks() {
+  return (FLAGS & kTrace) ? BA_LB_BLOCKS_TRACE : ((SCORING == kAA && (FLAGS & (kTrace | kXDrop | kExt)) == 0) ? BA_LB_BLOCKS_AA : BA_LB_BLOCKS);
+}
 template <int SCORING, int FLAGS, int FR>
-__global__ void __launch_bounds__(128, (FLAGS & kTrace) ? BA_LB_BLOCKS_TRACE : BA_LB_BLOCKS) ba_align_kernel(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(128, lb_blocks<SCORING, FLAGS>()) ba_align_kernel(const __grid_constant__ Params P) {
   extern __shared__ __align__(16) unsigned char ba_smem[];
   const int nm = SCORING == kNuc ? 128 : (SCORING == kAA ? 864 : 0);
   for (int i = threadIdx.x; i < nm; i += blockDim.x) ba_smem[i] = (unsigned char)P.matrix[i];

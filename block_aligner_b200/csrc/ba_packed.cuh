@@ -47,7 +47,10 @@ BA_DEV uint32_t pk2(int v) { return wp::h_pack(v, v); }
 // kernels sit at the edge of the SM's 32 KB instruction cache: sm__icc_request_hit_rate fell 96 -> 87 % (C2) and
 // 78 -> 68 % (C3), and both got slower on B200 (C2 1226 -> 1189 GCUPS, C3 635 -> 606, same box, profiles/r02_variants.txt)
 #ifndef BA_PK_KVAR
-#define BA_PK_KVAR 1
+#define BA_PK_KVAR 3
+#endif
+#ifndef BA_PK_GT
+#define BA_PK_GT 1
 #endif
 template <bool TRACE, int K> struct PkMc { static constexpr bool kSplit = BA_PK_SPLIT_MC && !TRACE; static constexpr int kN = kSplit ? 2 * K : K; };
 constexpr int kPkUnroll = BA_PK_UNROLL;    // 1, 2 or 4
@@ -176,13 +179,16 @@ BA_DEV uint32_t pk_eqmask(uint32_t y, uint32_t x) { return wp::viaddmin2(y, ~x, 
 // instead of 16 / 8 / 4 of them -- the grow rectangles and the shift steps of blocks 64 and 128 (C3: 42 % of the
 // kernel's instructions ran in that loop at 1/4 of the lanes, ncu r02). NST = Kogge-Stone stages executed (>= log2 G;
 // a stage whose shuffle distance reaches G returns the lane's own value and changes nothing because extend < 0).
-template <int KIND, bool XDROP, int NST, bool TRACE = false, int K = 4>
-BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int G, int lg, uint32_t cw0, uint32_t cw1,
+// GT: the group size when it is known at compile time (0: run-time `Gr`) -- shuffle widths become immediates instead of
+// operands that the generic phase, short of registers, rebuilds in every iteration of the column loop.
+template <int KIND, bool XDROP, int NST, bool TRACE = false, int K = 4, int GT = 0>
+BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int Gr, int lg, uint32_t cw0, uint32_t cw1,
                      uint32_t (&D)[K], uint32_t (&C)[K], uint32_t corner_lo, int cbase, uint32_t (&m)[K], uint32_t (&mc)[PkMc<TRACE, K>::kN],
                      uint32_t* fr, bool writer, uint32_t* tw = nullptr, bool tstore = false, int ncol8 = 8) {
   // ncol8 < 8: global-mode early break inside this group of eight columns (scan_block.rs:1216-1224): only the first
   // ncol8 columns exist; D / C then hold the last computed column, like the reference's D_col / C_col after its break
   static_assert(!TRACE || K == 4, "trace words are laid out for four registers per lane");
+  const int G = GT ? GT : Gr;
   constexpr bool SPLIT = PkMc<TRACE, K>::kSplit;
   // The uniform constants are copied into vector registers once per call (opaque_zero): ptxas otherwise rebuilds
   // every packed constant from its 16-bit halves at each use.
@@ -504,12 +510,12 @@ BA_DEV bool pk_rect_ok(const Params& P, const RectArgs& a, bool origin_ok = fals
 // TRACE: a.tw receives H / 8 words per column (Rect layout 3, see pk_cols8); TRACE keeps four registers per lane (its
 // trace words hold eight nibbles per lane), so rectangles below 256 rows use G < 32 lanes there. Without TRACE a
 // rectangle of 128 / 64 / 32 rows runs with 2 / 1 / 1 registers per lane on 32 / 32 / 16 lanes.
-template <int KIND, bool XDROP, bool TRACE, int K>
+template <int KIND, bool XDROP, bool TRACE, int K, int GT = 0>
 BA_DEV void place_rect_pk_k(const unsigned char* smem, const Params& P, const PkConst& kc, const uint8_t* vec, const uint8_t* col,
                             const RectArgs& a, uint32_t* fr, int& bv, unsigned& bkey) {
   const int lane = wp::lane_id();
   const int H = a.H, W = a.W;
-  const int G = H / (2 * K);
+  const int G = GT ? GT : H / (2 * K);
   const int lg = lane & (G - 1);
   uint32_t D[K], C[K];
   pk_loadk<K>(a.AD, lg, G, D);
@@ -535,7 +541,7 @@ BA_DEV void place_rect_pk_k(const unsigned char* smem, const Params& P, const Pk
   for (int cb = 0; cb < a.ncols; cb += 8) {      // a.ncols < W: early break (run_generic), the remaining columns do not exist
     const uint2 cw = *(const uint2*)(col + a.col_base + cb);
     const int n8 = wp::imin(8, a.ncols - cb);
-    pk_cols8<KIND, XDROP, 5, TRACE, K>(sc, kc, G, lg, cw.x, cw.y, D, C, (uint32_t)a.corner & 0xffffu, cb, m, mc, fr, writer, a.tw, lane < G, n8);
+    pk_cols8<KIND, XDROP, 5, TRACE, K, GT>(sc, kc, G, lg, cw.x, cw.y, D, C, (uint32_t)a.corner & 0xffffu, cb, m, mc, fr, writer, a.tw, lane < G, n8);
     wp::syncwarp();
     if (lane < n8) { const uint32_t v = fr[lane]; a.OD[cb + lane] = (int16_t)(v >> 16); a.OR_[cb + lane] = (int16_t)(v & 0xffffu); }
     wp::syncwarp();
@@ -553,9 +559,14 @@ BA_DEV void place_rect_pk(const unsigned char* smem, const Params& P, const PkCo
                           const RectArgs& a, uint32_t* fr, int& bv, unsigned& bkey) {
   constexpr int K128 = (TRACE || !(BA_PK_KVAR & 2)) ? 4 : 2, K64 = (TRACE || !(BA_PK_KVAR & 1)) ? 4 : 1;
   // (one call site per distinct K: every call is an inlined copy of the rectangle code)
-  if (K128 != 4 && a.H == 128) place_rect_pk_k<KIND, XDROP, TRACE, K128>(smem, P, kc, vec, col, a, fr, bv, bkey);
+  // With both variants on, 128- and 256-row rectangles always use all 32 lanes: their group size is a compile-time 32.
+  constexpr int G4 = (K128 != 4 && K64 != 4 && BA_PK_GT) ? 32 : 0, G2 = BA_PK_GT ? 32 : 0;
+  if (K128 != 4 && a.H == 128) place_rect_pk_k<KIND, XDROP, TRACE, K128, G2>(smem, P, kc, vec, col, a, fr, bv, bkey);
+#if BA_PK_GT > 1   // 64-row rectangles with a compile-time group size of their own (one more copy of the rectangle code)
+  else if (K64 != 4 && a.H == 64) place_rect_pk_k<KIND, XDROP, TRACE, K64, 32>(smem, P, kc, vec, col, a, fr, bv, bkey);
+#endif
   else if (K64 != 4 && a.H <= 64) place_rect_pk_k<KIND, XDROP, TRACE, K64>(smem, P, kc, vec, col, a, fr, bv, bkey);
-  else place_rect_pk_k<KIND, XDROP, TRACE, 4>(smem, P, kc, vec, col, a, fr, bv, bkey);
+  else place_rect_pk_k<KIND, XDROP, TRACE, 4, G4>(smem, P, kc, vec, col, a, fr, bv, bkey);
 }
 
 }  // namespace ba
