@@ -257,7 +257,11 @@ static int launch_traceback(const Params& P, uint32_t pair, uint32_t qi, uint32_
 }
 // one walk per lane over the pairs of a launch whose traces are resident (list = the launch's work list)
 // `stride`: every stride-th lane walks (32 / stride walks per warp, see launch_traceback_batch)
-__global__ void __launch_bounds__(128) ba_traceback_batch_kernel(const __grid_constant__ Params P, const uint32_t* list, uint32_t n, uint32_t stride) {
+// ten blocks per SM (48 registers): with 63 registers a launch of two walks per warp does not fit the GPU in one wave
+#ifndef BA_TB_LB
+#define BA_TB_LB 10
+#endif
+__global__ void __launch_bounds__(128, BA_TB_LB) ba_traceback_batch_kernel(const __grid_constant__ Params P, const uint32_t* list, uint32_t n, uint32_t stride) {
   __shared__ uint8_t lut[128];
   for (uint32_t i = threadIdx.x; i < 128; i += blockDim.x) lut[i] = tb_entry(i);
   __syncthreads();
@@ -298,7 +302,9 @@ static int launch_traceback_batch(const Params& P, const uint32_t* list, uint32_
     CK(cudaGetLastError());
     return 0;
   }
-  uint32_t stride = (uint32_t)std::min<uint64_t>(8, std::max<uint64_t>(1, (uint64_t)sms * 1024 / n));
+  // (round 2: the 74 ms of two walks per warp were a second wave -- at 63 registers 5000 warps do not fit at once. With
+  // the kernel capped at 48 registers they do: two walks per warp 45 ms, four 49 ms; C5 step 206 -> 196 ms.)
+  uint32_t stride = (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(1, (uint64_t)sms * 1280 / n));
   if (const char* e = getenv("BA_TB_STRIDE")) stride = (uint32_t)std::max(1, atoi(e));
   const uint64_t threads = (uint64_t)n * stride;
   ba_traceback_batch_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(P, list, n, stride);
