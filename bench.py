@@ -186,10 +186,10 @@ def parity_of(cb, out, cig, path):
 def newest_traffic(tag, n):
     """DRAM bytes per launch from the newest committed `ncu --set full` capture of this workload (per pair x pairs)."""
     best = None
-    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_align_kernel_summary.json"))):
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_*kernel_summary.json"))):
         try:
             for c in json.load(open(path))["captures"]:
-                if tag in c["capture"].split() and c.get("dram_bytes_per_pair"):
+                if tag in c["capture"].split() and "traceback" not in c["capture"] and c.get("dram_bytes_per_pair"):
                     best = (c["dram_bytes_per_pair"] * n, os.path.relpath(path, ROOT))
         except Exception:
             pass
