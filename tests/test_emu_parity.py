@@ -274,3 +274,17 @@ def test_full_slot_arena_parks_fast_phase_and_spills_to_pool(env, size, monkeypa
     assert got[3].kernel_launches == 2
     exp = parity.oracle_batch(w["scoring"], m, w["gaps"], size, 80, w["flags"], True, qa, qo, ra, ro)
     assert parity.compare("tiny-arena", got, exp) == 0
+
+
+@pytest.mark.parametrize("size", [(32, 256), (64, 2048)])
+def test_staged_batch_traceback(env, size, monkeypatch):
+    """BA_TB_STAGED=1: the opt-in batch traceback that stages each rectangle's trace words in shared memory (eight lanes per
+    walk, asynchronous copies). Same CIGARs as the oracle, including rectangles too large to stage and pool rectangles."""
+    lib, al = env
+    monkeypatch.setenv("BA_TB_STAGED", "1")
+    w = dict(scoring=api.SCORING_NUC, matrix=(2, -4), gaps=(-6, -2), size=size, x_drop=100, flags=api.TRACE | api.XDROP, stream=57,
+             gen=P(alphabet=0, len_dist=0, len_min=300, len_max=2500, suffix_len=150, big_indel_prob=0.5, big_indel_min=80,
+                   big_indel_max=300, **NOISY))
+    assert parity.check_workload(lib, al, w, 14, seed=5) == 0
+    monkeypatch.setenv("BA_TRACE_ARENA_WORDS", "4096")
+    assert parity.check_workload(lib, al, w, 6, seed=6) == 0
