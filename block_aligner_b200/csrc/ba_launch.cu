@@ -70,8 +70,12 @@ static int occupancy(int, size_t, int* blocks_per_sm) { *blocks_per_sm = 1; retu
 #ifndef BA_LB_BLOCKS_AA
 #define BA_LB_BLOCKS_AA 5
 #endif
+#ifndef BA_LB_BLOCKS_PROF
+#define BA_LB_BLOCKS_PROF BA_LB_BLOCKS
+#endif
 template <int SCORING, int FLAGS> constexpr int lb_blocks() {
-  return (FLAGS & kTrace) ? BA_LB_BLOCKS_TRACE : ((SCORING == kAA && (FLAGS & (kTrace | kXDrop | kExt)) == 0) ? BA_LB_BLOCKS_AA : BA_LB_BLOCKS);
+  return (FLAGS & kTrace) ? BA_LB_BLOCKS_TRACE : (SCORING == kProfile ? BA_LB_BLOCKS_PROF :
+         ((SCORING == kAA && (FLAGS & (kTrace | kXDrop | kExt)) == 0) ? BA_LB_BLOCKS_AA : BA_LB_BLOCKS));
 }
 template <int SCORING, int FLAGS, int FR>
 __global__ void __launch_bounds__(128, lb_blocks<SCORING, FLAGS>()) ba_align_kernel(const __grid_constant__ Params P) {
@@ -107,8 +111,8 @@ static int occupancy(int wpb, size_t smem_bytes, int* blocks_per_sm) {
 #define BA_FOR_SEQ(X, S) X(S, 0, 0) X(S, 1, 0) X(S, 2, 0) X(S, 3, 0) X(S, 4, 0) X(S, 5, 0) X(S, 6, 0) X(S, 7, 0) \
                          X(S, 0, 18) X(S, 1, 18) X(S, 2, 18) X(S, 3, 18) X(S, 0, 19) X(S, 1, 19) X(S, 2, 19) X(S, 3, 19) \
                          X(S, 0, 34) X(S, 1, 34) X(S, 2, 34) X(S, 3, 34) X(S, 0, 35) X(S, 1, 35) X(S, 2, 35) X(S, 3, 35)
-#ifdef BA_MINIMAL   // tuning builds (tools/build_variant.sh): only the kernels of the C2, C3 and C5 workloads
-#define BA_FOR_KERNELS(X) X(kNuc, 2, 0) X(kNuc, 2, 18) X(kNuc, 3, 19) X(kNuc, 3, 35) X(kAA, 0, 0) X(kAA, 0, 18)
+#ifdef BA_MINIMAL   // tuning builds (tools/build_variant.sh): only the kernels of the C2, C3, C4 and C5 workloads
+#define BA_FOR_KERNELS(X) X(kNuc, 2, 0) X(kNuc, 2, 18) X(kNuc, 3, 19) X(kNuc, 3, 35) X(kAA, 0, 0) X(kAA, 0, 18) X(kProfile, 2, 0) X(kProfile, 2, 18)
 #else
 #define BA_FOR_KERNELS(X) BA_FOR_SEQ(X, kNuc) BA_FOR_SEQ(X, kAA) BA_FOR_SEQ(X, kByte) \
   X(kProfile, 0, 0) X(kProfile, 1, 0) X(kProfile, 2, 0) X(kProfile, 3, 0) \
