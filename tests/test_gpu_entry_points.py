@@ -70,6 +70,39 @@ def test_align_batch_automatic_geometric_split_against_oracle(env):
     lib.check(lib.L.ba_trim(al.h))
 
 
+def test_align_batch_mid_size_geometric_split_and_staged_copy(env, monkeypatch):
+    """>= 16384 pairs and >= 128 MB: four geometric chunks (the shards of a multi-GPU call); the inputs are numpy arrays in
+    pageable memory, i.e. they go through the threaded staging copy (h2d_seq)."""
+    lib, al = env
+    if EMU:
+        pytest.skip("needs the GPU-sized batch")
+    qa, qo, ra, ro = _c2_like(17000, 3900, 4300, seed=9)
+    assert (128 << 20) <= int(qo[-1] + ro[-1]) < (512 << 20)
+    m = lib.builtin_matrix("NW1")[1]
+    cfg = al.config(api.SCORING_NUC, m, (-2, -1), (32, 256), 50, api.XDROP, False)
+    exp = parity.oracle_batch(api.SCORING_NUC, m, (-2, -1), (32, 256), 50, api.XDROP, False, qa, qo, ra, ro)
+    for stage_threads in ("4", "1", "8"):
+        monkeypatch.setenv("BA_STAGE_THREADS", stage_threads)
+        res, st = parity.abi_align_batch(lib, al, cfg, qa, qo, ra, ro)
+        assert st.kernel_launches == 8         # 4 chunks x (convert/pad + align)
+        assert parity.compare_abi(f"mid-geometric/threads{stage_threads}", res, None, st, exp) == 0
+    lib.check(lib.L.ba_trim(al.h))
+
+
+def test_staged_copy_of_small_batches(env, monkeypatch):
+    """BA_STAGE_MIN_BYTES=1: every sequence arena in pageable memory takes the staging path, whatever its size"""
+    lib, al = env
+    monkeypatch.setenv("BA_STAGE_MIN_BYTES", "1")
+    monkeypatch.setenv("BA_PIPELINE_CHUNKS", "3")
+    qa, qo, ra, ro = _c2_like(N(3000), 300, 3000, seed=21)
+    m = lib.builtin_matrix("NW1")[1]
+    cfg = al.config(api.SCORING_NUC, m, (-2, -1), (32, 256), 50, api.XDROP, False)
+    exp = parity.oracle_batch(api.SCORING_NUC, m, (-2, -1), (32, 256), 50, api.XDROP, False, qa, qo, ra, ro)
+    for rep in range(2):
+        res, st = parity.abi_align_batch(lib, al, cfg, qa, qo, ra, ro)
+        assert parity.compare_abi(f"staged-small/rep{rep}", res, None, st, exp) == 0
+
+
 @pytest.mark.parametrize("chunks", ["1", "2", "3"])
 def test_align_batch_cigar_against_oracle(env, chunks, monkeypatch):
     lib, al = env
