@@ -1010,7 +1010,7 @@ static int upload_common(BaAligner* al, const BaConfig* cfg, size_t n, const uin
       ba.kind = 1;
       const uint64_t sbytes = n ? pssm->score_off[n] - pssm->score_off[0] : 0;
       TRY3(pool_alloc(al, (void**)&d_src, sbytes));
-      if (n) TRY3(h2d(d_src, pssm->scores + pssm->score_off[0], sbytes, st));
+      if (n) TRY3(h2d_seq(al, d_src, (const uint8_t*)(pssm->scores + pssm->score_off[0]), sbytes, st));   // pageable caller memory: threaded staging copy
       ba.scores = (const int8_t*)d_src;
       if (pssm->gap_off) {
         const uint64_t gb = n ? pssm->gap_off[n] - pssm->gap_off[0] : 0;
