@@ -26,10 +26,9 @@ BA_DEV uint32_t pk2(int v) { return wp::h_pack(v, v); }
 #ifndef BA_PK_UNROLL
 #define BA_PK_UNROLL 1
 #endif
-// Tuning switches kept for the record (tools/build_variant.sh), both off: measured on B200 / C2 they change nothing
-// (1077-1087 GCUPS in every variant at 50 k pairs), i.e. the column loop is not limited by the ALU pipe alone.
-// BA_PK_IMAD = 1: the plain adds of the column loop are issued as IMAD (x * 1 + y, the 1 opaque to the compiler) and
-// run on the FMA pipe instead of the ALU pipe.
+// Tuning switches (tools/build_variant.sh; measurements in profiles/r02_variants.txt).
+// BA_PK_IMAD = 1: the plain adds of the column loop are issued as IMAD (x * 1 + y, the 1 opaque to the compiler). OFF:
+// measured neutral (ptxas already issues them as VIADD, which runs on the FMA pipe like IMAD).
 #ifndef BA_PK_IMAD
 #define BA_PK_IMAD 0
 #endif
@@ -42,10 +41,12 @@ BA_DEV uint32_t pk2(int v) { return wp::h_pack(v, v); }
 #define BA_PK_SPLIT_MC 1
 #endif
 // BA_PK_KVAR: rows-per-lane variants of the generic phase's packed rectangles (bit 0: one register per lane for 32 / 64
-// rows, bit 1: two registers per lane for 128 rows; 0: four registers per lane everywhere, fewer lanes busy). OFF:
-// the variants cut the executed instructions (C2 -9 %, C3 -19 %, ncu r02 k2) but add 2.5 KB of hot code each, and the
-// kernels sit at the edge of the SM's 32 KB instruction cache: sm__icc_request_hit_rate fell 96 -> 87 % (C2) and
-// 78 -> 68 % (C3), and both got slower on B200 (C2 1226 -> 1189 GCUPS, C3 635 -> 606, same box, profiles/r02_variants.txt)
+// rows, bit 1: two registers per lane for 128 rows; 0: four registers per lane everywhere, fewer lanes busy). Each
+// variant is one more copy of the rectangle code, and the kernels live at the edge of the SM's 32 KB instruction cache:
+// first measured as a loss (fewer instructions, sm__icc_request_hit_rate 96 -> 87 % on C2, 78 -> 68 % on C3), a gain
+// (C2 +2 %, C3 +5 %) once the rest of the generic phase had been made 12 KB smaller. BA_PK_GT = 1: rectangles that fill the
+// warp (128 / 256 rows with both variants on) use a compile-time group size of 32 (column loop 111 -> 98 instructions);
+// BA_PK_GT = 2 adds such a copy for 64-row rectangles (loop 70 -> 57) and is a loss again (C3 -8 %).
 #ifndef BA_PK_KVAR
 #define BA_PK_KVAR 3
 #endif
