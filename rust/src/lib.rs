@@ -56,6 +56,14 @@ extern "C" {
     fn ba_align_batch_cigar(a: *mut BaAligner, cfg: *const BaConfig, n: usize, q_bytes: *const u8, q_off: *const u64,
                             r_bytes: *const u8, r_off: *const u64, out: *mut AlignResult, runs: *mut u32, runs_cap: usize,
                             run_off: *mut u64, run_len: *mut u32, runs_used: *mut usize, stats: *mut BaStats) -> c_int;
+    fn ba_align_batch_exp(a: *mut BaAligner, cfg: *const BaConfig, n: usize, q_bytes: *const u8, q_off: *const u64,
+                          r_bytes: *const u8, r_off: *const u64, target_score: *const i32, out: *mut AlignResult,
+                          min_size_used: *mut usize, stats: *mut BaStats) -> c_int;
+    fn ba_device_count() -> c_int;
+    fn ba_align_batch_multi(devices: *const c_int, n_dev: c_int, cfg: *const BaConfig, n: usize, q_bytes: *const u8,
+                            q_off: *const u64, r_bytes: *const u8, r_off: *const u64, out: *mut AlignResult,
+                            stats: *mut BaStats) -> c_int;
+    fn ba_pack_nuc4(ascii: *const u8, len: usize, packed: *mut u8, nibble_off: u64) -> usize;
     fn ba_percent_len(len: usize, p: f32) -> usize;
     static NW1: NucMatrix;
     static BLOSUM62: AAMatrix;
@@ -303,6 +311,52 @@ pub fn align_batch<const TRACE: bool, const X_DROP: bool, M: Matrix>(
         check(unsafe { ba_align_batch(dev.h, &cfg, n, qa.as_ptr(), qo.as_ptr(), ra.as_ptr(), ro.as_ptr(), out.as_mut_ptr(), &mut stats) });
     }
     (out, cigars, stats)
+}
+
+/// One batch over several GPUs of the box in one call (`devices` empty: every visible device). Contiguous shards of equal
+/// sum(|q| + |r|), one host thread per GPU inside the library, results in the caller's order; no collective.
+pub fn align_batch_multi<const X_DROP: bool, M: Matrix>(
+    devices: &[i32], queries: &[&[u8]], references: &[&[u8]], matrix: &M, gaps: Gaps, size: RangeInclusive<usize>, x_drop: i32,
+) -> (Vec<AlignResult>, BaStats) {
+    assert_eq!(queries.len(), references.len());
+    let n = queries.len();
+    let offsets = |v: &[&[u8]]| { let mut o = vec![0u64; n + 1]; for k in 0..n { o[k + 1] = o[k] + v[k].len() as u64; } o };
+    let (qo, ro) = (offsets(queries), offsets(references));
+    let (qa, ra): (Vec<u8>, Vec<u8>) = (queries.concat(), references.concat());
+    let cfg = BaConfig { scoring: M::SCORING, flags: if X_DROP { BA_XDROP } else { 0 }, matrix: matrix.as_ptr(), gaps,
+                         size: SizeRange { min: *size.start(), max: *size.end() }, x_drop, cigar_eq: 0 };
+    let mut out = vec![AlignResult::default(); n];
+    let mut stats = BaStats::default();
+    let (dp, nd) = if devices.is_empty() { (std::ptr::null(), unsafe { ba_device_count() }) } else { (devices.as_ptr(), devices.len() as c_int) };
+    check(unsafe { ba_align_batch_multi(dp, nd, &cfg, n, qa.as_ptr(), qo.as_ptr(), ra.as_ptr(), ro.as_ptr(), out.as_mut_ptr(), &mut stats) });
+    (out, stats)
+}
+
+/// `Block::align_exp` (scan_block.rs:884-902) for a batch: `Some(min size that reached target_scores[k])` or `None` per pair.
+/// The batch stays on the device between the rounds; only the pairs still below their target are aligned again.
+pub fn align_batch_exp<const X_DROP: bool, M: Matrix>(
+    dev: &Device, queries: &[&[u8]], references: &[&[u8]], matrix: &M, gaps: Gaps, size: RangeInclusive<usize>, x_drop: i32,
+    target_scores: &[i32],
+) -> (Vec<AlignResult>, Vec<Option<usize>>) {
+    assert!(queries.len() == references.len() && queries.len() == target_scores.len());
+    let n = queries.len();
+    let offsets = |v: &[&[u8]]| { let mut o = vec![0u64; n + 1]; for k in 0..n { o[k + 1] = o[k] + v[k].len() as u64; } o };
+    let (qo, ro) = (offsets(queries), offsets(references));
+    let (qa, ra): (Vec<u8>, Vec<u8>) = (queries.concat(), references.concat());
+    let cfg = BaConfig { scoring: M::SCORING, flags: if X_DROP { BA_XDROP } else { 0 }, matrix: matrix.as_ptr(), gaps,
+                         size: SizeRange { min: *size.start(), max: *size.end() }, x_drop, cigar_eq: 0 };
+    let mut out = vec![AlignResult::default(); n];
+    let mut used = vec![0usize; n];
+    let mut stats = BaStats::default();
+    check(unsafe { ba_align_batch_exp(dev.h, &cfg, n, qa.as_ptr(), qo.as_ptr(), ra.as_ptr(), ro.as_ptr(), target_scores.as_ptr(),
+                                      out.as_mut_ptr(), used.as_mut_ptr(), &mut stats) });
+    (out, used.into_iter().map(|s| if s == 0 { None } else { Some(s) }).collect())
+}
+
+/// ASCII bases -> BAM nibble codes (two per byte) for `BA_INPUT_NUC4` batches; `Err(i)` = byte i is not an IUPAC base.
+pub fn pack_nuc4(ascii: &[u8]) -> Result<Vec<u8>, usize> {
+    let mut packed = vec![0u8; (ascii.len() + 1) / 2];
+    match unsafe { ba_pack_nuc4(ascii.as_ptr(), ascii.len(), packed.as_mut_ptr(), 0) } { 0 => Ok(packed), i => Err(i - 1) }
 }
 
 #[cfg(test)]
