@@ -309,7 +309,8 @@ def measure(name, n, steps, warmup, ctx, cpu_seconds, want_cpu, pageable_once=Fa
             out[:] = 0
             t2 = time.perf_counter()
             e2e_once(qp, rp)
-            pageable_s = time.perf_counter() - t2
+            e2e_once(qp, rp)
+            pageable_s = (time.perf_counter() - t2) / 2
             if not (out == e2e_out).all():
                 e2e_error = "pageable-input run returned different results"
             del qp, rp
@@ -379,7 +380,7 @@ def measure(name, n, steps, warmup, ctx, cpu_seconds, want_cpu, pageable_once=Fa
                                      "note": "same entry point, one ASCII byte per base (the reference's own input format)"}
     if pageable_s is not None:
         res["e2e"]["pageable_caller_buffers"] = {"value": cells_step / pageable_s / 1e9, "unit": "GCUPS", "ms_per_step": pageable_s * 1e3,
-                                                 "steps": 1, "note": "same call, inputs in ordinary malloc'ed memory (this rank only)"}
+                                                 "steps": 2, "note": "same call, inputs in ordinary malloc'ed memory (this rank only; the library stages them through pinned buffers with four copy threads)"}
     if e2e_error:
         res["e2e"] = {"value": None, "unit": "GCUPS", "error": e2e_error}
     res["_e2e_out"], res["_cig"] = e2e_out, cig
