@@ -221,7 +221,9 @@ int ba_batch_total_stats(const BaBatch* b, BaStats* stats);
 int ba_batch_pair_stats(const BaBatch* b, size_t k, uint64_t* cells, uint32_t* steps, uint32_t* status);
 void ba_batch_free(BaBatch* b);
 
-/* upload + run + download in one call: the end-to-end entry point */
+/* upload + run + download in one call: the end-to-end entry point. Large batches are cut into chunks whose uploads
+ * overlap the kernels of earlier chunks. q_bytes / r_bytes may live in pinned memory (fastest: one DMA per chunk) or in
+ * ordinary memory (copied by four host threads through pinned staging buffers; BA_STAGE_THREADS = 1..8). */
 int ba_align_batch(BaAligner* a, const BaConfig* cfg, size_t n,
                    const uint8_t* q_bytes, const uint64_t* q_off,
                    const uint8_t* r_bytes, const uint64_t* r_off,
