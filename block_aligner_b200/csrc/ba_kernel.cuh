@@ -483,7 +483,7 @@ BA_DEV void add_cells(AlnState& st, uint32_t n) {
 // layout: 0 = rows-per-lane from the height, 1 = forced 8 rows per lane (FREE_QUERY_END_GAPS), 3 = packed path
 // (one word per lane and column, word index = column * H / 8 + lane; ba_packed.cuh)
 BA_HD uint64_t rect_words(int H, int W, int layout = 0) {
-  if (layout == 3) return (uint64_t)(H >> 3) * (uint64_t)W;
+  if (layout == 3 || layout == 2) return (uint64_t)(H >> 3) * (uint64_t)W;     // packed path (2: taller than 256 rows, in 256-row chunks)
   const int R = layout == 1 ? 8 : rect_rows_per_lane(H);
   const int CH = 32 * R;
   const int nch = (H + CH - 1) / CH;
@@ -580,9 +580,11 @@ BA_DEV void traceback_rect(const uint8_t* lut, const uint32_t* words, const uint
     const uint32_t v = rc_right ? i - rc.row : j - rc.col;
     const uint32_t c = rc_right ? j - rc.col : i - rc.row;
     uint32_t nib;
-    if (layout == 3u) {     // packed path: word (column, lane in group), nibble (row mod 4) of the half-block's 16 bits
-      const uint32_t half = v >= hh ? 1u : 0u, vv = v - half * hh;
-      nib = (tw[(size_t)c * G + (vv >> 2)] >> (16u * half + 4u * (vv & 3u))) & 15u;
+    if (layout >= 2u) {     // packed path: word (column, lane in group), nibble (row mod 4) of the half-block's 16 bits;
+      // layout 2: the rectangle is a stack of 256-row chunks of 32 lanes each
+      const uint32_t chn = layout == 2u ? (v >> 8) : 0u, v8 = layout == 2u ? (v & 255u) : v, h2 = layout == 2u ? 128u : hh;
+      const uint32_t half = v8 >= h2 ? 1u : 0u, vv = v8 - half * h2;
+      nib = (tw[(size_t)c * G + chn * 32u + (vv >> 2)] >> (16u * half + 4u * (vv & 3u))) & 15u;
     } else {
       const uint32_t ch = v / CH, ln = (v % CH) / R, k = v % R;
       const size_t widx = (((size_t)ch * ngroups + (c >> 3)) * R + k) * 32 + ln;
@@ -856,7 +858,9 @@ BA_BIG_LOOP_FN int big_loop(const Params& P, AlnState* stp, const WarpMem* wp_, 
   return status;
 }
 
-template <int SCORING, int FLAGS>
+// TALL: rectangles taller than 256 rows may take the packed path (place_rect_pk_tall). Only kernels for max block sizes
+// >= 1024 (FM >= 32) carry that code: elsewhere it would be 9 KB that never (max <= 256) or hardly ever (512) runs.
+template <int SCORING, int FLAGS, bool TALL = false>
 BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const SlotMem& sm, uint32_t slot) {
   constexpr bool TRACE = (FLAGS & kTrace) != 0, XDROP = (FLAGS & kXDrop) != 0, EXT = (FLAGS & kExt) != 0;
   constexpr bool PROF = SCORING == kProfile;
@@ -981,19 +985,19 @@ BA_DEV int run_generic(const Params& P, AlnState& st, const WarpMem& w, const Sl
           origin_pk = true;
         }
       }
-      const bool pk_ok = !PROF && !EXT && P.pk_enable && !st.overflow && pk_rect_ok(P, a, origin_pk);
+      const bool pk_ok = !PROF && !EXT && P.pk_enable && !st.overflow && pk_rect_ok<TALL>(P, a, origin_pk);
       if (origin_pk && !pk_ok) { a.off_add = 0; a.corner = 0; }
       if (TRACE && a.W > 0 && a.H >= 0) {
         const uint32_t woff = st.widx;
         if (m_local && sm.zwords) a.tz = sm.zwords + woff;
-        a.tw = trace_push(P, st, sm, rect_right ? a.vec_base : a.col_base, rect_right ? a.col_base : a.vec_base, a.W, a.H, rect_right, lane == 0, pk_ok ? 3 : (m_fqe ? 1 : 0));
+        a.tw = trace_push(P, st, sm, rect_right ? a.vec_base : a.col_base, rect_right ? a.col_base : a.vec_base, a.W, a.H, rect_right, lane == 0, pk_ok ? (a.H > 256 ? 2 : 3) : (m_fqe ? 1 : 0));
       }
       add_cells(st, (uint32_t)(a.W * a.H));
       sc.vec = rect_right ? q : r; sc.col = rect_right ? r : q;
       int pbv = 0; unsigned pkey = 15u << kKeyClsShift;
       if (!st.overflow) {
         const bool done = pk_ok;
-        if (pk_ok) place_rect_pk<(PROF ? kAA : SCORING), XDROP, TRACE>(w.smem0, P, P.kc, sc.vec, sc.col, a, w.fr, pbv, pkey);
+        if (pk_ok) place_rect_pk<(PROF ? kAA : SCORING), XDROP, TRACE, TALL>(w.smem0, P, P.kc, sc.vec, sc.col, a, w.fr, pbv, pkey, w.ecarry);
 #ifdef BA_EMU
         if (wp::lane_id() == 0) { if (done) emu_stats::pk_cells += (uint64_t)a.W * a.H; else emu_stats::exact_cells += (uint64_t)a.W * a.H; }
 #endif
@@ -1495,7 +1499,7 @@ BA_DEV void warp_main(const Params& P, unsigned char* smem, int warp_in_block, u
         if (sg == kStNeedGrow) apply_grow(gs, w, TRACE);
       }
       int r = kRunDone;
-      if (sg != kStDone) r = run_generic<SCORING, FLAGS>(P, gs, w, sm, slot);
+      if (sg != kStDone) r = run_generic<SCORING, FLAGS, (FM >= 32)>(P, gs, w, sm, slot);
       if (r == kRunDone) {
         finish_alignment<SCORING, FLAGS>(P, gs, w, slot);
         if (mine) status = kStEmpty;
@@ -1721,10 +1725,11 @@ BA_DEV void lanes_traceback(const Params& P, const uint8_t* lut, const uint32_t*
           const uint32_t c = rc_right ? s.j - rc.col : s.i - rc.row;
           uint32_t nib;
           bool zstop = false;
-          if (layout == 3u) {
-            const uint32_t hh = (uint32_t)rc.h >> 1, G = (uint32_t)rc.h >> 3;
-            const uint32_t half = v >= hh ? 1u : 0u, vv = v - half * hh;
-            const uint32_t wi = c * G + (vv >> 2);
+          if (layout >= 2u) {
+            const uint32_t G = (uint32_t)rc.h >> 3;
+            const uint32_t chn = layout == 2u ? (v >> 8) : 0u, v8 = layout == 2u ? (v & 255u) : v, hh = layout == 2u ? 128u : ((uint32_t)rc.h >> 1);
+            const uint32_t half = v8 >= hh ? 1u : 0u, vv = v8 - half * hh;
+            const uint32_t wi = c * G + chn * 32u + (vv >> 2);
 #ifdef BA_EMU
             if (STAGED && stg) emu_stats::tb_staged++; else emu_stats::tb_global++;
 #endif

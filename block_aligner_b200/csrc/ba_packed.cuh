@@ -53,6 +53,10 @@ BA_DEV uint32_t pk2(int v) { return wp::h_pack(v, v); }
 #ifndef BA_PK_GT
 #define BA_PK_GT 1
 #endif
+// BA_PK_TALL = 1: rectangles taller than 256 rows on the packed path, in chained 256-row chunks (place_rect_pk_tall)
+#ifndef BA_PK_TALL
+#define BA_PK_TALL 1
+#endif
 template <bool TRACE, int K> struct PkMc { static constexpr bool kSplit = BA_PK_SPLIT_MC && !TRACE; static constexpr int kN = kSplit ? 2 * K : K; };
 constexpr int kPkUnroll = BA_PK_UNROLL;    // 1, 2 or 4
 
@@ -182,10 +186,16 @@ BA_DEV uint32_t pk_eqmask(uint32_t y, uint32_t x) { return wp::viaddmin2(y, ~x, 
 // a stage whose shuffle distance reaches G returns the lane's own value and changes nothing because extend < 0).
 // GT: the group size when it is known at compile time (0: run-time `Gr`) -- shuffle widths become immediates instead of
 // operands that the generic phase, short of registers, rebuilds in every iteration of the column loop.
-template <int KIND, bool XDROP, int NST, bool TRACE = false, int K = 4, int GT = 0>
+// CHAIN: the rectangle continues one above it (rectangles taller than 256 rows are swept in 256-row chunks, chunk-major):
+// `tops[c]` = R | D << 16 of the row just above for the eight columns (the bottom row the chunk above wrote to `fr`),
+// `dprev` = that row's D one column to the left of the first (the diagonal input of column 0), `etop` / `eout` = the
+// "R gap opened at this row" bit of that row and of this chunk's last row (TRACE), `tstride` = trace words per column.
+template <int KIND, bool XDROP, int NST, bool TRACE = false, int K = 4, int GT = 0, bool CHAIN = false>
 BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int Gr, int lg, uint32_t cw0, uint32_t cw1,
                      uint32_t (&D)[K], uint32_t (&C)[K], uint32_t corner_lo, int cbase, uint32_t (&m)[K], uint32_t (&mc)[PkMc<TRACE, K>::kN],
-                     uint32_t* fr, bool writer, uint32_t* tw = nullptr, bool tstore = false, int ncol8 = 8) {
+                     uint32_t* fr, bool writer, uint32_t* tw = nullptr, bool tstore = false, int ncol8 = 8,
+                     const uint32_t* tops = nullptr, uint32_t dprev = 0u, const uint8_t* etop = nullptr, uint8_t* eout = nullptr,
+                     int tstride = 0) {
   // ncol8 < 8: global-mode early break inside this group of eight columns (scan_block.rs:1216-1224): only the first
   // ncol8 columns exist; D / C then hold the last computed column, like the reference's D_col / C_col after its break
   static_assert(!TRACE || K == 4, "trace words are laid out for four registers per lane");
@@ -213,7 +223,14 @@ BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int Gr, int lg
       // rectangle's corner (first column only; MIN = 0 afterwards, scan_block.rs:1211), high half = row K G - 1,
       // which is the low half of the last lane's last register.
       uint32_t up = (uint32_t)wp::shfl_idx_w((int)D[K - 1], lg - 1, G);
-      if (lg == 0) up = (up << 16) | ((cbase + cidx == 0) ? corner_lo : 0u);
+      uint32_t topw = 0u;
+      if (CHAIN) {
+        topw = tops[cidx];
+        if (lg == 0) up = (up << 16) | (dprev & 0xffffu);
+        dprev = topw >> 16;                       // the next column's diagonal input
+      } else {
+        if (lg == 0) up = (up << 16) | ((cbase + cidx == 0) ? corner_lo : 0u);
+      }
       uint32_t dd[K], c11[K], uu[K];
       uint32_t acc[K];                            // trace nibbles of the lane's rows (TRACE)
 #pragma unroll
@@ -229,6 +246,8 @@ BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int Gr, int lg
       }
       // Kogge-Stone over the lane aggregates, both half-blocks at once; stage s decays by (K << s) * extend
       uint32_t inc = uu[K - 1];
+      // CHAIN: the U of the row above enters the scan through the first lane's aggregate (low half; the high half's 0 + K extend < 0 cannot win)
+      if (CHAIN && lg == 0) inc = wp::viaddmax2((topw - kc.or2) & 0xffffu, kge3, inc);
 #pragma unroll
       for (int s = 0; s < NST; s++) {
         const uint32_t u = (uint32_t)wp::shfl_up_w((int)inc, 1 << s, G);
@@ -239,7 +258,8 @@ BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int Gr, int lg
       // carry into the lane: the lanes above (same half) and, for the high half, the whole low half-block
       const uint32_t tl = (uint32_t)wp::shfl_idx_w((int)inc, G - 1, G);
       uint32_t ex = (uint32_t)wp::shfl_up_w((int)inc, 1, G);
-      if (lg == 0) ex = 0u;
+      // first lane: nothing above (T[top - 1] = 0, which cannot win); CHAIN: the U of the row above = its R - (open - extend)
+      if (lg == 0) ex = CHAIN ? ((topw - kc.or2) & 0xffffu) : 0u;
       const uint32_t cin = wp::viaddmax2(tl << 16, lanedec, ex);
       uint32_t UnL = 0;
       uint32_t eprev = 0u;                        // "R gap opened at this row" (T == x) of the previous row of the lane
@@ -279,10 +299,11 @@ BA_DEV void pk_cols8(const PkScorer<KIND>& sc, const PkConst& kc, int Gr, int lg
         // bit 3 of the lane's first rows comes from the last row of the lane above: lane 0's high half continues the
         // last lane's low half, lane 0's low half is the top of the rectangle (no row above: R01 = MIN)
         uint32_t eup = (uint32_t)wp::shfl_idx_w((int)eprev, lg - 1, G);
-        if (lg == 0) eup <<= 16;
+        if (lg == 0) eup = (eup << 16) | ((CHAIN && etop && etop[cidx]) ? 0xffffu : 0u);
         acc[0] |= eup & 0x00080008u;
         const uint32_t word = acc[0] | (acc[1 % K] << 4) | (acc[2 % K] << 8) | (acc[3 % K] << 12);
-        if (tstore) tw[(size_t)(cbase + cidx) * G + lg] = word;
+        if (tstore) tw[(size_t)(cbase + cidx) * (CHAIN ? tstride : G) + lg] = word;
+        if (CHAIN && writer) eout[cidx] = (uint8_t)(eprev >> 31);
       }
       if (writer) fr[cidx] = wp::prmt(wp::vadd2(UnL, or2), D[K - 1], 0x7632u);   // T.hi | D.hi << 16
     }
@@ -488,10 +509,12 @@ BA_DEV bool pk_in_range(const uint32_t (&a)[N], const uint32_t (&b)[N], int lo, 
 
 // Can this rectangle go through the packed path? Shape (32..256 rows, whole 8-column groups, not the forced origin
 // cell unless run_generic set it up) and value range of its inputs (pk_bounds). Nothing is modified.
+template <bool TALL = false>
 BA_DEV bool pk_rect_ok(const Params& P, const RectArgs& a, bool origin_ok = false) {
   const int lane = wp::lane_id();
   const int H = a.H, W = a.W;
-  if (!(H == 32 || H == 64 || H == 128 || H == 256) || W <= 0 || (W & 7) || W > 256 || a.ncols <= 0) return false;
+  const bool tall = BA_PK_TALL && TALL && H > 256 && (H & 255) == 0 && 2 * W <= (int)P.max_size;      // swept in 256-row chunks (place_rect_pk_tall)
+  if (!(H == 32 || H == 64 || H == 128 || H == 256 || tall) || W <= 0 || (W & 7) || W > (tall ? 4096 : 256) || a.ncols <= 0) return false;
   if (a.vec_base == 0 && a.col_base == 0 && !origin_ok) return false;   // forced origin cell (scan_block.rs:1130-1132): only as set up by run_generic
   int GL, GH;
   pk_bounds(W, P.gap_open, P.gap_extend, P.pk_smax, GL, GH);
@@ -499,10 +522,13 @@ BA_DEV bool pk_rect_ok(const Params& P, const RectArgs& a, bool origin_ok = fals
   // v is inside [GL - off_add, GH - off_add] (clipped to i16)
   const int lo_b = wp::imax(GL - a.off_add, kI16Min), hi_b = wp::imin(GH - a.off_add, kI16Max);
   // every lane tests 8 consecutive entries of both input borders (entries >= H: lanes mirror the first ones)
-  const int e = (8 * lane) & (H - 1);
-  const uint4 d = *(const uint4*)(a.AD + e), c = *(const uint4*)(a.AC + e);
-  const uint32_t D[4] = {d.x, d.y, d.z, d.w}, C[4] = {c.x, c.y, c.z, c.w};
-  const bool ok = lo_b <= hi_b && a.corner >= 0 && a.corner <= GH && pk_in_range<4>(D, C, lo_b, hi_b);
+  bool ok = lo_b <= hi_b && a.corner >= 0 && a.corner <= GH;
+  for (int e0 = 0; e0 < ((BA_PK_TALL && TALL) ? H : 1); e0 += 256) {
+    const int e = e0 + ((8 * lane) & (((BA_PK_TALL && TALL) ? wp::imin(H, 256) : H) - 1));
+    const uint4 d = *(const uint4*)(a.AD + e), c = *(const uint4*)(a.AC + e);
+    const uint32_t D[4] = {d.x, d.y, d.z, d.w}, C[4] = {c.x, c.y, c.z, c.w};
+    ok = ok && pk_in_range<4>(D, C, lo_b, hi_b);
+  }
   return wp::ballot(!ok) == 0u;
 }
 
@@ -555,9 +581,73 @@ BA_DEV void place_rect_pk_k(const unsigned char* smem, const Params& P, const Pk
   else bv = wp::imax(bv, wp::imax(wp::h_lo(m[0]), wp::h_hi(m[0])));
   wp::syncwarp();
 }
+// Rectangles taller than 256 rows (blocks 512 .. 16384: the grow rectangles of long alignments) as a stack of 256-row
+// chunks, chunk-major like the exact path: chunk ch sweeps all columns, reading the bottom row of chunk ch - 1 from
+// a.OD / a.OR_ (which it then overwrites with its own, so that the last chunk leaves the rectangle's bottom row there)
+// and, for TRACE, that row's "opened here" bits from `ecarry`. Trace words: layout 2 (H / 8 words per column, 32 per chunk).
 template <int KIND, bool XDROP, bool TRACE>
+BA_DEV void place_rect_pk_tall(const unsigned char* smem, const Params& P, const PkConst& kc, const uint8_t* vec, const uint8_t* col,
+                               const RectArgs& a, uint32_t* fr, int& bv, unsigned& bkey, uint8_t* ecarry) {
+  const int lane = wp::lane_id();
+  const int H = a.H;
+  // `ecarry` (max_size bytes) in two halves, written and read by alternate chunks: a rectangle this tall is at most
+  // max_size / 2 columns wide (grow rectangles) or 8 (shift steps)
+  const int ehalf = (int)(P.max_size >> 1);
+  constexpr int G = 32;
+  bv = 0; bkey = 15u << kKeyClsShift;
+  const uint32_t oa2 = pk2(a.off_add);
+  PkScorer<KIND> sc;
+  sc.init(smem, P);
+  uint32_t* tops = fr + 8;                 // staging of the row above (fr[0..8) is the column routine's own bottom row)
+  uint32_t corner = (uint32_t)a.corner & 0xffffu;
+  for (int ch = 0; ch * 256 < H; ch++) {
+    uint32_t D[4], C[4];
+    pk_loadk<4>(a.AD + 256 * ch, lane, G, D);
+    pk_loadk<4>(a.AC + 256 * ch, lane, G, C);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { D[k] = wp::vadd2(D[k], oa2); C[k] = wp::vadd2(C[k], oa2); }
+    // the old border value of this chunk's last row is the next chunk's corner (the store below overwrites it)
+    const uint32_t next_corner = (uint32_t)wp::shfl_idx((int)D[3], G - 1) >> 16;
+    sc.rows(*(const uint32_t*)(vec + a.vec_base + 256 * ch + 4 * lane), *(const uint32_t*)(vec + a.vec_base + 256 * ch + 128 + 4 * lane));
+    uint32_t m[4] = {0u, 0u, 0u, 0u}, mc[PkMc<TRACE, 4>::kN] = {};
+    uint32_t dprev = corner;
+    for (int cb = 0; cb < a.ncols; cb += 8) {
+      const uint2 cw = *(const uint2*)(col + a.col_base + cb);
+      const int n8 = wp::imin(8, a.ncols - cb);
+      // the row above: the bottom row of chunk ch - 1; for the top chunk R = open - extend (U = 0: cannot win) and D = MIN = 0
+      if (lane < 8) tops[lane] = ch > 0 ? ((uint32_t)(uint16_t)a.OR_[cb + lane] | ((uint32_t)(uint16_t)a.OD[cb + lane] << 16))
+                                        : (uint32_t)(uint16_t)kc.or2;
+      wp::syncwarp();
+      pk_cols8<KIND, XDROP, 5, TRACE, 4, 32, true>(sc, kc, G, lane, cw.x, cw.y, D, C, 0u, cb, m, mc, fr, lane == G - 1,
+                                                    a.tw ? a.tw + 32 * ch : nullptr, TRACE, n8, tops, dprev,
+                                                    ch > 0 ? ecarry + ((ch + 1) & 1) * ehalf + cb : nullptr, ecarry + (ch & 1) * ehalf + cb, H >> 3);
+      dprev = tops[7] >> 16;       // (the top chunk: 0, the diagonal input after column 0 is MIN)
+      wp::syncwarp();
+      if (lane < n8) { const uint32_t v = fr[lane]; a.OD[cb + lane] = (int16_t)(v >> 16); a.OR_[cb + lane] = (int16_t)(v & 0xffffu); }
+      wp::syncwarp();
+    }
+    pk_storek<4>(a.AD + 256 * ch, lane, G, D);
+    pk_storek<4>(a.AC + 256 * ch, lane, G, C);
+    corner = next_corner;
+    if (XDROP) {
+      // per-chunk maximum and key (row = 256 ch + row in chunk; 256 is a multiple of 16, the lane classes do not move)
+      const int cbv = pk_lane_max<4>(m);
+      if (wp::red_max(cbv) > a.key_thr) {
+        const unsigned ck = pk_lane_key<4, PkMc<TRACE, 4>::kN>(m, mc, lane, G, cbv) + (unsigned)(256 * ch);
+        if (cbv > bv || (cbv == bv && ck > bkey)) bkey = ck;
+      }
+      bv = wp::imax(bv, cbv);
+    } else {
+      bv = wp::imax(bv, wp::imax(wp::h_lo(m[0]), wp::h_hi(m[0])));
+    }
+    wp::syncwarp();
+  }
+}
+
+template <int KIND, bool XDROP, bool TRACE, bool TALL = false>
 BA_DEV void place_rect_pk(const unsigned char* smem, const Params& P, const PkConst& kc, const uint8_t* vec, const uint8_t* col,
-                          const RectArgs& a, uint32_t* fr, int& bv, unsigned& bkey) {
+                          const RectArgs& a, uint32_t* fr, int& bv, unsigned& bkey, uint8_t* ecarry = nullptr) {
+  if (BA_PK_TALL && TALL && a.H > 256) { place_rect_pk_tall<KIND, XDROP, TRACE>(smem, P, kc, vec, col, a, fr, bv, bkey, ecarry); return; }
   constexpr int K128 = (TRACE || !(BA_PK_KVAR & 2)) ? 4 : 2, K64 = (TRACE || !(BA_PK_KVAR & 1)) ? 4 : 1;
   // (one call site per distinct K: every call is an inlined copy of the rectangle code)
   // With both variants on, 128- and 256-row rectangles always use all 32 lanes: their group size is a compile-time 32.

@@ -46,7 +46,7 @@ def test_dna_packed_coverage(env, flags, size):
     if size[1] <= 256:
         assert packed > 4 * s["exact_cells"], s      # the packed path carries the bulk of the work
     else:
-        assert packed > 0, s                         # rectangles taller than 256 rows still take the exact path
+        assert packed > 0, s                         # (64, 512): no global-border kernel, rectangles taller than 256 rows take the exact path
     if size[0] in (32, 64):
         assert s["fast_steps"] > 0, s
 
@@ -112,3 +112,22 @@ def test_profile_fast_phase_coverage(env, flags, size):
     stats(lib)
     assert parity.check_pssm(lib, al, 12, 9, True, (1, 0), True, size=size, flags=flags | api.TRACE) == 0
     assert stats(lib)["fast_steps"] == 0      # TRACE profile batches stay on the exact path
+
+
+@pytest.mark.parametrize("flags", [0, api.XDROP, api.TRACE, api.TRACE | api.XDROP])
+@pytest.mark.parametrize("size", [(32, 1024), (64, 2048), (64, 4096)])
+def test_tall_rectangles_chained_chunks(env, flags, size):
+    """Rectangles taller than 256 rows on the packed path (place_rect_pk_tall): 256-row chunks chained through the bottom
+    row of the chunk above -- D, R (the vertical-gap scan has to continue across the chunk border: big insertions) and the
+    trace bit. Kernels with max block >= 1024 and a fast phase (min block 32 / 64) carry that code."""
+    lib, al = env
+    w = dict(scoring=api.SCORING_NUC, matrix=(2, -4), gaps=(-6, -2), size=size, x_drop=400, flags=flags, stream=52,
+             gen=P(alphabet=0, len_dist=0, len_min=2500, len_max=6000, suffix_len=200, big_indel_prob=0.9, big_indel_min=300,
+                   big_indel_max=1500, **NOISY))
+    stats(lib)
+    assert parity.check_workload(lib, al, w, 6, seed=3 + flags) == 0
+    s = stats(lib)
+    # the grow rectangles of 512+ rows went through the packed path (a 2048-column rectangle leaves the guard only
+    # 32767 - 2048 (max score + |open|) of input range: the grow to 4096 mostly stays on the exact path)
+    if size[1] <= 2048:
+        assert s["pk_cells"] > 4 * s["exact_cells"], s

@@ -48,6 +48,16 @@ def test_dna_min64(env, flags, size):
 
 
 @pytest.mark.parametrize("flags", [0, api.XDROP, api.TRACE, api.TRACE | api.XDROP])
+@pytest.mark.parametrize("size", [(32, 1024), (64, 2048), (64, 8192)])
+def test_tall_rectangles_chained_chunks(env, flags, size):
+    """big indels grow the block past 256 rows: packed rectangles in chained 256-row chunks (place_rect_pk_tall)"""
+    w = dict(scoring=api.SCORING_NUC, matrix=(2, -4), gaps=(-6, -2), size=size, x_drop=400, flags=flags, stream=52,
+             gen=P(alphabet=0, len_dist=0, len_min=2500, len_max=9000, suffix_len=200, big_indel_prob=0.9, big_indel_min=300,
+                   big_indel_max=3000, **NOISY))
+    assert parity.check_workload(*env, w, 300, seed=3 + flags) == 0
+
+
+@pytest.mark.parametrize("flags", [0, api.XDROP, api.TRACE, api.TRACE | api.XDROP])
 def test_dna_big_indels_force_growth(env, flags):
     w = dict(scoring=api.SCORING_NUC, matrix=(2, -4), gaps=(-6, -2), size=(32, 512), x_drop=200, flags=flags, stream=12,
              gen=P(alphabet=0, len_dist=0, len_min=1500, len_max=4000, suffix_len=100, big_indel_prob=0.8,
