@@ -54,7 +54,7 @@ def test_tall_rectangles_chained_chunks(env, flags, size):
     w = dict(scoring=api.SCORING_NUC, matrix=(2, -4), gaps=(-6, -2), size=size, x_drop=400, flags=flags, stream=52,
              gen=P(alphabet=0, len_dist=0, len_min=2500, len_max=9000, suffix_len=200, big_indel_prob=0.9, big_indel_min=300,
                    big_indel_max=3000, **NOISY))
-    assert parity.check_workload(*env, w, 300, seed=3 + flags) == 0
+    assert parity.check_workload(*env, w, 150, seed=3 + flags) == 0
 
 
 @pytest.mark.parametrize("flags", [0, api.XDROP, api.TRACE, api.TRACE | api.XDROP])
