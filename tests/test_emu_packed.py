@@ -131,3 +131,16 @@ def test_tall_rectangles_chained_chunks(env, flags, size):
     # 32767 - 2048 (max score + |open|) of input range: the grow to 4096 mostly stays on the exact path)
     if size[1] <= 2048:
         assert s["pk_cells"] > 4 * s["exact_cells"], s
+
+
+@pytest.mark.parametrize("flags", [api.XDROP, api.TRACE | api.XDROP])
+def test_tall_rectangles_protein(env, flags):
+    """the same on the AAMatrix scorer (two LDS.U16 per pair of cells instead of the nucleotide table)"""
+    lib, al = env
+    w = dict(scoring=api.SCORING_AA, matrix="BLOSUM62", gaps=(-11, -1), size=(32, 1024), x_drop=100, flags=flags, stream=77,
+             gen=P(alphabet=1, len_dist=0, len_min=2500, len_max=6000, suffix_len=200, big_indel_prob=0.9, big_indel_min=300,
+                   big_indel_max=1500, **NOISY))
+    stats(lib)
+    assert parity.check_workload(lib, al, w, 6, seed=3 + flags) == 0
+    s = stats(lib)
+    assert s["pk_cells"] > 4 * s["exact_cells"], s
