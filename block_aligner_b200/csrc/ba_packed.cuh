@@ -1,8 +1,8 @@
 // ba_packed.cuh -- the DP of one rectangle on packed 2 x i16 DPX instructions.
 //
 // Included by ba_kernel.cuh. Same recurrence as place_rect_r (reference: place_block, scan_block.rs:1083-1228;
-// prefix scan avx2.rs:297-338), but two rows per 32-bit register: a group of G lanes (G = H / 8, H = 32..256 rows)
-// owns one rectangle; lane lg keeps rows 4*lg + k in the low halfword and rows 4*G + 4*lg + k in the high
+// prefix scan avx2.rs:297-338), but two rows per 32-bit register: a group of G lanes (G = H / 8, H = 32..256 rows;
+// taller rectangles: a stack of 256-row chunks, place_rect_pk_tall) owns one rectangle; lane lg keeps rows 4*lg + k in the low halfword and rows 4*G + 4*lg + k in the high
 // halfword of register k (k = 0..3). Every add/max of the recurrence is one VIADDMNMX.S16x2 / VIMNMX.S16x2,
 // i.e. two cells per ALU instruction.
 //
@@ -53,7 +53,9 @@ BA_DEV uint32_t pk2(int v) { return wp::h_pack(v, v); }
 #ifndef BA_PK_GT
 #define BA_PK_GT 1
 #endif
-// BA_PK_TALL = 1: rectangles taller than 256 rows on the packed path, in chained 256-row chunks (place_rect_pk_tall)
+// BA_PK_TALL = 1: rectangles taller than 256 rows on the packed path, in chained 256-row chunks (place_rect_pk_tall), in
+// the kernels that have a fast phase and max block >= 1024. Measured on C5 (block 64..=2048, TRACE | X_DROP): kernel
+// 345 -> 373 GCUPS, instruction-cache hit rate 91 -> 98 % (profiles/r02_tall_ab.txt, r02_ncu_k_C5_metrics.csv).
 #ifndef BA_PK_TALL
 #define BA_PK_TALL 1
 #endif
